@@ -1,0 +1,338 @@
+"""Generate golden vectors from the UNMODIFIED reference (run in the dev container only).
+
+    python tests/golden/make_golden.py
+
+Loads /root/reference/gptools through oracle/ref_shim.py and dumps, for a set of
+seeded inputs covering SURVEY.md section 8 rows a1-a10 / configs C1-C5 (at sizes the
+reference evaluates in seconds), the reference's K entries, ll, ll gradient,
+alpha, predictive mean/std/cov and draw_sample output into tests/golden/*.npz.
+The library versions that produced the numbers are stored in every file.
+"""
+import json
+import os
+import pickle
+import sys
+import warnings
+
+import numpy as np
+import scipy
+from numpy.random import RandomState
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+warnings.simplefilter("ignore")
+
+from oracle.ref_shim import load_reference, REF_ROOT  # noqa: E402
+
+g = load_reference()
+
+META = json.dumps({
+    "numpy": np.__version__, "scipy": scipy.__version__, "python": sys.version.split()[0],
+    "reference": "markchil/gptools %s (unmodified, via oracle/ref_shim.py)" % g.__version__,
+})
+
+
+def save(name, **arrs):
+    arrs["meta"] = np.array(META)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrs)
+    print("wrote", name, {k: np.shape(v) for k, v in arrs.items() if k != "meta"})
+
+
+def gp_state(gp):
+    """Inputs exactly as the reference holds them after add_data."""
+    d = {"X": gp.X, "n": gp.n, "y": gp.y, "err_y": gp.err_y}
+    if gp.T is not None:
+        d["T"] = gp.T
+    return d
+
+
+def ll_and_grad(gp, with_grad):
+    gp.use_hyper_deriv = with_grad
+    gp.K_up_to_date = False
+    gp.compute_K_L_alpha_ll()
+    out = {"ll": gp.ll, "log_prior": gp.hyperprior(gp.params), "alpha": gp.alpha.ravel(),
+           "K": gp.K, "L": gp.L}
+    if with_grad:
+        out["ll_deriv"] = gp.ll_deriv
+    return out
+
+
+# ---------------------------------------------------------------- KAT-1: SE 2-D + gradients
+def case_se2d():
+    rs = RandomState(0)
+    X = rs.rand(6, 2)
+    y = np.sin(X).sum(1)
+    k = g.SquaredExponentialKernel(num_dim=2, initial_params=[1.3, 0.7, 1.1], param_bounds=[(0, 10)] * 3)
+    gp = g.GaussianProcess(k)
+    gp.add_data(X, y, err_y=0.01)
+    gp.add_data(X, np.cos(X[:, 0]), n=np.tile([1, 0], (6, 1)), err_y=0.01)
+    gp.add_data(X, np.cos(X[:, 1]), n=np.tile([0, 1], (6, 1)), err_y=0.01)
+    out = ll_and_grad(gp, True)
+    for p in range(3):
+        out["dK%d" % p] = gp.compute_Kij(gp.X, None, gp.n, None, hyper_deriv=p)
+    Xs = rs.rand(4, 2)
+    res = gp.predict(Xs, full_output=True)
+    out.update(Xs=Xs, mean=res["mean"], std=res["std"], cov=res["cov"])
+    res = gp.predict(Xs, n=np.tile([1, 0], (4, 1)), full_output=True)
+    out.update(mean_d1=res["mean"], std_d1=res["std"], cov_d1=res["cov"])
+    out["Kstar"] = gp.compute_Kij(gp.X, Xs, gp.n, np.zeros((4, 2), dtype=int))
+    save("se2d_kat1", params=k.params.copy(), **gp_state(gp), **out)
+
+
+# ---------------------------------------------------------------- SE pair list, orders 0-4
+def case_se_pairs():
+    rs = RandomState(11)
+    npair = 600
+    for D in (1, 2, 3):
+        Xi = rs.randn(npair, D)
+        Xj = rs.randn(npair, D)
+        Xj[:40] = Xi[:40]                      # tau == 0 pairs
+        Xj[40:60, 0] = Xi[40:60, 0]            # tau == 0 in one dimension only
+        ni = rs.randint(0, 3, size=(npair, D))
+        nj = rs.randint(0, 3, size=(npair, D))
+        ni[100:200] = 0
+        nj[200:300] = 0
+        params = np.concatenate(([1.7], 0.5 + rs.rand(D)))
+        k = g.SquaredExponentialKernel(num_dim=D, initial_params=params, param_bounds=[(0, 10)] * (D + 1))
+        out = {"val": k(Xi, Xj, ni, nj)}
+        for p in range(D + 1):
+            out["hd%d" % p] = k(Xi, Xj, ni, nj, hyper_deriv=p)
+        # value-only list (the reference's fast path, squared_exponential.py:110-113,169-171)
+        z = np.zeros_like(ni)
+        out["val0"] = k(Xi, Xj, z, z)
+        for p in range(D + 1):
+            out["hd0_%d" % p] = k(Xi, Xj, z, z, hyper_deriv=p)
+        save("se_pairs_D%d" % D, Xi=Xi, Xj=Xj, ni=ni, nj=nj, params=params, **out)
+
+
+# ---------------------------------------------------------------- KAT-2: Matern52 1-D, + 2-D K (tests/test_matern.py shape)
+def case_matern52():
+    rs = RandomState(1)
+    X = np.sort(rs.rand(8))
+    k = g.Matern52Kernel(num_dim=1, initial_params=[2.0, 0.4], param_bounds=[(0, 10)] * 2)
+    gp = g.GaussianProcess(k)
+    gp.add_data(X, np.sin(5 * X), err_y=0.02)
+    gp.add_data(X[::2], 5 * np.cos(5 * X[::2]), n=1, err_y=0.05)
+    out = ll_and_grad(gp, False)
+    Xs = np.array([0.1, 0.5, 0.9])
+    res = gp.predict(Xs, full_output=True)
+    out.update(Xs=Xs, mean=res["mean"], std=res["std"], cov=res["cov"])
+    res = gp.predict(Xs, n=1, full_output=True)
+    out.update(mean_d1=res["mean"], std_d1=res["std"], cov_d1=res["cov"])
+    save("matern52_kat2", params=k.params.copy(), **gp_state(gp), **out)
+
+    # the reference's own test (tests/test_matern.py:4-31) with seeded length scales
+    rs = RandomState(0)
+    X2 = rs.randn(5, 2)
+    ls = np.exp(RandomState(5).randn(2) * 0.5)
+    k2 = g.Matern52Kernel(num_dim=2, initial_params=[1.0, ls[0], ls[1]], param_bounds=[(0, 10)] * 3)
+    gp2 = g.GaussianProcess(k2)
+    yv = rs.randn(5)
+    gp2.add_data(X2, yv, err_y=0.1)
+    gp2.add_data(X2, rs.randn(5), n=np.tile([1, 0], (5, 1)), err_y=0.1)
+    gp2.add_data(X2, rs.randn(5), n=np.tile([0, 1], (5, 1)), err_y=0.1)
+    out = ll_and_grad(gp2, False)
+    # generic Matern at nu = 5/2 on the same data (kernel/matern.py:251-465)
+    k3 = g.MaternKernel(num_dim=2, initial_params=[1.0, 2.5, ls[0], ls[1]], param_bounds=[(0, 10)] * 4)
+    K_generic = g.GaussianProcess(k3).compute_Kij(gp2.X, None, gp2.n, None)
+    save("matern52_2d_testshape", params=k2.params.copy(), params_generic=k3.params.copy(),
+         K_generic=K_generic, **gp_state(gp2), **out)
+
+
+# ---------------------------------------------------------------- generic Matern incl. the series zone
+def case_matern_generic():
+    rs = RandomState(3)
+    X = np.sort(rs.rand(30)) * 3.0
+    X[5] = X[4] + 1e-3       # y = 2 nu r^2 inside (0, 5e-4]
+    X[11] = X[10] + 4e-3
+    X[20] = X[19]            # exact duplicate -> origin limits
+    for nu in (2.5, 3.5, 1.5):
+        k = g.MaternKernel(num_dim=1, initial_params=[1.4, nu, 0.6], param_bounds=[(0, 10)] * 3)
+        gp = g.GaussianProcess(k)
+        gp.add_data(X, np.sin(2 * X), err_y=0.05)
+        if nu > 2:
+            gp.add_data(X[::3], 2 * np.cos(2 * X[::3]), n=1, err_y=0.05)
+        out = ll_and_grad(gp, False)
+        Xs = np.linspace(0.05, 2.95, 7)
+        res = gp.predict(Xs, full_output=True)
+        out.update(Xs=Xs, mean=res["mean"], std=res["std"], cov=res["cov"])
+        save("matern_generic_nu%s" % str(nu).replace(".", "p"), params=k.params.copy(), **gp_state(gp), **out)
+    # 2-D, value + both gradient components, with near-coincident points
+    rs = RandomState(4)
+    X2 = rs.rand(12, 2)
+    X2[3] = X2[2] + [2e-3, 0.0]
+    X2[7] = X2[6]
+    k = g.MaternKernel(num_dim=2, initial_params=[0.9, 2.5, 0.5, 0.8], param_bounds=[(0, 10)] * 4)
+    gp = g.GaussianProcess(k)
+    gp.add_data(X2, np.sin(X2).sum(1), err_y=0.05)
+    gp.add_data(X2, np.cos(X2[:, 0]), n=np.tile([1, 0], (12, 1)), err_y=0.05)
+    gp.add_data(X2, np.cos(X2[:, 1]), n=np.tile([0, 1], (12, 1)), err_y=0.05)
+    out = ll_and_grad(gp, False)
+    save("matern_generic_2d", params=k.params.copy(), **gp_state(gp), **out)
+
+
+# ---------------------------------------------------------------- KAT-3: Gibbs-tanh + T + draw_sample
+def case_gibbs():
+    k = g.GibbsKernel1dTanh(initial_params=[1.5, 0.6, 0.1, 0.05, 0.9],
+                            param_bounds=[(0, 10), (0, 5), (0, 5), (0, 1), (0, 2)])
+    Xq = np.linspace(0, 1.1, 12)
+    T = np.zeros((3, 12))
+    T[0, :6] = T[1, 3:9] = T[2, 6:] = 1 / 6.0
+    gp = g.GaussianProcess(k)
+    gp.add_data(Xq, [2.5, 2.0, 1.0], err_y=0.05, T=T)
+    gp.add_data(0, 0, n=1)
+    out = ll_and_grad(gp, False)
+    Xs = np.array([0.0, 0.5, 1.0])
+    res = gp.predict(Xs, full_output=True)
+    out.update(Xs=Xs, mean=res["mean"], std=res["std"], cov=res["cov"])
+    res1 = gp.predict(Xs, n=1, full_output=True)
+    out.update(mean_d1=res1["mean"], std_d1=res1["std"], cov_d1=res1["cov"])
+    rv = RandomState(2).randn(3, 2)
+    out["rand_vars"] = rv
+    out["draw"] = gp.draw_sample(Xs, rand_vars=rv, method="cholesky")
+    save("gibbs_kat3", params=k.params.copy(), **gp_state(gp), **out)
+
+    # C5-shaped, reduced: 400 quadrature points -> 50 line integrals + core slope constraint
+    rs = RandomState(0)
+    Nq, Mo, W = 400, 50, 40
+    Xq = np.linspace(0, 1.1, Nq)
+    T = np.zeros((Mo, Nq))
+    starts = rs.randint(0, Nq - W, size=Mo)
+    for i, s in enumerate(starts):
+        T[i, s:s + W] = 1.1 / Nq
+    yy = rs.rand(Mo) * 0.3 + 0.1
+    gp = g.GaussianProcess(k)
+    gp.add_data(Xq, yy, err_y=0.02, T=T)
+    gp.add_data(0, 0, n=1)
+    out = ll_and_grad(gp, False)
+    del out["K"]
+    Xs = np.linspace(0, 1.1, 40)
+    res = gp.predict(Xs, full_output=True)
+    rv = rs.randn(40, 8)
+    out.update(Xs=Xs, mean=res["mean"], std=res["std"], cov=res["cov"], rand_vars=rv,
+               draw=gp.draw_sample(Xs, rand_vars=rv, method="cholesky"))
+    save("gibbs_c5_small", params=k.params.copy(), **gp_state(gp), **out)
+
+
+# ---------------------------------------------------------------- KAT-4: demo / config 1
+def case_demo():
+    with open(os.path.join(REF_ROOT, "demo", "sample_data_core.pkl"), "rb") as f:
+        d = pickle.load(f, encoding="latin1")
+    X, y, err = (np.asarray(d[kk], dtype=float) for kk in ("X", "y", "err_y"))
+    hp = g.UniformJointPrior([(0, 20)]) * g.GammaJointPriorAlt([1.0], [0.7])
+    k = g.SquaredExponentialKernel(initial_params=[1.8849006111246833, 0.97760159723344708], hyperprior=hp)
+    gp = g.GaussianProcess(k)
+    gp.add_data(X, y, err_y=err)
+    gp.add_data(0, 0, n=1)
+    out = ll_and_grad(gp, True)
+    Xs = np.linspace(0, 1.1, 400)
+    m, s = gp.predict(Xs)
+    m1, s1 = gp.predict(Xs, n=1)
+    out.update(Xs=Xs, mean=m, std=s, mean_d1=m1, std_d1=s1)
+    save("demo_c1_kat4", params=k.params.copy(), **gp_state(gp), **out)
+
+    # synthetic 200-point variant
+    rs = RandomState(0)
+    X = np.sort(rs.rand(200)) * 1.05
+    y = 3 - 1.2 * X ** 2 + 0.1 * rs.randn(200)
+    hp = g.UniformJointPrior([(0, 20)]) * g.GammaJointPriorAlt([1.0], [0.7])
+    k = g.SquaredExponentialKernel(initial_params=[1.9, 1.0], hyperprior=hp)
+    gp = g.GaussianProcess(k)
+    gp.add_data(X, y, err_y=0.1)
+    gp.add_data(0, 0, n=1)
+    out = ll_and_grad(gp, True)
+    del out["K"], out["L"]
+    m, s = gp.predict(Xs)
+    m1, s1 = gp.predict(Xs, n=1)
+    out.update(Xs=Xs, mean=m, std=s, mean_d1=m1, std_d1=s1)
+    save("c1_synth200", params=k.params.copy(), **gp_state(gp), **out)
+
+
+# ---------------------------------------------------------------- KAT-5: config 3 (headline), two theta of the batch
+def c3_problem():
+    rs = RandomState(0)
+    Xv = rs.rand(256, 2)
+    Xd1 = rs.rand(128, 2)
+    Xd2 = rs.rand(128, 2)
+    f = lambda x: np.sin(3 * x[:, 0]) * np.cos(2 * x[:, 1])
+    k = g.SquaredExponentialKernel(num_dim=2, initial_params=[1.0, 0.3, 0.4], param_bounds=[(0, 10)] * 3)
+    gp = g.GaussianProcess(k)
+    gp.add_data(Xv, f(Xv) + 0.05 * rs.randn(256), err_y=0.05)
+    gp.add_data(Xd1, 3 * np.cos(3 * Xd1[:, 0]) * np.cos(2 * Xd1[:, 1]) + 0.05 * rs.randn(128), err_y=0.05,
+                n=np.tile([1, 0], (128, 1)))
+    gp.add_data(Xd2, -2 * np.sin(3 * Xd2[:, 0]) * np.sin(2 * Xd2[:, 1]) + 0.05 * rs.randn(128), err_y=0.05,
+                n=np.tile([0, 1], (128, 1)))
+    th = np.array([1.0, 0.3, 0.4]) * np.exp(0.1 * RandomState(1).randn(4096, 3))
+    return gp, th
+
+
+def case_c3():
+    gp, th = c3_problem()
+    gp.use_hyper_deriv = True
+    idx = np.array([0, 1, 2, 3, 1000, 2047, 4094, 4095])
+    lls, grads = [], []
+    for b in idx:
+        f, gr = gp.update_hyperparameters(th[b])
+        lls.append(-f)
+        grads.append(-gr)
+    gp.update_hyperparameters(th[0])
+    Xs = RandomState(2).rand(5, 2)
+    m, s = gp.predict(Xs)
+    save("c3_kat5", theta_idx=idx, theta=th[idx], ll=np.array(lls), ll_deriv=np.array(grads),
+         log_prior=gp.hyperprior(gp.params), Xs=Xs, mean=m, std=s, alpha0=gp.alpha.ravel(),
+         **gp_state(gp))
+
+
+# ---------------------------------------------------------------- config 2, reduced (Matern52 and generic Matern, 1-D)
+def case_c2():
+    rs = RandomState(0)
+    X = np.sort(rs.rand(200)) * 10
+    yv = np.sin(X) + 0.05 * rs.randn(200)
+    yd = np.cos(X) + 0.05 * rs.randn(200)
+    Xs = np.linspace(0, 10, 500)
+    for name, k in (
+        ("c2_small_matern52", g.Matern52Kernel(num_dim=1, initial_params=[1.0, 0.8], param_bounds=[(0, 10)] * 2)),
+        ("c2_small_matern_generic", g.MaternKernel(num_dim=1, initial_params=[1.0, 2.5, 0.8],
+                                                   param_bounds=[(0, 10)] * 3)),
+    ):
+        gp = g.GaussianProcess(k)
+        gp.add_data(X, yv, err_y=0.05)
+        gp.add_data(X, yd, err_y=0.05, n=1)
+        out = ll_and_grad(gp, False)
+        del out["K"], out["L"]
+        m, s = gp.predict(Xs)
+        m1, s1 = gp.predict(Xs, n=1)
+        out.update(Xs=Xs, mean=m, std=s, mean_d1=m1, std_d1=s1)
+        save(name, params=k.params.copy(), **gp_state(gp), **out)
+
+
+# ---------------------------------------------------------------- DiagonalNoiseKernel + gradient (gaussian_process.py:1480-1488)
+def case_noise():
+    rs = RandomState(7)
+    X = rs.rand(20, 2)
+    y = np.sin(3 * X[:, 0]) + X[:, 1] + 0.1 * rs.randn(20)
+    k = g.SquaredExponentialKernel(num_dim=2, initial_params=[1.1, 0.4, 0.6], param_bounds=[(0, 10)] * 3)
+    nk = g.DiagonalNoiseKernel(num_dim=2, initial_noise=0.12, noise_bound=(0, 5))
+    gp = g.GaussianProcess(k, noise_k=nk)
+    gp.add_data(X, y, err_y=0.03)
+    gp.add_data(X[:5], np.ones(5), n=np.tile([0, 1], (5, 1)), err_y=0.2)
+    out = ll_and_grad(gp, True)
+    Xs = rs.rand(6, 2)
+    res = gp.predict(Xs, full_output=True)
+    out.update(Xs=Xs, mean=res["mean"], std=res["std"], cov=res["cov"])
+    resn = gp.predict(Xs, noise=True, full_output=True)
+    out.update(mean_noise=resn["mean"], std_noise=resn["std"], cov_noise=resn["cov"])
+    save("se_diagnoise", params=k.params.copy(), noise_sigma=nk.params.copy(), **gp_state(gp), **out)
+
+
+if __name__ == "__main__":
+    case_se2d()
+    case_se_pairs()
+    case_matern52()
+    case_matern_generic()
+    case_gibbs()
+    case_demo()
+    case_c3()
+    case_c2()
+    case_noise()

@@ -1,0 +1,55 @@
+"""Shared test helpers: golden-file loading and the case -> (kernel id, inputs) mapping."""
+import os
+
+import numpy as np
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+KERNEL_SE, KERNEL_MATERN52, KERNEL_MATERN, KERNEL_GIBBS_TANH = 0, 1, 2, 3
+
+# golden case -> kernel id
+CASE_KERNEL = {
+    "se2d_kat1": KERNEL_SE,
+    "matern52_kat2": KERNEL_MATERN52,
+    "matern52_2d_testshape": KERNEL_MATERN52,
+    "matern_generic_nu2p5": KERNEL_MATERN,
+    "matern_generic_nu3p5": KERNEL_MATERN,
+    "matern_generic_nu1p5": KERNEL_MATERN,
+    "matern_generic_2d": KERNEL_MATERN,
+    "gibbs_kat3": KERNEL_GIBBS_TANH,
+    "gibbs_c5_small": KERNEL_GIBBS_TANH,
+    "demo_c1_kat4": KERNEL_SE,
+    "c1_synth200": KERNEL_SE,
+    "c2_small_matern52": KERNEL_MATERN52,
+    "c2_small_matern_generic": KERNEL_MATERN,
+    "se_diagnoise": KERNEL_SE,
+}
+
+
+def load_golden(name):
+    with np.load(os.path.join(GOLDEN_DIR, name + ".npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=float)
+    b = np.asarray(b, dtype=float)
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)) if a.size else 0.0
+
+
+def assert_close(a, b, rtol=1e-9, atol=0.0, what=""):
+    a = np.asarray(a, dtype=float)
+    b = np.asarray(b, dtype=float)
+    assert a.shape == b.shape, "%s: shape %s vs %s" % (what, a.shape, b.shape)
+    bad = ~(np.abs(a - b) <= atol + rtol * np.abs(b))
+    bad &= ~(np.isnan(a) & np.isnan(b))
+    if bad.any():
+        i = np.argmax(np.where(bad, np.abs(a - b), 0))
+        raise AssertionError("%s: %d/%d entries differ; worst at %s: got %r want %r (rtol %g atol %g)" % (
+            what, bad.sum(), bad.size, np.unravel_index(i, a.shape), a.flat[i], b.flat[i], rtol, atol))
+
+
+def var_tol(cov_diag_prior, rtol=1e-9):
+    """predictive variance is a cancellation K** - |v|^2; agreement is bounded by
+    rtol * K** (the prior variance), not by rtol * var."""
+    return rtol * np.maximum(np.abs(cov_diag_prior), 1e-300)
