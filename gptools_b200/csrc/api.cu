@@ -1,0 +1,962 @@
+// C-ABI entry points (include/gptb200.h) and host-side orchestration of the blocked algorithms.
+// Everything numerical runs in the CUDA kernels of this library; the host code below only sequences
+// launches on the handle's stream.  No CPU fallback exists.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/gptb200.h"
+#include "common.cuh"
+#include "internal.h"
+
+#define NB GPT_NB
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace
+
+struct gpt_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+
+    // training data
+    int N = 0, M = 0, D = 0, Np = 0, Mp = 0;
+    bool hasT = false;
+    std::vector<double> h_err2;  // err_y^2
+    DevBuf X, n, y, diag, T, Tt;
+
+    // kernel
+    int kid = -1, nparams = 0;
+    double diag_factor = 1e2;
+
+    // single-theta factor state
+    bool factor_valid = false;
+    CovParams cp;
+    double noise_sigma = 0.0;
+    DevBuf A, Klat, W, Inv, P, z, zt, alpha, logdet, info, scal;
+    // gradient workspaces
+    DevBuf XT, Kinv, S, partials, gout, u, Sg, Yt;
+    // predict workspaces
+    DevBuf Xs, ns, Kst, Kso, kss, mean, var, cov, Rt, smp;
+    // batched
+    DevBuf b_thetas, b_y, b_ll, b_grad, b_status, b_alpha, b_ws, b_counter;
+};
+
+namespace {
+
+int fail(gpt_handle* h, int code, const char* fmt, const char* detail = "") {
+    char buf[512];
+    snprintf(buf, sizeof(buf), fmt, detail);
+    if (h) h->err = buf;
+    return code;
+}
+
+#define CUDA_OK(h, call)                                                                   \
+    do {                                                                                   \
+        cudaError_t e__ = (call);                                                          \
+        if (e__ != cudaSuccess) return fail((h), GPT_ERR_CUDA, "CUDA error: %s", cudaGetErrorString(e__)); \
+    } while (0)
+
+int ensure(gpt_handle* h, DevBuf& b, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    if (b.bytes >= bytes) return 0;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+    cudaError_t e = cudaMalloc(&b.p, bytes);
+    if (e != cudaSuccess) return fail(h, GPT_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e));
+    b.bytes = bytes;
+    e = cudaMemsetAsync(b.p, 0, bytes, h->stream);
+    if (e != cudaSuccess) return fail(h, GPT_ERR_CUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+void release(DevBuf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+}
+template <typename T>
+T* ptr(DevBuf& b) { return reinterpret_cast<T*>(b.p); }
+
+int check_launch(gpt_handle* h) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(h, GPT_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int supported_kernel(int kid, int D, int nparams) {
+    if (D < 1 || D > GPT_MAX_DIM) return 0;
+    switch (kid) {
+        case GPT_SE:
+        case GPT_MATERN52: return nparams == D + 1;
+        case GPT_MATERN: return nparams == D + 2;
+        case GPT_GIBBS_TANH: return D == 1 && nparams == 5;
+        default: return 0;
+    }
+}
+
+// Blocked right-looking Cholesky of the nblk*128 square matrix A (lower), in place.  Writes the
+// inverses of the diagonal blocks to inv (nblk x 128 x 128), per-block log-det shares, info, and
+// (optionally) overwrites rhs with L^{-1} rhs.  All heavy work is DMMA GEMM (gemm.cu).
+int blocked_potrf(gpt_handle* h, double* A, long ld, int nblk, double* inv, double* panel, double* rhs,
+                  double* logdet, int* info) {
+    cudaStream_t s = h->stream;
+    CUDA_OK(h, cudaMemsetAsync(info, 0, sizeof(int), s));
+    for (int k = 0; k < nblk; k++) {
+        double* Akk = A + (long)k * NB * ld + (long)k * NB;
+        double* inv_k = inv + (size_t)k * NB * NB;
+        launch_potrf_diag(Akk, ld, inv_k, rhs ? rhs + (long)k * NB : nullptr, logdet + k, info, k * NB, NB, s);
+        h->launches++;
+        const int rest = nblk - k - 1;
+        if (rest > 0) {
+            GemmParams g;
+            g.C = panel; g.ldc = NB;
+            g.A = A + (long)(k + 1) * NB * ld + (long)k * NB; g.lda = ld;
+            g.B = inv_k; g.ldb = NB;
+            g.tiles_m = rest; g.tiles_n = 1; g.K = NB;
+            g.alpha = 1.0; g.beta = 0.0; g.lower_only = 0; g.kbegin_row = 0;
+            launch_gemm_nt(g, s);
+            launch_copy2d(A + (long)(k + 1) * NB * ld + (long)k * NB, ld, panel, NB, rest * NB, NB, s);
+            if (rhs) launch_panel_gemv(panel, rest * NB, rhs + (long)k * NB, rhs + (long)(k + 1) * NB, s);
+            GemmParams u;
+            u.C = A + (long)(k + 1) * NB * ld + (long)(k + 1) * NB; u.ldc = ld;
+            u.A = panel; u.lda = NB;
+            u.B = panel; u.ldb = NB;
+            u.tiles_m = rest; u.tiles_n = rest; u.K = NB;
+            u.alpha = -1.0; u.beta = 1.0; u.lower_only = 1; u.kbegin_row = 0;
+            launch_gemm_nt(u, s);
+            h->launches += rhs ? 4 : 3;
+        }
+    }
+    return check_launch(h);
+}
+
+int upload(gpt_handle* h, DevBuf& b, const void* src, size_t bytes) {
+    int rc = ensure(h, b, bytes);
+    if (rc) return rc;
+    CUDA_OK(h, cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+
+int upload_padded(gpt_handle* h, DevBuf& b, const double* src, int rows, int cols, int rows_pad, int cols_pad) {
+    int rc = ensure(h, b, (size_t)rows_pad * cols_pad * sizeof(double));
+    if (rc) return rc;
+    CUDA_OK(h, cudaMemsetAsync(b.p, 0, (size_t)rows_pad * cols_pad * sizeof(double), h->stream));
+    CUDA_OK(h, cudaMemcpy2DAsync(b.p, (size_t)cols_pad * sizeof(double), src, (size_t)cols * sizeof(double),
+                                 (size_t)cols * sizeof(double), rows, cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+
+int refresh_diag(gpt_handle* h) {
+    // err_y^2 + diag_factor * eps  (gaussian_process.py:1449-1450)
+    std::vector<double> d(h->M);
+    const double jit = h->diag_factor * 2.220446049250313e-16;
+    for (int i = 0; i < h->M; i++) d[i] = h->h_err2[i] + jit;
+    int rc = upload(h, h->diag, d.data(), sizeof(double) * h->M);
+    if (rc) return rc;
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));  // d goes out of scope
+    return 0;
+}
+
+// Factor the matrix currently in h->A (Mp x Mp, K_tot with identity padding), then alpha and ll.
+int factor_and_solve(gpt_handle* h, double* ll, int* status) {
+    cudaStream_t s = h->stream;
+    const int Mp = h->Mp, M = h->M, nblk = Mp / NB;
+    int rc;
+    if ((rc = ensure(h, h->Inv, (size_t)nblk * NB * NB * sizeof(double)))) return rc;
+    if ((rc = ensure(h, h->P, (size_t)Mp * NB * sizeof(double)))) return rc;
+    if ((rc = ensure(h, h->z, (size_t)Mp * sizeof(double)))) return rc;
+    if ((rc = ensure(h, h->zt, (size_t)Mp * sizeof(double)))) return rc;
+    if ((rc = ensure(h, h->alpha, (size_t)Mp * sizeof(double)))) return rc;
+    if ((rc = ensure(h, h->logdet, (size_t)nblk * sizeof(double)))) return rc;
+    if ((rc = ensure(h, h->info, sizeof(int)))) return rc;
+    CUDA_OK(h, cudaMemsetAsync(h->z.p, 0, (size_t)Mp * sizeof(double), s));
+    CUDA_OK(h, cudaMemcpyAsync(h->z.p, h->y.p, (size_t)M * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    if ((rc = blocked_potrf(h, ptr<double>(h->A), Mp, nblk, ptr<double>(h->Inv), ptr<double>(h->P),
+                            ptr<double>(h->z), ptr<double>(h->logdet), ptr<int>(h->info))))
+        return rc;
+    CUDA_OK(h, cudaMemcpyAsync(h->zt.p, h->z.p, (size_t)Mp * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    for (int k = nblk - 1; k >= 0; k--) {
+        launch_backsolve_step(ptr<double>(h->A), Mp, k, ptr<double>(h->Inv) + (size_t)k * NB * NB,
+                              ptr<double>(h->zt), ptr<double>(h->alpha), s);
+        h->launches++;
+    }
+    if ((rc = check_launch(h))) return rc;
+    std::vector<double> hz(M), hl(nblk);
+    int hinfo = 0;
+    CUDA_OK(h, cudaMemcpyAsync(hz.data(), h->z.p, sizeof(double) * M, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(h, cudaMemcpyAsync(hl.data(), h->logdet.p, sizeof(double) * nblk, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(h, cudaMemcpyAsync(&hinfo, h->info.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(h, cudaStreamSynchronize(s));
+    double zz = 0.0, ld = 0.0;
+    for (int i = 0; i < M; i++) zz += hz[i] * hz[i];
+    for (int k = 0; k < nblk; k++) ld += hl[k];
+    if (hinfo > M) hinfo = 0;  // only padding rows (identity) could report beyond M; cannot happen, be safe
+    *status = hinfo;
+    *ll = -0.5 * zz - ld - 0.5 * M * log(2.0 * M_PI);
+    h->factor_valid = (hinfo == 0);
+    return 0;
+}
+
+// K_tot from a latent covariance already in h->Klat (Np x Np, symmetric, noise included): T K T' + diag
+int transform_latent(gpt_handle* h) {
+    cudaStream_t s = h->stream;
+    const int Mp = h->Mp, Np = h->Np;
+    int rc;
+    if ((rc = ensure(h, h->W, (size_t)Mp * Np * sizeof(double)))) return rc;
+    if ((rc = ensure(h, h->A, (size_t)Mp * Mp * sizeof(double)))) return rc;
+    GemmParams g;
+    g.C = ptr<double>(h->W); g.ldc = Np;
+    g.A = ptr<double>(h->T); g.lda = Np;
+    g.B = ptr<double>(h->Klat); g.ldb = Np;  // symmetric, so B[n][k] = K[k][n]
+    g.tiles_m = Mp / NB; g.tiles_n = Np / NB; g.K = Np;
+    g.alpha = 1.0; g.beta = 0.0; g.lower_only = 0; g.kbegin_row = 0;
+    launch_gemm_nt(g, s);
+    GemmParams g2 = g;
+    g2.C = ptr<double>(h->A); g2.ldc = Mp;
+    g2.A = ptr<double>(h->W); g2.lda = Np;
+    g2.B = ptr<double>(h->T); g2.ldb = Np;
+    g2.tiles_m = Mp / NB; g2.tiles_n = Mp / NB; g2.K = Np;
+    launch_gemm_nt(g2, s);
+    launch_add_diag(ptr<double>(h->A), Mp, ptr<double>(h->diag), h->M, s);
+    launch_set_identity_pad(ptr<double>(h->A), Mp, h->M, Mp, s);
+    h->launches += 4;
+    return check_launch(h);
+}
+
+int assemble_train(gpt_handle* h, const CovParams& cp, double noise_sigma, int hyper_deriv, double* out, int pad,
+                   bool add_diag) {
+    AssembleParams a;
+    a.cp = cp;
+    a.Xr = ptr<double>(h->X); a.nr = ptr<int32_t>(h->n); a.Mr = h->N;
+    a.Xc = a.Xr; a.nc = a.nr; a.Mc = h->N;
+    a.out = out; a.ldo = pad; a.rows_pad = pad; a.cols_pad = pad;
+    a.hyper_deriv = hyper_deriv; a.swap_roles = 0; a.symmetric = 1;
+    a.diag_add = add_diag ? ptr<double>(h->diag) : nullptr;
+    a.diag_const = noise_sigma * noise_sigma;
+    a.pad_identity = add_diag ? 1 : 0;
+    launch_assemble(a, h->stream);
+    h->launches++;
+    return check_launch(h);
+}
+
+// K^{-1} (lower triangle valid) into h->Kinv from the resident factor: XT = L^{-T} by block
+// substitution (all GEMM), then XT XT^T restricted to lower tiles.
+int compute_Kinv(gpt_handle* h) {
+    cudaStream_t s = h->stream;
+    const int Mp = h->Mp, nblk = Mp / NB;
+    int rc;
+    if ((rc = ensure(h, h->XT, (size_t)Mp * Mp * sizeof(double)))) return rc;
+    if ((rc = ensure(h, h->Kinv, (size_t)Mp * Mp * sizeof(double)))) return rc;
+    if ((rc = ensure(h, h->S, (size_t)Mp * NB * sizeof(double)))) return rc;
+    double* XT = ptr<double>(h->XT);
+    double* L = ptr<double>(h->A);
+    double* Inv = ptr<double>(h->Inv);
+    for (int k = 0; k < nblk; k++) {
+        launch_transpose(XT + (long)k * NB * Mp + (long)k * NB, Mp, Inv + (size_t)k * NB * NB, NB, NB, NB, s);
+        h->launches++;
+    }
+    for (int I = 1; I < nblk; I++) {
+        GemmParams g;
+        g.C = ptr<double>(h->S); g.ldc = NB;
+        g.A = XT; g.lda = Mp;
+        g.B = L + (long)I * NB * Mp; g.ldb = Mp;
+        g.tiles_m = I; g.tiles_n = 1; g.K = I * NB;
+        g.alpha = 1.0; g.beta = 0.0; g.lower_only = 0; g.kbegin_row = 1;
+        launch_gemm_nt(g, s);
+        GemmParams g2;
+        g2.C = XT + (long)I * NB; g2.ldc = Mp;
+        g2.A = ptr<double>(h->S); g2.lda = NB;
+        g2.B = Inv + (size_t)I * NB * NB; g2.ldb = NB;
+        g2.tiles_m = I; g2.tiles_n = 1; g2.K = NB;
+        g2.alpha = -1.0; g2.beta = 0.0; g2.lower_only = 0; g2.kbegin_row = 0;
+        launch_gemm_nt(g2, s);
+        h->launches += 2;
+    }
+    GemmParams g;
+    g.C = ptr<double>(h->Kinv); g.ldc = Mp;
+    g.A = XT; g.lda = Mp;
+    g.B = XT; g.ldb = Mp;
+    g.tiles_m = nblk; g.tiles_n = nblk; g.K = Mp;
+    g.alpha = 1.0; g.beta = 0.0; g.lower_only = 1; g.kbegin_row = 1;
+    launch_gemm_nt(g, s);
+    h->launches++;
+    return check_launch(h);
+}
+
+__global__ void symmetrize_from_lower_kernel(double* __restrict__ A, long lda, int n) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (c < n && r < n && c > r) A[(long)r * lda + c] = A[(long)c * lda + r];
+}
+
+__global__ void tril_kernel(double* __restrict__ A, long lda, int n) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (c < n && r < n && c > r) A[(long)r * lda + c] = 0.0;
+}
+
+__global__ void add_mean_kernel(double* __restrict__ out, long ldo, const double* __restrict__ mean, int rows, int cols) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (c < cols && r < rows) out[(long)r * ldo + c] += mean[r];
+}
+
+__global__ void elem_dot_lower_kernel(const double* __restrict__ W, long ldw, const double* __restrict__ a,
+                                      const double* __restrict__ dK, long ldk, int n, double* __restrict__ partial) {
+    // partial[block] = sum over this block's rows of sum_c (a_r a_c - W_rc) dK_rc   (full square, W symmetric-full)
+    __shared__ double sh[256];
+    const int r = blockIdx.x;
+    double s = 0.0;
+    for (int c = threadIdx.x; c < n; c += 256) s += (a[r] * a[c] - W[(long)r * ldw + c]) * dK[(long)r * ldk + c];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[r] = sh[0];
+}
+
+}  // namespace
+
+extern "C" {
+
+int gpt_version(void) { return 100; }
+
+int gpt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int gpt_create(int device, gpt_handle** out) {
+    if (!out) return GPT_ERR_USAGE;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device < 0 || device >= n) return GPT_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return GPT_ERR_CUDA;
+    gpt_handle* h = new gpt_handle();
+    h->device = device;
+    if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete h;
+        return GPT_ERR_CUDA;
+    }
+    h->stream = h->own_stream;
+    *out = h;
+    return 0;
+}
+
+void gpt_destroy(gpt_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    DevBuf* all[] = {&h->X, &h->n, &h->y, &h->diag, &h->T, &h->Tt, &h->A, &h->Klat, &h->W, &h->Inv, &h->P, &h->z,
+                     &h->zt, &h->alpha, &h->logdet, &h->info, &h->scal, &h->XT, &h->Kinv, &h->S, &h->partials,
+                     &h->gout, &h->u, &h->Sg, &h->Yt, &h->Xs, &h->ns, &h->Kst, &h->Kso, &h->kss, &h->mean, &h->var,
+                     &h->cov, &h->Rt, &h->smp, &h->b_thetas, &h->b_y, &h->b_ll, &h->b_grad, &h->b_status,
+                     &h->b_alpha, &h->b_ws, &h->b_counter};
+    for (DevBuf* b : all) release(*b);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+const char* gpt_last_error(gpt_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int gpt_set_stream(gpt_handle* h, void* cuda_stream) {
+    if (!h) return GPT_ERR_USAGE;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return 0;
+}
+
+int gpt_synchronize(gpt_handle* h) {
+    if (!h) return GPT_ERR_USAGE;
+    CUDA_OK(h, cudaSetDevice(h->device));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int64_t gpt_launch_count(gpt_handle* h) { return h ? h->launches : 0; }
+
+int gpt_set_data(gpt_handle* h, int N, int M, int D, const double* X, const int32_t* n, const double* y,
+                 const double* err_y, const double* T) {
+    if (!h || N < 1 || M < 1 || D < 1 || D > GPT_MAX_DIM || !X || !n || !y || !err_y)
+        return fail(h, GPT_ERR_USAGE, "gpt_set_data: bad arguments");
+    if (!T && N != M) return fail(h, GPT_ERR_USAGE, "gpt_set_data: N must equal M when T is NULL");
+    CUDA_OK(h, cudaSetDevice(h->device));
+    h->N = N; h->M = M; h->D = D;
+    h->Np = round_up(N, NB); h->Mp = round_up(M, NB);
+    h->hasT = (T != nullptr);
+    h->factor_valid = false;
+    int rc;
+    if ((rc = upload(h, h->X, X, sizeof(double) * N * D))) return rc;
+    if ((rc = upload(h, h->n, n, sizeof(int32_t) * N * D))) return rc;
+    if ((rc = upload(h, h->y, y, sizeof(double) * M))) return rc;
+    h->h_err2.resize(M);
+    for (int i = 0; i < M; i++) h->h_err2[i] = err_y[i] * err_y[i];
+    if (T) {
+        if ((rc = upload_padded(h, h->T, T, M, N, h->Mp, h->Np))) return rc;
+        if ((rc = ensure(h, h->Tt, (size_t)h->Np * h->Mp * sizeof(double)))) return rc;
+        CUDA_OK(h, cudaMemsetAsync(h->Tt.p, 0, (size_t)h->Np * h->Mp * sizeof(double), h->stream));
+        launch_transpose(ptr<double>(h->Tt), h->Mp, ptr<double>(h->T), h->Np, M, N, h->stream);
+        h->launches++;
+    }
+    if ((rc = refresh_diag(h))) return rc;
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    return check_launch(h);
+}
+
+int gpt_set_y(gpt_handle* h, const double* y) {
+    if (!h || !y || h->M < 1) return fail(h, GPT_ERR_USAGE, "gpt_set_y: no data set");
+    CUDA_OK(h, cudaSetDevice(h->device));
+    h->factor_valid = false;
+    int rc = upload(h, h->y, y, sizeof(double) * h->M);
+    if (rc) return rc;
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int gpt_set_kernel(gpt_handle* h, int kernel_id, int nparams, double diag_factor) {
+    if (!h) return GPT_ERR_USAGE;
+    if (kernel_id < 0 || kernel_id > GPT_GIBBS_TANH || nparams < 1 || nparams > GPT_MAX_PARAMS)
+        return fail(h, GPT_ERR_UNSUPPORTED, "gpt_set_kernel: unsupported kernel / parameter count");
+    CUDA_OK(h, cudaSetDevice(h->device));
+    h->kid = kernel_id;
+    h->nparams = nparams;
+    h->factor_valid = false;
+    if (diag_factor != h->diag_factor || h->diag.p == nullptr) {
+        h->diag_factor = diag_factor;
+        if (h->M > 0) {
+            int rc = refresh_diag(h);
+            if (rc) return rc;
+        }
+    }
+    return 0;
+}
+
+int gpt_cov_pairs(gpt_handle* h, int kernel_id, int D, int nparams, const double* params, int hyper_deriv,
+                  int64_t npairs, const double* Xi, const double* Xj, const int32_t* ni, const int32_t* nj,
+                  double* out) {
+    if (!h || !params || npairs < 0) return fail(h, GPT_ERR_USAGE, "gpt_cov_pairs: bad arguments");
+    if (!supported_kernel(kernel_id, D, nparams)) return fail(h, GPT_ERR_UNSUPPORTED, "gpt_cov_pairs: unsupported kernel");
+    if (hyper_deriv >= 0 && kernel_id != GPT_SE) return fail(h, GPT_ERR_UNSUPPORTED, "hyper_deriv: SE only");
+    if (npairs == 0) return 0;
+    CUDA_OK(h, cudaSetDevice(h->device));
+    CovParams cp;
+    cov_params_init(cp, kernel_id, D, nparams, params);
+    const size_t xb = sizeof(double) * npairs * D, nb_ = sizeof(int32_t) * npairs * D;
+    DevBuf dXi, dXj, dni, dnj, dout;
+    int rc = 0;
+    if ((rc = upload(h, dXi, Xi, xb)) || (rc = upload(h, dXj, Xj, xb)) || (rc = upload(h, dni, ni, nb_)) ||
+        (rc = upload(h, dnj, nj, nb_)) || (rc = ensure(h, dout, sizeof(double) * npairs))) {
+        release(dXi); release(dXj); release(dni); release(dnj); release(dout);
+        return rc;
+    }
+    launch_cov_pairs(cp, hyper_deriv, npairs, ptr<double>(dXi), ptr<double>(dXj), ptr<int32_t>(dni), ptr<int32_t>(dnj),
+                     ptr<double>(dout), h->stream);
+    h->launches++;
+    cudaError_t e = cudaMemcpyAsync(out, dout.p, sizeof(double) * npairs, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    release(dXi); release(dXj); release(dni); release(dnj); release(dout);
+    if (e != cudaSuccess) return fail(h, GPT_ERR_CUDA, "gpt_cov_pairs: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int gpt_compute_Kij(gpt_handle* h, int kernel_id, int D, int nparams, const double* params, int hyper_deriv,
+                    int Mi, const double* Xi, const int32_t* ni, int Mj, const double* Xj, const int32_t* nj,
+                    double* K_out) {
+    if (!h || !params || Mi < 1 || !Xi || !ni || !K_out) return fail(h, GPT_ERR_USAGE, "gpt_compute_Kij: bad arguments");
+    if (!supported_kernel(kernel_id, D, nparams)) return fail(h, GPT_ERR_UNSUPPORTED, "gpt_compute_Kij: unsupported kernel");
+    if (hyper_deriv >= 0 && kernel_id != GPT_SE) return fail(h, GPT_ERR_UNSUPPORTED, "hyper_deriv: SE only");
+    CUDA_OK(h, cudaSetDevice(h->device));
+    const bool sym = (Xj == nullptr);
+    if (sym) Mj = Mi;
+    CovParams cp;
+    cov_params_init(cp, kernel_id, D, nparams, params);
+    DevBuf dXi, dXj, dni, dnj, dout;
+    int rc = 0;
+    auto cleanup = [&]() { release(dXi); release(dXj); release(dni); release(dnj); release(dout); };
+    if ((rc = upload(h, dXi, Xi, sizeof(double) * Mi * D)) || (rc = upload(h, dni, ni, sizeof(int32_t) * Mi * D)) ||
+        (rc = ensure(h, dout, sizeof(double) * (size_t)Mi * Mj))) {
+        cleanup();
+        return rc;
+    }
+    if (!sym) {
+        if ((rc = upload(h, dXj, Xj, sizeof(double) * Mj * D)) || (rc = upload(h, dnj, nj, sizeof(int32_t) * Mj * D))) {
+            cleanup();
+            return rc;
+        }
+    }
+    AssembleParams a;
+    a.cp = cp;
+    a.Xr = ptr<double>(dXi); a.nr = ptr<int32_t>(dni); a.Mr = Mi;
+    a.Xc = sym ? a.Xr : ptr<double>(dXj); a.nc = sym ? a.nr : ptr<int32_t>(dnj); a.Mc = Mj;
+    a.out = ptr<double>(dout); a.ldo = Mj; a.rows_pad = Mi; a.cols_pad = Mj;
+    a.hyper_deriv = hyper_deriv; a.swap_roles = 0; a.symmetric = 0;
+    a.diag_add = nullptr; a.diag_const = 0.0; a.pad_identity = 0;
+    launch_assemble(a, h->stream);
+    h->launches++;
+    cudaError_t e = cudaMemcpyAsync(K_out, dout.p, sizeof(double) * (size_t)Mi * Mj, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cleanup();
+    if (e != cudaSuccess) return fail(h, GPT_ERR_CUDA, "gpt_compute_Kij: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int gpt_ll(gpt_handle* h, const double* params, double noise_sigma, double* ll, double* grad,
+           const int32_t* grad_idx, int P, int* status) {
+    if (!h || !params || !ll || !status) return fail(h, GPT_ERR_USAGE, "gpt_ll: bad arguments");
+    if (h->M < 1 || h->kid < 0) return fail(h, GPT_ERR_USAGE, "gpt_ll: set_data / set_kernel first");
+    if (!supported_kernel(h->kid, h->D, h->nparams)) return fail(h, GPT_ERR_UNSUPPORTED, "gpt_ll: kernel/dimension unsupported");
+    if (grad && P > 0) {
+        if (P > GPT_MAX_PARAMS || !grad_idx) return fail(h, GPT_ERR_USAGE, "gpt_ll: bad gradient request");
+        for (int q = 0; q < P; q++) {
+            if (grad_idx[q] < 0 || grad_idx[q] > h->nparams) return fail(h, GPT_ERR_USAGE, "gpt_ll: bad grad_idx");
+            if (grad_idx[q] < h->nparams && h->kid != GPT_SE)
+                return fail(h, GPT_ERR_UNSUPPORTED, "hyper-parameter derivatives: SquaredExponentialKernel only");
+        }
+    }
+    CUDA_OK(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    h->factor_valid = false;
+    cov_params_init(h->cp, h->kid, h->D, h->nparams, params);
+    h->noise_sigma = noise_sigma;
+    int rc;
+    if (h->hasT) {
+        if ((rc = ensure(h, h->Klat, (size_t)h->Np * h->Np * sizeof(double)))) return rc;
+        if ((rc = assemble_train(h, h->cp, noise_sigma, -1, ptr<double>(h->Klat), h->Np, false))) return rc;
+        if ((rc = transform_latent(h))) return rc;
+    } else {
+        if ((rc = ensure(h, h->A, (size_t)h->Mp * h->Mp * sizeof(double)))) return rc;
+        if ((rc = assemble_train(h, h->cp, noise_sigma, -1, ptr<double>(h->A), h->Mp, true))) return rc;
+    }
+    if ((rc = factor_and_solve(h, ll, status))) return rc;
+    if (!(grad && P > 0)) return 0;
+    for (int q = 0; q < P; q++) grad[q] = 0.0;
+    if (*status != 0) return 0;
+
+    // ---- gradient: 1/2 tr((alpha alpha^T - K^-1) dK_p), dK tiles regenerated on the fly ----
+    if ((rc = compute_Kinv(h))) return rc;
+    GradReduceParams gp;
+    gp.cp = h->cp;
+    gp.X = ptr<double>(h->X); gp.n = ptr<int32_t>(h->n); gp.N = h->N;
+    gp.nidx = 0;
+    int slot[GPT_MAX_PARAMS];
+    int noise_slot = -1;
+    for (int q = 0; q < P; q++) {
+        if (grad_idx[q] == h->nparams) noise_slot = q;
+        else { slot[gp.nidx] = q; gp.idx[gp.nidx++] = grad_idx[q]; }
+    }
+    const int nt = (h->N + 63) / 64;
+    if ((rc = ensure(h, h->partials, sizeof(double) * (size_t)nt * nt * GPT_MAX_PARAMS))) return rc;
+    if ((rc = ensure(h, h->gout, sizeof(double) * (GPT_MAX_PARAMS + 2)))) return rc;
+    gp.partials = ptr<double>(h->partials);
+    gp.out = ptr<double>(h->gout);
+    if (gp.nidx > 0) {
+        if (h->hasT) {
+            // W_latent = T' (alpha alpha' - K^-1) T = u u' - T' K^-1 T, u = T' alpha
+            const int Np = h->Np, Mp = h->Mp;
+            if ((rc = ensure(h, h->u, sizeof(double) * Np))) return rc;
+            if ((rc = ensure(h, h->Yt, sizeof(double) * (size_t)Np * Mp))) return rc;
+            if ((rc = ensure(h, h->Sg, sizeof(double) * (size_t)Np * Np))) return rc;
+            launch_rowdot(ptr<double>(h->Tt), Mp, h->N, h->M, ptr<double>(h->alpha), ptr<double>(h->u), s);
+            dim3 sg((Mp + 255) / 256, Mp);
+            symmetrize_from_lower_kernel<<<sg, 256, 0, s>>>(ptr<double>(h->Kinv), Mp, Mp);
+            GemmParams g;
+            g.C = ptr<double>(h->Yt); g.ldc = Mp;
+            g.A = ptr<double>(h->Tt); g.lda = Mp;
+            g.B = ptr<double>(h->Kinv); g.ldb = Mp;
+            g.tiles_m = Np / NB; g.tiles_n = Mp / NB; g.K = Mp;
+            g.alpha = 1.0; g.beta = 0.0; g.lower_only = 0; g.kbegin_row = 0;
+            launch_gemm_nt(g, s);
+            GemmParams g2 = g;
+            g2.C = ptr<double>(h->Sg); g2.ldc = Np;
+            g2.A = ptr<double>(h->Yt); g2.lda = Mp;
+            g2.B = ptr<double>(h->Tt); g2.ldb = Mp;
+            g2.tiles_m = Np / NB; g2.tiles_n = Np / NB; g2.K = Mp;
+            launch_gemm_nt(g2, s);
+            h->launches += 4;
+            gp.S = ptr<double>(h->Sg); gp.lds = Np; gp.a = ptr<double>(h->u);
+        } else {
+            gp.S = ptr<double>(h->Kinv); gp.lds = h->Mp; gp.a = ptr<double>(h->alpha);
+        }
+        launch_grad_reduce(gp, s);
+        h->launches += 2;
+    }
+    launch_trace_and_sumsq(ptr<double>(h->Kinv), h->Mp, ptr<double>(h->alpha), h->M, ptr<double>(h->gout) + GPT_MAX_PARAMS, s);
+    h->launches++;
+    if ((rc = check_launch(h))) return rc;
+    double hg[GPT_MAX_PARAMS + 2];
+    CUDA_OK(h, cudaMemcpyAsync(hg, h->gout.p, sizeof(hg), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(h, cudaStreamSynchronize(s));
+    for (int i = 0; i < gp.nidx; i++) grad[slot[i]] = hg[i];
+    if (noise_slot >= 0) {
+        // gaussian_process.py:1484-1488: dK = 2 sigma_n I_M  (identity over the observations, also with T)
+        grad[noise_slot] = noise_sigma * (hg[GPT_MAX_PARAMS + 1] - hg[GPT_MAX_PARAMS]);
+    }
+    return 0;
+}
+
+int gpt_ll_from_K(gpt_handle* h, const double* K_latent, double* ll, int* status) {
+    if (!h || !K_latent || !ll || !status) return fail(h, GPT_ERR_USAGE, "gpt_ll_from_K: bad arguments");
+    if (h->M < 1) return fail(h, GPT_ERR_USAGE, "gpt_ll_from_K: set_data first");
+    CUDA_OK(h, cudaSetDevice(h->device));
+    h->factor_valid = false;
+    int rc;
+    if (h->hasT) {
+        if ((rc = upload_padded(h, h->Klat, K_latent, h->N, h->N, h->Np, h->Np))) return rc;
+        if ((rc = transform_latent(h))) return rc;
+    } else {
+        if ((rc = upload_padded(h, h->A, K_latent, h->N, h->N, h->Mp, h->Mp))) return rc;
+        launch_add_diag(ptr<double>(h->A), h->Mp, ptr<double>(h->diag), h->M, h->stream);
+        launch_set_identity_pad(ptr<double>(h->A), h->Mp, h->M, h->Mp, h->stream);
+        h->launches += 2;
+    }
+    h->cp.kid = -1;  // predict must be driven with host-supplied K* for plugin kernels
+    return factor_and_solve(h, ll, status);
+}
+
+int gpt_grad_from_dK(gpt_handle* h, const double* dK_latent, double* g) {
+    if (!h || !dK_latent || !g) return fail(h, GPT_ERR_USAGE, "gpt_grad_from_dK: bad arguments");
+    if (!h->factor_valid) return fail(h, GPT_ERR_USAGE, "gpt_grad_from_dK: no valid factorisation");
+    CUDA_OK(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    int rc;
+    const int Mp = h->Mp, Np = h->Np;
+    if ((rc = compute_Kinv(h))) return rc;
+    dim3 sg((Mp + 255) / 256, Mp);
+    symmetrize_from_lower_kernel<<<sg, 256, 0, s>>>(ptr<double>(h->Kinv), Mp, Mp);
+    const double *W, *a;
+    long ldw;
+    int n;
+    if (h->hasT) {
+        // dK_obs = T dK T'  ->  W via two GEMMs into Sg (Mp x Mp reuse of A-shaped buffers)
+        if ((rc = upload_padded(h, h->Klat, dK_latent, h->N, h->N, Np, Np))) return rc;
+        if ((rc = ensure(h, h->W, (size_t)Mp * Np * sizeof(double)))) return rc;
+        if ((rc = ensure(h, h->Sg, (size_t)Mp * Mp * sizeof(double)))) return rc;
+        GemmParams g1;
+        g1.C = ptr<double>(h->W); g1.ldc = Np;
+        g1.A = ptr<double>(h->T); g1.lda = Np;
+        g1.B = ptr<double>(h->Klat); g1.ldb = Np;
+        g1.tiles_m = Mp / NB; g1.tiles_n = Np / NB; g1.K = Np;
+        g1.alpha = 1.0; g1.beta = 0.0; g1.lower_only = 0; g1.kbegin_row = 0;
+        launch_gemm_nt(g1, s);
+        GemmParams g2 = g1;
+        g2.C = ptr<double>(h->Sg); g2.ldc = Mp;
+        g2.A = ptr<double>(h->W); g2.lda = Np;
+        g2.B = ptr<double>(h->T); g2.ldb = Np;
+        g2.tiles_m = Mp / NB; g2.tiles_n = Mp / NB; g2.K = Np;
+        launch_gemm_nt(g2, s);
+        h->launches += 2;
+        W = ptr<double>(h->Sg); ldw = Mp;
+    } else {
+        if ((rc = upload_padded(h, h->Sg, dK_latent, h->N, h->N, Mp, Mp))) return rc;
+        W = ptr<double>(h->Sg); ldw = Mp;
+    }
+    a = ptr<double>(h->alpha);
+    n = h->M;
+    if ((rc = ensure(h, h->partials, sizeof(double) * (size_t)Mp))) return rc;
+    elem_dot_lower_kernel<<<n, 256, 0, s>>>(ptr<double>(h->Kinv), Mp, a, W, ldw, n, ptr<double>(h->partials));
+    h->launches += 2;
+    if ((rc = check_launch(h))) return rc;
+    std::vector<double> part(n);
+    CUDA_OK(h, cudaMemcpyAsync(part.data(), h->partials.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(h, cudaStreamSynchronize(s));
+    double sum = 0.0;
+    for (int i = 0; i < n; i++) sum += part[i];
+    *g = 0.5 * sum;
+    return 0;
+}
+
+int gpt_get_alpha(gpt_handle* h, double* alpha) {
+    if (!h || !alpha || !h->alpha.p) return fail(h, GPT_ERR_USAGE, "gpt_get_alpha: nothing computed");
+    CUDA_OK(h, cudaSetDevice(h->device));
+    CUDA_OK(h, cudaMemcpyAsync(alpha, h->alpha.p, sizeof(double) * h->M, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int gpt_get_L(gpt_handle* h, double* L) {
+    if (!h || !L || !h->A.p) return fail(h, GPT_ERR_USAGE, "gpt_get_L: nothing computed");
+    CUDA_OK(h, cudaSetDevice(h->device));
+    const int M = h->M;
+    CUDA_OK(h, cudaMemcpy2DAsync(L, sizeof(double) * M, h->A.p, sizeof(double) * h->Mp, sizeof(double) * M, M,
+                                 cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(h, cudaStreamSynchronize(h->stream));
+    for (int r = 0; r < M; r++)
+        for (int c = r + 1; c < M; c++) L[(size_t)r * M + c] = 0.0;
+    return 0;
+}
+
+int gpt_get_K(gpt_handle* h, double* K) {
+    if (!h || !K || h->kid < 0 || h->N < 1 || h->cp.kid < 0) return fail(h, GPT_ERR_USAGE, "gpt_get_K: nothing computed");
+    CUDA_OK(h, cudaSetDevice(h->device));
+    DevBuf tmp;
+    int rc = ensure(h, tmp, sizeof(double) * (size_t)h->N * h->N);
+    if (rc) return rc;
+    rc = assemble_train(h, h->cp, 0.0, -1, ptr<double>(tmp), h->N, false);
+    cudaError_t e = cudaSuccess;
+    if (!rc) {
+        e = cudaMemcpyAsync(K, tmp.p, sizeof(double) * (size_t)h->N * h->N, cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    }
+    release(tmp);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(h, GPT_ERR_CUDA, "gpt_get_K: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int gpt_predict(gpt_handle* h, int Ms, const double* Xs, const int32_t* ns, double* mean, double* var, double* cov) {
+    if (!h || Ms < 1 || !Xs || !ns || !mean) return fail(h, GPT_ERR_USAGE, "gpt_predict: bad arguments");
+    if (!h->factor_valid || h->cp.kid < 0) return fail(h, GPT_ERR_USAGE, "gpt_predict: no valid factorisation (call gpt_ll)");
+    CUDA_OK(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const int D = h->D, N = h->N, M = h->M, Np = h->Np, Mp = h->Mp, nblk = Mp / NB;
+    int rc;
+    // chunk of test points; the full covariance needs every test point in one chunk
+    int CH = cov ? round_up(Ms, NB) : round_up(Ms < 16384 ? Ms : 16384, NB);
+    // bound the chunk buffers to ~8 GB
+    while (!cov && CH > NB && (size_t)CH * (Np + Mp) * sizeof(double) > ((size_t)8 << 30)) CH = round_up(CH / 2, NB);
+    if ((rc = upload(h, h->Xs, Xs, sizeof(double) * (size_t)Ms * D))) return rc;
+    if ((rc = upload(h, h->ns, ns, sizeof(int32_t) * (size_t)Ms * D))) return rc;
+    if ((rc = ensure(h, h->Kst, sizeof(double) * (size_t)CH * Np))) return rc;
+    if (h->hasT && (rc = ensure(h, h->Kso, sizeof(double) * (size_t)CH * Mp))) return rc;
+    if ((rc = ensure(h, h->mean, sizeof(double) * (size_t)round_up(Ms, NB)))) return rc;
+    if (var || cov) {
+        if ((rc = ensure(h, h->kss, sizeof(double) * (size_t)round_up(Ms, NB)))) return rc;
+        if ((rc = ensure(h, h->var, sizeof(double) * (size_t)round_up(Ms, NB)))) return rc;
+    }
+    for (int s0 = 0; s0 < Ms; s0 += CH) {
+        const int rows = (Ms - s0 < CH) ? (Ms - s0) : CH;
+        const int rows_pad = round_up(rows, NB);
+        // K*^T (test points as rows): out[s][i] = k(X_i, X*_s; n_i, n*_s)  (gaussian_process.py:966)
+        AssembleParams a;
+        a.cp = h->cp;
+        a.Xr = ptr<double>(h->Xs) + (size_t)s0 * D; a.nr = ptr<int32_t>(h->ns) + (size_t)s0 * D; a.Mr = rows;
+        a.Xc = ptr<double>(h->X); a.nc = ptr<int32_t>(h->n); a.Mc = N;
+        a.out = ptr<double>(h->Kst); a.ldo = Np; a.rows_pad = rows_pad; a.cols_pad = Np;
+        a.hyper_deriv = -1; a.swap_roles = 1; a.symmetric = 0;
+        a.diag_add = nullptr; a.diag_const = 0.0; a.pad_identity = 0;
+        launch_assemble(a, s);
+        h->launches++;
+        double* Ko = ptr<double>(h->Kst);
+        long ldk = Np;
+        if (h->hasT) {
+            GemmParams g;  // (K*^T) T^T
+            g.C = ptr<double>(h->Kso); g.ldc = Mp;
+            g.A = ptr<double>(h->Kst); g.lda = Np;
+            g.B = ptr<double>(h->T); g.ldb = Np;
+            g.tiles_m = rows_pad / NB; g.tiles_n = Mp / NB; g.K = Np;
+            g.alpha = 1.0; g.beta = 0.0; g.lower_only = 0; g.kbegin_row = 0;
+            launch_gemm_nt(g, s);
+            h->launches++;
+            Ko = ptr<double>(h->Kso);
+            ldk = Mp;
+        }
+        launch_rowdot(Ko, ldk, rows, M, ptr<double>(h->alpha), ptr<double>(h->mean) + s0, s);
+        h->launches++;
+        if (var || cov) {
+            // V^T = K*^T L^{-T}: block forward substitution, every step a DMMA GEMM (gaussian_process.py:983)
+            for (int I = 0; I < nblk; I++) {
+                if (I > 0) {
+                    GemmParams g;
+                    g.C = Ko + (long)I * NB; g.ldc = ldk;
+                    g.A = Ko; g.lda = ldk;
+                    g.B = ptr<double>(h->A) + (long)I * NB * Mp; g.ldb = Mp;
+                    g.tiles_m = rows_pad / NB; g.tiles_n = 1; g.K = I * NB;
+                    g.alpha = -1.0; g.beta = 1.0; g.lower_only = 0; g.kbegin_row = 0;
+                    launch_gemm_nt(g, s);
+                    h->launches++;
+                }
+                GemmParams g2;
+                g2.C = Ko + (long)I * NB; g2.ldc = ldk;
+                g2.A = Ko + (long)I * NB; g2.lda = ldk;
+                g2.B = ptr<double>(h->Inv) + (size_t)I * NB * NB; g2.ldb = NB;
+                g2.tiles_m = rows_pad / NB; g2.tiles_n = 1; g2.K = NB;
+                g2.alpha = 1.0; g2.beta = 0.0; g2.lower_only = 0; g2.kbegin_row = 0;
+                launch_gemm_nt(g2, s);
+                h->launches++;
+            }
+            launch_prior_diag(h->cp, ptr<double>(h->Xs) + (size_t)s0 * D, ptr<int32_t>(h->ns) + (size_t)s0 * D, rows,
+                              ptr<double>(h->kss) + s0, s);
+            launch_row_var(Ko, ldk, rows, M, ptr<double>(h->kss) + s0, ptr<double>(h->var) + s0, s);
+            h->launches += 2;
+            if (cov) {
+                const int Sp = rows_pad;
+                if ((rc = ensure(h, h->cov, sizeof(double) * (size_t)Sp * Sp))) return rc;
+                AssembleParams c;
+                c.cp = h->cp;
+                c.Xr = ptr<double>(h->Xs); c.nr = ptr<int32_t>(h->ns); c.Mr = Ms;
+                c.Xc = c.Xr; c.nc = c.nr; c.Mc = Ms;
+                c.out = ptr<double>(h->cov); c.ldo = Sp; c.rows_pad = Sp; c.cols_pad = Sp;
+                c.hyper_deriv = -1; c.swap_roles = 0; c.symmetric = 0;
+                c.diag_add = nullptr; c.diag_const = 0.0; c.pad_identity = 0;
+                launch_assemble(c, s);
+                // padding columns (>= M) of V are zero rows of the identity-padded system: K* is zero there
+                GemmParams g;
+                g.C = ptr<double>(h->cov); g.ldc = Sp;
+                g.A = Ko; g.lda = ldk;
+                g.B = Ko; g.ldb = ldk;
+                g.tiles_m = Sp / NB; g.tiles_n = Sp / NB; g.K = Mp;
+                g.alpha = -1.0; g.beta = 1.0; g.lower_only = 0; g.kbegin_row = 0;
+                launch_gemm_nt(g, s);
+                h->launches += 2;
+            }
+        }
+        if ((rc = check_launch(h))) return rc;
+    }
+    CUDA_OK(h, cudaMemcpyAsync(mean, h->mean.p, sizeof(double) * Ms, cudaMemcpyDeviceToHost, s));
+    if (var) CUDA_OK(h, cudaMemcpyAsync(var, h->var.p, sizeof(double) * Ms, cudaMemcpyDeviceToHost, s));
+    if (cov) {
+        const int Sp = round_up(Ms, NB);
+        CUDA_OK(h, cudaMemcpy2DAsync(cov, sizeof(double) * Ms, h->cov.p, sizeof(double) * Sp, sizeof(double) * Ms, Ms,
+                                     cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_OK(h, cudaStreamSynchronize(s));
+    return 0;
+}
+
+int gpt_draw_sample(gpt_handle* h, int Ms, int S, const double* mean, const double* cov, const double* rand_vars,
+                    double jitter, double* out, int* status) {
+    if (!h || Ms < 1 || S < 1 || !mean || !cov || !rand_vars || !out || !status)
+        return fail(h, GPT_ERR_USAGE, "gpt_draw_sample: bad arguments");
+    CUDA_OK(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const int Sp = round_up(Ms, NB), nblk = Sp / NB, Rp = round_up(S, NB);
+    int rc;
+    DevBuf C, inv, panel, logdet, info, R, Rt, O, mu, jit;
+    auto cleanup = [&]() { release(C); release(inv); release(panel); release(logdet); release(info); release(R);
+                           release(Rt); release(O); release(mu); release(jit); };
+    std::vector<double> hj(Ms, jitter);
+    if ((rc = upload_padded(h, C, cov, Ms, Ms, Sp, Sp)) || (rc = upload(h, jit, hj.data(), sizeof(double) * Ms)) ||
+        (rc = ensure(h, inv, sizeof(double) * (size_t)nblk * NB * NB)) ||
+        (rc = ensure(h, panel, sizeof(double) * (size_t)Sp * NB)) || (rc = ensure(h, logdet, sizeof(double) * nblk)) ||
+        (rc = ensure(h, info, sizeof(int))) || (rc = upload_padded(h, R, rand_vars, Ms, S, Sp, Rp)) ||
+        (rc = ensure(h, Rt, sizeof(double) * (size_t)Rp * Sp)) || (rc = ensure(h, O, sizeof(double) * (size_t)Sp * Rp)) ||
+        (rc = upload(h, mu, mean, sizeof(double) * Ms))) {
+        cleanup();
+        return rc;
+    }
+    launch_add_diag(ptr<double>(C), Sp, ptr<double>(jit), Ms, s);
+    launch_set_identity_pad(ptr<double>(C), Sp, Ms, Sp, s);
+    rc = blocked_potrf(h, ptr<double>(C), Sp, nblk, ptr<double>(inv), ptr<double>(panel), nullptr, ptr<double>(logdet),
+                       ptr<int>(info));
+    if (!rc) {
+        dim3 tg((Sp + 255) / 256, Sp);
+        tril_kernel<<<tg, 256, 0, s>>>(ptr<double>(C), Sp, Sp);
+        cudaMemsetAsync(Rt.p, 0, sizeof(double) * (size_t)Rp * Sp, s);
+        launch_transpose(ptr<double>(Rt), Sp, ptr<double>(R), Rp, Ms, S, s);
+        GemmParams g;
+        g.C = ptr<double>(O); g.ldc = Rp;
+        g.A = ptr<double>(C); g.lda = Sp;
+        g.B = ptr<double>(Rt); g.ldb = Sp;
+        g.tiles_m = Sp / NB; g.tiles_n = Rp / NB; g.K = Sp;
+        g.alpha = 1.0; g.beta = 0.0; g.lower_only = 0; g.kbegin_row = 0;
+        launch_gemm_nt(g, s);
+        dim3 mg((S + 255) / 256, Ms);
+        add_mean_kernel<<<mg, 256, 0, s>>>(ptr<double>(O), Rp, ptr<double>(mu), Ms, S);
+        h->launches += 6;
+        rc = check_launch(h);
+    }
+    cudaError_t e = cudaSuccess;
+    int hinfo = 0;
+    if (!rc) {
+        e = cudaMemcpy2DAsync(out, sizeof(double) * S, O.p, sizeof(double) * Rp, sizeof(double) * S, Ms,
+                              cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&hinfo, info.p, sizeof(int), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    }
+    cleanup();
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(h, GPT_ERR_CUDA, "gpt_draw_sample: %s", cudaGetErrorString(e));
+    *status = hinfo;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batched many-theta path
+// ------------------------------------------------------------------------------------------------
+static int batched_common(gpt_handle* h, int B, const double* d_thetas, const double* d_y, double* d_ll,
+                          double* d_grad, const int32_t* grad_idx, int P, int* d_status, double* d_alpha) {
+    if (h->hasT) return fail(h, GPT_ERR_UNSUPPORTED, "gpt_ll_batched: transformed observations (T) use gpt_ll");
+    if (!supported_kernel(h->kid, h->D, h->nparams)) return fail(h, GPT_ERR_UNSUPPORTED, "gpt_ll_batched: kernel unsupported");
+    if (P < 0 || P > GPT_MAX_PARAMS) return fail(h, GPT_ERR_USAGE, "gpt_ll_batched: bad P");
+    BatchedParams bp;
+    bp.kid = h->kid; bp.D = h->D; bp.nparams = h->nparams;
+    bp.M = h->M; bp.nT = (h->M + 63) / 64;
+    if (bp.nT > 32) return fail(h, GPT_ERR_UNSUPPORTED, "gpt_ll_batched: M > 2048 uses gpt_ll");
+    bp.X = ptr<double>(h->X); bp.n = ptr<int32_t>(h->n);
+    bp.y = d_y ? d_y : ptr<double>(h->y); bp.y_stride = d_y ? h->M : 0;
+    bp.diag = ptr<double>(h->diag);
+    bp.B = B; bp.thetas = d_thetas;
+    bp.nidx = (d_grad && P > 0) ? P : 0;
+    for (int q = 0; q < bp.nidx; q++) {
+        if (grad_idx[q] < 0 || grad_idx[q] > h->nparams) return fail(h, GPT_ERR_USAGE, "gpt_ll_batched: bad grad_idx");
+        if (grad_idx[q] < h->nparams && h->kid != GPT_SE)
+            return fail(h, GPT_ERR_UNSUPPORTED, "hyper-parameter derivatives: SquaredExponentialKernel only");
+        bp.idx[q] = grad_idx[q];
+    }
+    bp.ll = d_ll; bp.grad = d_grad; bp.status = d_status; bp.alpha_out = d_alpha;
+    int ctas = batched_max_ctas(h->device);
+    if (ctas > B) ctas = B;
+    bp.ws_per_cta = batched_ws_doubles_per_cta(bp.nT);
+    int rc;
+    if ((rc = ensure(h, h->b_ws, sizeof(double) * bp.ws_per_cta * (size_t)ctas))) return rc;
+    if ((rc = ensure(h, h->b_counter, sizeof(int)))) return rc;
+    bp.workspace = ptr<double>(h->b_ws);
+    bp.counter = ptr<int>(h->b_counter);
+    CUDA_OK(h, cudaMemsetAsync(bp.counter, 0, sizeof(int), h->stream));
+    launch_ll_batched(bp, ctas, h->stream);
+    h->launches++;
+    return check_launch(h);
+}
+
+int gpt_ll_batched_dev(gpt_handle* h, int B, const double* d_thetas, const double* d_y_batch, double* d_ll,
+                       double* d_grad, const int32_t* grad_idx, int P, int* d_status, double* d_alpha_out) {
+    if (!h || B < 1 || !d_thetas || !d_ll || !d_status) return fail(h, GPT_ERR_USAGE, "gpt_ll_batched_dev: bad arguments");
+    if (h->M < 1 || h->kid < 0) return fail(h, GPT_ERR_USAGE, "gpt_ll_batched: set_data / set_kernel first");
+    CUDA_OK(h, cudaSetDevice(h->device));
+    return batched_common(h, B, d_thetas, d_y_batch, d_ll, d_grad, grad_idx, P, d_status, d_alpha_out);
+}
+
+int gpt_ll_batched(gpt_handle* h, int B, const double* thetas, const double* y_batch, double* ll, double* grad,
+                   const int32_t* grad_idx, int P, int* status, double* alpha_out) {
+    if (!h || B < 1 || !thetas || !ll || !status) return fail(h, GPT_ERR_USAGE, "gpt_ll_batched: bad arguments");
+    if (h->M < 1 || h->kid < 0) return fail(h, GPT_ERR_USAGE, "gpt_ll_batched: set_data / set_kernel first");
+    CUDA_OK(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const int np1 = h->nparams + 1, M = h->M;
+    const bool want_grad = (grad && P > 0);
+    int rc;
+    if ((rc = upload(h, h->b_thetas, thetas, sizeof(double) * (size_t)B * np1))) return rc;
+    if (y_batch && (rc = upload(h, h->b_y, y_batch, sizeof(double) * (size_t)B * M))) return rc;
+    if ((rc = ensure(h, h->b_ll, sizeof(double) * B))) return rc;
+    if ((rc = ensure(h, h->b_status, sizeof(int) * B))) return rc;
+    if (want_grad && (rc = ensure(h, h->b_grad, sizeof(double) * (size_t)B * P))) return rc;
+    if (alpha_out && (rc = ensure(h, h->b_alpha, sizeof(double) * (size_t)B * M))) return rc;
+    rc = batched_common(h, B, ptr<double>(h->b_thetas), y_batch ? ptr<double>(h->b_y) : nullptr, ptr<double>(h->b_ll),
+                        want_grad ? ptr<double>(h->b_grad) : nullptr, grad_idx, P, ptr<int>(h->b_status),
+                        alpha_out ? ptr<double>(h->b_alpha) : nullptr);
+    if (rc) return rc;
+    CUDA_OK(h, cudaMemcpyAsync(ll, h->b_ll.p, sizeof(double) * B, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(h, cudaMemcpyAsync(status, h->b_status.p, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
+    if (want_grad) CUDA_OK(h, cudaMemcpyAsync(grad, h->b_grad.p, sizeof(double) * (size_t)B * P, cudaMemcpyDeviceToHost, s));
+    if (alpha_out) CUDA_OK(h, cudaMemcpyAsync(alpha_out, h->b_alpha.p, sizeof(double) * (size_t)B * M, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(h, cudaStreamSynchronize(s));
+    return 0;
+}
+
+}  // extern "C"

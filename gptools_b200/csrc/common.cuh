@@ -1,0 +1,32 @@
+// Shared device helpers: FP64 tensor-core MMA (DMMA m8n8k4), cp.async staging, small reductions.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+// mma.sync.aligned.m8n8k4.row.col.f64: D(8x8) += A(8x4) * B(4x8).
+// Lane l: g = l >> 2, t = l & 3.  a = A[g][t];  b = B[t][g];  c0 = C[g][2t], c1 = C[g][2t+1].
+// sm_100a lowers this to one DMMA.8x8x4 (measured 37.1 TFLOP/s issue peak on B200,
+// profiles/r01_fp64_peak_microbench.txt).
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }

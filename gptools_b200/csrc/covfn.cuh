@@ -1,0 +1,376 @@
+// Pairwise covariance closed forms with derivative orders -- the bodies of the reference's
+// Kernel.__call__ plugins, written as scalar __host__ __device__ functions so that the very
+// same source is (a) inlined into the tile-generating CUDA kernels and (b) compiled for the
+// host by csrc/hostmath.cpp and checked against the golden vectors without a GPU.
+//
+// Reference semantics followed (paths under /root/reference/gptools):
+//   SE          kernel/squared_exponential.py:110-174, kernel/core.py:384-421
+//   MATERN52    kernel/matern.py:543-555, kernel/src/matern.c:61-186
+//   MATERN      kernel/matern.py:296-459, kernel/core.py:728-750, utils.py:1429-1518
+//               (half-integer nu, total derivative order <= 2, incl. the 0 < y <= 5e-4 series zone)
+//   GIBBS_TANH  kernel/gibbs.py:324-423, 458-461
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define GPT_HD __host__ __device__ __forceinline__
+#else
+#define GPT_HD inline
+#endif
+
+#define GPT_KERNEL_SE 0
+#define GPT_KERNEL_MATERN52 1
+#define GPT_KERNEL_MATERN 2
+#define GPT_KERNEL_GIBBS_TANH 3
+
+#define GPT_MAX_DIM 6
+#define GPT_MAX_PARAMS 10
+
+// Kernel hyperparameters in the reference's order plus quantities derived once per theta.
+struct CovParams {
+    int kid;
+    int D;
+    int nparams;
+    double p[GPT_MAX_PARAMS];  // the reference's params vector
+    // derived
+    double sig2;               // sigma_f^2
+    double inv_l[GPT_MAX_DIM]; // 1 / l_d
+    // generic Matern (half-integer nu): derivative-series constants, utils.py:1496-1516
+    int matern_p;              // nu = matern_p + 1/2
+    double mat_c;              // 2^{1-nu} / Gamma(nu)
+    double mat_A[3];           // value of f^{(n)}(0), n = 1,2 (index n)
+    double mat_B[3];           // c * Gamma(-nu) (1+nu-n)_n / 2^{1+nu}
+};
+
+GPT_HD void cov_params_init(CovParams& cp, int kid, int D, int nparams, const double* params) {
+    cp.kid = kid;
+    cp.D = D;
+    cp.nparams = nparams;
+    for (int i = 0; i < GPT_MAX_PARAMS; i++) cp.p[i] = (i < nparams) ? params[i] : 0.0;
+    cp.sig2 = cp.p[0] * cp.p[0];
+    const int loff = (kid == GPT_KERNEL_MATERN) ? 2 : 1;
+    for (int d = 0; d < GPT_MAX_DIM; d++) cp.inv_l[d] = 0.0;
+    if (kid != GPT_KERNEL_GIBBS_TANH)
+        for (int d = 0; d < D; d++) cp.inv_l[d] = 1.0 / cp.p[loff + d];
+    cp.matern_p = 0;
+    cp.mat_c = 0.0;
+    for (int i = 0; i < 3; i++) { cp.mat_A[i] = 0.0; cp.mat_B[i] = 0.0; }
+    if (kid == GPT_KERNEL_MATERN) {
+        const double nu = cp.p[1];
+        cp.matern_p = (int)floor(nu);
+        const double g_nu = tgamma(nu);
+        const double g_mnu = tgamma(-nu);
+        cp.mat_c = pow(2.0, 1.0 - nu) / g_nu;
+        for (int n = 1; n <= 2; n++) {
+            double poch1 = 1.0, poch2 = 1.0;  // (1-nu)_n and (1+nu-n)_n
+            for (int k = 0; k < n; k++) { poch1 *= (1.0 - nu + k); poch2 *= (1.0 + nu - n + k); }
+            // Gamma(nu) n! / (2^{1-nu+2n} (1-nu)_n n!)   (utils.py:1503-1507 with k = n, nterms = 1)
+            cp.mat_A[n] = cp.mat_c * g_nu / (pow(2.0, 1.0 - nu + 2.0 * n) * poch1);
+            // Gamma(-nu) (1+nu-n)_n y^{nu-n} / 2^{1+nu}   (utils.py:1508-1515 with k = 0)
+            cp.mat_B[n] = cp.mat_c * g_mnu * poch2 / pow(2.0, 1.0 + nu);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Squared exponential, arbitrary derivative orders.
+//   K = s2 e^{-r2/2} (-1)^{sum nj} prod_d c_d^{m_d} H_{m_d}(x_d),  c = -1/(sqrt2 l), x = tau/(sqrt2 l)
+// f = c^m H_m(x); g = d f e^{..}/dl / e^{..} in the singular-free form:
+//   g = c^m [ H_m(x) (tau^2/l^3 - m/l) - (sqrt2 m tau / l^2) H_{m-1}(x) ]
+// ------------------------------------------------------------------------------------------
+GPT_HD void se_dim_factor(double tau, double inv_l, int m, bool want_g, double& f, double& g) {
+    const double RSQRT2 = 0.70710678118654752440;
+    const double SQRT2 = 1.41421356237309504880;
+    if (m == 0) {
+        f = 1.0;
+        g = want_g ? tau * tau * inv_l * inv_l * inv_l : 0.0;
+        return;
+    }
+    const double c = -RSQRT2 * inv_l;
+    const double x = tau * RSQRT2 * inv_l;
+    // physicists' Hermite recurrence H_{k+1} = 2x H_k - 2k H_{k-1}
+    double hm1 = 1.0;       // H_0
+    double h = 2.0 * x;     // H_1
+    double cm = c;          // c^1
+    for (int k = 1; k < m; k++) {
+        const double hn = 2.0 * x * h - 2.0 * k * hm1;
+        hm1 = h;
+        h = hn;
+        cm *= c;
+    }
+    f = cm * h;
+    if (want_g) {
+        const double il2 = inv_l * inv_l;
+        g = cm * (h * (tau * tau * il2 * inv_l - m * inv_l) - SQRT2 * m * tau * il2 * hm1);
+    } else {
+        g = 0.0;
+    }
+}
+
+// hyper_deriv: -1 none, 0 sigma_f, 1+d length scale d.
+GPT_HD double se_cov(const CovParams& cp, const double* xi, const int32_t* ni, const double* xj,
+                     const int32_t* nj, int hyper_deriv) {
+    double r2 = 0.0, prod = 1.0;
+    int ntot_j = 0;
+    for (int d = 0; d < cp.D; d++) {
+        const double tau = xi[d] - xj[d];
+        double tl = tau * cp.inv_l[d];
+        if (tau == 0.0) tl = 0.0;  // core.py:416 (0/0 -> 0)
+        r2 += tl * tl;
+        const int m = ni[d] + nj[d];
+        ntot_j += nj[d];
+        double f, g;
+        se_dim_factor(tau, cp.inv_l[d], m, hyper_deriv == d + 1, f, g);
+        prod *= (hyper_deriv == d + 1) ? g : f;
+    }
+    double k = cp.sig2 * exp(-0.5 * r2) * prod;
+    if (ntot_j & 1) k = -k;
+    if (hyper_deriv == 0) k = (cp.p[0] != 0.0) ? 2.0 * k / cp.p[0] : 0.0;
+    return k;
+}
+
+// Value and all (1 + D) hyper-derivatives in one pass (one exp). out[0] = K, out[1] = dK/dsigma,
+// out[2 + d] = dK/dl_d.
+GPT_HD void se_cov_all(const CovParams& cp, const double* xi, const int32_t* ni, const double* xj,
+                       const int32_t* nj, double* out) {
+    double r2 = 0.0;
+    int ntot_j = 0;
+    double f[GPT_MAX_DIM], g[GPT_MAX_DIM];
+    for (int d = 0; d < cp.D; d++) {
+        const double tau = xi[d] - xj[d];
+        double tl = tau * cp.inv_l[d];
+        if (tau == 0.0) tl = 0.0;
+        r2 += tl * tl;
+        ntot_j += nj[d];
+        se_dim_factor(tau, cp.inv_l[d], ni[d] + nj[d], true, f[d], g[d]);
+    }
+    double base = cp.sig2 * exp(-0.5 * r2);
+    if (ntot_j & 1) base = -base;
+    double prod = 1.0;
+    for (int d = 0; d < cp.D; d++) prod *= f[d];
+    out[0] = base * prod;
+    out[1] = (cp.p[0] != 0.0) ? 2.0 * out[0] / cp.p[0] : 0.0;
+    for (int d = 0; d < cp.D; d++) {
+        double pr = g[d];
+        for (int e = 0; e < cp.D; e++)
+            if (e != d) pr *= f[e];
+        out[2 + d] = base * pr;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Matern 5/2, value / first derivative / mixed second derivative (matern.c:61-186).
+// ------------------------------------------------------------------------------------------
+GPT_HD int first_one(const int32_t* n, int D) {
+    for (int d = 0; d < D; d++)
+        if (n[d] == 1) return d;
+    return -1;
+}
+
+GPT_HD double matern52_cov(const CovParams& cp, const double* xi, const int32_t* ni, const double* xj,
+                           const int32_t* nj) {
+    const double SQRT_5 = 2.2360679774997898;
+    const double FIVE_THIRDS = 1.6666666666666667;
+    double r2 = 0.0;
+    for (int d = 0; d < cp.D; d++) {
+        const double disp = xi[d] - xj[d];
+        const double var = cp.p[1 + d] * cp.p[1 + d];
+        r2 = r2 + disp * disp / var;
+    }
+    const int a = first_one(ni, cp.D);
+    const int b = first_one(nj, cp.D);
+    double v;
+    if (a < 0 && b < 0) {
+        if (r2 == 0.0) {
+            v = 1.0;
+        } else {
+            const double s = SQRT_5 * sqrt(r2);
+            v = (1.0 + s + FIVE_THIRDS * r2) * exp(-s);
+        }
+    } else if (a < 0 || b < 0) {
+        if (r2 == 0.0) {
+            v = 0.0;
+        } else {
+            const int n = (a >= 0) ? a : b;
+            const double var = cp.p[1 + n] * cp.p[1 + n];
+            double disp = xi[n] - xj[n];
+            if (a < 0) disp = -disp;  // derivative w.r.t. Xj: arguments swapped (matern.c:182-184)
+            const double s = SQRT_5 * sqrt(r2);
+            v = -FIVE_THIRDS * (1.0 + s) * exp(-s) * (disp / var);
+        }
+    } else {
+        const double varn = cp.p[1 + a] * cp.p[1 + a];
+        const double varm = cp.p[1 + b] * cp.p[1 + b];
+        if (r2 == 0.0) {
+            v = (a == b) ? FIVE_THIRDS / varn : 0.0;
+        } else {
+            const double r = sqrt(r2);
+            const double dn = xi[a] - xj[a];
+            const double dm = xi[b] - xj[b];
+            const double dr_dXn = dn / (r * varn);
+            const double dr_dYm = -dm / (r * varm);
+            double d2r_r3 = dn * dm / (varn * varm);
+            if (a == b) d2r_r3 -= r * r / varn;
+            const double s = SQRT_5 * r;
+            const double e = exp(-s);
+            const double dk_over_r = -FIVE_THIRDS * (1.0 + s) * e;
+            const double d2k = FIVE_THIRDS * (5.0 * r2 - s - 1.0) * e;
+            v = dk_over_r * d2r_r3 / r2 + d2k * dr_dXn * dr_dYm;
+        }
+    }
+    return cp.sig2 * v;
+}
+
+// ------------------------------------------------------------------------------------------
+// Generic Matern, nu = p + 1/2, total derivative order <= 2.
+//   f(y) = c y^{nu/2} K_nu(sqrt y),  c = 2^{1-nu}/Gamma(nu),  y = 2 nu r2l2
+//   g_mu(y) := y^{mu/2} K_|mu|(sqrt y);  d/dy g_mu = -1/2 g_{mu-1}   =>   f^{(n)} = c (-1/2)^n g_{nu-n}
+//   K_{q+1/2}(r) = sqrt(pi/(2r)) e^{-r} sum_{k<=q} (q+k)!/(k!(q-k)!) (2r)^{-k}
+// ------------------------------------------------------------------------------------------
+GPT_HD double bessel_k_half(int q, double r) {
+    // K_{q+1/2}(r), q >= 0 (K_{-1/2} = K_{1/2} handled by the caller)
+    double sum = 1.0, term = 1.0;
+    for (int k = 1; k <= q; k++) {
+        term *= (double)(q + k) * (double)(q - k + 1) / ((double)k * 2.0 * r);
+        sum += term;
+    }
+    return sqrt(1.5707963267948966 / r) * exp(-r) * sum;
+}
+
+GPT_HD double matern_fn(const CovParams& cp, double y, int n) {
+    // exact f^{(n)}(y) for y > 0 and half-integer nu
+    const double nu = cp.p[1];
+    const double r = sqrt(y);
+    const double mu = nu - n;  // half-integer, may be negative
+    const double amu = fabs(mu);
+    const int q = (int)floor(amu);
+    double s = (n & 1) ? -1.0 : 1.0;
+    for (int k = 0; k < n; k++) s *= 0.5;
+    return cp.mat_c * s * pow(r, mu) * bessel_k_half(q, r);
+}
+
+GPT_HD double matern_dk_dy(const CovParams& cp, double y, int n) {
+    // utils.py:1429-1518 for n >= 1 (value n == 0 is handled by the caller)
+    const double nu = cp.p[1];
+    if (y == 0.0) {
+        if ((double)n > nu) {
+            // Gamma(-nu) (1+nu-n)_n * inf (utils.py:1487-1488)
+            double poch = 1.0;
+            for (int k = 0; k < n; k++) poch *= (1.0 + nu - n + k);
+            return cp.mat_c * (tgamma(-nu) * poch) * INFINITY;
+        }
+        return cp.mat_A[n];
+    }
+    if (y <= 5e-4) return cp.mat_A[n] + cp.mat_B[n] * pow(y, nu - n);
+    return matern_fn(cp, y, n);
+}
+
+GPT_HD double matern_cov(const CovParams& cp, const double* xi, const int32_t* ni, const double* xj,
+                         const int32_t* nj) {
+    const double nu = cp.p[1];
+    double r2 = 0.0;
+    int ntot_j = 0, order = 0;
+    int dims[2] = {-1, -1};
+    double tau_d[2] = {0.0, 0.0};
+    for (int d = 0; d < cp.D; d++) {
+        const double tau = xi[d] - xj[d];
+        double tl = tau * cp.inv_l[d];
+        if (tau == 0.0) tl = 0.0;
+        r2 += tl * tl;
+        ntot_j += nj[d];
+        const int m = ni[d] + nj[d];
+        for (int k = 0; k < m; k++) {
+            if (order < 2) { dims[order] = d; tau_d[order] = tau; }
+            order++;
+        }
+    }
+    const double y = 2.0 * nu * r2;
+    double v;
+    if (order == 0) {
+        v = (r2 == 0.0) ? 1.0 : matern_fn(cp, y, 0);
+    } else if (order == 1) {
+        // single partition {a}: f'(y) * dy/dtau_a, dy/dtau = 4 nu tau / l^2 (matern.py:404-405)
+        const double il = cp.inv_l[dims[0]];
+        double dk = matern_dk_dy(cp, y, 1);
+        if (y == 0.0) {
+            const double tau_pow = 2.0 * (nu - 1.0) + 1.0;  // matern.py:448-455
+            if (tau_pow == 0.0) dk = NAN;
+            else if (tau_pow > 0.0) dk = 0.0;
+        }
+        v = dk * (4.0 * nu * tau_d[0] * il * il);
+    } else if (order == 2) {
+        // partitions {a,b} (one block) and {a},{b} (two blocks)
+        const double ila = cp.inv_l[dims[0]], ilb = cp.inv_l[dims[1]];
+        double t1 = 0.0;
+        if (dims[0] == dims[1]) t1 = matern_dk_dy(cp, y, 1) * (4.0 * nu * ila * ila);
+        double dk2 = matern_dk_dy(cp, y, 2);
+        if (y == 0.0) {
+            const double tau_pow = 2.0 * (nu - 2.0) + 2.0;
+            if (tau_pow == 0.0) dk2 = NAN;
+            else if (tau_pow > 0.0) dk2 = 0.0;
+        }
+        const double t2 = dk2 * (4.0 * nu * tau_d[0] * ila * ila) * (4.0 * nu * tau_d[1] * ilb * ilb);
+        v = t1 + t2;
+    } else {
+        v = NAN;  // rejected on the host before any device call
+    }
+    if (ntot_j & 1) v = -v;
+    return cp.sig2 * v;
+}
+
+// ------------------------------------------------------------------------------------------
+// Gibbs kernel with tanh length-scale warp, 1-D, (ni, nj) in {0,1}^2.
+//   k00 = sqrt(2 lx ly / S) exp(-d^2/S), S = lx^2 + ly^2, d = x - y
+//   k10 = k00 A_x, k01 = k00 A_y, k11 = k00 (A_x A_y + d/dy A_x)       
+// ------------------------------------------------------------------------------------------
+GPT_HD void gibbs_tanh_l(const CovParams& cp, double x, double& l, double& l1) {
+    const double la = cp.p[1], lb = cp.p[2], lw = cp.p[3], x0 = cp.p[4];
+    const double t = tanh((x - x0) / lw);
+    l = 0.5 * (la + lb) - 0.5 * (la - lb) * t;
+    l1 = -(la - lb) / (2.0 * lw) * (1.0 - t * t);  // cosh^-2 = 1 - tanh^2
+}
+
+GPT_HD double gibbs_cov_l(const CovParams& cp, double x, double lx, double lx1, int a, double y, double ly,
+                          double ly1, int b) {
+    const double d = x - y;
+    const double S = lx * lx + ly * ly;
+    const double iS = 1.0 / S;
+    const double k00 = sqrt(2.0 * lx * ly * iS) * exp(-d * d * iS);
+    double v = k00;
+    if (a | b) {
+        const double Ax = lx1 / (2.0 * lx) - lx * lx1 * iS - 2.0 * d * iS + 2.0 * d * d * lx * lx1 * iS * iS;
+        const double Ay = ly1 / (2.0 * ly) - ly * ly1 * iS + 2.0 * d * iS + 2.0 * d * d * ly * ly1 * iS * iS;
+        if (a && b) {
+            const double dAx = 2.0 * lx * lx1 * ly * ly1 * iS * iS + 2.0 * iS + 4.0 * d * ly * ly1 * iS * iS -
+                               4.0 * d * lx * lx1 * iS * iS - 8.0 * d * d * lx * lx1 * ly * ly1 * iS * iS * iS;
+            v = k00 * (Ax * Ay + dAx);
+        } else if (a) {
+            v = k00 * Ax;
+        } else {
+            v = k00 * Ay;
+        }
+    }
+    return cp.sig2 * v;
+}
+
+GPT_HD double gibbs_cov(const CovParams& cp, const double* xi, const int32_t* ni, const double* xj,
+                        const int32_t* nj) {
+    double lx, lx1, ly, ly1;
+    gibbs_tanh_l(cp, xi[0], lx, lx1);
+    gibbs_tanh_l(cp, xj[0], ly, ly1);
+    return gibbs_cov_l(cp, xi[0], lx, lx1, ni[0], xj[0], ly, ly1, nj[0]);
+}
+
+// ------------------------------------------------------------------------------------------
+// dispatch
+// ------------------------------------------------------------------------------------------
+GPT_HD double cov_eval(const CovParams& cp, const double* xi, const int32_t* ni, const double* xj,
+                       const int32_t* nj, int hyper_deriv) {
+    switch (cp.kid) {
+        case GPT_KERNEL_SE: return se_cov(cp, xi, ni, xj, nj, hyper_deriv);
+        case GPT_KERNEL_MATERN52: return matern52_cov(cp, xi, ni, xj, nj);
+        case GPT_KERNEL_MATERN: return matern_cov(cp, xi, ni, xj, nj);
+        default: return gibbs_cov(cp, xi, ni, xj, nj);
+    }
+}

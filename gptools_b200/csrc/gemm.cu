@@ -1,0 +1,114 @@
+// FP64 tensor-core GEMM for the blocked single-matrix algorithms:  C = beta*C + alpha * A * B^T.
+//
+// Both operands are row-major with the contraction index contiguous ("NT"), which is the only
+// form the blocked Cholesky / trtri / lauum / T K T^T / triangular-solve paths need (symmetric
+// operands and pre-transposed inverses make every product NT).
+//
+// Tile 128x128x16, 256 threads = 8 warps (2 x 4), warp tile 64x32 = 8x4 DMMA.8x8x4 tiles,
+// 3-stage cp.async pipeline.  Shared rows are padded to 20 doubles: the fragment read
+// A[g][k0+t] then maps the 16 lanes of a half-warp to 16 distinct 8-byte banks (g*20+t mod 16
+// = 4g+t), i.e. conflict-free LDS.64 for both operands.
+// Roofline: FP64 tensor pipe (measured cuBLAS Dgemm 35.5 TFLOP/s on this pool's B200).
+#include "common.cuh"
+#include "internal.h"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16, STAGES = 3, LDS_ = BK + 4;
+constexpr int THREADS = 256;
+constexpr size_t SMEM_BYTES = (size_t)STAGES * (BM + BN) * LDS_ * sizeof(double);
+
+__global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(GemmParams p) {
+    extern __shared__ __align__(16) double smem[];
+    const int bm = blockIdx.y, bn = blockIdx.x;
+    if (p.lower_only && bn > bm) return;
+    const int kstart = p.kbegin_row ? bm * BM : 0;
+    const int nk = (p.K - kstart) / BK;
+    const double* __restrict__ Ag = p.A + (long)bm * BM * p.lda + kstart;
+    const double* __restrict__ Bg = p.B + (long)bn * BN * p.ldb + kstart;
+    double* sA = smem;
+    double* sB = smem + STAGES * BM * LDS_;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 2, wn = warp & 3;
+
+    auto load_stage = [&](int stage, int kc) {
+        double* a_dst = sA + stage * BM * LDS_;
+        double* b_dst = sB + stage * BN * LDS_;
+#pragma unroll
+        for (int i = tid; i < BM * (BK / 2); i += THREADS) {
+            const int r = i >> 3, c = (i & 7) * 2;
+            cp_async16(a_dst + r * LDS_ + c, Ag + (long)r * p.lda + kc * BK + c);
+        }
+#pragma unroll
+        for (int i = tid; i < BN * (BK / 2); i += THREADS) {
+            const int r = i >> 3, c = (i & 7) * 2;
+            cp_async16(b_dst + r * LDS_ + c, Bg + (long)r * p.ldb + kc * BK + c);
+        }
+    };
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) {
+        if (s < nk) load_stage(s, s);
+        cp_async_commit();
+    }
+    for (int kc = 0; kc < nk; kc++) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        const int nxt = kc + STAGES - 1;
+        if (nxt < nk) load_stage(nxt % STAGES, nxt);
+        cp_async_commit();
+        const double* a_s = sA + (kc % STAGES) * BM * LDS_ + (wm * 64 + g) * LDS_ + t;
+        const double* b_s = sB + (kc % STAGES) * BN * LDS_ + (wn * 32 + g) * LDS_ + t;
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; kk++) {
+            double a[8], b[4];
+#pragma unroll
+            for (int i = 0; i < 8; i++) a[i] = a_s[i * 8 * LDS_ + kk * 4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) b[j] = b_s[j * 8 * LDS_ + kk * 4];
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue: each lane owns C[g][2t], C[g][2t+1] of every 8x8 tile -> one 16-byte store
+    const long row0 = (long)bm * BM + wm * 64 + g;
+    const long col0 = (long)bn * BN + wn * 32 + 2 * t;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            double2* dst = reinterpret_cast<double2*>(p.C + (row0 + i * 8) * p.ldc + col0 + j * 8);
+            double2 v;
+            v.x = p.alpha * acc[i][j][0];
+            v.y = p.alpha * acc[i][j][1];
+            if (p.beta != 0.0) {
+                const double2 old = *dst;
+                v.x += p.beta * old.x;
+                v.y += p.beta * old.y;
+            }
+            *dst = v;
+        }
+    }
+}
+
+}  // namespace
+
+void launch_gemm_nt(const GemmParams& p, cudaStream_t s) {
+    cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (p.tiles_m <= 0 || p.tiles_n <= 0) return;
+    dim3 grid(p.tiles_n, p.tiles_m);
+    gemm_nt_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(p);
+}

@@ -1,0 +1,29 @@
+// Host build of the device covariance closed forms (covfn.cuh) for CPU-side unit tests.
+// NOT part of the product path: only tests/test_covfn_host.py loads libgptb200_hostcheck.so,
+// to check the exact source the CUDA kernels inline against the golden vectors without a GPU.
+#include "covfn.cuh"
+
+extern "C" {
+
+int gpt_hostcheck_cov_pairs(int kid, int D, int nparams, const double* params, int hyper_deriv,
+                            long npairs, const double* Xi, const double* Xj, const int32_t* ni,
+                            const int32_t* nj, double* out) {
+    if (D > GPT_MAX_DIM || nparams > GPT_MAX_PARAMS) return -1;
+    CovParams cp;
+    cov_params_init(cp, kid, D, nparams, params);
+    for (long p = 0; p < npairs; p++)
+        out[p] = cov_eval(cp, Xi + p * D, ni + p * D, Xj + p * D, nj + p * D, hyper_deriv);
+    return 0;
+}
+
+// out is (npairs, 2 + D): value, d/dsigma, d/dl_1..d/dl_D
+int gpt_hostcheck_se_all(int D, const double* params, long npairs, const double* Xi, const double* Xj,
+                         const int32_t* ni, const int32_t* nj, double* out) {
+    if (D > GPT_MAX_DIM) return -1;
+    CovParams cp;
+    cov_params_init(cp, GPT_KERNEL_SE, D, D + 1, params);
+    for (long p = 0; p < npairs; p++)
+        se_cov_all(cp, Xi + p * D, ni + p * D, Xj + p * D, nj + p * D, out + p * (2 + D));
+    return 0;
+}
+}

@@ -1,0 +1,119 @@
+// Internal (non-ABI) declarations shared by the .cu translation units of libgptb200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "covfn.cuh"
+
+#define GPT_NB 128  // block size of the blocked single-matrix algorithms (= GEMM tile edge)
+
+// ---- gemm.cu : FP64 DMMA GEMM, C = beta*C + alpha * A * B^T -------------------------------
+// A: (tiles_m*128) x K, B: (tiles_n*128) x K, C: (tiles_m*128) x (tiles_n*128); all row-major,
+// K a multiple of 16, leading dimensions even, base pointers 16-byte aligned.
+struct GemmParams {
+    double* C;
+    long ldc;
+    const double* A;
+    long lda;
+    const double* B;
+    long ldb;
+    int tiles_m, tiles_n;
+    int K;
+    double alpha, beta;
+    int lower_only;  // only tiles with tile_n <= tile_m (symmetric rank-k updates, lauum)
+    int kbegin_row;  // contraction starts at k = tile_m*128 (A upper block-triangular)
+};
+void launch_gemm_nt(const GemmParams& p, cudaStream_t s);
+
+// ---- assemble.cu : covariance tile generation ------------------------------------------------
+struct AssembleParams {
+    CovParams cp;
+    const double* Xr;   // row points  (Mr x D)
+    const int32_t* nr;  // row derivative orders
+    int Mr;
+    const double* Xc;   // column points (Mc x D)
+    const int32_t* nc;
+    int Mc;
+    double* out;        // (rows_pad x cols_pad) row-major
+    long ldo;
+    int rows_pad, cols_pad;
+    int hyper_deriv;    // -1: value
+    int swap_roles;     // 0: out[r][c] = k(row_r, col_c); 1: out[r][c] = k(col_c, row_r)
+    int symmetric;      // rows and cols are the same set: add diag terms, identity padding
+    const double* diag_add;  // optional per-row additive diagonal (err_y^2 + jitter [+ noise]) or NULL
+    double diag_const;       // added to every diagonal element r < Mr (sigma_n^2 for the latent K)
+    int pad_identity;        // symmetric: out[r][r] = 1 for r >= Mr
+};
+void launch_assemble(const AssembleParams& p, cudaStream_t s);
+void launch_cov_pairs(const CovParams& cp, int hyper_deriv, long npairs, const double* Xi, const double* Xj,
+                      const int32_t* ni, const int32_t* nj, double* out, cudaStream_t s);
+
+// ---- factor.cu : blocked Cholesky pieces, solves, reductions -----------------------------------
+// Factor one 128x128 diagonal block in place (lower), write its inverse (lower, zero above) to
+// inv, optionally z_k = inv * y_k (in place on y), accumulate sum(log diag) and the LAPACK-style info.
+void launch_potrf_diag(double* Ablk, long lda, double* inv, double* yk, double* logdet_part, int* info,
+                       int row0, int nvalid, cudaStream_t s);
+// y[r] -= sum_c P[r][c] * zk[c], r < rows (P is rows x 128, ld 128)
+void launch_panel_gemv(const double* P, int rows, const double* zk, double* y, cudaStream_t s);
+// back substitution step k: alpha_k = inv_k^T z_k ; z[0 : k*128] -= L[k-block rows, 0 : k*128]^T alpha_k
+void launch_backsolve_step(const double* L, long ld, int k, const double* inv_k, double* z, double* alpha,
+                           cudaStream_t s);
+void launch_transpose(double* out, long ldo, const double* in, long ldi, int rows, int cols, cudaStream_t s);
+void launch_copy2d(double* out, long ldo, const double* in, long ldi, int rows, int cols, cudaStream_t s);
+void launch_add_diag(double* A, long lda, const double* d, int n, cudaStream_t s);
+void launch_fill(double* p, long n, double v, cudaStream_t s);
+// set the strictly-upper block triangle + padding of a lower-block matrix to a clean state
+void launch_set_identity_pad(double* A, long lda, int n_valid, int n_pad, cudaStream_t s);
+
+// gradient reduction: for every requested hyper-parameter p,
+//   g[p] = sum_{i>j} W_ij dK_ij(p) + 1/2 sum_i W_ii dK_ii(p),  W = w_outer * a a^T - S  (S lower-valid)
+struct GradReduceParams {
+    CovParams cp;
+    const double* X;
+    const int32_t* n;
+    int N;               // points (matrix dimension that is valid)
+    const double* S;     // N_pad x N_pad, lower triangle valid
+    long lds;
+    const double* a;     // vector for the outer product (alpha) or NULL
+    int nidx;
+    int idx[GPT_MAX_PARAMS];  // hyper_deriv indices
+    double* partials;    // (num_ctas x nidx) scratch
+    double* out;         // nidx
+};
+void launch_grad_reduce(const GradReduceParams& p, cudaStream_t s);
+// out[0] = sum_{i<n} A[i][i], out[1] = sum_{i<n} v[i]^2
+void launch_trace_and_sumsq(const double* A, long lda, const double* v, int n, double* out, cudaStream_t s);
+
+// ---- predict.cu ------------------------------------------------------------------------------------
+// mean[s] = sum_i Kst[s][i] * alpha[i]  (Kst: rows x ld, first n columns)
+void launch_rowdot(const double* Kst, long ld, int rows, int n, const double* alpha, double* mean, cudaStream_t s);
+// var[s] = kss[s] - sum_{c<n} V[s][c]^2
+void launch_row_var(const double* V, long ld, int rows, int n, const double* kss, double* var, cudaStream_t s);
+// kss[s] = k(x*_s, x*_s) with orders ns
+void launch_prior_diag(const CovParams& cp, const double* Xs, const int32_t* ns, int rows, double* kss, cudaStream_t s);
+
+// ---- batched.cu : many-theta persistent kernel ---------------------------------------------------
+struct BatchedParams {
+    int kid, D, nparams;
+    int M;                 // observations (= latent points; no T on this path)
+    int nT;                // 64-row tiles, ceil(M / 64)
+    const double* X;       // M x D
+    const int32_t* n;      // M x D
+    const double* y;       // M (shared) or B x M when y_stride != 0
+    long y_stride;
+    const double* diag;    // err_y^2 + diag_factor*eps, length M
+    int B;
+    const double* thetas;  // B x (nparams + 1): kernel params then sigma_noise
+    int nidx;              // number of gradient entries (0: ll only)
+    int idx[GPT_MAX_PARAMS];  // hyper_deriv index per entry; nparams = noise sigma
+    double* ll;            // B
+    double* grad;          // B x nidx
+    int* status;           // B
+    double* alpha_out;     // B x M or NULL
+    double* workspace;     // per-CTA tile storage
+    size_t ws_per_cta;     // in doubles
+    int* counter;          // dynamic theta scheduler
+};
+size_t batched_ws_doubles_per_cta(int nT);
+int batched_max_ctas(int device);
+void launch_ll_batched(const BatchedParams& p, int num_ctas, cudaStream_t s);

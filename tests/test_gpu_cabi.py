@@ -1,0 +1,248 @@
+"""GPU parity tests proper: the CUDA path, called through the C-ABI (ctypes), against the golden vectors of
+the unmodified reference and against the pinned numpy oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): ll, gradient, predictive mean/std within 1e-9 relative; the
+predictive variance is compared with the absolute floor 1e-9 * prior variance."""
+import numpy as np
+import pytest
+
+from helpers import CASE_KERNEL, KERNEL_MATERN, KERNEL_SE, assert_close, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from gptools_b200._lib import Device
+    d = Device(0)
+    yield d
+    d.close()
+
+
+def _T(gd):
+    return gd["T"] if "T" in gd else None
+
+
+def _setup(dev, case, gd, diag_factor=1e2):
+    dev.set_data(gd["X"], gd["n"], gd["y"], gd["err_y"], _T(gd))
+    dev.set_kernel(CASE_KERNEL[case], len(gd["params"]), diag_factor)
+
+
+@pytest.mark.parametrize("D", [1, 2, 3])
+def test_cov_pairs_se(dev, D):
+    gd = load_golden("se_pairs_D%d" % D)
+    a = (gd["params"], gd["Xi"], gd["Xj"], gd["ni"], gd["nj"])
+    scale = np.abs(gd["val"]).max()
+    assert_close(dev.cov_pairs(KERNEL_SE, *a), gd["val"], rtol=2e-12, atol=1e-14 * scale, what="value")
+    for p in range(D + 1):
+        ref = gd["hd%d" % p]
+        assert_close(dev.cov_pairs(KERNEL_SE, *a, hyper_deriv=p), ref, rtol=1e-9, atol=1e-12 * np.abs(ref).max(),
+                     what="hyper_deriv %d" % p)
+
+
+@pytest.mark.parametrize("case", [c for c in CASE_KERNEL if c not in ("c1_synth200", "c2_small_matern52",
+                                                                     "c2_small_matern_generic", "gibbs_c5_small")])
+def test_compute_Kij(dev, case):
+    gd = load_golden(case)
+    kid = CASE_KERNEL[case]
+    K = dev.compute_Kij(kid, gd["params"], gd["X"], gd["n"])
+    tol = dict(rtol=1e-9, atol=1e-9 * np.abs(gd["K"]).max()) if kid == KERNEL_MATERN else \
+        dict(rtol=1e-12, atol=1e-13 * np.abs(gd["K"]).max())
+    assert_close(K, gd["K"], what=case, **tol)
+    if case == "se2d_kat1":
+        for p in range(3):
+            dK = dev.compute_Kij(kid, gd["params"], gd["X"], gd["n"], hyper_deriv=p)
+            assert_close(dK, gd["dK%d" % p], rtol=1e-10, atol=1e-13 * np.abs(gd["dK%d" % p]).max(), what="dK%d" % p)
+        Ks = dev.compute_Kij(kid, gd["params"], gd["X"], gd["n"], gd["Xs"], np.zeros((4, 2), dtype=int))
+        assert_close(Ks, gd["Kstar"], rtol=1e-12, atol=1e-14, what="Kstar")
+
+
+@pytest.mark.parametrize("case", sorted(CASE_KERNEL))
+def test_ll_alpha_L(dev, case):
+    gd = load_golden(case)
+    _setup(dev, case, gd)
+    ns = float(gd["noise_sigma"][0]) if "noise_sigma" in gd else 0.0
+    ll, _, status = dev.ll(gd["params"], ns)
+    assert status == 0
+    assert_close(ll + gd["log_prior"], gd["ll"], rtol=1e-9, what=case + " ll")
+    alpha = dev.get_alpha()
+    # generic Matern: the reference's K entries carry ~2e-10 abs round-off from its kvp / Bell-polynomial
+    # sums; alpha = K^-1 y amplifies that by cond(K), so alpha/L can only agree to ~1e-6
+    tol = 2e-6 if CASE_KERNEL[case] == KERNEL_MATERN else 1e-9
+    assert_close(alpha, gd["alpha"], rtol=tol, atol=tol * np.abs(gd["alpha"]).max(), what=case + " alpha")
+    if "L" in gd:
+        L = dev.get_L()
+        assert_close(L, gd["L"], rtol=tol, atol=tol * np.abs(gd["L"]).max(), what=case + " L")
+
+
+@pytest.mark.parametrize("case", ["se2d_kat1", "se_diagnoise", "demo_c1_kat4", "c1_synth200"])
+def test_ll_gradient(dev, case):
+    from oracle import gp_oracle as orc
+    gd = load_golden(case)
+    _setup(dev, case, gd)
+    nk = len(gd["params"])
+    ns = float(gd["noise_sigma"][0]) if "noise_sigma" in gd else 0.0
+    idx = list(range(nk)) + ([nk] if ns else [])
+    ll, grad, status = dev.ll(gd["params"], ns, grad_idx=idx)
+    assert status == 0
+    if case in ("se2d_kat1", "se_diagnoise"):      # uniform priors: golden gradient == likelihood gradient
+        assert_close(grad, gd["ll_deriv"], rtol=1e-9, atol=1e-9 * np.abs(gd["ll_deriv"]).max(), what=case + " grad")
+    else:                                          # non-uniform prior in the golden: compare with the oracle
+        r = orc.compute_K_L_alpha_ll(KERNEL_SE, gd["params"], gd["X"], gd["n"], gd["y"], gd["err_y"], grad_idx=idx)
+        assert_close(grad, r["ll_deriv"], rtol=1e-8, atol=1e-9 * np.abs(r["ll_deriv"]).max(), what=case + " grad")
+
+
+@pytest.mark.parametrize("case", ["se2d_kat1", "matern52_kat2", "gibbs_kat3", "gibbs_c5_small", "se_diagnoise",
+                                  "matern_generic_nu2p5", "matern_generic_nu3p5"])
+def test_predict_full(dev, case):
+    gd = load_golden(case)
+    _setup(dev, case, gd)
+    kid = CASE_KERNEL[case]
+    ns = float(gd["noise_sigma"][0]) if "noise_sigma" in gd else 0.0
+    ll, _, status = dev.ll(gd["params"], ns)
+    assert status == 0
+    Xs = np.atleast_2d(gd["Xs"])
+    if Xs.shape[0] == 1 and gd["X"].shape[1] == 1:
+        Xs = Xs.T
+    z = np.zeros(Xs.shape, dtype=int)
+    mean, var, cov = dev.predict(Xs, z, want_cov=True)
+    assert_close(mean, gd["mean"], rtol=1e-9, atol=1e-9 * np.abs(gd["mean"]).max(), what=case + " mean")
+    prior = np.diag(dev.compute_Kij(kid, gd["params"], Xs, z))
+    assert np.all(np.abs(cov - gd["cov"]) <= 1e-9 * prior.max()), case + " cov"
+    assert np.all(np.abs(var - gd["std"] ** 2) <= 1e-9 * prior), case + " var"
+    mean2, var2, _ = dev.predict(Xs, z, want_var=True)
+    assert_close(mean2, mean, rtol=0, atol=0)
+    assert np.all(np.abs(var2 - np.diag(cov)) <= 1e-12 * prior)
+    if "mean_d1" in gd:
+        o = np.ones(Xs.shape, dtype=int)
+        m1, v1, c1 = dev.predict(Xs, o, want_cov=True)
+        assert_close(m1, gd["mean_d1"], rtol=1e-9, atol=1e-9 * np.abs(gd["mean_d1"]).max(), what=case + " mean_d1")
+        prior1 = np.diag(dev.compute_Kij(kid, gd["params"], Xs, o))
+        assert np.all(np.abs(c1 - gd["cov_d1"]) <= 1e-9 * prior1.max())
+    if "draw" in gd:
+        samp, st = dev.draw_sample(gd["mean"], gd["cov"], gd["rand_vars"], 1e3 * 2.220446049250313e-16)
+        assert st == 0
+        assert_close(samp, gd["draw"], rtol=1e-8, atol=1e-8 * np.abs(gd["draw"]).max(), what=case + " draw")
+
+
+@pytest.mark.parametrize("case", ["demo_c1_kat4", "c1_synth200", "c2_small_matern52", "c2_small_matern_generic"])
+def test_predict_mean_std_many_points(dev, case):
+    gd = load_golden(case)
+    _setup(dev, case, gd)
+    kid = CASE_KERNEL[case]
+    ll, _, status = dev.ll(gd["params"], 0.0)
+    assert status == 0
+    Xs = gd["Xs"][:, None]
+    for order, suffix in ((0, ""), (1, "_d1")):
+        ns = np.full(Xs.shape, order, dtype=int)
+        mean, var, _ = dev.predict(Xs, ns)
+        scale = np.abs(gd["mean" + suffix]).max()
+        assert_close(mean, gd["mean" + suffix], rtol=1e-9, atol=1e-9 * scale, what=case + " mean" + suffix)
+        prior = dev.compute_Kij(kid, gd["params"], Xs[:1], ns[:1])[0, 0]
+        ref_var = gd["std" + suffix] ** 2
+        ok = np.abs(var - ref_var) <= 1e-9 * prior
+        ok |= np.isnan(ref_var) & (var < 1e-9 * prior)   # reference sqrt(negative) -> NaN
+        assert ok.all(), case + " var" + suffix
+
+
+def test_batched_c3_kat5(dev):
+    """Headline path: batched ll + gradient on the config-3 problem vs the reference's values."""
+    gd = load_golden("c3_kat5")
+    dev.set_data(gd["X"], gd["n"], gd["y"], gd["err_y"])
+    dev.set_kernel(KERNEL_SE, 3, 1e2)
+    thetas = np.hstack([gd["theta"], np.zeros((len(gd["theta"]), 1))])
+    ll, grad, status = dev.ll_batched(thetas, grad_idx=[0, 1, 2])
+    assert (status == 0).all()
+    assert_close(ll + gd["log_prior"], gd["ll"], rtol=1e-9, what="batched ll")
+    assert_close(grad, gd["ll_deriv"], rtol=1e-9, atol=1e-9 * np.abs(gd["ll_deriv"]).max(), what="batched grad")
+    # ll-only launch and alpha output
+    ll2, g2, st2, alpha = dev.ll_batched(thetas[:3], return_alpha=True)
+    assert g2 is None
+    assert_close(ll2, ll[:3], rtol=1e-13)
+    assert_close(alpha[0], gd["alpha0"], rtol=1e-9, atol=1e-9 * np.abs(gd["alpha0"]).max(), what="alpha")
+    # single-theta path agrees with the batched path
+    for b in (0, 7):
+        l1, g1, s1 = dev.ll(gd["theta"][b], 0.0, grad_idx=[0, 1, 2])
+        assert s1 == 0
+        assert_close(l1, ll[b], rtol=1e-11)
+        assert_close(g1, grad[b], rtol=1e-9, atol=1e-9 * np.abs(grad[b]).max())
+    # predict at theta[0] (KAT-5)
+    dev.ll(gd["theta"][0], 0.0)
+    mean, var, _ = dev.predict(gd["Xs"], np.zeros((5, 2), dtype=int))
+    assert_close(mean, gd["mean"], rtol=1e-9, atol=1e-9)
+    assert np.all(np.abs(var - gd["std"] ** 2) <= 1e-9 * gd["theta"][0][0] ** 2)
+
+
+@pytest.mark.parametrize("case", ["se2d_kat1", "matern52_kat2", "matern_generic_nu2p5", "c1_synth200",
+                                  "c2_small_matern52", "se_diagnoise"])
+def test_batched_matches_golden_small_and_ragged(dev, case):
+    """M not a multiple of the 64-row tile, several kernels, noise kernel, B = 1 and B > #CTAs."""
+    gd = load_golden(case)
+    if "T" in gd:
+        pytest.skip("batched path has no T")
+    _setup(dev, case, gd)
+    ns = float(gd["noise_sigma"][0]) if "noise_sigma" in gd else 0.0
+    th = np.concatenate([gd["params"], [ns]])[None, :]
+    ll, _, status = dev.ll_batched(th)
+    assert status[0] == 0
+    assert_close(ll[0] + gd["log_prior"], gd["ll"], rtol=1e-9, what=case + " batched ll")
+    if CASE_KERNEL[case] == KERNEL_SE and case in ("se2d_kat1", "se_diagnoise"):
+        idx = list(range(len(gd["params"]))) + ([len(gd["params"])] if ns else [])
+        B = 700
+        ths = np.repeat(th, B, axis=0)
+        llB, gB, stB = dev.ll_batched(ths, grad_idx=idx)
+        assert (stB == 0).all()
+        assert np.all(llB == llB[0]) and np.all(gB == gB[0]), "identical thetas must give identical bits"
+        assert_close(gB[0], gd["ll_deriv"], rtol=1e-9, atol=1e-9 * np.abs(gd["ll_deriv"]).max(), what=case + " grad")
+
+
+def test_not_positive_definite_is_reported_per_theta(dev):
+    """Duplicate noiseless points => singular K: the reference raises LinAlgError (gaussian_process.py:1452),
+    mapped to +inf by update_hyperparameters; here a LAPACK-style status per theta."""
+    rs = np.random.RandomState(0)
+    X = rs.rand(40, 1)
+    X[7] = X[3]
+    X[30] = X[3]
+    y = np.sin(X[:, 0])
+    dev.set_data(X, np.zeros((40, 1), dtype=int), y, np.zeros(40))
+    dev.set_kernel(KERNEL_SE, 2, 0.0)
+    ll, g, st = dev.ll(np.array([1.0, 0.5]), 0.0)
+    assert st > 0
+    good = np.array([1.0, 0.5, 0.3])
+    bad = np.array([1.0, 0.5, 0.0])
+    llb, gb, stb = dev.ll_batched(np.stack([good, bad, good]), grad_idx=[0, 1])
+    assert stb[0] == 0 and stb[2] == 0 and stb[1] > 0
+    assert llb[0] == llb[2] and np.isfinite(llb[0])
+    assert np.all(gb[1] == 0.0)
+
+
+def test_multiblock_single_path_vs_oracle(dev):
+    """M = 700 (6 blocks of 128 with ragged tail): blocked potrf / trtri / lauum / fused gradient vs numpy."""
+    from oracle import gp_oracle as orc
+    rs = np.random.RandomState(5)
+    Xv = rs.rand(400, 2)
+    Xd = rs.rand(300, 2)
+    f = lambda x: np.sin(3 * x[:, 0]) * np.cos(2 * x[:, 1])
+    X = np.vstack([Xv, Xd])
+    n = np.vstack([np.zeros((400, 2), dtype=int), np.tile([1, 0], (300, 1))])
+    y = np.concatenate([f(Xv), 3 * np.cos(3 * Xd[:, 0]) * np.cos(2 * Xd[:, 1])]) + 0.05 * rs.randn(700)
+    err = np.full(700, 0.05)
+    params = np.array([1.1, 0.35, 0.45])
+    r = orc.compute_K_L_alpha_ll(KERNEL_SE, params, X, n, y, err, grad_idx=[0, 1, 2])
+    dev.set_data(X, n, y, err)
+    dev.set_kernel(KERNEL_SE, 3, 1e2)
+    ll, grad, st = dev.ll(params, 0.0, grad_idx=[0, 1, 2])
+    assert st == 0
+    assert_close(ll, r["ll"], rtol=1e-9)
+    assert_close(grad, r["ll_deriv"], rtol=1e-9, atol=1e-9 * np.abs(r["ll_deriv"]).max())
+    assert_close(dev.get_alpha(), r["alpha"].ravel(), rtol=1e-8, atol=1e-8 * np.abs(r["alpha"]).max())
+    llb, gb, stb = dev.ll_batched(np.concatenate([params, [0.0]])[None, :], grad_idx=[0, 1, 2])
+    assert stb[0] == 0
+    assert_close(llb[0], r["ll"], rtol=1e-9)
+    assert_close(gb[0], r["ll_deriv"], rtol=1e-9, atol=1e-9 * np.abs(r["ll_deriv"]).max())
+    Xs = rs.rand(300, 2)
+    ns = np.zeros((300, 2), dtype=int)
+    mean_o, std_o = orc.predict_blocked(KERNEL_SE, params, X, n, r["L"], r["alpha"], Xs, ns, block=150)
+    mean, var, _ = dev.predict(Xs, ns)
+    assert_close(mean, mean_o, rtol=1e-9, atol=1e-9)
+    assert np.all(np.abs(var - std_o ** 2) <= 1e-9 * params[0] ** 2)
