@@ -26,6 +26,7 @@ SIGNATURES = {
     "gpt_destroy": (None, [_vp]),
     "gpt_last_error": (ctypes.c_char_p, [_vp]),
     "gpt_set_stream": (ctypes.c_int, [_vp, _vp]),
+    "gpt_use_own_stream": (ctypes.c_int, [_vp]),
     "gpt_synchronize": (ctypes.c_int, [_vp]),
     "gpt_set_data": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_double_p, _c_int32_p,
                                     _c_double_p, _c_double_p, _c_double_p]),
@@ -142,7 +143,11 @@ class Device(object):
 
     # -- plumbing ---------------------------------------------------------------------------
     def set_stream(self, cuda_stream_ptr):
+        """Issue all work on the given cudaStream_t (integer handle; 0 / None = legacy default stream)."""
         self._check(self._lib.gpt_set_stream(self._h, _vp(cuda_stream_ptr) if cuda_stream_ptr else None), "gpt_set_stream")
+
+    def use_own_stream(self):
+        self._check(self._lib.gpt_use_own_stream(self._h), "gpt_use_own_stream")
 
     def synchronize(self):
         self._check(self._lib.gpt_synchronize(self._h), "gpt_synchronize")

@@ -378,7 +378,15 @@ int gpt_set_stream(gpt_handle* h, void* cuda_stream) {
     if (!h) return GPT_ERR_USAGE;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    h->stream = (cudaStream_t)cuda_stream;
+    return 0;
+}
+
+int gpt_use_own_stream(gpt_handle* h) {
+    if (!h) return GPT_ERR_USAGE;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    h->stream = h->own_stream;
     return 0;
 }
 

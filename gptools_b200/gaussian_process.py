@@ -1,0 +1,1034 @@
+"""GaussianProcess: the reference's public class (gptools/gaussian_process.py:56-1605) with its numerical
+core -- covariance assembly, Cholesky, alpha, log-likelihood, gradient, prediction, sampling -- executed by
+the CUDA library through the C-ABI (include/gptb200.h).  Host code here is bookkeeping only: argument
+canonicalisation (bit-exact with the reference's add_data / predict preamble), hyperparameter plumbing,
+hyperpriors and mean functions (O(P) / O(M) numpy), and the optimizer / sampler drivers.
+
+There is no CPU fallback for the numerics: every path below ends in a ``Device`` call.
+"""
+import multiprocessing
+import sys
+import traceback
+import warnings
+
+import numpy as np
+import numpy.linalg
+import scipy.linalg
+import scipy.optimize
+import scipy.stats
+
+from .error_handling import GPArgumentError, GPImpossibleParamsError
+from .kernel import DiagonalNoiseKernel, Kernel, ZeroKernel
+from .utils import CombinedBounds
+
+__all__ = ["GaussianProcess", "Constraint"]
+
+EPS = sys.float_info.epsilon
+
+
+def _has_iter(v):
+    try:
+        iter(v)
+    except TypeError:
+        return False
+    return True
+
+
+class GaussianProcess(object):
+    """Gaussian process with derivative observations and linearly transformed observations.
+
+    Same constructor and public attributes as the reference (gaussian_process.py:196-238):
+    ``GaussianProcess(k, noise_k=None, X=None, y=None, err_y=0, n=0, T=None, diag_factor=1e2, mu=None,
+    use_hyper_deriv=False, verbose=False)``; one extra keyword, ``device``, selects the CUDA device
+    (default: ``LOCAL_RANK`` or 0).
+
+    ``K``, ``noise_K``, ``L`` and ``alpha`` are fetched from the device on first access after each update
+    instead of being copied back eagerly (at M = 49152 the factor alone is 19 GB).
+    """
+
+    def __init__(self, k, noise_k=None, X=None, y=None, err_y=0, n=0, T=None, diag_factor=1e2, mu=None,
+                 use_hyper_deriv=False, verbose=False, device=None):
+        if not isinstance(k, Kernel):
+            raise TypeError("Argument k must be an instance of Kernel when constructing GaussianProcess!")
+        if noise_k is None:
+            noise_k = ZeroKernel(k.num_dim)
+        elif not isinstance(noise_k, Kernel):
+            raise TypeError("Keyword noise_k must be an instance of Kernel when constructing GaussianProcess!")
+        self.mu = mu
+        self.diag_factor = diag_factor
+        self.k = k
+        self.noise_k = noise_k
+        self.use_hyper_deriv = use_hyper_deriv
+        self.verbose = verbose
+        self.y = np.array([], dtype=float)
+        self.X = None
+        self.err_y = np.array([], dtype=float)
+        self.n = None
+        self.T = None
+        self._device_index = device
+        self._dev_obj = None
+        self._dev_data_version = -1
+        self._data_version = 0
+        self._dev_y_key = None
+        self._dev_kernel_key = None
+        self._cache = {}
+        self._up_to_date = False
+        self.ll = None
+        self.ll_deriv = None
+        if X is not None:
+            if y is None:
+                raise GPArgumentError("Must pass both X and y when constructing GaussianProcess!")
+            self.add_data(X, y, err_y=err_y, n=n, T=T)
+        elif y is not None:
+            raise GPArgumentError("Must pass both X and y when constructing GaussianProcess!")
+
+    # ------------------------------------------------------------------------------------------
+    # state flags / lazily fetched device results
+    # ------------------------------------------------------------------------------------------
+    @property
+    def K_up_to_date(self):
+        return self._up_to_date
+
+    @K_up_to_date.setter
+    def K_up_to_date(self, value):
+        self._up_to_date = bool(value)
+        if not value:
+            self._cache = {}
+
+    def _lazy(self, name, fetch):
+        self.compute_K_L_alpha_ll()
+        if name not in self._cache:
+            self._cache[name] = fetch()
+        return self._cache[name]
+
+    @property
+    def K(self):
+        """Latent covariance K(X, X) without noise (N x N)."""
+        if self._device_mode():
+            return self._lazy("K", lambda: self._dev().get_K())
+        return self._lazy("K", lambda: self.compute_Kij(self.X, None, self.n, None, noise=False))
+
+    @property
+    def noise_K(self):
+        def build():
+            N = self.X.shape[0]
+            if isinstance(self.noise_k, ZeroKernel):
+                return np.zeros((N, N))
+            if isinstance(self.noise_k, DiagonalNoiseKernel):
+                return self.noise_k.params[0] ** 2.0 * np.eye(N)
+            return self.compute_Kij(self.X, None, self.n, None, noise=True)
+        return self._lazy("noise_K", build)
+
+    @property
+    def L(self):
+        """Lower Cholesky factor of the total observation covariance (M x M)."""
+        return self._lazy("L", lambda: self._dev().get_L())
+
+    @property
+    def alpha(self):
+        """K_tot^{-1} (y - T mu), shape (M, 1) like the reference."""
+        return self._lazy("alpha", lambda: self._dev().get_alpha()[:, None])
+
+    def __getstate__(self):
+        # device handles are per process: drop on pickle, re-create lazily (GP objects are pickled to
+        # worker pools by the reference's drivers, gaussian_process.py:730, 1951)
+        d = dict(self.__dict__)
+        d["_dev_obj"] = None
+        d["_dev_data_version"] = -1
+        d["_dev_y_key"] = None
+        d["_dev_kernel_key"] = None
+        d["_cache"] = {}
+        d["_up_to_date"] = False
+        return d
+
+    # ------------------------------------------------------------------------------------------
+    # hyperparameter plumbing (gaussian_process.py:246-374)
+    # ------------------------------------------------------------------------------------------
+    def _parts(self):
+        return [self.k, self.noise_k] + ([self.mu] if self.mu is not None else [])
+
+    def _combined(self, attr):
+        out = CombinedBounds(getattr(self.k, attr), getattr(self.noise_k, attr))
+        if self.mu is not None:
+            out = CombinedBounds(out, getattr(self.mu, attr))
+        return out
+
+    def _scatter(self, attr, value, counts):
+        pos = 0
+        for part, cnt in zip(self._parts(), counts):
+            setattr(part, attr, value[pos:pos + cnt])
+            pos += cnt
+
+    def _num_params_each(self):
+        return [p.num_params for p in self._parts()]
+
+    def _num_free_each(self):
+        return [p.num_free_params for p in self._parts()]
+
+    @property
+    def hyperprior(self):
+        hp = self.k.hyperprior * self.noise_k.hyperprior
+        if self.mu is not None:
+            hp = hp * self.mu.hyperprior
+        return hp
+
+    @property
+    def fixed_params(self):
+        return self._combined("fixed_params")
+
+    @fixed_params.setter
+    def fixed_params(self, value):
+        self._scatter("fixed_params", np.asarray(value, dtype=bool), self._num_params_each())
+
+    @property
+    def params(self):
+        return self._combined("params")
+
+    @params.setter
+    def params(self, value):
+        self.K_up_to_date = False
+        self._scatter("params", np.asarray(value, dtype=float), self._num_params_each())
+
+    @property
+    def param_bounds(self):
+        return self.hyperprior.bounds
+
+    @param_bounds.setter
+    def param_bounds(self, value):
+        self.hyperprior.bounds = value
+
+    @property
+    def param_names(self):
+        return self._combined("param_names")
+
+    @param_names.setter
+    def param_names(self, value):
+        self._scatter("param_names", value, self._num_params_each())
+
+    @property
+    def free_params(self):
+        return self._combined("free_params")
+
+    @free_params.setter
+    def free_params(self, value):
+        self.K_up_to_date = False
+        self._scatter("free_params", np.asarray(value, dtype=float), self._num_free_each())
+
+    @property
+    def free_param_bounds(self):
+        return self._combined("free_param_bounds")
+
+    @free_param_bounds.setter
+    def free_param_bounds(self, value):
+        self._scatter("free_param_bounds", np.asarray(value, dtype=float), self._num_free_each())
+
+    @property
+    def free_param_names(self):
+        return self._combined("free_param_names")
+
+    @free_param_names.setter
+    def free_param_names(self, value):
+        self.K_up_to_date = False
+        self._scatter("free_param_names", np.asarray(value, dtype=str), self._num_free_each())
+
+    @property
+    def num_dim(self):
+        return self.k.num_dim
+
+    # ------------------------------------------------------------------------------------------
+    # data (gaussian_process.py:376-503) -- row order of X, n, T, y, err_y is part of the contract
+    # ------------------------------------------------------------------------------------------
+    def add_data(self, X, y, err_y=0, n=0, T=None):
+        y = np.atleast_1d(np.asarray(y, dtype=float))
+        if len(y.shape) != 1:
+            raise ValueError("Training targets y must have only one dimension with length greater than one! "
+                             "Shape of y given is {}".format(y.shape))
+        if not _has_iter(err_y):
+            err_y = err_y * np.ones_like(y, dtype=float)
+        else:
+            err_y = np.asarray(err_y, dtype=float)
+            if err_y.shape != y.shape:
+                raise ValueError("When using array-like err_y, shape must match shape of y! Shape of err_y given "
+                                 "is {}, shape of y given is {}.".format(err_y.shape, y.shape))
+        if (err_y < 0).any():
+            raise ValueError("All elements of err_y must be non-negative!")
+
+        X = np.atleast_2d(np.asarray(X, dtype=float))
+        if self.num_dim == 1 and X.shape[0] == 1:
+            X = X.T
+        if T is None and X.shape != (len(y), self.num_dim):
+            raise ValueError("Shape of training inputs must be (len(y), k.num_dim)! X given has shape {}, shape of "
+                             "y is {} and num_dim={:d}.".format(X.shape, y.shape, self.num_dim))
+
+        if not _has_iter(n):
+            n = n * np.ones_like(X, dtype=int)
+        else:
+            n = np.atleast_2d(np.asarray(n, dtype=int))
+            if self.num_dim == 1 and n.shape[1] != 1:
+                n = n.T
+            if n.shape != X.shape:
+                raise ValueError("When using array-like n, shape must be (len(y), k.num_dim)! Shape of n given is "
+                                 "{}, shape of y given is {} and num_dim={:d}.".format(n.shape, y.shape, self.num_dim))
+        if (n < 0).any():
+            raise ValueError("All elements of n must be non-negative integers!")
+
+        if T is None and self.T is not None:
+            T = np.eye(len(y))
+        if T is not None:
+            T = np.atleast_2d(np.asarray(T, dtype=float))
+            if T.ndim != 2:
+                raise ValueError("T must have exactly 2 dimensions!")
+            if T.shape[0] != len(y):
+                raise ValueError("T must have as many rows are there are elements in y!")
+            if T.shape[1] != X.shape[0]:
+                raise ValueError("There must be as many columns in T as there are rows in X!")
+            if self.T is None and self.X is not None:
+                self.T = np.eye(len(self.y))
+            self.T = T if self.T is None else scipy.linalg.block_diag(self.T, T)
+
+        self.X = X if self.X is None else np.vstack((self.X, X))
+        self.y = np.append(self.y, y)
+        self.err_y = np.append(self.err_y, err_y)
+        self.n = n if self.n is None else np.vstack((self.n, n))
+        self._data_version += 1
+        self.K_up_to_date = False
+
+    def condense_duplicates(self):
+        """Merge duplicate (X, n) rows through the transformation matrix (gaussian_process.py:505-533)."""
+        from .utils import unique_rows
+        unique, inv = unique_rows(np.hstack((self.X, self.n)), return_inverse=True)
+        if len(unique) != len(self.X):
+            if self.T is None:
+                self.T = np.eye(len(self.y))
+            new_T = np.zeros((len(self.y), unique.shape[0]))
+            for j in range(len(inv)):
+                new_T[:, inv[j]] += self.T[:, j]
+            self.T = new_T
+            self.n = np.asarray(unique[:, self.X.shape[1]:], dtype=int)
+            self.X = unique[:, :self.X.shape[1]]
+            self._data_version += 1
+            self.K_up_to_date = False
+
+    def remove_outliers(self, thresh=3, **predict_kwargs):
+        """Drop points more than ``thresh`` standard errors from the GP mean (gaussian_process.py:535-621).
+        Not supported with transformed observations (same restriction as the reference)."""
+        if self.T is not None:
+            raise NotImplementedError("remove_outliers is not supported with transformed observations")
+        mean = self.predict(self.X, n=self.n, noise=False, return_std=False, output_transform=None, **predict_kwargs)
+        deltas = np.abs(self.y - mean) / np.where(self.err_y > 0, self.err_y, 1.0)
+        deltas[self.err_y == 0] = 0
+        bad = deltas >= thresh
+        good = ~bad
+        X_bad, y_bad, err_bad, n_bad = self.X[bad], self.y[bad], self.err_y[bad], self.n[bad]
+        self.X, self.y, self.err_y, self.n = self.X[good], self.y[good], self.err_y[good], self.n[good]
+        self._data_version += 1
+        self.K_up_to_date = False
+        return (X_bad, y_bad, err_bad, n_bad, bad)
+
+    # ------------------------------------------------------------------------------------------
+    # device plumbing
+    # ------------------------------------------------------------------------------------------
+    def _dev(self):
+        if self._dev_obj is None:
+            from ._lib import Device
+            self._dev_obj = Device(self._device_index)
+            self._dev_data_version = -1
+            self._dev_y_key = None
+        return self._dev_obj
+
+    def _device_mode(self):
+        """True when the whole path (assembly included) runs on the device: an accelerated kernel plus the
+        diagonal / zero noise kernels the reference special-cases (gaussian_process.py:1434-1439)."""
+        return self.k.device_descriptor() is not None and isinstance(self.noise_k, DiagonalNoiseKernel)
+
+    def _noise_sigma(self):
+        if isinstance(self.noise_k, ZeroKernel):
+            return 0.0
+        return float(self.noise_k.params[0])
+
+    def _y_minus_mean(self):
+        """y - T mu(X, n) (gaussian_process.py:1455-1461)."""
+        if self.mu is None:
+            return self.y
+        mu_alph = self.mu(self.X, self.n)
+        if self.T is not None:
+            mu_alph = self.T.dot(mu_alph)
+        return self.y - mu_alph
+
+    def _sync_device(self):
+        dev = self._dev()
+        y_alph = self._y_minus_mean()
+        if self._dev_data_version != self._data_version:
+            if self.X is None or len(self.y) == 0:
+                raise GPArgumentError("No training data: call add_data first")
+            dev.set_data(self.X, self.n, y_alph, self.err_y, self.T)
+            self._dev_data_version = self._data_version
+            self._dev_y_key = None if self.mu is None else tuple(self.mu.params)
+            self._dev_kernel_key = None
+        elif self.mu is not None and self._dev_y_key != tuple(self.mu.params):
+            dev.set_y(y_alph)
+            self._dev_y_key = tuple(self.mu.params)
+        desc = self.k.device_descriptor()
+        kid, nparams = (desc[0], len(desc[1])) if desc is not None else (0, self.num_dim + 1)
+        key = (kid, nparams, float(self.diag_factor))
+        if self._dev_kernel_key != key:
+            dev.set_kernel(kid, nparams, float(self.diag_factor))
+            self._dev_kernel_key = key
+        return dev, y_alph
+
+    # ------------------------------------------------------------------------------------------
+    # the hot path
+    # ------------------------------------------------------------------------------------------
+    def compute_Kij(self, Xi, Xj, ni, nj, noise=False, hyper_deriv=None, k=None):
+        """Covariance matrix between (Xi, ni) and (Xj, nj); Xj=None means symmetric
+        (gaussian_process.py:1535-1605).  Accelerated kernels are assembled tile-wise on the device;
+        other kernels are called on the flattened pair lists exactly like the reference."""
+        if k is None:
+            k = self.noise_k if noise else self.k
+        Xi = np.atleast_2d(np.asarray(Xi, dtype=float))
+        ni = np.atleast_2d(np.asarray(ni, dtype=int))
+        desc = k.device_descriptor()
+        if desc is not None:
+            if hyper_deriv is not None and not k.supports_hyper_deriv:
+                raise NotImplementedError("Hyperparameter derivatives have not been implemented!")
+            k._check_orders(ni, ni if nj is None else np.atleast_2d(np.asarray(nj, dtype=int)))
+            if Xj is None:
+                return self._dev().compute_Kij(desc[0], desc[1], Xi, ni, hyper_deriv=hyper_deriv)
+            return self._dev().compute_Kij(desc[0], desc[1], Xi, ni, np.atleast_2d(np.asarray(Xj, dtype=float)),
+                                           np.atleast_2d(np.asarray(nj, dtype=int)), hyper_deriv=hyper_deriv)
+        symmetric = Xj is None
+        if symmetric:
+            Xj, nj = Xi, ni
+        Xj = np.atleast_2d(np.asarray(Xj, dtype=float))
+        nj = np.atleast_2d(np.asarray(nj, dtype=int))
+        Mi, Mj = Xi.shape[0], Xj.shape[0]
+        Kij = k(np.repeat(Xi, Mj, axis=0), np.tile(Xj, (Mi, 1)), np.repeat(ni, Mj, axis=0), np.tile(nj, (Mi, 1)),
+                hyper_deriv=hyper_deriv, symmetric=symmetric)
+        return np.reshape(Kij, (Mi, -1))
+
+    def _grad_layout(self):
+        """Positions of the free parameters in ll_deriv: kernel, noise kernel, mean function (in that order).
+
+        The reference writes the mean-function entries at ``i + len(knk.free_params)`` (gaussian_process.py:1514),
+        which collides with the DiagonalNoiseKernel entry (:1485); here they follow the noise entries."""
+        nk, nn = self.k.num_free_params, self.noise_k.num_free_params
+        return nk, nn
+
+    def compute_K_L_alpha_ll(self):
+        """K, L, alpha and the log-posterior (gaussian_process.py:1418-1522), on the device.
+
+        Raises numpy.linalg.LinAlgError when K_tot is not positive definite, like scipy.linalg.cholesky."""
+        if self.K_up_to_date:
+            return
+        dev, y_alph = self._sync_device()
+        nk_free, nn_free = self._grad_layout()
+        n_free = len(self.free_params)
+        want_grad = bool(self.use_hyper_deriv)
+        if want_grad:
+            warnings.warn("Use of hyperparameter derivatives is experimental!")
+        ll_deriv = np.zeros(n_free) if want_grad else None
+        if self._device_mode():
+            kid, kparams = self.k.device_descriptor()
+            grad_idx = None
+            if want_grad:
+                if not self.k.supports_hyper_deriv and nk_free > 0:
+                    raise NotImplementedError("Hyperparameter derivatives have not been implemented!")
+                grad_idx = list(self.k.free_param_idxs)
+                if nn_free > 0:
+                    grad_idx.append(len(kparams))
+            ll, grad, status = dev.ll(kparams, self._noise_sigma(), grad_idx=grad_idx)
+            if status != 0:
+                raise numpy.linalg.LinAlgError(
+                    "%d-th leading minor of the array is not positive definite" % status)
+            if want_grad and grad is not None:
+                ll_deriv[:len(grad)] = grad
+        else:
+            K = self.compute_Kij(self.X, None, self.n, None, noise=False)
+            if isinstance(self.noise_k, ZeroKernel):
+                Kn = K
+            elif isinstance(self.noise_k, DiagonalNoiseKernel):
+                Kn = K + self.noise_k.params[0] ** 2.0 * np.eye(self.X.shape[0])
+            else:
+                Kn = K + self.compute_Kij(self.X, None, self.n, None, noise=True)
+            ll, status = dev.ll_from_K(Kn)
+            if status != 0:
+                raise numpy.linalg.LinAlgError(
+                    "%d-th leading minor of the array is not positive definite" % status)
+            self._cache["K"] = K
+            if want_grad:
+                if isinstance(self.noise_k, DiagonalNoiseKernel):
+                    knk = self.k
+                    if nn_free > 0:
+                        ll_deriv[nk_free] = dev.grad_from_dK(
+                            2.0 * self.noise_k.params[0] * np.eye(self.X.shape[0])) if self.T is None else \
+                            self._noise_grad_with_T(dev)
+                else:
+                    knk = self.k + self.noise_k
+                idxs = np.arange(0, len(knk.params), dtype=int)[~np.asarray(knk.fixed_params, dtype=bool)]
+                for i, pi in enumerate(idxs):
+                    dK = self.compute_Kij(self.X, None, self.n, None, k=knk, hyper_deriv=int(pi))
+                    ll_deriv[i] = dev.grad_from_dK(dK)
+        self.ll = ll + self.hyperprior(self.params)
+        if want_grad:
+            if self.mu is not None:
+                alpha = dev.get_alpha()
+                for i, pi in enumerate(self.mu.free_param_idxs):
+                    dmu = self.mu(self.X, self.n, hyper_deriv=int(pi))
+                    if self.T is not None:
+                        dmu = self.T.dot(dmu)
+                    ll_deriv[nk_free + nn_free + i] = dmu.dot(alpha)
+            all_idx = np.arange(0, len(self.params), dtype=int)[~np.asarray(self.fixed_params[:], dtype=bool)]
+            params = self.params
+            hp = self.hyperprior
+            for i, pi in enumerate(all_idx):
+                ll_deriv[i] += hp(params, hyper_deriv=int(pi))
+            self.ll_deriv = ll_deriv
+        self._up_to_date = True
+
+    def _noise_grad_with_T(self, dev):
+        # gaussian_process.py:1484-1488 uses 2 sigma_n I_M over the observations, also when T is present
+        alpha = dev.get_alpha()
+        L = dev.get_L()
+        Kinv = scipy.linalg.cho_solve((L, True), np.eye(len(alpha)))
+        return self.noise_k.params[0] * (alpha.dot(alpha) - np.trace(Kinv))
+
+    def update_hyperparameters(self, new_params, hyper_deriv_handling='default', exit_on_bounds=True,
+                               inf_on_error=True):
+        """Set the free hyperparameters and return -ll [and -grad] (gaussian_process.py:1332-1416)."""
+        use_hyper_deriv = self.use_hyper_deriv
+        if hyper_deriv_handling == 'value':
+            self.use_hyper_deriv = False
+        elif hyper_deriv_handling == 'deriv':
+            self.use_hyper_deriv = True
+        nk, nn = self.k.num_free_params, self.noise_k.num_free_params
+        self.k.set_hyperparams(new_params[:nk])
+        self.noise_k.set_hyperparams(new_params[nk:nk + nn])
+        if self.mu is not None:
+            self.mu.set_hyperparams(new_params[nk + nn:])
+        self.K_up_to_date = False
+        try:
+            if exit_on_bounds and np.isinf(self.hyperprior(self.params)):
+                raise GPImpossibleParamsError("Impossible values for params!")
+            self.compute_K_L_alpha_ll()
+        except Exception as e:
+            self.use_hyper_deriv = use_hyper_deriv
+            if not inf_on_error:
+                raise e
+            if not isinstance(e, GPImpossibleParamsError) and self.verbose:
+                warnings.warn("Unhandled exception when updating GP! Exception was:\n{:s}\nState of params is: "
+                              "{:s}".format(traceback.format_exc(), str(self.free_params[:])))
+            if use_hyper_deriv and hyper_deriv_handling == 'default':
+                return (np.inf, np.zeros(len(self.free_params)))
+            if hyper_deriv_handling == 'deriv':
+                return np.zeros(len(self.free_params))
+            return np.inf
+        self.use_hyper_deriv = use_hyper_deriv
+        if use_hyper_deriv and hyper_deriv_handling == 'default':
+            return (-1.0 * self.ll, -1.0 * self.ll_deriv)
+        if hyper_deriv_handling == 'deriv':
+            return -1.0 * self.ll_deriv
+        return -1.0 * self.ll
+
+    # aliases named in the task description
+    def compute_ll(self):
+        self.compute_K_L_alpha_ll()
+        return self.ll
+
+    # ------------------------------------------------------------------------------------------
+    # many hyperparameter vectors at once (the batched device entry; no counterpart in the reference,
+    # where every theta is a separate update_hyperparameters call, possibly in a worker process)
+    # ------------------------------------------------------------------------------------------
+    def update_hyperparameters_batch(self, thetas, with_deriv=None, rank=None, world_size=None):
+        """Evaluate -ll (and -grad) for B free-parameter vectors in one device launch.
+
+        thetas : (B, num_free_params).  Returns ``neg_ll`` (B,) or ``(neg_ll, neg_grad)``; entries whose
+        parameters have zero prior probability or whose covariance is not positive definite are ``inf``
+        with zero gradient -- the per-theta result ``update_hyperparameters(inf_on_error=True)`` gives.
+        The GP's own hyperparameters are left unchanged.
+        """
+        thetas = np.atleast_2d(np.asarray(thetas, dtype=float))
+        B = thetas.shape[0]
+        if with_deriv is None:
+            with_deriv = bool(self.use_hyper_deriv)
+        if not self._device_mode() or self.T is not None:
+            return self._batch_by_loop(thetas, with_deriv)
+        nk, nn = self.k.num_free_params, self.noise_k.num_free_params
+        n_free = len(self.free_params)
+        if thetas.shape[1] != n_free:
+            raise ValueError("thetas must have shape (B, %d)" % n_free)
+        dev, y_alph = self._sync_device()
+        kid, kparams = self.k.device_descriptor()
+        nparams = len(kparams)
+        full = np.tile(np.concatenate([kparams, [self._noise_sigma()]]), (B, 1))
+        kfree = self.k.free_param_idxs
+        full[:, kfree] = thetas[:, :nk]
+        if nn > 0:
+            full[:, nparams] = thetas[:, nk]
+        # hyperprior per theta (host, O(P) each) over ALL parameters, fixed ones included (gaussian_process.py:1469)
+        all_params = np.tile(np.asarray(self.params[:], dtype=float), (B, 1))
+        free_mask = ~np.asarray(self.fixed_params[:], dtype=bool)
+        all_params[:, free_mask] = thetas
+        hp = self.hyperprior
+        logp = np.array([hp(p) for p in all_params], dtype=float)
+        ok = np.isfinite(logp)
+        y_batch = None
+        if self.mu is not None and self.mu.num_free_params > 0:
+            y_batch = np.empty((B, len(self.y)))
+            saved = np.array(self.mu.params, dtype=float)
+            try:
+                for b in range(B):
+                    self.mu.set_hyperparams(thetas[b, nk + nn:])
+                    y_batch[b] = self._y_minus_mean()
+            finally:
+                self.mu.params[:] = saved
+        grad_idx = None
+        if with_deriv:
+            if not self.k.supports_hyper_deriv and nk > 0:
+                raise NotImplementedError("Hyperparameter derivatives have not been implemented!")
+            grad_idx = list(kfree) + ([nparams] if nn > 0 else [])
+        need_alpha = with_deriv and self.mu is not None and self.mu.num_free_params > 0
+        full_eval = np.where(ok[:, None], full, np.tile(np.concatenate([kparams, [self._noise_sigma()]]), (B, 1)))
+        res = dev.ll_batched(full_eval, grad_idx=grad_idx, y_batch=y_batch, return_alpha=need_alpha)
+        ll, grad, status = res[0], res[1], res[2]
+        good = ok & (status == 0)
+        neg_ll = np.where(good, -(ll + logp), np.inf)
+        if not with_deriv:
+            return neg_ll
+        g = np.zeros((B, n_free))
+        if grad is not None and grad.shape[1] > 0:
+            g[:, :grad.shape[1]] = grad
+        if need_alpha:
+            alpha = res[3]
+            saved = np.array(self.mu.params, dtype=float)
+            try:
+                for b in np.nonzero(good)[0]:
+                    self.mu.set_hyperparams(thetas[b, nk + nn:])
+                    for i, pi in enumerate(self.mu.free_param_idxs):
+                        g[b, nk + nn + i] = self.mu(self.X, self.n, hyper_deriv=int(pi)).dot(alpha[b])
+            finally:
+                self.mu.params[:] = saved
+        free_idx = np.nonzero(free_mask)[0]
+        for b in np.nonzero(good)[0]:
+            for i, pi in enumerate(free_idx):
+                g[b, i] += hp(all_params[b], hyper_deriv=int(pi))
+        g[~good] = 0.0
+        return neg_ll, -g
+
+    def _batch_by_loop(self, thetas, with_deriv):
+        saved = np.array(self.free_params[:], dtype=float)
+        saved_flag = self.use_hyper_deriv
+        out, grads = [], []
+        try:
+            self.use_hyper_deriv = with_deriv
+            for th in thetas:
+                r = self.update_hyperparameters(th)
+                if with_deriv:
+                    out.append(r[0])
+                    grads.append(r[1])
+                else:
+                    out.append(r)
+        finally:
+            self.use_hyper_deriv = saved_flag
+            self.free_params = saved
+        if with_deriv:
+            return np.asarray(out), np.asarray(grads)
+        return np.asarray(out)
+
+    # ------------------------------------------------------------------------------------------
+    # prediction (gaussian_process.py:785-1034)
+    # ------------------------------------------------------------------------------------------
+    def predict(self, Xstar, n=0, noise=False, return_std=True, return_cov=False, full_output=False,
+                return_samples=False, num_samples=1, samp_kwargs={}, return_mean_func=False, use_MCMC=False,
+                full_MC=False, rejection_func=None, ddof=1, output_transform=None, full_covar=None, **kwargs):
+        if full_covar is not None:  # alias named in the task description
+            return_cov = bool(full_covar)
+        if use_MCMC:
+            res = self.predict_MCMC(
+                Xstar, n=n, noise=noise, return_std=return_std or full_output, return_cov=return_cov or full_output,
+                return_samples=full_output and (return_samples or rejection_func),
+                return_mean_func=full_output and return_mean_func, num_samples=num_samples, samp_kwargs=samp_kwargs,
+                full_MC=full_MC, rejection_func=rejection_func, ddof=ddof, output_transform=output_transform, **kwargs)
+            if full_output:
+                return res
+            if return_cov:
+                return (res['mean'], res['cov'])
+            if return_std:
+                return (res['mean'], res['std'])
+            return res['mean']
+
+        Xstar = np.atleast_2d(np.asarray(Xstar, dtype=float))
+        if self.num_dim == 1 and Xstar.shape[0] == 1:
+            Xstar = Xstar.T
+        if Xstar.shape[1] != self.num_dim:
+            raise ValueError("Second dimension of Xstar must be equal to self.num_dim! Shape of Xstar given is "
+                             "{}, num_dim is {:d}.".format(Xstar.shape, self.num_dim))
+        if output_transform is not None:
+            output_transform = np.atleast_2d(np.asarray(output_transform, dtype=float))
+            if output_transform.ndim != 2:
+                raise ValueError("output_transform must have exactly 2 dimensions! Shape of output_transform given "
+                                 "is {}.".format(output_transform.shape))
+            if output_transform.shape[1] != Xstar.shape[0]:
+                raise ValueError("output_transform must have the same number of columns the number of rows in "
+                                 "Xstar! Shape of output_transform given is {}, shape of Xstar is "
+                                 "{}.".format(output_transform.shape, Xstar.shape))
+        if not _has_iter(n):
+            n = n * np.ones(Xstar.shape, dtype=int)
+        else:
+            n = np.atleast_2d(np.asarray(n, dtype=int))
+            if self.num_dim == 1 and n.shape[0] == 1:
+                n = n.T
+            if n.shape != Xstar.shape:
+                raise ValueError("When using array-like n, shape must match shape of Xstar! Shape of n given is "
+                                 "{}, shape of Xstar given is {}.".format(n.shape, Xstar.shape))
+        if (n < 0).any():
+            raise ValueError("All elements of n must be non-negative integers!")
+
+        self.compute_K_L_alpha_ll()
+        need_second = return_std or return_cov or full_output or full_MC
+        # the full M* x M* covariance is only formed when somebody asks for it; std alone needs diag(K**) - |v|^2
+        need_cov = need_second and (return_cov or full_output or full_MC or return_samples or
+                                    output_transform is not None)
+        if not self._device_mode():
+            raise NotImplementedError("predict with a user-defined (host) kernel is not available yet: the device "
+                                      "needs K* tiles; use an accelerated kernel")
+        self.k._check_orders(self.n, n)  # unsupported derivative orders raise before any device call
+        mean, var, covariance = self._dev().predict(Xstar, n, want_var=need_second and not need_cov, want_cov=need_cov)
+        mean_func = None
+        if self.mu is not None:
+            mean_func = self.mu(Xstar, n)
+            mean = mean + mean_func
+        if output_transform is not None:
+            mean = output_transform.dot(mean)
+            if return_mean_func and mean_func is not None:
+                mean_func = output_transform.dot(mean_func)
+        if not need_second:
+            return mean
+        if noise and not isinstance(self.noise_k, ZeroKernel):
+            if need_cov:
+                covariance = covariance + self.compute_Kij(Xstar, None, n, None, noise=True)
+            else:
+                var = var + np.diagonal(self.compute_Kij(Xstar, None, n, None, noise=True))
+        if need_cov and output_transform is not None:
+            covariance = output_transform.dot(covariance.dot(output_transform.T))
+        samps = None
+        if return_samples or full_MC:
+            samps = self.draw_sample(Xstar, n=n, num_samp=num_samples, mean=mean, cov=covariance, **samp_kwargs)
+            if rejection_func:
+                good = [s for s in samps.T if rejection_func(s)]
+                if len(good) == 0:
+                    raise ValueError("Did not get any good samples!")
+                samps = np.asarray(good, dtype=float).T
+            if full_MC:
+                mean = np.mean(samps, axis=1)
+                covariance = np.cov(samps, rowvar=1, ddof=ddof)
+        with np.errstate(invalid="ignore"):
+            std = np.sqrt(np.diagonal(covariance)) if need_cov else np.sqrt(var)
+        if full_output:
+            out = {'mean': mean, 'std': std, 'cov': covariance}
+            if samps is not None:
+                out['samp'] = samps
+            if return_mean_func and self.mu is not None:
+                out['mean_func'] = mean_func
+                out['cov_func'] = np.zeros((len(mean_func), len(mean_func)), dtype=float)
+                out['std_func'] = np.zeros_like(mean_func)
+                out['mean_without_func'] = mean - mean_func
+                out['cov_without_func'] = covariance
+                out['std_without_func'] = std
+            return out
+        if return_cov:
+            return (mean, covariance)
+        return (mean, std)
+
+    # ------------------------------------------------------------------------------------------
+    # sampling (gaussian_process.py:1155-1330)
+    # ------------------------------------------------------------------------------------------
+    def draw_sample(self, Xstar, n=0, num_samp=1, rand_vars=None, rand_type='standard normal', diag_factor=1e3,
+                    method='cholesky', num_eig=None, mean=None, cov=None, modify_sign=None, **kwargs):
+        if mean is None or cov is None:
+            out = self.predict(Xstar, n=n, full_output=True, **kwargs)
+            mean, cov = out['mean'], out['cov']
+        if rand_vars is None and method != 'eig':
+            try:
+                # same sampler and global RNG as the reference (gaussian_process.py:1269)
+                return np.random.multivariate_normal(mean, cov, num_samp).T
+            except numpy.linalg.LinAlgError as e:
+                if self.verbose:
+                    warnings.warn("Failure when drawing from MVN! Falling back on eig. Exception was:\n{}".format(e),
+                                  RuntimeWarning)
+                method = 'eig'
+        if num_eig is None or num_eig > len(mean):
+            num_eig = len(mean)
+        elif num_eig < 1:
+            num_eig = 1
+        if rand_vars is None:
+            rand_vars = np.random.standard_normal((num_eig, num_samp))
+        valid_types = ('standard normal', 'uniform')
+        if rand_type not in valid_types:
+            raise ValueError("rand_type {} not recognized! Valid options are: {}.".format(rand_type, valid_types))
+        if rand_type == 'uniform':
+            rand_vars = scipy.stats.norm.ppf(rand_vars)
+        rand_vars = np.atleast_2d(np.asarray(rand_vars, dtype=float))
+        if method == 'cholesky':
+            rv = rand_vars[:num_eig, :]
+            if rv.shape[0] != len(mean):
+                raise ValueError("rand_vars must have one row per test point for method='cholesky'")
+            samp, status = self._dev().draw_sample(mean, cov, rv, diag_factor * EPS)
+            if status != 0:
+                raise numpy.linalg.LinAlgError(
+                    "%d-th leading minor of the array is not positive definite" % status)
+            return samp
+        if method == 'eig':
+            # eigen-decomposition branch: off the hot path, plain LAPACK on the host
+            Mx = len(mean)
+            eig, Q = scipy.linalg.eigh(cov + diag_factor * EPS * np.eye(Mx),
+                                       subset_by_index=(Mx - 1 - (num_eig - 1), Mx - 1))
+            if modify_sign is not None:
+                tests = {
+                    'left value': lambda Q: Q[0, :] < 0.0,
+                    'right value': lambda Q: Q[-1, :] < 0.0,
+                    'left slope': lambda Q: (Q[1, :] - Q[0, :]) < 0.0,
+                    'right slope': lambda Q: (Q[-1, :] - Q[-2, :]) < 0.0,
+                    'left concavity': lambda Q: (Q[2, :] - 2 * Q[1, :] + Q[0, :]) < 0.0,
+                    'right concavity': lambda Q: (Q[-1, :] - 2 * Q[-2, :] + Q[-3, :]) < 0.0,
+                }
+                if modify_sign not in tests:
+                    raise ValueError("modify_sign {} not recognized!".format(modify_sign))
+                Q[:, tests[modify_sign](Q)] *= -1.0
+            Lq = Q.dot(np.diag(np.sqrt(eig)))
+            return np.atleast_2d(mean).T + Lq.dot(rand_vars[:num_eig, :])
+        raise ValueError("method {} not recognized!".format(method))
+
+    # ------------------------------------------------------------------------------------------
+    # MAP estimation (gaussian_process.py:623-783)
+    # ------------------------------------------------------------------------------------------
+    def optimize_hyperparameters(self, method='SLSQP', opt_kwargs={}, verbose=False, random_starts=None,
+                                 num_proc=None, max_tries=1):
+        """Maximise the log-posterior with scipy.optimize.minimize from ``random_starts`` starting points drawn
+        from the hyperprior.  ``num_proc`` is accepted for compatibility: every likelihood evaluation already
+        runs on the GPU, so the starts are run one after the other in this process instead of in a pool."""
+        opt_kwargs = {} if opt_kwargs is None else dict(opt_kwargs)
+        if 'method' in opt_kwargs:
+            method = opt_kwargs['method']
+            if self.verbose:
+                warnings.warn("Key 'method' is present in opt_kwargs, will override option specified with method "
+                              "kwarg.", RuntimeWarning)
+        else:
+            opt_kwargs['method'] = method
+        if num_proc is None:
+            num_proc = multiprocessing.cpu_count()
+        param_ranges = np.asarray(self.free_param_bounds[:], dtype=float)
+        param_ranges[np.isnan(param_ranges[:, 0]) | np.isinf(param_ranges[:, 0]), 0] = -1e16
+        param_ranges[np.isnan(param_ranges[:, 1]) | np.isinf(param_ranges[:, 1]), 1] = 1e16
+        free_mask = ~np.asarray(self.fixed_params[:], dtype=bool)
+
+        def draw_starts():
+            if random_starts == 0:
+                return [np.array(self.free_params[:], dtype=float)]
+            nstart = max(num_proc, 1) if random_starts is None else random_starts
+            samples = self.hyperprior.random_draw(size=nstart).T
+            return list(samples[:, free_mask])
+
+        if 'bounds' not in opt_kwargs:
+            opt_kwargs['bounds'] = param_ranges
+        if self.use_hyper_deriv:
+            opt_kwargs['jac'] = True
+        trial = 0
+        res_min = None
+        res = []
+        while trial < max_tries and res_min is None:
+            if trial >= 1 and self.verbose:
+                warnings.warn("No solutions found on trial {:d}, retrying random starts.".format(trial - 1),
+                              RuntimeWarning)
+            starts = draw_starts()
+            trial += 1
+            res = []
+            for samp in starts:
+                try:
+                    r = scipy.optimize.minimize(self.update_hyperparameters, samp, **opt_kwargs)
+                except Exception:
+                    if self.verbose:
+                        warnings.warn("Minimizer failed, skipping sample. Error is:\n{:s}\nState of params is: "
+                                      "{:s}".format(traceback.format_exc(), str(self.free_params[:])), RuntimeWarning)
+                    continue
+                res.append(r)
+            finite = [r for r in res if not (np.isnan(r.fun) or np.isinf(r.fun))]
+            res_min = min(finite, key=lambda r: r.fun) if finite else None
+        if res_min is None:
+            raise ValueError("Optimizer failed to find a valid solution. Try changing the parameter bounds, picking "
+                             "a new initial guess or increasing the number of random starts.")
+        self.update_hyperparameters(res_min.x)
+        if verbose:
+            print("Got {:d} completed starts, optimal result is:".format(len(res)))
+            print(res_min)
+            print("\nLL\t{:.3g}".format(-1 * res_min.fun))
+            for v, l in zip(res_min.x, self.free_param_names):
+                print("{:s}\t{:.3g}".format(str(l).replace('\\', ''), v))
+        if not res_min.success:
+            warnings.warn("Optimizer {:s} reports failure, selected hyperparameters are likely NOT optimal. Status: "
+                          "{:d}, Message: '{:s}'. Try adjusting bounds, initial guesses or the number of random "
+                          "starts used.".format(method, res_min.status, str(res_min.message)), RuntimeWarning)
+        bounds = np.asarray(self.free_param_bounds[:], dtype=float)
+        if ((res_min.x <= 1.001 * bounds[:, 0]).any() or (res_min.x >= 0.999 * bounds[:, 1]).any()):
+            warnings.warn("Optimizer appears to have hit/exceeded the bounds. Bounds are:\n{:s}\n, solution is:\n"
+                          "{:s}. Try adjusting bounds, initial guesses or the number of random starts "
+                          "used.".format(str(bounds), str(res_min.x)))
+        return (res_min, len(res))
+
+    # ------------------------------------------------------------------------------------------
+    # ll over a grid of hyperparameters (gaussian_process.py:1607-1692): one batched device launch
+    # ------------------------------------------------------------------------------------------
+    def compute_ll_matrix(self, bounds, num_pts):
+        """Log-posterior on a regular grid over the free parameters.  Returns (ll_vals, param_vals) with
+        ll_vals of shape (num_pts[0], ..., num_pts[P-1]) like the reference."""
+        present = np.array(self.free_params[:], dtype=float)
+        bounds = np.atleast_2d(np.asarray(bounds, dtype=float))
+        if bounds.shape[1] != 2:
+            raise ValueError("Argument bounds must have shape (n, 2)!")
+        if bounds.shape[0] == 1:
+            bounds = np.tile(bounds, (len(present), 1))
+        if not _has_iter(num_pts):
+            num_pts = num_pts * np.ones(bounds.shape[0], dtype=int)
+        else:
+            num_pts = np.asarray(num_pts, dtype=int)
+            if len(num_pts) != len(present):
+                raise ValueError("Length of num_pts must match the number of free parameters!")
+        param_vals = [np.linspace(b[0], b[1], int(npt)) for b, npt in zip(bounds, num_pts)]
+        grid = np.stack(np.meshgrid(*param_vals, indexing='ij'), axis=-1).reshape(-1, len(param_vals))
+        neg_ll = self.update_hyperparameters_batch(grid, with_deriv=False)
+        ll_vals = -np.asarray(neg_ll).reshape([len(v) for v in param_vals])
+        return (ll_vals, param_vals)
+
+    # ------------------------------------------------------------------------------------------
+    # MCMC over the hyperparameters (gaussian_process.py:1694-1838): ensemble sampler fed by the batched call
+    # ------------------------------------------------------------------------------------------
+    def sample_hyperparameter_posterior(self, nwalkers=200, nsamp=500, burn=0, thin=1, num_proc=None, sampler=None,
+                                        plot_posterior=False, plot_chains=False, sampler_type='ensemble',
+                                        ntemps=20, sampler_a=2.0, **plot_kwargs):
+        """Run an affine-invariant ensemble sampler (stretch move, the algorithm of emcee.EnsembleSampler used by
+        the reference at gaussian_process.py:1757-1787) on the hyperparameter posterior.  Each half-ensemble
+        proposal is evaluated as ONE batched device launch instead of ``nwalkers`` Python calls / worker processes.
+        Returns the sampler object (``chain`` (nwalkers, nsamp, ndim), ``lnprobability``, ``flatchain``,
+        ``acceptance_fraction``), which can be passed back in through ``sampler=`` to continue the chains."""
+        from .sampler import EnsembleSampler
+        if sampler_type != 'ensemble':
+            raise NotImplementedError("only sampler_type='ensemble' is available")
+        if plot_posterior or plot_chains:
+            warnings.warn("plotting is out of scope of gptools_b200; ignoring plot_* keywords")
+        ndim = len(self.free_params)
+        if sampler is None:
+            sampler = EnsembleSampler(nwalkers, ndim, lambda th: -self.update_hyperparameters_batch(th, with_deriv=False),
+                                      a=sampler_a)
+        else:
+            sampler.lnprob_batch = lambda th: -self.update_hyperparameters_batch(th, with_deriv=False)
+        if sampler.chain.shape[1] == 0:
+            theta0 = self.hyperprior.random_draw(size=nwalkers).T
+            theta0 = theta0[:, ~np.asarray(self.fixed_params[:], dtype=bool)]
+        else:
+            theta0 = sampler.chain[:, -1, :]
+        sampler.run_mcmc(theta0, nsamp)
+        return sampler
+
+    def compute_from_MCMC(self, X, n=0, return_mean=True, return_std=True, return_cov=False, return_samples=False,
+                          return_mean_func=False, num_samples=1, noise=False, samp_kwargs={}, sampler=None,
+                          flat_trace=None, burn=0, thin=1, **kwargs):
+        """Predict at every retained hyperparameter sample (gaussian_process.py:1840-1990)."""
+        output_transform = kwargs.pop('output_transform', None)
+        if flat_trace is None:
+            if sampler is None:
+                sampler = self.sample_hyperparameter_posterior(burn=burn, **kwargs)
+            flat_trace = sampler.chain[:, burn::thin, :]
+            flat_trace = flat_trace.reshape((-1, flat_trace.shape[2]))
+        else:
+            flat_trace = np.asarray(flat_trace, dtype=float)
+        saved = np.array(self.free_params[:], dtype=float)
+        out = {k_: [] for k_ in ('mean', 'std', 'cov', 'samp', 'mean_func')}
+        try:
+            for th in flat_trace:
+                val = self.update_hyperparameters(th)
+                if np.isinf(val if np.isscalar(val) else val[0]):
+                    continue
+                res = self.predict(X, n=n, noise=noise, full_output=True, return_samples=return_samples,
+                                   num_samples=num_samples, samp_kwargs=samp_kwargs,
+                                   return_mean_func=return_mean_func, output_transform=output_transform)
+                out['mean'].append(res['mean'])
+                out['std'].append(res['std'])
+                if return_cov:
+                    out['cov'].append(res['cov'])
+                if return_samples:
+                    out['samp'].append(res['samp'])
+                if return_mean_func and self.mu is not None:
+                    out['mean_func'].append(res['mean_func'])
+        finally:
+            self.update_hyperparameters(saved)
+        return {k_: v for k_, v in out.items() if len(v) > 0}
+
+    def predict_MCMC(self, X, ddof=1, full_MC=False, rejection_func=None, **kwargs):
+        """Prediction marginalised over the hyperparameter samples by the law of total (co)variance
+        (gaussian_process.py:2136-2254)."""
+        return_std = kwargs.get('return_std', True)
+        return_cov = kwargs.get('return_cov', False)
+        kwargs['return_cov'] = True if (return_cov or full_MC) else return_cov
+        res = self.compute_from_MCMC(X, **kwargs)
+        means = np.array(res['mean'], dtype=float)
+        out = {'mean': means.mean(axis=0)}
+        if return_cov and 'cov' in res:
+            covs = np.array(res['cov'], dtype=float)
+            out['cov'] = covs.mean(axis=0) + np.cov(means, rowvar=0, ddof=ddof)
+            out['std'] = np.sqrt(np.diagonal(out['cov']))
+        elif return_std:
+            stds = np.array(res['std'], dtype=float)
+            out['std'] = np.sqrt((stds ** 2).mean(axis=0) + np.var(means, axis=0, ddof=ddof))
+        if 'samp' in res:
+            out['samp'] = np.hstack(res['samp'])
+        return out
+
+
+class Constraint(object):
+    """Inequality constraint on the GP mean (or a derivative) for constrained optimizers
+    (gaussian_process.py:2488-2656): ``c(params) >= 0`` when the constraint is satisfied."""
+
+    def __init__(self, gp, boundary_val=0.0, n=0, loc='min', type_='gt', bounds=None):
+        if not isinstance(gp, GaussianProcess):
+            raise TypeError("Argument gp must be an instance of GaussianProcess.")
+        self.gp = gp
+        self.boundary_val = boundary_val
+        self.n = int(n)
+        if self.n < 0:
+            raise ValueError("n must be a non-negative int!")
+        D = gp.num_dim
+        if loc in ('min', 'max'):
+            self.loc = loc
+        else:
+            loc = np.atleast_1d(np.asarray(loc, dtype=float))
+            if loc.shape != (D,):
+                raise ValueError("Argument loc must be 'min', 'max' or an array of length {:d}".format(D))
+            self.loc = loc
+        if type_ not in ('gt', 'lt'):
+            raise ValueError("Argument type_ must be 'gt' or 'lt'.")
+        self.type_ = type_
+        if bounds is None:
+            lo = np.asarray(gp.X.min(axis=0), dtype=float).flatten()
+            hi = np.asarray(gp.X.max(axis=0), dtype=float).flatten()
+        else:
+            bounds = list(bounds)
+            if len(bounds) != 2:
+                raise ValueError("Argument bounds must have length 2!")
+            lo, hi = (np.atleast_1d(np.asarray(b, dtype=float)) for b in bounds)
+            if lo.shape != (D,) or hi.shape != (D,):
+                raise ValueError("Each element in argument bounds must have length {:d}".format(D))
+        self.bounds = list(zip(lo, hi))
+
+    def __call__(self, params):
+        self.gp.update_hyperparameters(params)
+        if not isinstance(self.loc, str):
+            val = self.gp.predict(self.loc, n=self.n, return_std=False)[0]
+        else:
+            factor = -1.0 if self.loc == 'max' else 1.0
+            res = scipy.optimize.minimize(
+                lambda X: factor * self.gp.predict(X, n=self.n, return_std=False)[0],
+                np.mean(self.bounds, axis=1), method='SLSQP', bounds=self.bounds)
+            if not res.success:
+                warnings.warn("Solver reports failure, extremum was likely NOT found. Status: {:d}, Message: "
+                              "'{:s}'".format(res.status, str(res.message)), RuntimeWarning)
+            val = factor * res.fun
+        return val - self.boundary_val if self.type_ == 'gt' else self.boundary_val - val

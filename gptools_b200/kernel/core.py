@@ -1,0 +1,149 @@
+"""Kernel base class and the device-dispatch plumbing.
+
+``Kernel`` keeps the reference's constructor, parameter views and call signature
+(kernel/core.py:44-421).  A kernel whose closed form exists in the CUDA library exposes a *device
+descriptor* ``(kernel_id, params)``; GaussianProcess then runs assembly, factorisation, gradient and
+prediction on the device without ever calling the Python ``__call__``.  ``__call__`` itself (the
+flattened pair-list contract, kernel/core.py:220-257) is also served by the device
+(``gpt_cov_pairs``), so user code and tests that call kernels directly keep working.  There is no
+CPU evaluation of the accelerated kernels anywhere in the package.
+
+User-defined kernels simply subclass ``Kernel`` and implement ``__call__`` in numpy; they have no
+descriptor and GaussianProcess assembles K by calling them on the pair lists exactly like the reference
+(gaussian_process.py:1591-1602), then ships K to the device for the factorisation.
+"""
+import numpy as np
+
+from .._params import ParamHolder
+from ..error_handling import GPArgumentError
+
+__all__ = ["Kernel", "DeviceKernel", "SumKernel"]
+
+_default_device = None
+
+
+def default_device():
+    """Process-wide Device used by direct kernel calls (lazy; one per process)."""
+    global _default_device
+    if _default_device is None:
+        from .._lib import Device
+        _default_device = Device()
+    return _default_device
+
+
+class Kernel(ParamHolder):
+    """Covariance kernel base class (kernel/core.py:44-218 for the parameter semantics)."""
+
+    kernel_id = None  # set by device-accelerated subclasses
+
+    def __init__(self, num_dim=1, num_params=0, initial_params=None, fixed_params=None, param_bounds=None,
+                 param_names=None, enforce_bounds=False, hyperprior=None):
+        if num_dim < 1 or not isinstance(num_dim, (int, np.integer)):
+            raise ValueError("num_dim must be an integer > 0!")
+        self.num_dim = int(num_dim)
+        self._init_params(num_params, initial_params, fixed_params, param_bounds, param_names, enforce_bounds,
+                          hyperprior, warn_default_bounds=True, arg_error=GPArgumentError)
+
+    def __call__(self, Xi, Xj, ni, nj, hyper_deriv=None, symmetric=False):
+        """Covariance of d^ni f(Xi) and d^nj f(Xj) for M flattened pairs -> (M,) (kernel/core.py:220-257)."""
+        raise NotImplementedError("This is an abstract method -- please use one of the implementing subclasses!")
+
+    def device_descriptor(self):
+        """(kernel_id, params) when the closed form lives in the CUDA library, else None."""
+        return None
+
+    def __add__(self, other):
+        return SumKernel(self, other)
+
+    def _compute_r2l2(self, tau, return_l=False):
+        """sum_d tau_d^2 / l_d^2 with 0/0 -> 0 (kernel/core.py:384-421); a host helper for user-defined
+        kernels -- the accelerated kernels compute this inside their device functions."""
+        l_mat = np.tile(self.params[-self.num_dim:], (tau.shape[0], 1))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            tau_over_l = tau / l_mat
+        tau_over_l[(tau == 0) & (l_mat == 0)] = 0.0
+        r2l2 = np.sum(tau_over_l ** 2, axis=1)
+        return (r2l2, l_mat) if return_l else r2l2
+
+
+class DeviceKernel(Kernel):
+    """A kernel evaluated by libgptb200 (``kernel_id`` names the device function in csrc/covfn.cuh)."""
+
+    supports_hyper_deriv = False
+
+    def device_descriptor(self):
+        self._check_params_for_device()
+        return (self.kernel_id, np.array(self.params, dtype=float))
+
+    def _check_params_for_device(self):
+        pass
+
+    def _check_orders(self, ni, nj):
+        pass
+
+    def __call__(self, Xi, Xj, ni, nj, hyper_deriv=None, symmetric=False):
+        if hyper_deriv is not None and not self.supports_hyper_deriv:
+            raise NotImplementedError("Hyperparameter derivatives have not been implemented!")
+        Xi = np.atleast_2d(np.asarray(Xi, dtype=float))
+        Xj = np.atleast_2d(np.asarray(Xj, dtype=float))
+        ni = np.atleast_2d(np.asarray(ni, dtype=int))
+        nj = np.atleast_2d(np.asarray(nj, dtype=int))
+        self._check_orders(ni, nj)
+        kid, params = self.device_descriptor()
+        return default_device().cov_pairs(kid, params, Xi, Xj, ni, nj, hyper_deriv=hyper_deriv)
+
+
+class SumKernel(Kernel):
+    """k1 + k2 with concatenated hyperparameters (kernel/core.py:424-548 + 549-600, sum rule only).
+
+    Used by the GP when the noise kernel is neither ZeroKernel nor DiagonalNoiseKernel
+    (gaussian_process.py:1489-1490).  Host-side composition: each operand is evaluated through its own
+    ``__call__``."""
+
+    def __init__(self, k1, k2):
+        if not isinstance(k1, Kernel) or not isinstance(k2, Kernel):
+            raise TypeError("Argument to SumKernel must be instances of type Kernel.")
+        if k1.num_dim != k2.num_dim:
+            raise ValueError("Both kernels must have the same number of dimensions!")
+        self.k1 = k1
+        self.k2 = k2
+        self.num_dim = k1.num_dim
+
+    @property
+    def num_params(self):
+        return self.k1.num_params + self.k2.num_params
+
+    @property
+    def params(self):
+        return np.concatenate((self.k1.params, self.k2.params))
+
+    @property
+    def fixed_params(self):
+        return np.concatenate((self.k1.fixed_params, self.k2.fixed_params))
+
+    @property
+    def param_names(self):
+        return np.concatenate((self.k1.param_names, self.k2.param_names))
+
+    @property
+    def hyperprior(self):
+        return self.k1.hyperprior * self.k2.hyperprior
+
+    @property
+    def enforce_bounds(self):
+        return self.k1.enforce_bounds or self.k2.enforce_bounds
+
+    def set_hyperparams(self, new_params):
+        new_params = np.asarray(new_params, dtype=float)
+        n1 = self.k1.num_free_params
+        if len(new_params) != n1 + self.k2.num_free_params:
+            raise ValueError("Length of new_params must be {:d}!".format(n1 + self.k2.num_free_params))
+        self.k1.set_hyperparams(new_params[:n1])
+        self.k2.set_hyperparams(new_params[n1:])
+
+    def __call__(self, Xi, Xj, ni, nj, hyper_deriv=None, symmetric=False):
+        if hyper_deriv is None:
+            return (self.k1(Xi, Xj, ni, nj, symmetric=symmetric) + self.k2(Xi, Xj, ni, nj, symmetric=symmetric))
+        if hyper_deriv < self.k1.num_params:
+            return self.k1(Xi, Xj, ni, nj, hyper_deriv=hyper_deriv, symmetric=symmetric)
+        return self.k2(Xi, Xj, ni, nj, hyper_deriv=hyper_deriv - self.k1.num_params, symmetric=symmetric)

@@ -1,0 +1,53 @@
+"""Matern kernels: the fixed nu = 5/2 form and the generic-order form."""
+import numpy as np
+
+from .core import DeviceKernel
+
+__all__ = ["Matern52Kernel", "MaternKernel"]
+
+
+class Matern52Kernel(DeviceKernel):
+    r"""Matern nu = 5/2, value and first derivatives only; params = [sigma_f, l_1, ..., l_D]
+    (kernel/matern.py:468-555; closed forms of kernel/src/matern.c:61-186 in ``matern52_cov``)."""
+
+    kernel_id = 1
+
+    def __init__(self, num_dim=1, **kwargs):
+        names = [r'\sigma_f'] + ['l_{:d}'.format(i + 1) for i in range(num_dim)]
+        super(Matern52Kernel, self).__init__(num_dim=num_dim, num_params=num_dim + 1, param_names=names, **kwargs)
+
+    def _check_orders(self, ni, nj):
+        # kernel/matern.py:545-546 (the C code would exit(1), matern.c:173-176)
+        if np.any(np.sum(ni, axis=1) > 1) or np.any(np.sum(nj, axis=1) > 1):
+            raise ValueError("Matern52Kernel only supports 0th and 1st order derivatives")
+
+
+class MaternKernel(DeviceKernel):
+    r"""Generic Matern; params = [sigma_f, nu, l_1, ..., l_D] (kernel/matern.py:251-465).
+
+    The device function ``matern_cov`` reproduces the reference's behaviour -- including its one-term
+    power series for derivative orders >= 1 when 0 < 2 nu r^2 <= 5e-4 (utils.py:1493-1516) and the origin
+    limits (kernel/matern.py:444-457) -- for half-integer nu and total derivative order <= 2 per pair,
+    which covers value + first-derivative observations and predictions."""
+
+    kernel_id = 2
+
+    def __init__(self, num_dim=1, **kwargs):
+        names = [r'\sigma_f', r'\nu'] + ['l_{:d}'.format(i + 1) for i in range(num_dim)]
+        super(MaternKernel, self).__init__(num_dim=num_dim, num_params=num_dim + 2, param_names=names, **kwargs)
+
+    @property
+    def nu(self):
+        return self.params[1]
+
+    def _check_params_for_device(self):
+        nu = float(self.params[1])
+        if abs(2.0 * nu - round(2.0 * nu)) > 1e-12 or int(round(2.0 * nu)) % 2 == 0 or nu <= 0:
+            raise NotImplementedError("MaternKernel on the device supports half-integer nu (1/2, 3/2, 5/2, ...); "
+                                      "got nu = %r" % nu)
+
+    def _check_orders(self, ni, nj):
+        ti, tj = np.sum(ni, axis=1), np.sum(nj, axis=1)
+        too_high = np.any(ti + tj > 2) if len(ti) == len(tj) else (ti.max() + tj.max() > 2)
+        if too_high:
+            raise NotImplementedError("MaternKernel on the device supports a total derivative order <= 2 per pair")

@@ -44,8 +44,10 @@ int gpt_device_count(void);
 int gpt_create(int device, gpt_handle** out);
 void gpt_destroy(gpt_handle* h);
 const char* gpt_last_error(gpt_handle* h);
-/* Run on an existing cudaStream_t (e.g. torch's current stream); NULL restores the handle's own stream. */
+/* Run on an existing cudaStream_t (e.g. torch's current stream); NULL is the legacy default stream. */
 int gpt_set_stream(gpt_handle* h, void* cuda_stream);
+/* Go back to the handle's own (non-blocking) stream. */
+int gpt_use_own_stream(gpt_handle* h);
 int gpt_synchronize(gpt_handle* h);
 
 /* Training set exactly as GaussianProcess.add_data leaves it (gaussian_process.py:376-503):

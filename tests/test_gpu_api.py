@@ -1,0 +1,253 @@
+"""GPU tests at the public-API level: the GaussianProcess / Kernel classes running on the real device against
+the reference's golden vectors, plus size-independent properties at BASELINE.json's full sizes."""
+import warnings
+
+import numpy as np
+import pytest
+
+import gptools_b200 as g
+from helpers import assert_close, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _quiet():
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        yield
+
+
+def test_native_library_is_loaded():
+    """The product must run on libgptb200.so (in-tree), not on any fallback."""
+    from gptools_b200 import _lib
+    assert _lib.load_library().gpt_device_count() >= 1
+    maps = open("/proc/self/maps").read()
+    assert "libgptb200.so" in maps
+
+
+def test_kat1_se2d_end_to_end():
+    gd = load_golden("se2d_kat1")
+    rs = np.random.RandomState(0)
+    X = rs.rand(6, 2)
+    k = g.SquaredExponentialKernel(num_dim=2, initial_params=[1.3, 0.7, 1.1], param_bounds=[(0, 10)] * 3)
+    gp = g.GaussianProcess(k, use_hyper_deriv=True)
+    gp.add_data(X, np.sin(X).sum(1), err_y=0.01)
+    gp.add_data(X, np.cos(X[:, 0]), n=np.tile([1, 0], (6, 1)), err_y=0.01)
+    gp.add_data(X, np.cos(X[:, 1]), n=np.tile([0, 1], (6, 1)), err_y=0.01)
+    f, df = gp.update_hyperparameters(np.array([1.3, 0.7, 1.1]))
+    assert_close(-f, gd["ll"], rtol=1e-9)
+    assert_close(-df, gd["ll_deriv"], rtol=1e-9)
+    assert_close(gp.K, gd["K"], rtol=1e-12, atol=1e-14)
+    assert_close(gp.L, gd["L"], rtol=1e-9, atol=1e-12)
+    assert_close(gp.alpha.ravel(), gd["alpha"], rtol=1e-9)
+    mean, std = gp.predict(gd["Xs"])
+    assert_close(mean, gd["mean"], rtol=1e-9)
+    assert_close(std, gd["std"], rtol=1e-6)          # std = sqrt(cancellation), see SURVEY H4
+    mean, cov = gp.predict(gd["Xs"], return_cov=True)
+    assert np.abs(cov - gd["cov"]).max() <= 1e-9 * 1.3 ** 2
+    m1, s1 = gp.predict(gd["Xs"], n=np.tile([1, 0], (4, 1)))
+    assert_close(m1, gd["mean_d1"], rtol=1e-9)
+    assert_close(s1, gd["std_d1"], rtol=1e-6)
+    # Kernel.__call__ on flattened pair lists, straight on the device
+    Xi = np.repeat(gp.X, 18, axis=0)
+    Xj = np.tile(gp.X, (18, 1))
+    ni = np.repeat(gp.n, 18, axis=0)
+    nj = np.tile(gp.n, (18, 1))
+    assert_close(k(Xi, Xj, ni, nj).reshape(18, 18), gd["K"], rtol=1e-12, atol=1e-14)
+    assert_close(k(Xi, Xj, ni, nj, hyper_deriv=2).reshape(18, 18), gd["dK2"], rtol=1e-10, atol=1e-13)
+
+
+def test_kat2_matern52_and_kat3_gibbs_T_draw():
+    gd = load_golden("matern52_kat2")
+    k = g.Matern52Kernel(num_dim=1, initial_params=[2.0, 0.4], param_bounds=[(0, 10)] * 2)
+    gp = g.GaussianProcess(k)
+    X = gd["X"][:8, 0]
+    gp.add_data(X, np.sin(5 * X), err_y=0.02)
+    gp.add_data(X[::2], 5 * np.cos(5 * X[::2]), n=1, err_y=0.05)
+    gp.compute_K_L_alpha_ll()
+    assert_close(gp.ll, gd["ll"], rtol=1e-9)
+    mean, std = gp.predict(gd["Xs"])
+    assert_close(mean, gd["mean"], rtol=1e-9)
+    assert_close(std, gd["std"], rtol=1e-7)
+
+    gd = load_golden("gibbs_kat3")
+    k = g.GibbsKernel1dTanh(initial_params=[1.5, 0.6, 0.1, 0.05, 0.9],
+                            param_bounds=[(0, 10), (0, 5), (0, 5), (0, 1), (0, 2)])
+    Xq = np.linspace(0, 1.1, 12)
+    T = np.zeros((3, 12))
+    T[0, :6] = T[1, 3:9] = T[2, 6:] = 1 / 6.0
+    gp = g.GaussianProcess(k)
+    gp.add_data(Xq, [2.5, 2.0, 1.0], err_y=0.05, T=T)
+    gp.add_data(0, 0, n=1)
+    gp.compute_K_L_alpha_ll()
+    assert_close(gp.ll, gd["ll"], rtol=1e-9)
+    mean, std = gp.predict(gd["Xs"])
+    assert_close(mean, gd["mean"], rtol=1e-9)
+    assert_close(std, gd["std"], rtol=1e-7)
+    samp = gp.draw_sample(gd["Xs"], rand_vars=gd["rand_vars"], method="cholesky")
+    assert_close(samp, gd["draw"], rtol=1e-7, atol=1e-7)
+
+
+def test_demo_config1_map_estimate():
+    """Config 1 / KAT-4: ll, gradient, predictions at the documented MAP point, and SLSQP with the device
+    gradient started nearby converges to the values printed in the reference's demo (demo/demo.py:190-192)."""
+    gd = load_golden("demo_c1_kat4")
+    hp = g.UniformJointPrior([(0, 20)]) * g.GammaJointPriorAlt([1.0], [0.7])
+    k = g.SquaredExponentialKernel(initial_params=[1.5, 0.8], hyperprior=hp)
+    gp = g.GaussianProcess(k, use_hyper_deriv=True)
+    gp.add_data(gd["X"][:-1], gd["y"][:-1], err_y=gd["err_y"][:-1])
+    gp.add_data(0, 0, n=1)
+    f, df = gp.update_hyperparameters(gd["params"])
+    assert_close(-f, gd["ll"], rtol=1e-9)
+    assert_close(-df, gd["ll_deriv"], rtol=1e-6, atol=1e-8)
+    Xs = gd["Xs"]
+    mean, std = gp.predict(Xs)
+    assert_close(mean, gd["mean"], rtol=1e-9, atol=1e-9)
+    assert np.all(np.abs(std ** 2 - gd["std"] ** 2) <= 1e-9 * gd["params"][0] ** 2)
+    m1, s1 = gp.predict(Xs, n=1)
+    assert_close(m1, gd["mean_d1"], rtol=1e-9, atol=1e-9 * np.abs(gd["mean_d1"]).max())
+    gp.update_hyperparameters(np.array([1.5, 0.8]))
+    res, nres = gp.optimize_hyperparameters(random_starts=0)
+    assert_close(res.x, [1.8849006111246833, 0.97760159723344708], rtol=2e-4)
+    np.random.seed(0)
+    res, nres = gp.optimize_hyperparameters(random_starts=4, num_proc=0)
+    assert nres >= 1 and np.isfinite(res.fun)
+
+
+def test_c3_full_batch_properties():
+    """BASELINE config 3 at full size (4096 thetas x M=512): reference values at the golden thetas, finite
+    differences of ll against the fused gradient, run-to-run bit reproducibility, and order independence."""
+    import bench
+    gd = load_golden("c3_kat5")
+    X, n, y, err = bench.c3_problem()
+    assert np.array_equal(X, gd["X"]) and np.array_equal(n, gd["n"]) and np.array_equal(y, gd["y"])
+    k = g.SquaredExponentialKernel(num_dim=2, initial_params=[1.0, 0.3, 0.4], param_bounds=[(0, 10)] * 3)
+    gp = g.GaussianProcess(k, X=X, y=y, err_y=err, n=n, use_hyper_deriv=True)
+    th = bench.theta_batch(4096)
+    f, df = gp.update_hyperparameters_batch(th)
+    assert np.isfinite(f).all() and np.isfinite(df).all()
+    idx = gd["theta_idx"]
+    assert_close(-f[idx], gd["ll"], rtol=1e-9)
+    assert_close(-df[idx], gd["ll_deriv"], rtol=1e-9)
+    f2, df2 = gp.update_hyperparameters_batch(th)
+    assert np.array_equal(f, f2) and np.array_equal(df, df2), "batched results must be bit-reproducible"
+    perm = np.random.RandomState(0).permutation(4096)
+    f3, df3 = gp.update_hyperparameters_batch(th[perm])
+    assert np.array_equal(f3, f[perm]) and np.array_equal(df3, df[perm]), "a theta's result must not depend on its slot"
+    for b in (5, 2222):
+        for p in range(3):
+            e = np.zeros(3)
+            e[p] = 1e-6 * th[b, p]
+            fp = gp.update_hyperparameters_batch(np.stack([th[b] + e, th[b] - e]), with_deriv=False)
+            fd = (fp[0] - fp[1]) / (2 * e[p])
+            assert_close(df[b, p], fd, rtol=2e-5, atol=1e-4)
+    # impossible parameters and the scalar entry agree with the batch entry
+    bad = th[:4].copy()
+    bad[2, 1] = -0.1
+    fb, dfb = gp.update_hyperparameters_batch(bad)
+    assert np.isinf(fb[2]) and np.all(dfb[2] == 0) and np.array_equal(fb[[0, 1, 3]], f[[0, 1, 3]])
+    fs, dfs = gp.update_hyperparameters(th[7])
+    assert_close(fs, f[7], rtol=1e-11)
+    assert_close(dfs, df[7], rtol=1e-9, atol=1e-9 * np.abs(df[7]).max())
+
+
+def test_c3_variant_M1536_value_plus_both_gradients():
+    """512 locations with value + both gradient components (M = 1536 = 24 tiles): batched vs single path."""
+    rs = np.random.RandomState(3)
+    X0 = rs.rand(512, 2)
+    X = np.vstack([X0, X0, X0])
+    n = np.vstack([np.zeros((512, 2), int), np.tile([1, 0], (512, 1)), np.tile([0, 1], (512, 1))])
+    y = np.concatenate([np.sin(3 * X0[:, 0]) * np.cos(2 * X0[:, 1]), 3 * np.cos(3 * X0[:, 0]) * np.cos(2 * X0[:, 1]),
+                        -2 * np.sin(3 * X0[:, 0]) * np.sin(2 * X0[:, 1])]) + 0.05 * rs.randn(1536)
+    k = g.SquaredExponentialKernel(num_dim=2, initial_params=[1.0, 0.3, 0.4], param_bounds=[(0, 10)] * 3)
+    gp = g.GaussianProcess(k, X=X, y=y, err_y=0.05, n=n, use_hyper_deriv=True)
+    th = np.array([1.0, 0.3, 0.4]) * np.exp(0.05 * rs.randn(3, 3))
+    f, df = gp.update_hyperparameters_batch(th)
+    for b in range(3):
+        fs, dfs = gp.update_hyperparameters(th[b])
+        assert_close(f[b], fs, rtol=1e-10)
+        assert_close(df[b], dfs, rtol=1e-8, atol=1e-9 * np.abs(dfs).max())
+
+
+def test_large_single_gp_residual_property():
+    """Config-4-shaped problem at M = 12288 (4096 locations x (value, d/dx1, d/dx2)): K_tot alpha = y to working
+    accuracy, Cholesky factor reproduces K_tot, prediction at training locations recovers smoothed data."""
+    rs = np.random.RandomState(0)
+    X0 = rs.rand(4096, 2)
+    f = lambda x: np.sin(3 * x[:, 0]) * np.cos(2 * x[:, 1])
+    X = np.vstack([X0, X0, X0])
+    n = np.vstack([np.zeros((4096, 2), int), np.tile([1, 0], (4096, 1)), np.tile([0, 1], (4096, 1))])
+    y = np.concatenate([f(X0), 3 * np.cos(3 * X0[:, 0]) * np.cos(2 * X0[:, 1]),
+                        -2 * np.sin(3 * X0[:, 0]) * np.sin(2 * X0[:, 1])]) + 0.05 * rs.randn(12288)
+    k = g.SquaredExponentialKernel(num_dim=2, initial_params=[1.0, 0.1, 0.1], param_bounds=[(0, 10)] * 3)
+    gp = g.GaussianProcess(k, X=X, y=y, err_y=0.05, n=n)
+    gp.compute_K_L_alpha_ll()
+    assert np.isfinite(gp.ll)
+    alpha = gp.alpha.ravel()
+    K = gp.K
+    Ktot_alpha = K.dot(alpha) + (0.05 ** 2 + 1e2 * np.finfo(float).eps) * alpha
+    assert np.abs(Ktot_alpha - y).max() <= 1e-8 * np.abs(y).max()
+    # a few rows of L L^T against K_tot
+    L = gp.L
+    rows = [0, 5000, 12287]
+    for r in rows:
+        rec = L[r, :r + 1].dot(L[:r + 1, :r + 1].T)
+        want = K[r, :r + 1].copy()
+        want[r] += 0.05 ** 2 + 1e2 * np.finfo(float).eps
+        assert np.abs(rec - want).max() <= 1e-11 * K[0, 0]
+    # log-det consistency: ll recomputed from alpha and diag(L)
+    ll = -0.5 * y.dot(alpha) - np.log(np.diag(L)).sum() - 0.5 * len(y) * np.log(2 * np.pi) + gp.hyperprior(gp.params)
+    assert_close(gp.ll, ll, rtol=1e-10)
+    mean, std = gp.predict(X0[:2000])
+    assert np.abs(mean - f(X0[:2000])).max() < 0.05 and np.all(std >= 0) and np.all(std < 0.05)
+
+
+def test_c5_shape_gibbs_T_draw_sample_property():
+    """Config-5-shaped, reduced 4x (1000 quadrature points -> 125 line integrals + slope constraint): samples drawn
+    with explicit rand_vars have the predictive mean / covariance they were built from."""
+    rs = np.random.RandomState(0)
+    Nq, Mo, W = 1000, 125, 100
+    Xq = np.linspace(0, 1.1, Nq)
+    T = np.zeros((Mo, Nq))
+    for i, s in enumerate(rs.randint(0, Nq - W, size=Mo)):
+        T[i, s:s + W] = 1.1 / Nq
+    k = g.GibbsKernel1dTanh(initial_params=[1.5, 0.6, 0.1, 0.05, 0.9],
+                            param_bounds=[(0, 10), (0, 5), (0, 5), (0, 1), (0, 2)])
+    gp = g.GaussianProcess(k)
+    gp.add_data(Xq, rs.rand(Mo) * 0.3 + 0.1, err_y=0.02, T=T)
+    gp.add_data(0, 0, n=1)
+    gp.compute_K_L_alpha_ll()
+    Xs = np.linspace(0, 1.1, 100)
+    out = gp.predict(Xs, full_output=True)
+    S = 4000
+    rv = rs.randn(100, S)
+    samp = gp.draw_sample(Xs, rand_vars=rv, method="cholesky", mean=out["mean"], cov=out["cov"])
+    assert samp.shape == (100, S)
+    # linearity in rand_vars: sample(u1 + u2) - mean = (sample(u1) - mean) + (sample(u2) - mean)
+    s12 = gp.draw_sample(Xs, rand_vars=rv[:, :1] + rv[:, 1:2], method="cholesky", mean=out["mean"], cov=out["cov"])
+    lin = (samp[:, :1] - out["mean"][:, None]) + (samp[:, 1:2] - out["mean"][:, None])
+    assert np.abs(s12 - out["mean"][:, None] - lin).max() <= 1e-10 * np.abs(lin).max()
+    emp = np.cov(samp)
+    assert np.abs(emp - out["cov"]).max() <= 0.15 * np.abs(out["cov"]).max()
+    assert np.abs(samp.mean(axis=1) - out["mean"]).max() <= 5 * np.sqrt(np.diag(out["cov"]).max() / S) + 1e-12
+
+
+def test_sampler_runs_on_device():
+    gd = load_golden("demo_c1_kat4")
+    hp = g.UniformJointPrior([(0, 20)]) * g.GammaJointPriorAlt([1.0], [0.7])
+    k = g.SquaredExponentialKernel(initial_params=gd["params"], hyperprior=hp)
+    gp = g.GaussianProcess(k)
+    gp.add_data(gd["X"][:-1], gd["y"][:-1], err_y=gd["err_y"][:-1])
+    gp.add_data(0, 0, n=1)
+    np.random.seed(1)
+    s = gp.sample_hyperparameter_posterior(nwalkers=32, nsamp=60)
+    flat = s.chain[:, 30:, :].reshape(-1, 2)
+    lnp = s.lnprobability[:, 30:].reshape(-1)
+    # no sample beats the MAP of demo.py:191, and the best sample sits next to it
+    assert lnp.max() <= gd["ll"] + 1e-6
+    best = flat[np.argmax(lnp)]
+    assert abs(best[0] - 1.88) < 0.6 and abs(best[1] - 0.98) < 0.3 and lnp.max() > gd["ll"] - 0.5
+    assert 0.1 < s.acceptance_fraction.mean() < 0.9
+    res = gp.predict_MCMC(np.linspace(0, 1.1, 20), flat_trace=flat[::200])
+    assert res["mean"].shape == (20,) and np.all(res["std"] > 0)

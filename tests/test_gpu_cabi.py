@@ -114,15 +114,26 @@ def test_predict_full(dev, case):
     assert_close(mean2, mean, rtol=0, atol=0)
     assert np.all(np.abs(var2 - np.diag(cov)) <= 1e-12 * prior)
     if "mean_d1" in gd:
-        o = np.ones(Xs.shape, dtype=int)
+        o = np.zeros(Xs.shape, dtype=int)
+        o[:, 0] = 1                      # d/dx_1 (the goldens use n = [1, 0, ...])
         m1, v1, c1 = dev.predict(Xs, o, want_cov=True)
         assert_close(m1, gd["mean_d1"], rtol=1e-9, atol=1e-9 * np.abs(gd["mean_d1"]).max(), what=case + " mean_d1")
         prior1 = np.diag(dev.compute_Kij(kid, gd["params"], Xs, o))
         assert np.all(np.abs(c1 - gd["cov_d1"]) <= 1e-9 * prior1.max())
     if "draw" in gd:
-        samp, st = dev.draw_sample(gd["mean"], gd["cov"], gd["rand_vars"], 1e3 * 2.220446049250313e-16)
+        jit = 1e3 * 2.220446049250313e-16
+        samp, st = dev.draw_sample(gd["mean"], gd["cov"], gd["rand_vars"], jit)
         assert st == 0
-        assert_close(samp, gd["draw"], rtol=1e-8, atol=1e-8 * np.abs(gd["draw"]).max(), what=case + " draw")
+        # The sample is mean + chol(cov + jitter) u.  For the 40-point posterior covariance cond(cov + jitter)
+        # ~ 1e12, so two correct Cholesky factors differ far above 1e-9 in their trailing columns: compare the
+        # samples at the conditioning-limited level and pin the factor by its defining property instead.
+        tol = 1e-8 if gd["cov"].shape[0] <= 3 else 1e-5
+        assert_close(samp, gd["draw"], rtol=tol, atol=tol * np.abs(gd["draw"]).max(), what=case + " draw")
+        Ms = gd["cov"].shape[0]
+        Lc, st = dev.draw_sample(np.zeros(Ms), gd["cov"], np.eye(Ms), jit)
+        assert st == 0 and np.all(np.triu(Lc, 1) == 0.0)
+        target = gd["cov"] + jit * np.eye(Ms)
+        assert np.abs(Lc @ Lc.T - target).max() <= 1e-13 * np.abs(target).max()
 
 
 @pytest.mark.parametrize("case", ["demo_c1_kat4", "c1_synth200", "c2_small_matern52", "c2_small_matern_generic"])

@@ -1,0 +1,390 @@
+"""CPU tests of the host side: the C-ABI boundary loads and exports every declared symbol, the product fails
+loudly without a GPU, and the GaussianProcess / Kernel / prior bookkeeping reproduces the reference's
+(bit-exact for index / derivative-order / row-order work).  The numerics are supplied by a fake device
+backed by the pinned oracle (tests/fake_device.py), so what is tested here is the HOST logic only."""
+import os
+import pickle
+import re
+import warnings
+
+import numpy as np
+import pytest
+
+import gptools_b200 as g
+from fake_device import FakeDevice
+from helpers import assert_close, load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def with_fake(gp):
+    gp._dev_obj = FakeDevice()
+    return gp
+
+
+# ------------------------------------------------------------------ boundary
+def test_library_exports_every_declared_symbol():
+    from gptools_b200 import _lib
+    lib = _lib.load_library()
+    hdr = open(os.path.join(ROOT, "include", "gptb200.h")).read()
+    declared = set(re.findall(r"\b(gpt_[a-z_A-Z0-9]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.gpt_version() >= 100
+
+
+def test_product_fails_loudly_without_gpu():
+    from gptools_b200 import _lib
+    if _lib.load_library().gpt_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(_lib.GPTLibraryError):
+        _lib.Device()
+    k = g.SquaredExponentialKernel(num_dim=1, initial_params=[1.0, 1.0], param_bounds=[(0, 10)] * 2)
+    gp = g.GaussianProcess(k, X=[0.0, 1.0], y=[0.0, 1.0])
+    with pytest.raises(_lib.GPTLibraryError):
+        gp.compute_K_L_alpha_ll()
+    with pytest.raises(_lib.GPTLibraryError):
+        k(np.zeros((1, 1)), np.zeros((1, 1)), np.zeros((1, 1), int), np.zeros((1, 1), int))
+
+
+def test_product_never_imports_oracle():
+    import ast
+    pkg = os.path.join(ROOT, "gptools_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                tree = ast.parse(open(os.path.join(dirpath, f)).read())
+                for node in ast.walk(tree):
+                    names = []
+                    if isinstance(node, ast.Import):
+                        names = [a.name for a in node.names]
+                    elif isinstance(node, ast.ImportFrom) and node.module:
+                        names = [node.module]
+                    assert not any(n.split(".")[0] in ("oracle", "fake_device") for n in names), (f, names)
+
+
+# ------------------------------------------------------------------ add_data bookkeeping (bit-exact)
+def _kat1_gp(**kw):
+    rs = np.random.RandomState(0)
+    X = rs.rand(6, 2)
+    y = np.sin(X).sum(1)
+    k = g.SquaredExponentialKernel(num_dim=2, initial_params=[1.3, 0.7, 1.1], param_bounds=[(0, 10)] * 3)
+    gp = g.GaussianProcess(k, **kw)
+    gp.add_data(X, y, err_y=0.01)
+    gp.add_data(X, np.cos(X[:, 0]), n=np.tile([1, 0], (6, 1)), err_y=0.01)
+    gp.add_data(X, np.cos(X[:, 1]), n=np.tile([0, 1], (6, 1)), err_y=0.01)
+    return gp
+
+
+def test_add_data_matches_reference_rows_bit_exact():
+    gd = load_golden("se2d_kat1")
+    gp = _kat1_gp()
+    for name in ("X", "n", "y", "err_y"):
+        assert np.array_equal(getattr(gp, name), gd[name]), name
+    assert gp.n.dtype.kind == "i" and gp.T is None
+
+
+def test_add_data_with_T_and_scalar_point_bit_exact():
+    gd = load_golden("gibbs_kat3")
+    k = g.GibbsKernel1dTanh(initial_params=[1.5, 0.6, 0.1, 0.05, 0.9],
+                            param_bounds=[(0, 10), (0, 5), (0, 5), (0, 1), (0, 2)])
+    Xq = np.linspace(0, 1.1, 12)
+    T = np.zeros((3, 12))
+    T[0, :6] = T[1, 3:9] = T[2, 6:] = 1 / 6.0
+    gp = g.GaussianProcess(k)
+    gp.add_data(Xq, [2.5, 2.0, 1.0], err_y=0.05, T=T)
+    gp.add_data(0, 0, n=1)      # identity back-fill + block_diag (gaussian_process.py:471-491)
+    assert gp.T.shape == (4, 13)
+    for name in ("X", "n", "y", "err_y", "T"):
+        assert np.array_equal(getattr(gp, name), gd[name]), name
+
+
+def test_add_data_rejects_what_the_reference_rejects():
+    k = g.SquaredExponentialKernel(num_dim=2, initial_params=[1, 1, 1], param_bounds=[(0, 10)] * 3)
+    gp = g.GaussianProcess(k)
+    with pytest.raises(ValueError):
+        gp.add_data(np.zeros((3, 1)), np.zeros(3))
+    with pytest.raises(ValueError):
+        gp.add_data(np.zeros((3, 2)), np.zeros(3), err_y=-1.0)
+    with pytest.raises(ValueError):
+        gp.add_data(np.zeros((3, 2)), np.zeros(3), n=-1)
+    with pytest.raises(ValueError):
+        gp.add_data(np.zeros((3, 2)), np.zeros(3), err_y=np.zeros(2))
+    with pytest.raises(ValueError):
+        gp.add_data(np.zeros((3, 2)), np.zeros(2), T=np.zeros((2, 4)))
+    with pytest.raises(TypeError):
+        g.GaussianProcess("not a kernel")
+    with pytest.raises(g.GPArgumentError):
+        g.GaussianProcess(k, X=np.zeros((1, 2)))
+
+
+def test_condense_duplicates_keeps_the_likelihood():
+    rs = np.random.RandomState(3)
+    Xu = rs.rand(5, 1)
+    X = np.vstack([Xu, Xu[:2]])
+    y = np.sin(3 * X[:, 0]) + 0.01 * rs.randn(7)
+    k = g.SquaredExponentialKernel(num_dim=1, initial_params=[1.0, 0.5], param_bounds=[(0, 10)] * 2)
+    gp1 = with_fake(g.GaussianProcess(k, X=X, y=y, err_y=0.1))
+    gp1.compute_K_L_alpha_ll()
+    gp2 = with_fake(g.GaussianProcess(k, X=X, y=y, err_y=0.1))
+    gp2.condense_duplicates()
+    assert gp2.X.shape == (5, 1) and gp2.T.shape == (7, 5)
+    assert np.array_equal(gp2.T.sum(axis=1), np.ones(7))
+    gp2.compute_K_L_alpha_ll()
+    assert_close(gp2.ll, gp1.ll, rtol=1e-10)
+
+
+# ------------------------------------------------------------------ ll / gradient / priors through the host layer
+def test_ll_and_gradient_kat1_through_GaussianProcess():
+    gd = load_golden("se2d_kat1")
+    gp = with_fake(_kat1_gp(use_hyper_deriv=True))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        gp.compute_K_L_alpha_ll()
+    assert_close(gp.ll, gd["ll"], rtol=1e-12)
+    assert_close(gp.ll_deriv, gd["ll_deriv"], rtol=1e-10)
+    assert gp.alpha.shape == (18, 1)
+    assert_close(gp.alpha.ravel(), gd["alpha"], rtol=1e-9)
+    assert_close(gp.K, gd["K"], rtol=1e-12, atol=1e-14)
+    assert np.array_equal(gp.noise_K, np.zeros((18, 18)))
+    # update_hyperparameters returns (-ll, -grad) and restores use_hyper_deriv (gaussian_process.py:1411-1416)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        f, df = gp.update_hyperparameters(np.array([1.3, 0.7, 1.1]))
+        assert_close(f, -gd["ll"], rtol=1e-12)
+        assert_close(df, -gd["ll_deriv"], rtol=1e-10)
+        assert np.isscalar(gp.update_hyperparameters(np.array([1.3, 0.7, 1.1]), hyper_deriv_handling='value'))
+        # outside the prior support -> (inf, zeros) without touching the device
+        ncalls = len(gp._dev_obj.calls)
+        f, df = gp.update_hyperparameters(np.array([11.0, 0.7, 1.1]))
+        assert np.isinf(f) and np.all(df == 0) and len(gp._dev_obj.calls) == ncalls
+
+
+def test_demo_prior_and_fixed_parameter_quirk():
+    """ll includes the log-prior of ALL parameters, fixed ones too: the ZeroKernel's fixed sigma_n = 0 with bounds
+    (0, 1e16) contributes -log(1e16)."""
+    gd = load_golden("demo_c1_kat4")
+    hp = g.UniformJointPrior([(0, 20)]) * g.GammaJointPriorAlt([1.0], [0.7])
+    k = g.SquaredExponentialKernel(initial_params=gd["params"], hyperprior=hp)
+    gp = with_fake(g.GaussianProcess(k, use_hyper_deriv=True))
+    gp.add_data(gd["X"][:-1], gd["y"][:-1], err_y=gd["err_y"][:-1])
+    gp.add_data(0, 0, n=1)
+    assert np.array_equal(gp.X, gd["X"]) and np.array_equal(gp.n, gd["n"])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        gp.compute_K_L_alpha_ll()
+    assert_close(gp.hyperprior(gp.params), gd["log_prior"], rtol=1e-13)
+    assert_close(gp.ll, gd["ll"], rtol=1e-12)
+    assert_close(gp.ll_deriv, gd["ll_deriv"], rtol=1e-7, atol=1e-9)
+
+
+def test_diagonal_noise_kernel_layout_and_gradient():
+    gd = load_golden("se_diagnoise")
+    k = g.SquaredExponentialKernel(num_dim=2, initial_params=gd["params"], param_bounds=[(0, 10)] * 3)
+    nk = g.DiagonalNoiseKernel(num_dim=2, initial_noise=float(gd["noise_sigma"][0]), noise_bound=(0, 5))
+    gp = with_fake(g.GaussianProcess(k, noise_k=nk, use_hyper_deriv=True))
+    gp.add_data(gd["X"][:20], gd["y"][:20], err_y=0.03)
+    gp.add_data(gd["X"][20:], gd["y"][20:], n=np.tile([0, 1], (5, 1)), err_y=0.2)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        gp.compute_K_L_alpha_ll()
+    assert_close(gp.ll, gd["ll"], rtol=1e-12)
+    assert_close(gp.ll_deriv, gd["ll_deriv"], rtol=1e-9)
+    assert len(gp.free_params) == 4 and list(gp.free_param_names[:])[-1] == r'\sigma_n'
+
+
+def test_mean_function_enters_as_rhs_and_gradient_slot():
+    rs = np.random.RandomState(2)
+    X = rs.rand(12, 1)
+    y = 2.0 + np.sin(4 * X[:, 0])
+    k = g.SquaredExponentialKernel(num_dim=1, initial_params=[1.0, 0.3], param_bounds=[(0, 10)] * 2)
+    mu = g.ConstantMeanFunction(initial_params=[1.5])
+    gp = with_fake(g.GaussianProcess(k, mu=mu, X=X, y=y, err_y=0.05, use_hyper_deriv=True))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        f0, g0 = gp.update_hyperparameters(np.array([1.0, 0.3, 1.5]))
+        eps = 1e-6
+        fp, _ = gp.update_hyperparameters(np.array([1.0, 0.3, 1.5 + eps]))
+        fm, _ = gp.update_hyperparameters(np.array([1.0, 0.3, 1.5 - eps]))
+    assert_close(g0[2], (fp - fm) / (2 * eps), rtol=1e-6)
+    assert "set_y" in gp._dev_obj.calls      # only the right-hand side was re-sent, not the whole data set
+
+
+# ------------------------------------------------------------------ batched entry (host logic)
+def test_update_hyperparameters_batch_matches_scalar_calls():
+    gp = with_fake(_kat1_gp(use_hyper_deriv=True))
+    rs = np.random.RandomState(1)
+    th = np.array([1.3, 0.7, 1.1]) * np.exp(0.1 * rs.randn(6, 3))
+    th[3, 0] = 12.0       # outside the prior support
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        f, df = gp.update_hyperparameters_batch(th)
+        before = np.array(gp.free_params[:])
+        for b in range(6):
+            fb, dfb = gp.update_hyperparameters(th[b])
+            if b == 3:
+                assert np.isinf(f[b]) and np.all(df[b] == 0)
+            else:
+                assert_close(f[b], fb, rtol=1e-12)
+                assert_close(df[b], dfb, rtol=1e-10)
+    assert np.array_equal(before, np.array([1.3, 0.7, 1.1]))       # batch call leaves the GP's state alone
+    assert gp.update_hyperparameters_batch(th, with_deriv=False).shape == (6,)
+
+
+def test_compute_ll_matrix_shape_and_values():
+    gp = with_fake(_kat1_gp())
+    ll_vals, pv = gp.compute_ll_matrix([(1.0, 1.5), (0.5, 0.9), (0.9, 1.3)], [2, 3, 2])
+    assert ll_vals.shape == (2, 3, 2)
+    v = gp.update_hyperparameters(np.array([pv[0][1], pv[1][2], pv[2][0]]))
+    assert_close(ll_vals[1, 2, 0], -v, rtol=1e-12)
+
+
+# ------------------------------------------------------------------ predict / draw_sample host logic
+def test_predict_return_conventions_and_output_transform():
+    gd = load_golden("se2d_kat1")
+    gp = with_fake(_kat1_gp())
+    Xs = gd["Xs"]
+    mean, std = gp.predict(Xs)
+    assert_close(mean, gd["mean"], rtol=1e-9)
+    assert_close(std, gd["std"], rtol=1e-6)
+    mean2, cov = gp.predict(Xs, return_cov=True)
+    assert cov.shape == (4, 4)
+    assert gp.predict(Xs, return_std=False).shape == (4,)
+    out = gp.predict(Xs, full_output=True)
+    assert set(out) == {"mean", "std", "cov"}
+    m1, s1 = gp.predict(Xs, n=np.tile([1, 0], (4, 1)))
+    assert_close(m1, gd["mean_d1"], rtol=1e-9)
+    W = np.array([[0.25, 0.25, 0.25, 0.25], [1.0, -1.0, 0.0, 0.0]])
+    mt, ct = gp.predict(Xs, return_cov=True, output_transform=W)
+    assert_close(mt, W.dot(gd["mean"]), rtol=1e-9)
+    assert_close(ct, W.dot(gd["cov"]).dot(W.T), rtol=1e-6, atol=1e-12)
+    with pytest.raises(ValueError):
+        gp.predict(np.zeros((3, 3)))
+    with pytest.raises(ValueError):
+        gp.predict(Xs, n=-1)
+    # full_covar is accepted as an alias of return_cov
+    assert gp.predict(Xs, full_covar=True)[1].shape == (4, 4)
+
+
+def test_draw_sample_cholesky_with_rand_vars():
+    gd = load_golden("gibbs_kat3")
+    k = g.GibbsKernel1dTanh(initial_params=gd["params"], param_bounds=[(0, 10), (0, 5), (0, 5), (0, 1), (0, 2)])
+    gp = with_fake(g.GaussianProcess(k))
+    gp.add_data(gd["X"][:12, 0], gd["y"][:3], err_y=0.05, T=gd["T"][:3, :12])
+    gp.add_data(0, 0, n=1)
+    gp.compute_K_L_alpha_ll()
+    assert_close(gp.ll, gd["ll"], rtol=1e-12)
+    samp = gp.draw_sample(gd["Xs"], rand_vars=gd["rand_vars"], method="cholesky")
+    assert_close(samp, gd["draw"], rtol=1e-7, atol=1e-7)
+    with pytest.raises(ValueError):
+        gp.draw_sample(gd["Xs"], rand_vars=gd["rand_vars"], method="nope")
+
+
+def test_unsupported_orders_raise_before_any_device_call():
+    k = g.Matern52Kernel(num_dim=1, initial_params=[1.0, 0.5], param_bounds=[(0, 10)] * 2)
+    gp = with_fake(g.GaussianProcess(k, X=np.linspace(0, 1, 5), y=np.zeros(5), err_y=0.1))
+    gp.compute_K_L_alpha_ll()
+    n0 = len(gp._dev_obj.calls)
+    with pytest.raises(ValueError):
+        gp.predict(np.array([0.5]), n=2)
+    assert len(gp._dev_obj.calls) == n0
+    gk = g.GibbsKernel1dTanh(initial_params=[1, 1, 1, 1, 1], param_bounds=[(0, 10)] * 5)
+    with pytest.raises(NotImplementedError):
+        gk._check_orders(np.array([[2]]), np.array([[0]]))
+    mk = g.MaternKernel(num_dim=1, initial_params=[1.0, 2.0, 0.5], param_bounds=[(0, 10)] * 3)
+    with pytest.raises(NotImplementedError):
+        mk.device_descriptor()            # integer nu is not available on the device
+    with pytest.raises(NotImplementedError):
+        g.Matern52Kernel(num_dim=1, initial_params=[1.0, 0.5], param_bounds=[(0, 10)] * 2)(
+            np.zeros((1, 1)), np.zeros((1, 1)), np.zeros((1, 1), int), np.zeros((1, 1), int), hyper_deriv=0)
+
+
+def test_pickle_drops_the_device_handle():
+    gp = with_fake(_kat1_gp())
+    gp.compute_K_L_alpha_ll()
+    gp2 = pickle.loads(pickle.dumps(gp))
+    assert gp2._dev_obj is None and not gp2.K_up_to_date
+    assert np.array_equal(gp2.X, gp.X) and np.array_equal(gp2.k.params, gp.k.params)
+
+
+# ------------------------------------------------------------------ priors
+def test_priors_logpdf_and_derivatives():
+    hp = g.UniformJointPrior([(0, 20)]) * g.GammaJointPriorAlt([1.0], [0.7]) * g.NormalJointPrior([0.5], [2.0]) * \
+        g.LogNormalJointPrior([0.1], [0.4])
+    th = np.array([1.9, 0.98, 0.3, 1.7])
+    import scipy.stats as st
+    b = (1.0 + np.sqrt(1.0 + 4 * 0.49)) / (2 * 0.49)
+    want = (-np.log(20.0) + st.gamma.logpdf(0.98, 1.0 + b, scale=1.0 / b) + st.norm.logpdf(0.3, 0.5, 2.0) +
+            st.lognorm.logpdf(1.7, 0.4, scale=np.exp(0.1)))
+    assert_close(hp(th), want, rtol=1e-13)
+    for i in range(4):
+        e = np.zeros(4)
+        e[i] = 1e-6
+        fd = (hp(th + e) - hp(th - e)) / 2e-6
+        assert_close(hp(th, hyper_deriv=i), fd, rtol=1e-6, atol=1e-8)
+    assert np.isinf(hp(np.array([21.0, 0.98, 0.3, 1.7])))
+    draw = hp.random_draw(size=5)
+    assert draw.shape == (4, 5)
+    assert len(hp.bounds) == 4
+    u = hp.elementwise_cdf(th)
+    assert_close(hp.sample_u(u), th, rtol=1e-9)
+    su = g.SortedUniformJointPrior(3, 0.0, 2.0)
+    assert_close(su(np.array([0.1, 0.5, 1.5])), np.log(6.0) - 3 * np.log(2.0), rtol=1e-13)
+
+
+@pytest.mark.refonly
+def test_priors_and_bookkeeping_against_the_reference_itself():
+    from oracle.ref_shim import load_reference, reference_available
+    if not reference_available():
+        pytest.skip("reference tree not present")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        r = load_reference()
+        for mod in (r, g):
+            pass
+        th = np.array([1.9, 0.98])
+        hp_r = r.UniformJointPrior([(0, 20)]) * r.GammaJointPriorAlt([1.0], [0.7])
+        hp_g = g.UniformJointPrior([(0, 20)]) * g.GammaJointPriorAlt([1.0], [0.7])
+        assert hp_r(th) == hp_g(th)
+        assert hp_r(th, hyper_deriv=1) == hp_g(th, hyper_deriv=1)
+        # add_data: same calls, same rows, bit for bit
+        rs = np.random.RandomState(4)
+        X = rs.rand(7, 2)
+        outs = []
+        for mod in (r, g):
+            k = mod.SquaredExponentialKernel(num_dim=2, initial_params=[1, 1, 1], param_bounds=[(0, 10)] * 3)
+            gp = mod.GaussianProcess(k)
+            gp.add_data(X, X[:, 0], err_y=0.1)
+            gp.add_data(X[:3], X[:3, 1], n=[[1, 0]] * 3)
+            gp.add_data(X[:2], [1.0], T=[[0.5, 0.5]], err_y=[0.2])
+            outs.append((gp.X, gp.n, gp.y, gp.err_y, gp.T))
+        for a, b in zip(*outs):
+            assert np.array_equal(a, b)
+
+
+# ------------------------------------------------------------------ sampler
+def test_ensemble_sampler_recovers_a_gaussian():
+    from gptools_b200.sampler import EnsembleSampler
+    mu, sig = np.array([1.0, -2.0]), np.array([0.5, 2.0])
+    s = EnsembleSampler(40, 2, lambda th: -0.5 * (((th - mu) / sig) ** 2).sum(axis=1),
+                        random_state=np.random.RandomState(0))
+    p0 = mu + 0.1 * np.random.RandomState(1).randn(40, 2)
+    s.run_mcmc(p0, 600)
+    assert s.chain.shape == (40, 600, 2) and s.lnprobability.shape == (40, 600)
+    flat = s.chain[:, 200:, :].reshape(-1, 2)
+    assert np.all(np.abs(flat.mean(0) - mu) < 0.15 * sig)
+    assert np.all(np.abs(flat.std(0) / sig - 1) < 0.15)
+    assert 0.2 < s.acceptance_fraction.mean() < 0.95
+    s.run_mcmc(s.chain[:, -1, :], 10)       # chains can be continued
+    assert s.chain.shape[1] == 610
+
+
+def test_sample_hyperparameter_posterior_uses_batched_calls():
+    gp = with_fake(_kat1_gp())
+    np.random.seed(0)
+    s = gp.sample_hyperparameter_posterior(nwalkers=8, nsamp=3)
+    assert s.chain.shape == (8, 3, 3)
+    assert gp._dev_obj.calls.count("ll_batched") == 1 + 2 * 3     # initial ensemble + two half-moves per step
+    assert np.isfinite(s.lnprobability).any()
