@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libgptb200.so")
+LIB_PATH = os.environ.get("GPTB200_LIB", os.path.join(_HERE, "csrc", "libgptb200.so"))  # override: development builds
 
 GPT_SE, GPT_MATERN52, GPT_MATERN, GPT_GIBBS_TANH = 0, 1, 2, 3
 

@@ -33,6 +33,7 @@ struct gpt_handle {
     // training data
     int N = 0, M = 0, D = 0, Np = 0, Mp = 0;
     bool hasT = false;
+    int max_order = 0;  // largest derivative order in n
     std::vector<double> h_err2;  // err_y^2
     DevBuf X, n, y, diag, T, Tt;
 
@@ -409,6 +410,11 @@ int gpt_set_data(gpt_handle* h, int N, int M, int D, const double* X, const int3
     h->Np = round_up(N, NB); h->Mp = round_up(M, NB);
     h->hasT = (T != nullptr);
     h->factor_valid = false;
+    h->max_order = 0;
+    for (long i = 0; i < (long)N * D; i++) {
+        if (n[i] < 0) return fail(h, GPT_ERR_USAGE, "gpt_set_data: negative derivative order");
+        if (n[i] > h->max_order) h->max_order = n[i];
+    }
     int rc;
     if ((rc = upload(h, h->X, X, sizeof(double) * N * D))) return rc;
     if ((rc = upload(h, h->n, n, sizeof(int32_t) * N * D))) return rc;
@@ -907,6 +913,7 @@ static int batched_common(gpt_handle* h, int B, const double* d_thetas, const do
     bp.M = h->M; bp.nT = (h->M + 63) / 64;
     if (bp.nT > 32) return fail(h, GPT_ERR_UNSUPPORTED, "gpt_ll_batched: M > 2048 uses gpt_ll");
     bp.X = ptr<double>(h->X); bp.n = ptr<int32_t>(h->n);
+    bp.low_order = (h->max_order <= 1) ? 1 : 0;
     bp.y = d_y ? d_y : ptr<double>(h->y); bp.y_stride = d_y ? h->M : 0;
     bp.diag = ptr<double>(h->diag);
     bp.B = B; bp.thetas = d_thetas;
@@ -926,9 +933,28 @@ static int batched_common(gpt_handle* h, int B, const double* d_thetas, const do
     if ((rc = ensure(h, h->b_counter, sizeof(int)))) return rc;
     bp.workspace = ptr<double>(h->b_ws);
     bp.counter = ptr<int>(h->b_counter);
+    bp.phase_cycles = nullptr;
+#ifdef GPT_PHASE_TIMING
+    if ((rc = ensure(h, h->scal, 8 * sizeof(long long)))) return rc;
+    CUDA_OK(h, cudaMemsetAsync(h->scal.p, 0, 8 * sizeof(long long), h->stream));
+    bp.phase_cycles = ptr<long long>(h->scal);
+#endif
     CUDA_OK(h, cudaMemsetAsync(bp.counter, 0, sizeof(int), h->stream));
     launch_ll_batched(bp, ctas, h->stream);
     h->launches++;
+#ifdef GPT_PHASE_TIMING
+    {
+        long long pc[8];
+        cudaMemcpyAsync(pc, h->scal.p, sizeof(pc), cudaMemcpyDeviceToHost, h->stream);
+        cudaStreamSynchronize(h->stream);
+        static const char* names[8] = {"gemm jobs", "K generation", "potrf+inv", "panel products", "residual/z", "backsolve", "gradient", "other"};
+        long long tot = 0;
+        for (int q = 0; q < 8; q++) tot += pc[q];
+        fprintf(stderr, "[phase timing] B=%d, CTA-cycles per theta (thread 0 of each CTA):\n", B);
+        for (int q = 0; q < 8; q++) fprintf(stderr, "   %-16s %10.0f  %5.1f%%\n", names[q], (double)pc[q] / B, 100.0 * pc[q] / (double)tot);
+        fprintf(stderr, "   %-16s %10.0f\n", "total", (double)tot / B);
+    }
+#endif
     return check_launch(h);
 }
 

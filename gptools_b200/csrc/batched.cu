@@ -17,8 +17,26 @@
 // Every matrix product is mma.sync.m8n8k4.f64 (DMMA) with operands streamed global->shared by a
 // 3-stage cp.async pipeline in 64x16 chunks (XOR-swizzled, conflict-free fragment reads).
 // Algorithmic work: M^3 flop per theta (potrf M^3/3 + inverse 2M^3/3); roofline = FP64 tensor pipe.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "internal.h"
+
+// Per-phase cycle accounting (development aid): build with -DGPT_PHASE_TIMING and pass BatchedParams::phase_cycles.
+#ifdef GPT_PHASE_TIMING
+#define PT_DECL long long pt_t0 = clock64(), pt_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define PT_MARK(slot)                          \
+    do {                                       \
+        const long long pt_t1 = clock64();     \
+        pt_acc[slot] += pt_t1 - pt_t0;         \
+        pt_t0 = pt_t1;                         \
+    } while (0)
+#else
+#define PT_DECL
+#define PT_MARK(slot)
+#endif
+// slots: 0 GEMM jobs, 1 K-tile generation, 2 potrf+inverse of the diagonal tile, 3 panel products + stores,
+//        4 residual / z, 5 back substitution, 6 gradient contraction, 7 everything else
 
 namespace {
 
@@ -42,6 +60,8 @@ struct Smem {
     const double* a0[MAXT];
     const double* a1[MAXT];
     const double* b[MAXT];
+    unsigned char flag[MAXT];  // per step: bit0 A0 upper-triangular, bit1 A1 upper-triangular, bit2 B upper-triangular
+    int skip_th;               // job: tile (0/1) whose OUTPUT is a diagonal tile (upper 32x32 block not needed), or -1
     CovParams cp;
     double noise2;
     int theta;
@@ -90,7 +110,13 @@ __device__ __forceinline__ void run_job(Smem& sm, const Lane& L, int nsteps, dou
         cp_async_commit();
         const int s = q >> 2;
         const double* ap = L.th ? sm.a1[s] : sm.a0[s];
-        if (ap != nullptr) {
+        // structural zeros, skipped at warp (32x32) granularity: an upper-triangular 64x64 operand ([row][c],
+        // c >= row) has nothing in columns < 32 of its rows >= 32; the upper-right block of a symmetric
+        // diagonal output tile is never used.
+        const int fl = sm.flag[s];
+        const bool half_zero = (((fl >> L.th) & 1) && L.wr == 1) || ((fl & 4) && L.wc == 1);
+        const bool dead = (sm.skip_th == L.th) && L.wr == 0 && L.wc == 1;
+        if (ap != nullptr && !dead && !(half_zero && (q & 3) < 2)) {
             const double* aS = sm.R + (q % STAGES) * STAGE_D + L.th * CHUNK + (L.wr * 32 + L.g) * BK;
             const double* bS = sm.R + (q % STAGES) * STAGE_D + 2 * CHUNK + (L.wc * 32 + L.g) * BK;
 #pragma unroll
@@ -161,75 +187,87 @@ __device__ __forceinline__ void acc_to_global(double* tile, const Lane& L, const
         }
 }
 
-// Factor the 64x64 SPD tile in sm.Dg (stride LDT) and replace it by the inverse of its Cholesky factor
-// (lower triangular, zeros above).  Returns sum(log L_ii) to thread 0 via sm.red[0][0]; flags sm.info.
+// Replace the 64x64 SPD tile in sm.Dg (stride LDT; lower triangle valid) by X = chol(tile)^{-1} (lower
+// triangular, zeros above).  Returns sum(log L_ii) via sm.red[0][0]; flags sm.info (LAPACK-style).
+//
+// In-place Gauss-Jordan sweep held in REGISTERS (tools/tile_model.py: gj_inverse_factor).  Thread (r, q) =
+// (tid >> 2, tid & 3) owns the 16 entries V[r][q + 4s].  After step j, position (r, c) holds, for c > j, the
+// Schur complement a_rc and, for c <= j, e_rc = (L_unit^{-1})_rc where tile = L_unit D L_unit^T; finally
+// X = D^{-1/2} L_unit^{-1}.  Per column one barrier: the pivot column / row vector w_j (64 doubles) is
+// published through a double buffer in shared memory (sm.dvec / sm.xdiag).  The factor L itself is never
+// needed by the batched path (only its inverse, the pivots and z_k).  ~64 x (18 LDS + 16 DFMA + 1 rcp) per
+// thread instead of the serialized shared-memory rank-1 updates of the first version (35% of the phase-1
+// samples in profiles/r01b).
 __device__ void potrf_inv_tile(Smem& sm, const Lane& L, int row0) {
     double* Dg = sm.Dg;
     const int tid = L.tid;
-    const int ta = tid >> 4, tb = tid & 15;
-    for (int j = 0; j < TB - 1; j++) {
-        double d = Dg[j * LDT + j];
-        if (!(d > 0.0)) {
-            if (tid == 0 && sm.info == 0) sm.info = row0 + j + 1;
-            d = 1.0;
-        }
-        const double invd = 1.0 / d;
-        for (int i = j + 1 + ta; i < TB; i += 16) {
-            const double lij = Dg[i * LDT + j] * invd;
-            for (int c = j + 1 + tb; c <= i; c += 16) Dg[i * LDT + c] -= lij * Dg[c * LDT + j];
-        }
-        __syncthreads();
+    const int r = tid >> 2, q = tid & 3;
+    double v[16];
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+        const int c = q + 4 * s;
+        v[s] = (c <= r) ? Dg[r * LDT + c] : 0.0;
     }
-    if (tid < TB) {
-        double d = Dg[tid * LDT + tid];
-        if (!(d > 0.0)) {
-            if (tid == TB - 1 && sm.info == 0) sm.info = row0 + TB;
-            d = 1.0;
-        }
-        const double sd = sqrt(d);
-        sm.dvec[tid] = sd;
-        sm.xdiag[tid] = 1.0 / sd;
-    }
+    double* const wA = sm.dvec;
+    double* const wB = sm.xdiag;
+    if (q == 0) wA[r] = v[0];  // w_0 = column 0 (pivot at r = 0)
     __syncthreads();
-    for (int idx = tid; idx < TB * TB; idx += THREADS) {
-        const int r = idx >> 6, c = idx & (TB - 1);
-        if (c < r) Dg[r * LDT + c] *= sm.xdiag[c];
-    }
-    if (L.warp == 0) {
-        double s = log(sm.dvec[L.lane]) + log(sm.dvec[L.lane + 32]);
-        s = warp_sum(s);
-        if (L.lane == 0) sm.red[0][0] = s;
-    }
-    __syncthreads();
-    // X = L^{-1}: column j by the lane quad (4j..4j+3); X^T lives in the strict upper triangle
-    {
-        const int j = tid >> 2, h = tid & 3;
-        const double xjj = sm.xdiag[j];
-        for (int i = 1; i < TB; i++) {
-            double s = 0.0;
-            if (i > j) {
-                for (int m = j + h; m < i; m += 4) {
-                    const double x = (m == j) ? xjj : Dg[j * LDT + m];
-                    s += Dg[i * LDT + m] * x;
+    double dr = 1.0;  // pivot of my row
+    // 16 unrolled groups of 4 columns (the 4 columns of a group run in a rolled loop): register t always holds
+    // column q + 4t, so every shared-memory offset below is a compile-time constant relative to W + q.
+    // Entries above the diagonal carry harmless garbage (never published, never written back).
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+#pragma unroll 1
+        for (int qq = 0; qq < 4; qq++) {
+            const int j = 4 * s + qq;
+            const double* W = (qq & 1) ? wB : wA;  // j & 1 == qq & 1
+            double* Wn = (qq & 1) ? wA : wB;
+            double d = W[j];
+            if (!(d > 0.0)) {
+                if (tid == 0 && sm.info == 0) sm.info = row0 + j + 1;
+                d = 1.0;
+            }
+            if (r == j) dr = d;
+            if (r > j) {
+                const double mult = W[r] * __drcp_rn(d);
+                const double* Wq = W + q;
+#pragma unroll
+                for (int t = 0; t < 16; t++) {
+                    if (t == s) v[t] = (q == qq) ? -mult : v[t] - mult * Wq[4 * t];
+                    else v[t] -= mult * Wq[4 * t];
                 }
             }
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            if (i > j && h == 0) Dg[j * LDT + i] = -s * sm.xdiag[i];
-            __syncwarp();
+            const int jn = j + 1;
+            if (jn < TB) {
+                // column jn of the Schur complement (rows >= jn) ...
+                if (q == (jn & 3) && r >= jn) Wn[r] = (qq == 3) ? v[(s + 1) & 15] : v[s];
+                // ... and row jn of L_unit^{-1} (columns < jn)
+                if (r == jn) {
+#pragma unroll
+                    for (int t = 0; t < 16; t++)
+                        if (q + 4 * t < jn) Wn[q + 4 * t] = v[t];
+                }
+            }
+            __syncthreads();
         }
     }
+    const double rs = 1.0 / sqrt(dr);
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+        const int c = q + 4 * t;
+        Dg[r * LDT + c] = (c < r) ? v[t] * rs : ((c == r) ? rs : 0.0);
+    }
+    {
+        double s = (q == 0) ? 0.5 * log(dr) : 0.0;
+        s = warp_sum(s);
+        if (L.lane == 0) sm.zk[L.warp] = s;  // zk is free here (z_k is formed after this call)
+    }
     __syncthreads();
-    // in place: lower <- X, diagonal <- 1/L_ii, upper <- 0
-    for (int idx = tid; idx < TB * TB; idx += THREADS) {
-        const int r = idx >> 6, c = idx & (TB - 1);
-        if (c < r) {
-            const double x = Dg[c * LDT + r];
-            Dg[r * LDT + c] = x;
-            Dg[c * LDT + r] = 0.0;
-        } else if (c == r) {
-            Dg[r * LDT + r] = sm.xdiag[r];
-        }
+    if (tid == 0) {
+        double s = 0.0;
+        for (int w = 0; w < 8; w++) s += sm.zk[w];
+        sm.red[0][0] = s;
     }
     __syncthreads();
 }
@@ -244,7 +282,332 @@ __device__ __forceinline__ double ktot_entry(const Smem& sm, const BatchedParams
     return (gi == gj) ? 1.0 : 0.0;
 }
 
-__global__ void __launch_bounds__(THREADS, 2) ll_batched_kernel(BatchedParams p) {
+// ---- register-resident squared-exponential evaluation, input dimension known at compile time ----------
+// (the generic cov_eval keeps per-dimension arrays in local memory and re-reads the parameters from shared
+// memory for every entry; ncu showed ~60% of all warp samples there, profiles/r01a_*)
+template <int D>
+struct SEHoist {
+    double sig2, sig;
+    double il[D];
+};
+
+template <int D>
+__device__ __forceinline__ SEHoist<D> se_hoist(const CovParams& cp) {
+    SEHoist<D> h;
+    h.sig2 = cp.sig2;
+    h.sig = cp.p[0];
+#pragma unroll
+    for (int d = 0; d < D; d++) h.il[d] = cp.inv_l[d];
+    return h;
+}
+
+template <int D>
+struct PointReg {
+    double x[D];
+    int n[D];
+};
+
+template <int D>
+__device__ __forceinline__ PointReg<D> load_point(const double* __restrict__ X, const int32_t* __restrict__ n, int gi) {
+    PointReg<D> q;
+#pragma unroll
+    for (int d = 0; d < D; d++) {
+        q.x[d] = __ldg(X + (size_t)gi * D + d);
+        q.n[d] = __ldg(n + (size_t)gi * D + d);
+    }
+    return q;
+}
+
+// value only
+template <int D>
+__device__ __forceinline__ double se_value(const SEHoist<D>& h, const PointReg<D>& a, const PointReg<D>& b) {
+    double r2 = 0.0, prod = 1.0;
+    int sj = 0;
+#pragma unroll
+    for (int d = 0; d < D; d++) {
+        const double tau = a.x[d] - b.x[d];
+        double tl = tau * h.il[d];
+        if (tau == 0.0) tl = 0.0;
+        r2 += tl * tl;
+        sj += b.n[d];
+        double f, g;
+        se_dim_factor(tau, h.il[d], a.n[d] + b.n[d], false, f, g);
+        prod *= f;
+    }
+    double k = h.sig2 * exp_nonpos(-0.5 * r2) * prod;
+    return (sj & 1) ? -k : k;
+}
+
+// value K and dK/dl_d for every dimension (dK/dsigma = 2K/sigma is formed by the caller)
+template <int D>
+__device__ __forceinline__ void se_value_grad(const SEHoist<D>& h, const PointReg<D>& a, const PointReg<D>& b,
+                                              double& K, double (&dl)[D]) {
+    double r2 = 0.0;
+    int sj = 0;
+    double f[D], g[D];
+#pragma unroll
+    for (int d = 0; d < D; d++) {
+        const double tau = a.x[d] - b.x[d];
+        double tl = tau * h.il[d];
+        if (tau == 0.0) tl = 0.0;
+        r2 += tl * tl;
+        sj += b.n[d];
+        se_dim_factor(tau, h.il[d], a.n[d] + b.n[d], true, f[d], g[d]);
+    }
+    double base = h.sig2 * exp_nonpos(-0.5 * r2);
+    if (sj & 1) base = -base;
+    double prod = 1.0;
+#pragma unroll
+    for (int d = 0; d < D; d++) prod *= f[d];
+    K = base * prod;
+#pragma unroll
+    for (int d = 0; d < D; d++) {
+        double pr = g[d];
+#pragma unroll
+        for (int e = 0; e < D; e++)
+            if (e != d) pr *= f[e];
+        dl[d] = base * pr;
+    }
+}
+
+// Branch-free versions for derivative orders <= 1 on both sides (m_d <= 2): selects only, so that the compiler
+// can interleave the unrolled evaluations (a conditional branch per entry serialises them -- measured).
+template <int D>
+__device__ __forceinline__ double se_value_low(const SEHoist<D>& h, const PointReg<D>& a, const PointReg<D>& b) {
+    double r2 = 0.0, prod = 1.0;
+    int sj = 0;
+#pragma unroll
+    for (int d = 0; d < D; d++) {
+        const double tau = a.x[d] - b.x[d];
+        const double tl = (tau == 0.0) ? 0.0 : tau * h.il[d];
+        r2 = fma(tl, tl, r2);
+        sj += b.n[d];
+        double f, g;
+        se_dim_factor_low(tau, h.il[d], a.n[d] + b.n[d], f, g);
+        prod *= f;
+    }
+    const double k = h.sig2 * exp_nonpos_nobranch(-0.5 * r2) * prod;
+    return (sj & 1) ? -k : k;
+}
+
+template <int D>
+__device__ __forceinline__ void se_value_grad_low(const SEHoist<D>& h, const PointReg<D>& a, const PointReg<D>& b,
+                                                  double& K, double (&dl)[D]) {
+    double r2 = 0.0;
+    int sj = 0;
+    double f[D], g[D];
+#pragma unroll
+    for (int d = 0; d < D; d++) {
+        const double tau = a.x[d] - b.x[d];
+        const double tl = (tau == 0.0) ? 0.0 : tau * h.il[d];
+        r2 = fma(tl, tl, r2);
+        sj += b.n[d];
+        se_dim_factor_low(tau, h.il[d], a.n[d] + b.n[d], f[d], g[d]);
+    }
+    double base = h.sig2 * exp_nonpos_nobranch(-0.5 * r2);
+    base = (sj & 1) ? -base : base;
+    double prod = 1.0;
+#pragma unroll
+    for (int d = 0; d < D; d++) prod *= f[d];
+    K = base * prod;
+#pragma unroll
+    for (int d = 0; d < D; d++) {
+        double pr = g[d];
+#pragma unroll
+        for (int e = 0; e < D; e++)
+            if (e != d) pr *= f[e];
+        dl[d] = base * pr;
+    }
+}
+
+// ---- row points of the (up to) two tiles of a job, staged in the 512 spare doubles behind the staging tiles ----
+// With 2 x 113 KB of shared memory per SM the L1 data cache is gone: every per-entry global load of a point
+// is an L2 round trip (measured: 1200 cycles per entry, 35% of the kernel).  Layout (doubles from PTS_OFF):
+// x[set][r][d] at (set*64+r)*FD+d (< 256), alpha[set][r] at 256.., packed orders (int) at double offset 384.
+constexpr int PTS_OFF = 2 * DG_D;
+constexpr int PTS_ALPHA = 256;
+constexpr int PTS_ORD = 384;
+
+template <int FD>
+__device__ __forceinline__ void stage_rows(Smem& sm, const BatchedParams& p, const Lane& L, int I0, int I1, bool has1,
+                                           const double* avec) {
+    if constexpr (FD == 1 || FD == 2) {
+        if (L.tid < 128) {
+            const int set = L.tid >> 6, r = L.tid & 63;
+            const int gi = (set ? I1 : I0) * TB + r;
+            const bool ok = (set == 0 || has1) && gi < p.M;
+            double* pts = sm.R + PTS_OFF;
+            int pk = 0;
+#pragma unroll
+            for (int d = 0; d < FD; d++) {
+                pts[(set * 64 + r) * FD + d] = ok ? p.X[(size_t)gi * FD + d] : 0.0;
+                pk |= (ok ? (p.n[(size_t)gi * FD + d] & 255) : 0) << (8 * d);
+            }
+            reinterpret_cast<int*>(pts + PTS_ORD)[set * 64 + r] = pk;
+            if (avec != nullptr) pts[PTS_ALPHA + set * 64 + r] = ok ? avec[gi] : 0.0;
+        }
+    }
+}
+
+template <int FD>
+__device__ __forceinline__ PointReg<FD> staged_point(const double* pts, int set, int r) {
+    PointReg<FD> q;
+    const int pk = reinterpret_cast<const int*>(pts + PTS_ORD)[set * 64 + r];
+#pragma unroll
+    for (int d = 0; d < FD; d++) {
+        q.x[d] = pts[(set * 64 + r) * FD + d];
+        q.n[d] = (pk >> (8 * d)) & 255;
+    }
+    return q;
+}
+
+// K_tot tile (Imine, Jc) into the staging tile St. Thread tl owns column c = tl & 63 and rows (tl >> 6) + 2u.
+// C = K_tot - S in place: St holds S (the accumulated L L^T part); the result goes to Cout (St itself, or the
+// diagonal-tile buffer).  Running after the accumulators were dumped keeps their 64 registers free for ILP.
+template <int FD>
+__device__ __forceinline__ void gen_ktot_tile(const Smem& sm, const BatchedParams& p, const double* St, double* Cout,
+                                              int tl, int set, int Imine, int Jc) {
+    const bool diag_tile = (Imine == Jc);
+    const int c = tl & (TB - 1);
+    const int gj = Jc * TB + c;
+    if constexpr (FD == 0) {
+#pragma unroll 1
+        for (int u = 0; u < 32; u++) {
+            const int r = (tl >> 6) + 2 * u;
+            if (diag_tile && c > r) continue;  // the factorisation only reads the lower triangle
+            Cout[r * LDT + c] = ktot_entry(sm, p, Imine * TB + r, gj) - St[r * LDT + c];
+        }
+    } else {
+        const SEHoist<FD> h = se_hoist<FD>(sm.cp);
+        const bool col_ok = gj < p.M;
+        const PointReg<FD> pj = load_point<FD>(p.X, p.n, col_ok ? gj : 0);
+        const double dj = col_ok ? sm.noise2 + __ldg(p.diag + gj) : 0.0;
+        const double* pts = sm.R + PTS_OFF;
+        if (FD <= 2 && p.low_order) {
+            // branch-free body: always evaluate (staged rows are zero-filled when out of range), select, predicated store
+#pragma unroll 8
+            for (int u = 0; u < 32; u++) {
+                const int r = (tl >> 6) + 2 * u;
+                const int gi = Imine * TB + r;
+                const PointReg<FD> pi = staged_point<FD>(pts, set, r);
+                double v = se_value_low<FD>(h, pi, pj);
+                v = (gi == gj) ? v + dj : v;
+                const double pad = (gi == gj) ? 1.0 : 0.0;
+                v = (col_ok && gi < p.M) ? v : pad;
+                if (!(diag_tile && c > r)) Cout[r * LDT + c] = v - St[r * LDT + c];
+            }
+        } else {
+#pragma unroll 2
+            for (int u = 0; u < 32; u++) {
+                const int r = (tl >> 6) + 2 * u;
+                if (diag_tile && c > r) continue;
+                const int gi = Imine * TB + r;
+                double v;
+                if (col_ok && gi < p.M) {
+                    PointReg<FD> pi;
+                    if constexpr (FD <= 2) pi = staged_point<FD>(pts, set, r);
+                    else pi = load_point<FD>(p.X, p.n, gi);
+                    v = se_value<FD>(h, pi, pj);
+                    if (gi == gj) v += dj;
+                } else {
+                    v = (gi == gj) ? 1.0 : 0.0;
+                }
+                Cout[r * LDT + c] = v - St[r * LDT + c];
+            }
+        }
+    }
+}
+
+// gradient contraction of one K^{-1} tile held in St:  gall[q] += sum w_ij dK_ij/dparam_q  (SE kernel)
+template <int FD>
+__device__ __forceinline__ void grad_tile(const Smem& sm, const BatchedParams& p, const double* St, int tl, int set,
+                                          int Imine, int J, const double* __restrict__ avec,
+                                          double (&gall)[1 + GPT_MAX_DIM], double& tr_kinv) {
+    const bool diag_tile = (Imine == J);
+    const int c = tl & (TB - 1);
+    const int gj = J * TB + c;
+    if (gj >= p.M) return;
+    const double aj = avec[gj];
+    if constexpr (FD == 0) {
+#pragma unroll 1
+        for (int u = 0; u < 32; u++) {
+            const int r = (tl >> 6) + 2 * u;
+            const int gi = Imine * TB + r;
+            if (gi >= p.M || (diag_tile && c > r)) continue;
+            const double kinv = St[r * LDT + c];
+            double w = avec[gi] * aj - kinv;
+            if (diag_tile && c == r) {
+                tr_kinv += kinv;
+                w *= 0.5;
+            }
+            double dk[2 + GPT_MAX_DIM];
+            se_cov_all(sm.cp, p.X + (size_t)gi * p.D, p.n + (size_t)gi * p.D, p.X + (size_t)gj * p.D,
+                       p.n + (size_t)gj * p.D, dk);
+#pragma unroll
+            for (int q = 0; q < 1 + GPT_MAX_DIM; q++)
+                if (q <= p.D) gall[q] += w * dk[1 + q];
+        }
+    } else {
+        const SEHoist<FD> h = se_hoist<FD>(sm.cp);
+        const PointReg<FD> pj = load_point<FD>(p.X, p.n, gj);
+        const double* pts = sm.R + PTS_OFF;
+        double wk = 0.0;  // sum w * K  (-> dK/dsigma = 2K/sigma)
+        if (FD <= 2 && p.low_order) {
+            double trl = 0.0;
+#pragma unroll 8
+            for (int u = 0; u < 32; u++) {
+                const int r = (tl >> 6) + 2 * u;
+                const int gi = Imine * TB + r;
+                const bool use = (gi < p.M) && !(diag_tile && c > r);
+                const bool on_diag = diag_tile && (c == r);
+                const double kinv = St[r * LDT + c];
+                const PointReg<FD> pi = staged_point<FD>(pts, set, r);
+                const double ai = pts[PTS_ALPHA + set * 64 + r];
+                double w = ai * aj - kinv;
+                w = on_diag ? 0.5 * w : w;
+                w = use ? w : 0.0;
+                trl += (use && on_diag) ? kinv : 0.0;
+                double K, dl[FD];
+                se_value_grad_low<FD>(h, pi, pj, K, dl);
+                wk = fma(w, K, wk);
+#pragma unroll
+                for (int d = 0; d < FD; d++) gall[1 + d] = fma(w, dl[d], gall[1 + d]);
+            }
+            tr_kinv += trl;
+        } else {
+#pragma unroll 2
+            for (int u = 0; u < 32; u++) {
+                const int r = (tl >> 6) + 2 * u;
+                const int gi = Imine * TB + r;
+                if (gi >= p.M || (diag_tile && c > r)) continue;
+                const double kinv = St[r * LDT + c];
+                PointReg<FD> pi;
+                double ai;
+                if constexpr (FD <= 2) {
+                    pi = staged_point<FD>(pts, set, r);
+                    ai = pts[PTS_ALPHA + set * 64 + r];
+                } else {
+                    pi = load_point<FD>(p.X, p.n, gi);
+                    ai = avec[gi];
+                }
+                double w = ai * aj - kinv;
+                if (diag_tile && c == r) {
+                    tr_kinv += kinv;
+                    w *= 0.5;
+                }
+                double K, dl[FD];
+                se_value_grad<FD>(h, pi, pj, K, dl);
+                wk += w * K;
+#pragma unroll
+                for (int d = 0; d < FD; d++) gall[1 + d] += w * dl[d];
+            }
+        }
+        gall[0] += (h.sig != 0.0) ? 2.0 * wk / h.sig : 0.0;
+    }
+}
+
+template <int FD>
+__global__ void __launch_bounds__(THREADS, 2) ll_batched_kernel_t(BatchedParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     Lane L;
@@ -280,6 +643,7 @@ __global__ void __launch_bounds__(THREADS, 2) ll_batched_kernel(BatchedParams p)
         }
         __syncthreads();
         const double* yb = p.y + (size_t)b * p.y_stride;
+        PT_DECL;
         double logdet = 0.0, zz = 0.0;  // meaningful in thread 0
 
         // =========================== phase 1: Cholesky ===========================
@@ -291,41 +655,27 @@ __global__ void __launch_bounds__(THREADS, 2) ll_batched_kernel(BatchedParams p)
                     sm.a0[L.tid] = slot(ws, I0, L.tid);
                     sm.a1[L.tid] = has1 ? slot(ws, I1, L.tid) : nullptr;
                     sm.b[L.tid] = slot(ws, k, L.tid);
+                    sm.flag[L.tid] = 0;
                 }
+                if (L.tid == 0) sm.skip_th = (I0 == k) ? 0 : -1;
                 zero_acc(acc);
+                PT_MARK(7);
                 run_job(sm, L, k, acc);
+                PT_MARK(0);
                 // K_tot tile generated into the (now idle) staging area, then C = K_tot - acc in registers
                 const int Imine = L.th ? I1 : I0;
                 const bool active = L.th ? has1 : true;
-                if (active) {
-                    double* St = sm.R + L.th * DG_D;
-                    const int tl = L.tid & 127;
-                    const bool diag_tile = (Imine == k);
-#pragma unroll 1
-                    for (int u = 0; u < 32; u++) {
-                        const int e = tl + 128 * u;
-                        const int r = e >> 6, c = e & (TB - 1);
-                        if (diag_tile && c > r) continue;  // the factorisation only reads the lower triangle
-                        St[r * LDT + c] = ktot_entry(sm, p, Imine * TB + r, k * TB + c);
-                    }
-                }
+                // dump S = sum_j L(I,j) L(k,j)^T to the staging tiles, then C = K_tot - S in place (K_tot generated
+                // from the closed forms; never stored anywhere else).  The diagonal tile is written to Dg.
+                acc_to_tile(sm.R + L.th * DG_D, L, acc);
+                stage_rows<FD>(sm, p, L, I0, I1, has1, nullptr);
                 __syncthreads();
                 if (active) {
-                    const double* St = sm.R + L.th * DG_D;
-#pragma unroll
-                    for (int i = 0; i < 4; i++)
-#pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            const double2 kv = *reinterpret_cast<const double2*>(
-                                St + (L.wr * 32 + i * 8 + L.g) * LDT + L.wc * 32 + j * 8 + 2 * L.t);
-                            acc[i][j][0] = kv.x - acc[i][j][0];
-                            acc[i][j][1] = kv.y - acc[i][j][1];
-                        }
+                    double* St = sm.R + L.th * DG_D;
+                    gen_ktot_tile<FD>(sm, p, St, (Imine == k) ? sm.Dg : St, L.tid & 127, L.th, Imine, k);
                 }
+                PT_MARK(1);
                 if (I0 == k) {
-                    // diagonal tile -> Dg ; optional second tile -> staging 1
-                    if (L.th == 0) acc_to_tile(sm.Dg, L, acc);
-                    else if (has1) acc_to_tile(sm.R + DG_D, L, acc);
                     // residual r_k = y_k - sum_j L(k,j) z_j  (4 threads per row, 16 columns each)
                     {
                         const int r = L.tid >> 2, qd = L.tid & 3;
@@ -344,7 +694,9 @@ __global__ void __launch_bounds__(THREADS, 2) ll_batched_kernel(BatchedParams p)
                         }
                     }
                     __syncthreads();
+                    PT_MARK(4);
                     potrf_inv_tile(sm, L, k * TB);
+                    PT_MARK(2);
                     if (L.tid == 0) logdet += sm.red[0][0];
                     // Inv_k and Inv_k^T to the workspace; z_k = Inv_k r_k
                     {
@@ -376,7 +728,6 @@ __global__ void __launch_bounds__(THREADS, 2) ll_batched_kernel(BatchedParams p)
                         }
                     }
                 } else {
-                    acc_to_tile(sm.R + L.th * DG_D, L, acc);
                     __syncthreads();
                     if (active) {
                         double out[4][4][2];
@@ -385,38 +736,50 @@ __global__ void __launch_bounds__(THREADS, 2) ll_batched_kernel(BatchedParams p)
                     }
                 }
                 __syncthreads();  // L(I,k) tiles / z visible to the whole CTA before the next job reads them
+                PT_MARK(3);
             }
         }
         __threadfence_block();
 
         const bool need_alpha = (p.nidx > 0) || (p.alpha_out != nullptr);
         if (need_alpha) {
+            PT_MARK(7);
             // ======================= alpha = L^{-T} z (block back substitution) =======================
             for (int i = L.tid; i < nT * TB; i += THREADS) rvec[i] = zvec[i];
             __syncthreads();
             for (int J = nT - 1; J >= 0; J--) {
-                if (L.tid < TB) {
-                    // alpha_J = Inv_J^T r_J : row a of DT(J)
-                    const double* row = slotDT(ws, nT, J) + L.tid * TB;
+                {
+                    // alpha_J = Inv_J^T r_J : row a of DT(J) (upper triangular), 4 threads per row x 16 columns
+                    const int a = L.tid >> 2, qd = L.tid & 3;
+                    const double* row = slotDT(ws, nT, J) + a * TB + qd * 16;
+                    const double* rj = rvec + J * TB + qd * 16;
                     double s = 0.0;
-                    for (int c = L.tid; c < TB; c++) s += row[c] * rvec[J * TB + c];
-                    sm.zk[L.tid] = s;
-                    avec[J * TB + L.tid] = s;
+#pragma unroll
+                    for (int c = 0; c < 16; c++) s += row[c] * rj[c];
+                    s += __shfl_xor_sync(0xffffffffu, s, 1);
+                    s += __shfl_xor_sync(0xffffffffu, s, 2);
+                    if (qd == 0) {
+                        sm.zk[a] = s;
+                        avec[J * TB + a] = s;
+                    }
                 }
                 __syncthreads();
-                // r_I -= L(J,I)^T alpha_J for I < J : one thread per column
-                for (int col = L.tid; col < J * TB; col += THREADS) {
-                    const int I = col >> 6, c = col & (TB - 1);
-                    const double* tile = slot(ws, J, I) + c;
+                // r_I -= L(J,I)^T alpha_J for I < J : 4 threads per column (16 rows each), 64 columns per pass
+                for (int I = 0; I < J; I++) {
+                    const int c = L.tid >> 2, qd = L.tid & 3;
+                    const double* tile = slot(ws, J, I) + (qd * 16) * TB + c;
                     double s = 0.0;
-#pragma unroll 8
-                    for (int r = 0; r < TB; r++) s += tile[r * TB] * sm.zk[r];
-                    rvec[col] -= s;
+#pragma unroll
+                    for (int r = 0; r < 16; r++) s += tile[r * TB] * sm.zk[qd * 16 + r];
+                    s += __shfl_xor_sync(0xffffffffu, s, 1);
+                    s += __shfl_xor_sync(0xffffffffu, s, 2);
+                    if (qd == 0) rvec[I * TB + c] -= s;
                 }
                 __syncthreads();
             }
             if (p.alpha_out != nullptr)
                 for (int i = L.tid; i < p.M; i += THREADS) p.alpha_out[(size_t)b * p.M + i] = avec[i];
+            PT_MARK(5);
         }
 
         double gall[1 + GPT_MAX_DIM];  // sum w * dK/dparam for every SE parameter (sigma_f, l_1..l_D)
@@ -444,9 +807,13 @@ __global__ void __launch_bounds__(THREADS, 2) ll_batched_kernel(BatchedParams p)
                         sm.a0[L.tid] = a0;
                         sm.a1[L.tid] = a1;
                         sm.b[L.tid] = slot(ws, I, m);
+                        sm.flag[L.tid] = (unsigned char)((m == J0 ? 1 : 0) | ((has1 && m == J1) ? 2 : 0));
                     }
+                    if (L.tid == 0) sm.skip_th = -1;
                     zero_acc(acc);
+                    PT_MARK(7);
                     run_job(sm, L, nsteps, acc);
+                    PT_MARK(0);
                     const bool active = L.th ? has1 : true;
                     acc_to_tile(sm.R + L.th * DG_D, L, acc);
                     __syncthreads();
@@ -456,6 +823,7 @@ __global__ void __launch_bounds__(THREADS, 2) ll_batched_kernel(BatchedParams p)
                         acc_to_global(slot(ws, I, L.th ? J1 : J0), L, out, -1.0);
                     }
                     __syncthreads();
+                    PT_MARK(3);
                 }
             }
             __threadfence_block();
@@ -468,48 +836,37 @@ __global__ void __launch_bounds__(THREADS, 2) ll_batched_kernel(BatchedParams p)
                     if (L.tid < nsteps) {
                         const int m = I0 + L.tid;
                         const double *a0, *a1 = nullptr, *bb;
+                        int fl = 0;
                         if (m == I0) {
                             a0 = slotDT(ws, nT, I0);
                             bb = (I0 == J) ? slotDT(ws, nT, J) : slot(ws, I0, J);
+                            fl = 1 | ((I0 == J) ? 4 : 0);
                         } else {
                             a0 = slot(ws, m, I0);
                             bb = slot(ws, m, J);
-                            if (has1) a1 = (m == I1) ? slotDT(ws, nT, I1) : slot(ws, m, I1);
+                            if (has1) {
+                                a1 = (m == I1) ? slotDT(ws, nT, I1) : slot(ws, m, I1);
+                                if (m == I1) fl = 2;
+                            }
                         }
                         sm.a0[L.tid] = a0;
                         sm.a1[L.tid] = a1;
                         sm.b[L.tid] = bb;
+                        sm.flag[L.tid] = (unsigned char)fl;
                     }
+                    if (L.tid == 0) sm.skip_th = (I0 == J) ? 0 : -1;
                     zero_acc(acc);
+                    PT_MARK(7);
                     run_job(sm, L, nsteps, acc);
+                    PT_MARK(0);
                     const int Imine = L.th ? I1 : I0;
                     const bool active = L.th ? has1 : true;
                     acc_to_tile(sm.R + L.th * DG_D, L, acc);
+                    stage_rows<FD>(sm, p, L, I0, I1, has1, avec);
                     __syncthreads();
-                    if (active) {
-                        const double* St = sm.R + L.th * DG_D;
-                        const int tl = L.tid & 127;
-                        const bool diag_tile = (Imine == J);
-#pragma unroll 1
-                        for (int u = 0; u < 32; u++) {
-                            const int e = tl + 128 * u;
-                            const int r = e >> 6, c = e & (TB - 1);
-                            const int gi = Imine * TB + r, gj = J * TB + c;
-                            if (gi >= p.M || gj >= p.M || (diag_tile && c > r)) continue;
-                            const double kinv = St[r * LDT + c];
-                            double w = avec[gi] * avec[gj] - kinv;
-                            if (diag_tile && c == r) {
-                                tr_kinv += kinv;
-                                w *= 0.5;
-                            }
-                            double dk[2 + GPT_MAX_DIM];
-                            se_cov_all(sm.cp, p.X + (size_t)gi * p.D, p.n + (size_t)gi * p.D, p.X + (size_t)gj * p.D,
-                                       p.n + (size_t)gj * p.D, dk);
-#pragma unroll
-                            for (int q = 0; q < 1 + GPT_MAX_DIM; q++)
-                                if (q <= p.D) gall[q] += w * dk[1 + q];
-                        }
-                    }
+                    if (active)
+                        grad_tile<FD>(sm, p, sm.R + L.th * DG_D, L.tid & 127, L.th, Imine, J, avec, gall, tr_kinv);
+                    PT_MARK(6);
                 }
             }
         }
@@ -525,10 +882,20 @@ __global__ void __launch_bounds__(THREADS, 2) ll_batched_kernel(BatchedParams p)
             const double s = warp_sum(tr_kinv);
             if (L.lane == 0) sm.red[L.warp][GPT_MAX_PARAMS] = s;
             __syncthreads();
+            bool want_noise = false;
+            for (int q = 0; q < p.nidx; q++) want_noise |= (p.idx[q] == p.nparams);
+            double aa = 0.0;
+            if (want_noise) {
+                double part = 0.0;
+                for (int i = L.tid; i < p.M; i += THREADS) part += avec[i] * avec[i];
+                part = warp_sum(part);
+                if (L.lane == 0) sm.red[L.warp][GPT_MAX_PARAMS + 1] = part;
+                __syncthreads();
+                for (int w = 0; w < 8; w++) aa += sm.red[w][GPT_MAX_PARAMS + 1];
+            }
             if (L.tid == 0) {
-                double tr = 0.0, aa = 0.0;
+                double tr = 0.0;
                 for (int w = 0; w < 8; w++) tr += sm.red[w][GPT_MAX_PARAMS];
-                for (int i = 0; i < p.M; i++) aa += avec[i] * avec[i];
                 const double sn = p.thetas[(size_t)b * np1 + p.nparams];
                 for (int q = 0; q < p.nidx; q++) {
                     double gsum = 0.0;
@@ -545,6 +912,10 @@ __global__ void __launch_bounds__(THREADS, 2) ll_batched_kernel(BatchedParams p)
         if (L.tid == 0) {
             p.ll[b] = -0.5 * zz - logdet - 0.5 * p.M * 1.8378770664093453;  // log(2 pi)
             p.status[b] = sm.info;
+#ifdef GPT_PHASE_TIMING
+            PT_MARK(7);
+            if (p.phase_cycles) for (int q = 0; q < 8; q++) atomicAdd((unsigned long long*)p.phase_cycles + q, (unsigned long long)pt_acc[q]);
+#endif
         }
     }
 }
@@ -556,12 +927,26 @@ size_t batched_ws_doubles_per_cta(int nT) {
 }
 
 int batched_max_ctas(int device) {
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return 148 * 2;
-    return prop.multiProcessorCount * 2;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    int per_sm = 2;
+    if (const char* e = getenv("GPT_BATCHED_CTAS_PER_SM")) {  // experiments only
+        const int v = atoi(e);
+        if (v == 1 || v == 2) per_sm = v;
+    }
+    return sms * per_sm;
+}
+
+template <int FD>
+static void launch_t(const BatchedParams& p, int num_ctas, cudaStream_t s) {
+    cudaFuncSetAttribute(ll_batched_kernel_t<FD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    ll_batched_kernel_t<FD><<<num_ctas, THREADS, sizeof(Smem), s>>>(p);
 }
 
 void launch_ll_batched(const BatchedParams& p, int num_ctas, cudaStream_t s) {
-    cudaFuncSetAttribute(ll_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
-    ll_batched_kernel<<<num_ctas, THREADS, sizeof(Smem), s>>>(p);
+    // SE kernel with D <= 3: register-resident fast evaluators; everything else: generic closed forms
+    if (p.kid == GPT_KERNEL_SE && p.D == 1) launch_t<1>(p, num_ctas, s);
+    else if (p.kid == GPT_KERNEL_SE && p.D == 2) launch_t<2>(p, num_ctas, s);
+    else if (p.kid == GPT_KERNEL_SE && p.D == 3) launch_t<3>(p, num_ctas, s);
+    else launch_t<0>(p, num_ctas, s);
 }

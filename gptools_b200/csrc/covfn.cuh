@@ -12,6 +12,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define GPT_HD __host__ __device__ __forceinline__
@@ -42,6 +43,87 @@ struct CovParams {
     double mat_A[3];           // value of f^{(n)}(0), n = 1,2 (index n)
     double mat_B[3];           // c * Gamma(-nu) (1+nu-n)_n / 2^{1+nu}
 };
+
+// exp(x) for x <= 0 (the squared-exponential / Gibbs exponents): Cody-Waite reduction x = k ln2 + r,
+// |r| <= ln2/2, degree-13 Taylor polynomial evaluated with Estrin's scheme (16 FP64 operations at dependency
+// depth 5, instead of the ~20-deep Horner chain of the library exp -- on B200 scalar FP64 shares its pipe with
+// DMMA, so chain depth is what limits tile generation next to a CTA doing tensor work).  Relative error
+// < 4e-16 on [-708, 0]; outside that range the library exp takes over.
+GPT_HD double exp_nonpos(double x) {
+    if (!(x >= -708.0) || x > 0.0) return exp(x);
+    const double kf = rint(x * 1.4426950408889634074);
+    double r = fma(-kf, 6.93147180369123816490e-01, x);
+    r = fma(-kf, 1.90821492927058770002e-10, r);
+    const double r2 = r * r;
+    const double a0 = fma(r, 1.0, 1.0);
+    const double a1 = fma(r, 1.6666666666666665741e-01, 0.5);
+    const double a2 = fma(r, 8.3333333333333332177e-03, 4.1666666666666664354e-02);
+    const double a3 = fma(r, 1.9841269841269841253e-04, 1.3888888888888889419e-03);
+    const double a4 = fma(r, 2.7557319223985892511e-06, 2.4801587301587301566e-05);
+    const double a5 = fma(r, 2.5052108385441720224e-08, 2.7557319223985888276e-07);
+    const double a6 = fma(r, 1.6059043836821613341e-10, 2.0876756987868100187e-09);
+    const double r4 = r2 * r2;
+    const double b0 = fma(a1, r2, a0);
+    const double b1 = fma(a3, r2, a2);
+    const double b2 = fma(a5, r2, a4);
+    const double r8 = r4 * r4;
+    const double d0 = fma(b1, r4, b0);
+    const double d1 = fma(a6, r4, b2);
+    const double pr = fma(d1, r8, d0);
+    // 2^k with k in [-1022, 0]
+#if defined(__CUDA_ARCH__)
+    const double sc = __longlong_as_double((long long)(__double2int_rn(kf) + 1023) << 52);
+#else
+    const long long bits = (long long)((int)kf + 1023) << 52;
+    double sc;
+    memcpy(&sc, &bits, sizeof(sc));
+#endif
+    return pr * sc;
+}
+
+// Branch-free variant for the unrolled tile loops: the argument is clamped to [-708, 0] (results below
+// 3e-308 are flushed to that value; irrelevant next to sigma_f^2) so that no basic-block boundary separates
+// the interleaved evaluations of neighbouring entries.
+GPT_HD double exp_nonpos_nobranch(double x) {
+    x = fmax(x, -708.0);
+    const double kf = rint(x * 1.4426950408889634074);
+    double r = fma(-kf, 6.93147180369123816490e-01, x);
+    r = fma(-kf, 1.90821492927058770002e-10, r);
+    const double r2 = r * r;
+    const double a0 = fma(r, 1.0, 1.0);
+    const double a1 = fma(r, 1.6666666666666665741e-01, 0.5);
+    const double a2 = fma(r, 8.3333333333333332177e-03, 4.1666666666666664354e-02);
+    const double a3 = fma(r, 1.9841269841269841253e-04, 1.3888888888888889419e-03);
+    const double a4 = fma(r, 2.7557319223985892511e-06, 2.4801587301587301566e-05);
+    const double a5 = fma(r, 2.5052108385441720224e-08, 2.7557319223985888276e-07);
+    const double a6 = fma(r, 1.6059043836821613341e-10, 2.0876756987868100187e-09);
+    const double r4 = r2 * r2;
+    const double b0 = fma(a1, r2, a0);
+    const double b1 = fma(a3, r2, a2);
+    const double b2 = fma(a5, r2, a4);
+    const double r8 = r4 * r4;
+    const double d0 = fma(b1, r4, b0);
+    const double d1 = fma(a6, r4, b2);
+    const double pr = fma(d1, r8, d0);
+#if defined(__CUDA_ARCH__)
+    const double sc = __longlong_as_double((long long)(__double2int_rn(kf) + 1023) << 52);
+#else
+    const long long bits = (long long)((int)kf + 1023) << 52;
+    double sc;
+    memcpy(&sc, &bits, sizeof(sc));
+#endif
+    return pr * sc;
+}
+
+// se_dim_factor restricted to m in {0, 1, 2}, written with selects only (no branches).
+GPT_HD void se_dim_factor_low(double tau, double inv_l, int m, double& f, double& g) {
+    const double il2 = inv_l * inv_l;
+    const double u = tau * tau * il2;
+    const double f1 = -tau * il2, f2 = il2 * (u - 1.0);
+    const double g0 = u * inv_l, g1 = tau * il2 * inv_l * (2.0 - u), g2 = il2 * inv_l * (2.0 + u * (u - 5.0));
+    f = (m == 0) ? 1.0 : ((m == 1) ? f1 : f2);
+    g = (m == 0) ? g0 : ((m == 1) ? g1 : g2);
+}
 
 GPT_HD void cov_params_init(CovParams& cp, int kid, int D, int nparams, const double* params) {
     cp.kid = kid;
@@ -82,9 +164,22 @@ GPT_HD void cov_params_init(CovParams& cp, int kid, int D, int nparams, const do
 GPT_HD void se_dim_factor(double tau, double inv_l, int m, bool want_g, double& f, double& g) {
     const double RSQRT2 = 0.70710678118654752440;
     const double SQRT2 = 1.41421356237309504880;
-    if (m == 0) {
-        f = 1.0;
-        g = want_g ? tau * tau * inv_l * inv_l * inv_l : 0.0;
+    const double il2 = inv_l * inv_l;
+    // orders 0..2 (value / first-derivative observations and predictions) in closed form:
+    //   f_0 = 1, f_1 = -tau/l^2, f_2 = (u - 1)/l^2 with u = tau^2/l^2;
+    //   g_0 = u/l, g_1 = tau (2 - u)/l^3, g_2 = (2 - 5u + u^2)/l^3
+    if (m <= 2) {
+        const double u = tau * tau * il2;
+        if (m == 0) {
+            f = 1.0;
+            g = want_g ? u * inv_l : 0.0;
+        } else if (m == 1) {
+            f = -tau * il2;
+            g = want_g ? tau * il2 * inv_l * (2.0 - u) : 0.0;
+        } else {
+            f = il2 * (u - 1.0);
+            g = want_g ? il2 * inv_l * (2.0 + u * (u - 5.0)) : 0.0;
+        }
         return;
     }
     const double c = -RSQRT2 * inv_l;
@@ -93,15 +188,19 @@ GPT_HD void se_dim_factor(double tau, double inv_l, int m, bool want_g, double& 
     double hm1 = 1.0;       // H_0
     double h = 2.0 * x;     // H_1
     double cm = c;          // c^1
+    double twok = 2.0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
     for (int k = 1; k < m; k++) {
-        const double hn = 2.0 * x * h - 2.0 * k * hm1;
+        const double hn = 2.0 * x * h - twok * hm1;
         hm1 = h;
         h = hn;
         cm *= c;
+        twok += 2.0;
     }
     f = cm * h;
     if (want_g) {
-        const double il2 = inv_l * inv_l;
         g = cm * (h * (tau * tau * il2 * inv_l - m * inv_l) - SQRT2 * m * tau * il2 * hm1);
     } else {
         g = 0.0;
@@ -124,7 +223,7 @@ GPT_HD double se_cov(const CovParams& cp, const double* xi, const int32_t* ni, c
         se_dim_factor(tau, cp.inv_l[d], m, hyper_deriv == d + 1, f, g);
         prod *= (hyper_deriv == d + 1) ? g : f;
     }
-    double k = cp.sig2 * exp(-0.5 * r2) * prod;
+    double k = cp.sig2 * exp_nonpos(-0.5 * r2) * prod;
     if (ntot_j & 1) k = -k;
     if (hyper_deriv == 0) k = (cp.p[0] != 0.0) ? 2.0 * k / cp.p[0] : 0.0;
     return k;
@@ -145,7 +244,7 @@ GPT_HD void se_cov_all(const CovParams& cp, const double* xi, const int32_t* ni,
         ntot_j += nj[d];
         se_dim_factor(tau, cp.inv_l[d], ni[d] + nj[d], true, f[d], g[d]);
     }
-    double base = cp.sig2 * exp(-0.5 * r2);
+    double base = cp.sig2 * exp_nonpos(-0.5 * r2);
     if (ntot_j & 1) base = -base;
     double prod = 1.0;
     for (int d = 0; d < cp.D; d++) prod *= f[d];

@@ -99,6 +99,7 @@ struct BatchedParams {
     int nT;                // 64-row tiles, ceil(M / 64)
     const double* X;       // M x D
     const int32_t* n;      // M x D
+    int low_order;         // every derivative order <= 1: branch-free closed forms in the tile loops
     const double* y;       // M (shared) or B x M when y_stride != 0
     long y_stride;
     const double* diag;    // err_y^2 + diag_factor*eps, length M
@@ -113,6 +114,7 @@ struct BatchedParams {
     double* workspace;     // per-CTA tile storage
     size_t ws_per_cta;     // in doubles
     int* counter;          // dynamic theta scheduler
+    long long* phase_cycles;  // optional (8): per-phase cycle sums, only with -DGPT_PHASE_TIMING
 };
 size_t batched_ws_doubles_per_cta(int nT);
 int batched_max_ctas(int device);

@@ -569,7 +569,7 @@ class GaussianProcess(object):
         free_mask = ~np.asarray(self.fixed_params[:], dtype=bool)
         all_params[:, free_mask] = thetas
         hp = self.hyperprior
-        logp = np.array([hp(p) for p in all_params], dtype=float)
+        logp = np.asarray(hp.logpdf_batch(all_params), dtype=float)
         ok = np.isfinite(logp)
         y_batch = None
         if self.mu is not None and self.mu.num_free_params > 0:
@@ -608,9 +608,8 @@ class GaussianProcess(object):
             finally:
                 self.mu.params[:] = saved
         free_idx = np.nonzero(free_mask)[0]
-        for b in np.nonzero(good)[0]:
-            for i, pi in enumerate(free_idx):
-                g[b, i] += hp(all_params[b], hyper_deriv=int(pi))
+        for i, pi in enumerate(free_idx):
+            g[good, i] += hp.dlogpdf_batch(all_params[good], int(pi))
         g[~good] = 0.0
         return neg_ll, -g
 

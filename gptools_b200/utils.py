@@ -44,9 +44,14 @@ class JointPrior(object):
     def __mul__(self, other):
         return ProductJointPrior(self, other)
 
-    # batched evaluation used by the many-theta entry points (not in the reference)
+    # batched evaluation used by the many-theta entry points (not in the reference); subclasses vectorise
     def logpdf_batch(self, thetas):
+        """log-pdf of every row of ``thetas`` (B, num_params) -> (B,)."""
         return np.array([self(t) for t in np.atleast_2d(thetas)], dtype=float)
+
+    def dlogpdf_batch(self, thetas, hyper_deriv):
+        """d log-pdf / d theta[hyper_deriv] for every row -> (B,)."""
+        return np.array([self(t, hyper_deriv=hyper_deriv) for t in np.atleast_2d(thetas)], dtype=float)
 
 
 class CombinedBounds(object):
@@ -159,6 +164,18 @@ class ProductJointPrior(JointPrior):
             return self.p2(t2, hyper_deriv=hyper_deriv - n1)
         return self.p1(t1) + self.p2(t2)
 
+    def logpdf_batch(self, thetas):
+        thetas = np.atleast_2d(thetas)
+        n1 = len(self.p1.bounds)
+        return self.p1.logpdf_batch(thetas[:, :n1]) + self.p2.logpdf_batch(thetas[:, n1:])
+
+    def dlogpdf_batch(self, thetas, hyper_deriv):
+        thetas = np.atleast_2d(thetas)
+        n1 = len(self.p1.bounds)
+        if hyper_deriv < n1:
+            return self.p1.dlogpdf_batch(thetas[:, :n1], hyper_deriv)
+        return self.p2.dlogpdf_batch(thetas[:, n1:], hyper_deriv - n1)
+
     def sample_u(self, q):
         q1, q2, _ = self._split(q)
         return np.concatenate((self.p1.sample_u(q1), self.p2.sample_u(q2)))
@@ -206,6 +223,22 @@ class UniformJointPrior(JointPrior):
             else:
                 return -np.inf
         return ll
+
+    def logpdf_batch(self, thetas):
+        thetas = np.atleast_2d(thetas)
+        nb = min(thetas.shape[1], len(self.bounds))
+        if nb == 0:
+            return np.zeros(thetas.shape[0])
+        lo = np.array([self.bounds[i][0] for i in range(nb)], dtype=float)
+        hi = np.array([self.bounds[i][1] for i in range(nb)], dtype=float)
+        inside = ((thetas[:, :nb] >= lo) & (thetas[:, :nb] <= hi)).all(axis=1)
+        ll = 0.0
+        for width in (hi - lo):           # same accumulation order as the scalar call
+            ll += -np.log(width)
+        return np.where(inside, ll, -np.inf)
+
+    def dlogpdf_batch(self, thetas, hyper_deriv):
+        return np.zeros(np.atleast_2d(thetas).shape[0])
 
     def sample_u(self, q):
         q = _check_unit_vector(q, len(self.bounds))
@@ -276,6 +309,13 @@ class _StatsPrior(JointPrior):
         for v, d in zip(theta, self._dists()):
             ll += d.logpdf(v)
         return ll
+
+    def logpdf_batch(self, thetas):
+        thetas = np.atleast_2d(thetas)
+        ll = 0
+        for j, d in enumerate(self._dists()):
+            ll = ll + d.logpdf(thetas[:, j])
+        return np.asarray(ll, dtype=float) * np.ones(thetas.shape[0])
 
     @property
     def bounds(self):

@@ -89,3 +89,39 @@ if __name__ == "__main__":
         K = A @ A.T + M * np.eye(M)
         assert run(K, rs.randn(M))
     print("tile model OK")
+
+
+def gj_inverse_factor(A):
+    """Model of potrf_inv_tile (batched.cu): in-place sweep returning X = chol(A)^{-1} and the pivots d.
+    Position (r, c): for c > j still holds the Schur complement a_rc, for c <= j holds e_rc = (L_unit^{-1})_rc."""
+    n = A.shape[0]
+    V = np.tril(A).copy()
+    d = np.zeros(n)
+    for j in range(n):
+        w = np.empty(n)
+        w[j:] = V[j:, j]          # column j of the current Schur complement (incl. pivot)
+        w[:j] = V[j, :j]          # row j of L_unit^{-1}
+        d[j] = w[j]
+        invd = 1.0 / d[j]
+        for r in range(j + 1, n):
+            mult = w[r] * invd
+            for c in range(r + 1):
+                if c == j:
+                    V[r, c] = -mult
+                else:
+                    V[r, c] -= mult * w[c]
+    rs = 1.0 / np.sqrt(d)
+    X = np.tril(V, -1) * rs[:, None] + np.diag(rs)
+    return X, d
+
+
+if __name__ == "__main__":
+    rs_ = np.random.RandomState(1)
+    for n in (1, 5, 64):
+        B = rs_.randn(n, n)
+        A = B @ B.T + n * np.eye(n)
+        X, d = gj_inverse_factor(A)
+        Lc = np.linalg.cholesky(A)
+        assert np.allclose(X, np.linalg.inv(Lc), rtol=1e-10, atol=1e-12)
+        assert np.allclose(0.5 * np.log(d).sum(), np.log(np.diag(Lc)).sum())
+    print("gj_inverse_factor OK")
