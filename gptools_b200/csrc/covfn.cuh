@@ -117,12 +117,29 @@ GPT_HD double exp_nonpos_nobranch(double x) {
 
 // se_dim_factor restricted to m in {0, 1, 2}, written with selects only (no branches).
 GPT_HD void se_dim_factor_low(double tau, double inv_l, int m, double& f, double& g) {
+    // written as guarded assignments: the compiler predicates the three short bodies, so only the arithmetic
+    // of the order that is actually present runs on the FP64 pipe
     const double il2 = inv_l * inv_l;
     const double u = tau * tau * il2;
-    const double f1 = -tau * il2, f2 = il2 * (u - 1.0);
-    const double g0 = u * inv_l, g1 = tau * il2 * inv_l * (2.0 - u), g2 = il2 * inv_l * (2.0 + u * (u - 5.0));
-    f = (m == 0) ? 1.0 : ((m == 1) ? f1 : f2);
-    g = (m == 0) ? g0 : ((m == 1) ? g1 : g2);
+    f = 1.0;
+    g = u * inv_l;
+    if (m == 1) {
+        f = -tau * il2;
+        g = tau * il2 * inv_l * (2.0 - u);
+    }
+    if (m == 2) {
+        f = il2 * (u - 1.0);
+        g = il2 * inv_l * (2.0 + u * (u - 5.0));
+    }
+}
+
+// value-only variant (K-tile generation does not need the length-scale derivative factor)
+GPT_HD double se_dim_value_low(double tau, double inv_l, int m) {
+    const double il2 = inv_l * inv_l;
+    double f = 1.0;
+    if (m == 1) f = -tau * il2;
+    if (m == 2) f = il2 * (tau * tau * il2 - 1.0);
+    return f;
 }
 
 GPT_HD void cov_params_init(CovParams& cp, int kid, int D, int nparams, const double* params) {

@@ -119,3 +119,6 @@ struct BatchedParams {
 size_t batched_ws_doubles_per_cta(int nT);
 int batched_max_ctas(int device);
 void launch_ll_batched(const BatchedParams& p, int num_ctas, cudaStream_t s);
+// batched4.cu : second-generation kernel, 4 CTAs (= 4 thetas) per SM
+int batched4_ctas_per_sm();
+void launch_ll_batched4(const BatchedParams& p, int num_ctas, cudaStream_t s);

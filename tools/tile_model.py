@@ -125,3 +125,47 @@ if __name__ == "__main__":
         assert np.allclose(X, np.linalg.inv(Lc), rtol=1e-10, atol=1e-12)
         assert np.allclose(0.5 * np.log(d).sum(), np.log(np.diag(Lc)).sum())
     print("gj_inverse_factor OK")
+
+
+def blocked_gj_inverse_factor(A, b=8):
+    """Model of the BLOCKED sweep (batched4.cu potrf_inv_tile): 8x8 pivot blocks, every rank-8 update a pair of
+    DMMAs, in place.  Position (I,K): K > J Schur complement; (I,J) panel L_IJ then Y_IJ; K < J: Y_IK / X_JK."""
+    n = A.shape[0]
+    nb = n // b
+    V = np.tril(A).copy()
+    for i in range(nb):           # keep the diagonal blocks symmetric-full like the tile in shared memory
+        V[i*b:(i+1)*b, i*b:(i+1)*b] = A[i*b:(i+1)*b, i*b:(i+1)*b]
+    B = lambda I, K: V[I*b:(I+1)*b, K*b:(K+1)*b]
+    logdet = 0.0
+    def diag8(P):
+        X, d = gj_inverse_factor(P)
+        return X, 0.5 * np.log(np.prod(d))
+    X0, ld = diag8(B(0, 0)); B(0, 0)[:] = X0; logdet += ld
+    for J in range(nb):
+        Xp = B(J, J).copy()
+        for K in range(J):                      # (b) X_JK = Xp Y_JK
+            B(J, K)[:] = Xp @ B(J, K)
+        for I in range(J + 1, nb):              # (c) L_IJ = V_IJ Xp^T
+            B(I, J)[:] = B(I, J) @ Xp.T
+        for I in range(J + 1, nb):              # (d) trailing, (e) inverse part
+            for K in range(J + 1, I + 1):
+                B(I, K)[:] -= B(I, J) @ B(K, J).T
+            for K in range(J):
+                B(I, K)[:] -= B(I, J) @ B(J, K)
+        for I in range(J + 1, nb):              # (e') Y_IJ = -L_IJ Xp
+            B(I, J)[:] = -B(I, J) @ Xp
+        if J + 1 < nb:                          # (a) next pivot block
+            Xn, ld = diag8(B(J + 1, J + 1)); B(J + 1, J + 1)[:] = Xn; logdet += ld
+    return np.tril(V), logdet
+
+
+if __name__ == "__main__":
+    rs_ = np.random.RandomState(2)
+    for n in (8, 16, 64):
+        Bm = rs_.randn(n, n)
+        A = Bm @ Bm.T + n * np.eye(n)
+        X, ld = blocked_gj_inverse_factor(A)
+        Lc = np.linalg.cholesky(A)
+        assert np.allclose(X, np.linalg.inv(Lc), rtol=1e-10, atol=1e-12), n
+        assert np.allclose(ld, np.log(np.diag(Lc)).sum())
+    print("blocked_gj_inverse_factor OK")
