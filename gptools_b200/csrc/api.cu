@@ -46,7 +46,7 @@ struct gpt_handle {
     bool factor_valid = false;
     CovParams cp;
     double noise_sigma = 0.0;
-    DevBuf A, Klat, W, Inv, P, z, zt, alpha, logdet, info, scal;
+    DevBuf A, Klat, W, Inv, P, Pres, z, zt, alpha, logdet, info, scal;
     // gradient workspaces
     DevBuf XT, Kinv, S, partials, gout, u, Sg, Yt;
     // predict workspaces
@@ -111,8 +111,8 @@ int supported_kernel(int kid, int D, int nparams) {
 // Blocked right-looking Cholesky of the nblk*128 square matrix A (lower), in place.  Writes the
 // inverses of the diagonal blocks to inv (nblk x 128 x 128), per-block log-det shares, info, and
 // (optionally) overwrites rhs with L^{-1} rhs.  All heavy work is DMMA GEMM (gemm.cu).
-int blocked_potrf(gpt_handle* h, double* A, long ld, int nblk, double* inv, double* panel, double* rhs,
-                  double* logdet, int* info) {
+int blocked_potrf(gpt_handle* h, double* A, long ld, int nblk, double* inv, double* panel, double* resid,
+                  double* rhs, double* logdet, int* info) {
     cudaStream_t s = h->stream;
     CUDA_OK(h, cudaMemsetAsync(info, 0, sizeof(int), s));
     for (int k = 0; k < nblk; k++) {
@@ -122,14 +122,31 @@ int blocked_potrf(gpt_handle* h, double* A, long ld, int nblk, double* inv, doub
         h->launches++;
         const int rest = nblk - k - 1;
         if (rest > 0) {
+            double* A21 = A + (long)(k + 1) * NB * ld + (long)k * NB;
+            // panel P = A21 L11^{-T} through the explicit block inverse (a DMMA GEMM) ...
             GemmParams g;
             g.C = panel; g.ldc = NB;
-            g.A = A + (long)(k + 1) * NB * ld + (long)k * NB; g.lda = ld;
+            g.A = A21; g.lda = ld;
             g.B = inv_k; g.ldb = NB;
             g.tiles_m = rest; g.tiles_n = 1; g.K = NB;
             g.alpha = 1.0; g.beta = 0.0; g.lower_only = 0; g.kbegin_row = 0;
             launch_gemm_nt(g, s);
-            launch_copy2d(A + (long)(k + 1) * NB * ld + (long)k * NB, ld, panel, NB, rest * NB, NB, s);
+            // ... plus one step of iterative refinement, P += (A21 - P L11^T) L11^{-T}: multiplying by an explicit
+            // inverse alone loses cond(L11)*eps, which matters for the nearly singular covariances draw_sample factors
+            launch_copy2d(resid, NB, A21, ld, rest * NB, NB, s);
+            GemmParams r1 = g;
+            r1.C = resid; r1.ldc = NB;
+            r1.A = panel; r1.lda = NB;
+            r1.B = Akk; r1.ldb = ld;
+            r1.alpha = -1.0; r1.beta = 1.0;
+            launch_gemm_nt(r1, s);
+            GemmParams r2 = g;
+            r2.C = panel; r2.ldc = NB;
+            r2.A = resid; r2.lda = NB;
+            r2.B = inv_k; r2.ldb = NB;
+            r2.alpha = 1.0; r2.beta = 1.0;
+            launch_gemm_nt(r2, s);
+            launch_copy2d(A21, ld, panel, NB, rest * NB, NB, s);
             if (rhs) launch_panel_gemv(panel, rest * NB, rhs + (long)k * NB, rhs + (long)(k + 1) * NB, s);
             GemmParams u;
             u.C = A + (long)(k + 1) * NB * ld + (long)(k + 1) * NB; u.ldc = ld;
@@ -138,7 +155,7 @@ int blocked_potrf(gpt_handle* h, double* A, long ld, int nblk, double* inv, doub
             u.tiles_m = rest; u.tiles_n = rest; u.K = NB;
             u.alpha = -1.0; u.beta = 1.0; u.lower_only = 1; u.kbegin_row = 0;
             launch_gemm_nt(u, s);
-            h->launches += rhs ? 4 : 3;
+            h->launches += rhs ? 7 : 6;
         }
     }
     return check_launch(h);
@@ -178,6 +195,7 @@ int factor_and_solve(gpt_handle* h, double* ll, int* status) {
     int rc;
     if ((rc = ensure(h, h->Inv, (size_t)nblk * NB * NB * sizeof(double)))) return rc;
     if ((rc = ensure(h, h->P, (size_t)Mp * NB * sizeof(double)))) return rc;
+    if ((rc = ensure(h, h->Pres, (size_t)Mp * NB * sizeof(double)))) return rc;
     if ((rc = ensure(h, h->z, (size_t)Mp * sizeof(double)))) return rc;
     if ((rc = ensure(h, h->zt, (size_t)Mp * sizeof(double)))) return rc;
     if ((rc = ensure(h, h->alpha, (size_t)Mp * sizeof(double)))) return rc;
@@ -186,7 +204,7 @@ int factor_and_solve(gpt_handle* h, double* ll, int* status) {
     CUDA_OK(h, cudaMemsetAsync(h->z.p, 0, (size_t)Mp * sizeof(double), s));
     CUDA_OK(h, cudaMemcpyAsync(h->z.p, h->y.p, (size_t)M * sizeof(double), cudaMemcpyDeviceToDevice, s));
     if ((rc = blocked_potrf(h, ptr<double>(h->A), Mp, nblk, ptr<double>(h->Inv), ptr<double>(h->P),
-                            ptr<double>(h->z), ptr<double>(h->logdet), ptr<int>(h->info))))
+                            ptr<double>(h->Pres), ptr<double>(h->z), ptr<double>(h->logdet), ptr<int>(h->info))))
         return rc;
     CUDA_OK(h, cudaMemcpyAsync(h->zt.p, h->z.p, (size_t)Mp * sizeof(double), cudaMemcpyDeviceToDevice, s));
     for (int k = nblk - 1; k >= 0; k--) {
@@ -364,7 +382,7 @@ void gpt_destroy(gpt_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf* all[] = {&h->X, &h->n, &h->y, &h->diag, &h->T, &h->Tt, &h->A, &h->Klat, &h->W, &h->Inv, &h->P, &h->z,
+    DevBuf* all[] = {&h->X, &h->n, &h->y, &h->diag, &h->T, &h->Tt, &h->A, &h->Klat, &h->W, &h->Inv, &h->P, &h->Pres, &h->z,
                      &h->zt, &h->alpha, &h->logdet, &h->info, &h->scal, &h->XT, &h->Kinv, &h->S, &h->partials,
                      &h->gout, &h->u, &h->Sg, &h->Yt, &h->Xs, &h->ns, &h->Kst, &h->Kso, &h->kss, &h->mean, &h->var,
                      &h->cov, &h->Rt, &h->smp, &h->b_thetas, &h->b_y, &h->b_ll, &h->b_grad, &h->b_status,
@@ -747,6 +765,29 @@ int gpt_predict(gpt_handle* h, int Ms, const double* Xs, const int32_t* ns, doub
     while (!cov && CH > NB && (size_t)CH * (Np + Mp) * sizeof(double) > ((size_t)8 << 30)) CH = round_up(CH / 2, NB);
     if ((rc = upload(h, h->Xs, Xs, sizeof(double) * (size_t)Ms * D))) return rc;
     if ((rc = upload(h, h->ns, ns, sizeof(int32_t) * (size_t)Ms * D))) return rc;
+    if (!var && !cov) {
+        // mean only: K(X*, X) alpha fused with tile generation, nothing materialised (u = alpha, or T^T alpha)
+        int max_ns = 0;
+        for (size_t i = 0; i < (size_t)Ms * D; i++) max_ns = ns[i] > max_ns ? ns[i] : max_ns;
+        const double* u = ptr<double>(h->alpha);
+        if (h->hasT) {
+            if ((rc = ensure(h, h->u, sizeof(double) * Np))) return rc;
+            launch_rowdot(ptr<double>(h->Tt), Mp, N, M, ptr<double>(h->alpha), ptr<double>(h->u), s);
+            h->launches++;
+            u = ptr<double>(h->u);
+        }
+        const int nsplit = predict_mean_nsplit(N, Ms);
+        if ((rc = ensure(h, h->Kst, sizeof(double) * (size_t)nsplit * Ms))) return rc;
+        if ((rc = ensure(h, h->mean, sizeof(double) * (size_t)round_up(Ms, NB)))) return rc;
+        launch_predict_mean_fused(h->cp, ptr<double>(h->X), ptr<int32_t>(h->n), u, N, ptr<double>(h->Xs),
+                                  ptr<int32_t>(h->ns), Ms, (h->max_order <= 1 && max_ns <= 1) ? 1 : 0,
+                                  ptr<double>(h->Kst), ptr<double>(h->mean), s);
+        h->launches += 2;
+        if ((rc = check_launch(h))) return rc;
+        CUDA_OK(h, cudaMemcpyAsync(mean, h->mean.p, sizeof(double) * Ms, cudaMemcpyDeviceToHost, s));
+        CUDA_OK(h, cudaStreamSynchronize(s));
+        return 0;
+    }
     if ((rc = ensure(h, h->Kst, sizeof(double) * (size_t)CH * Np))) return rc;
     if (h->hasT && (rc = ensure(h, h->Kso, sizeof(double) * (size_t)CH * Mp))) return rc;
     if ((rc = ensure(h, h->mean, sizeof(double) * (size_t)round_up(Ms, NB)))) return rc;
@@ -852,13 +893,14 @@ int gpt_draw_sample(gpt_handle* h, int Ms, int S, const double* mean, const doub
     cudaStream_t s = h->stream;
     const int Sp = round_up(Ms, NB), nblk = Sp / NB, Rp = round_up(S, NB);
     int rc;
-    DevBuf C, inv, panel, logdet, info, R, Rt, O, mu, jit;
-    auto cleanup = [&]() { release(C); release(inv); release(panel); release(logdet); release(info); release(R);
+    DevBuf C, inv, panel, resid, logdet, info, R, Rt, O, mu, jit;
+    auto cleanup = [&]() { release(C); release(inv); release(panel); release(resid); release(logdet); release(info); release(R);
                            release(Rt); release(O); release(mu); release(jit); };
     std::vector<double> hj(Ms, jitter);
     if ((rc = upload_padded(h, C, cov, Ms, Ms, Sp, Sp)) || (rc = upload(h, jit, hj.data(), sizeof(double) * Ms)) ||
         (rc = ensure(h, inv, sizeof(double) * (size_t)nblk * NB * NB)) ||
-        (rc = ensure(h, panel, sizeof(double) * (size_t)Sp * NB)) || (rc = ensure(h, logdet, sizeof(double) * nblk)) ||
+        (rc = ensure(h, panel, sizeof(double) * (size_t)Sp * NB)) || (rc = ensure(h, resid, sizeof(double) * (size_t)Sp * NB)) ||
+        (rc = ensure(h, logdet, sizeof(double) * nblk)) ||
         (rc = ensure(h, info, sizeof(int))) || (rc = upload_padded(h, R, rand_vars, Ms, S, Sp, Rp)) ||
         (rc = ensure(h, Rt, sizeof(double) * (size_t)Rp * Sp)) || (rc = ensure(h, O, sizeof(double) * (size_t)Sp * Rp)) ||
         (rc = upload(h, mu, mean, sizeof(double) * Ms))) {
@@ -867,8 +909,8 @@ int gpt_draw_sample(gpt_handle* h, int Ms, int S, const double* mean, const doub
     }
     launch_add_diag(ptr<double>(C), Sp, ptr<double>(jit), Ms, s);
     launch_set_identity_pad(ptr<double>(C), Sp, Ms, Sp, s);
-    rc = blocked_potrf(h, ptr<double>(C), Sp, nblk, ptr<double>(inv), ptr<double>(panel), nullptr, ptr<double>(logdet),
-                       ptr<int>(info));
+    rc = blocked_potrf(h, ptr<double>(C), Sp, nblk, ptr<double>(inv), ptr<double>(panel), ptr<double>(resid), nullptr,
+                       ptr<double>(logdet), ptr<int>(info));
     if (!rc) {
         dim3 tg((Sp + 255) / 256, Sp);
         tril_kernel<<<tg, 256, 0, s>>>(ptr<double>(C), Sp, Sp);

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
     __syncthreads();
     for (int idx = tid; idx < NB * NB; idx += 256) {
         const int r = idx >> 7, c = idx & (NB - 1);
-        if (c <= r) A[(long)r * lda + c] = Lb[r * LDB + c];
+        A[(long)r * lda + c] = (c <= r) ? Lb[r * LDB + c] : 0.0;  // clean lower-triangular block (a GEMM operand later)
     }
     if (tid < 32) {
         double s = 0.0;

@@ -89,6 +89,11 @@ void launch_trace_and_sumsq(const double* A, long lda, const double* v, int n, d
 void launch_rowdot(const double* Kst, long ld, int rows, int n, const double* alpha, double* mean, cudaStream_t s);
 // var[s] = kss[s] - sum_{c<n} V[s][c]^2
 void launch_row_var(const double* V, long ld, int rows, int n, const double* kss, double* var, cudaStream_t s);
+// fused predictive mean (K* never stored): mean[s] = sum_i k(X_i, x*_s) u_i; partial: nsplit x Ms scratch
+int predict_mean_nsplit(int N, int Ms);
+void launch_predict_mean_fused(const CovParams& cp, const double* X, const int32_t* n, const double* u, int N,
+                               const double* Xs, const int32_t* ns, int Ms, int low_order, double* partial,
+                               double* mean, cudaStream_t s);
 // kss[s] = k(x*_s, x*_s) with orders ns
 void launch_prior_diag(const CovParams& cp, const double* Xs, const int32_t* ns, int rows, double* kss, cudaStream_t s);
 

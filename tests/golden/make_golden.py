@@ -215,6 +215,32 @@ def case_gibbs():
     save("gibbs_c5_small", params=k.params.copy(), **gp_state(gp), **out)
 
 
+# ---------------------------------------------------------------- config 5 at full size (4001 latent -> 501 observations)
+def case_c5_full():
+    k = g.GibbsKernel1dTanh(initial_params=[1.5, 0.6, 0.1, 0.05, 0.9],
+                            param_bounds=[(0, 10), (0, 5), (0, 5), (0, 1), (0, 2)])
+    rs = RandomState(0)
+    Nq, Mo, W = 4000, 500, 400
+    Xq = np.linspace(0, 1.1, Nq)
+    T = np.zeros((Mo, Nq))
+    starts = rs.randint(0, Nq - W, size=Mo)
+    for i, s in enumerate(starts):
+        T[i, s:s + W] = 1.1 / Nq
+    yy = rs.rand(Mo) * 0.3 + 0.1
+    gp = g.GaussianProcess(k)
+    gp.add_data(Xq, yy, err_y=0.02, T=T)
+    gp.add_data(0, 0, n=1)
+    gp.compute_K_L_alpha_ll()
+    Xs = np.linspace(0, 1.1, 400)
+    res = gp.predict(Xs, full_output=True)
+    rv = rs.randn(400, 4)
+    draw = gp.draw_sample(Xs, rand_vars=rv, method="cholesky", mean=res["mean"], cov=res["cov"])
+    # inputs are regenerated by the test from the same seeds (T alone is 16 MB); only results are stored
+    save("gibbs_c5_full", params=k.params.copy(), starts=starts, y=gp.y, ll=gp.ll, log_prior=gp.hyperprior(gp.params),
+         alpha=gp.alpha.ravel(), Xs=Xs, mean=res["mean"], std=res["std"], cov_diag=np.diag(res["cov"]).copy(),
+         rand_vars=rv, draw=draw)
+
+
 # ---------------------------------------------------------------- KAT-4: demo / config 1
 def case_demo():
     with open(os.path.join(REF_ROOT, "demo", "sample_data_core.pkl"), "rb") as f:
@@ -332,6 +358,7 @@ if __name__ == "__main__":
     case_matern52()
     case_matern_generic()
     case_gibbs()
+    case_c5_full()
     case_demo()
     case_c3()
     case_c2()
