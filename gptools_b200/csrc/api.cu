@@ -28,6 +28,8 @@ struct gpt_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t side_stream = nullptr;  // lookahead stream of the blocked Cholesky
+    cudaEvent_t ev_col = nullptr, ev_panel = nullptr;
     std::string err;
     int64_t launches = 0;
 
@@ -111,16 +113,36 @@ int supported_kernel(int kid, int D, int nparams) {
 // Blocked right-looking Cholesky of the nblk*128 square matrix A (lower), in place.  Writes the
 // inverses of the diagonal blocks to inv (nblk x 128 x 128), per-block log-det shares, info, and
 // (optionally) overwrites rhs with L^{-1} rhs.  All heavy work is DMMA GEMM (gemm.cu).
-int blocked_potrf(gpt_handle* h, double* A, long ld, int nblk, double* inv, double* panel, double* resid,
+// Blocked right-looking Cholesky of the nblk*128 square matrix A (lower), in place, with one-block LOOKAHEAD:
+// the trailing update of step k is split into the strip that finalises block column k+1 and the rest; the
+// (serial) diagonal-block factorisation and the panel of step k+1 run on a side stream while the rest of the
+// step-k update keeps the machine busy.  panel / resid hold TWO panels (double buffered).  Writes the inverses of
+// the diagonal blocks to inv (nblk x 128 x 128), per-block log-det shares, info, and (optionally) overwrites rhs
+// with L^{-1} rhs.  All heavy work is DMMA GEMM (gemm.cu).
+int blocked_potrf(gpt_handle* h, double* A, long ld, int nblk, double* inv, double* panel2, double* resid,
                   double* rhs, double* logdet, int* info) {
-    cudaStream_t s = h->stream;
-    CUDA_OK(h, cudaMemsetAsync(info, 0, sizeof(int), s));
+    cudaStream_t sm = h->stream;
+    if (!h->side_stream) {
+        // highest priority: its few CTAs are placed as soon as an SM frees up, ahead of the queued update tiles
+        int prio_lo = 0, prio_hi = 0;
+        CUDA_OK(h, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CUDA_OK(h, cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, prio_hi));
+        CUDA_OK(h, cudaEventCreateWithFlags(&h->ev_col, cudaEventDisableTiming));
+        CUDA_OK(h, cudaEventCreateWithFlags(&h->ev_panel, cudaEventDisableTiming));
+    }
+    cudaStream_t ss = h->side_stream;
+    CUDA_OK(h, cudaMemsetAsync(info, 0, sizeof(int), sm));
+    // the side stream starts after everything queued so far on the main stream (assembly, rhs set-up)
+    CUDA_OK(h, cudaEventRecord(h->ev_col, sm));
     for (int k = 0; k < nblk; k++) {
         double* Akk = A + (long)k * NB * ld + (long)k * NB;
         double* inv_k = inv + (size_t)k * NB * NB;
-        launch_potrf_diag(Akk, ld, inv_k, rhs ? rhs + (long)k * NB : nullptr, logdet + k, info, k * NB, NB, s);
-        h->launches++;
+        double* panel = panel2 + (size_t)(k & 1) * (size_t)nblk * NB * NB;
         const int rest = nblk - k - 1;
+        // ---- side stream: diagonal block + panel of step k (needs block column k final: ev_col) ----
+        CUDA_OK(h, cudaStreamWaitEvent(ss, h->ev_col, 0));
+        launch_potrf_diag(Akk, ld, inv_k, rhs ? rhs + (long)k * NB : nullptr, logdet + k, info, k * NB, NB, ss);
+        h->launches++;
         if (rest > 0) {
             double* A21 = A + (long)(k + 1) * NB * ld + (long)k * NB;
             // panel P = A21 L11^{-T} through the explicit block inverse (a DMMA GEMM) ...
@@ -130,34 +152,53 @@ int blocked_potrf(gpt_handle* h, double* A, long ld, int nblk, double* inv, doub
             g.B = inv_k; g.ldb = NB;
             g.tiles_m = rest; g.tiles_n = 1; g.K = NB;
             g.alpha = 1.0; g.beta = 0.0; g.lower_only = 0; g.kbegin_row = 0;
-            launch_gemm_nt(g, s);
+            launch_gemm_nt(g, ss);
             // ... plus one step of iterative refinement, P += (A21 - P L11^T) L11^{-T}: multiplying by an explicit
             // inverse alone loses cond(L11)*eps, which matters for the nearly singular covariances draw_sample factors
-            launch_copy2d(resid, NB, A21, ld, rest * NB, NB, s);
+            launch_copy2d(resid, NB, A21, ld, rest * NB, NB, ss);
             GemmParams r1 = g;
             r1.C = resid; r1.ldc = NB;
             r1.A = panel; r1.lda = NB;
             r1.B = Akk; r1.ldb = ld;
             r1.alpha = -1.0; r1.beta = 1.0;
-            launch_gemm_nt(r1, s);
+            launch_gemm_nt(r1, ss);
             GemmParams r2 = g;
             r2.C = panel; r2.ldc = NB;
             r2.A = resid; r2.lda = NB;
             r2.B = inv_k; r2.ldb = NB;
             r2.alpha = 1.0; r2.beta = 1.0;
-            launch_gemm_nt(r2, s);
-            launch_copy2d(A21, ld, panel, NB, rest * NB, NB, s);
-            if (rhs) launch_panel_gemv(panel, rest * NB, rhs + (long)k * NB, rhs + (long)(k + 1) * NB, s);
-            GemmParams u;
-            u.C = A + (long)(k + 1) * NB * ld + (long)(k + 1) * NB; u.ldc = ld;
-            u.A = panel; u.lda = NB;
-            u.B = panel; u.ldb = NB;
-            u.tiles_m = rest; u.tiles_n = rest; u.K = NB;
-            u.alpha = -1.0; u.beta = 1.0; u.lower_only = 1; u.kbegin_row = 0;
-            launch_gemm_nt(u, s);
-            h->launches += rhs ? 7 : 6;
+            launch_gemm_nt(r2, ss);
+            launch_copy2d(A21, ld, panel, NB, rest * NB, NB, ss);
+            if (rhs) launch_panel_gemv(panel, rest * NB, rhs + (long)k * NB, rhs + (long)(k + 1) * NB, ss);
+            h->launches += rhs ? 6 : 5;
+        }
+        CUDA_OK(h, cudaEventRecord(h->ev_panel, ss));
+        // ---- main stream: trailing update of step k, next block column first ----
+        CUDA_OK(h, cudaStreamWaitEvent(sm, h->ev_panel, 0));
+        if (rest > 0) {
+            GemmParams c;  // strip: block column k+1, rows >= k+1
+            c.C = A + (long)(k + 1) * NB * ld + (long)(k + 1) * NB; c.ldc = ld;
+            c.A = panel; c.lda = NB;
+            c.B = panel; c.ldb = NB;
+            c.tiles_m = rest; c.tiles_n = 1; c.K = NB;
+            c.alpha = -1.0; c.beta = 1.0; c.lower_only = 0; c.kbegin_row = 0;
+            launch_gemm_nt(c, sm);
+            CUDA_OK(h, cudaEventRecord(h->ev_col, sm));
+            h->launches++;
+            if (rest > 1) {
+                GemmParams u;  // rest: block columns >= k+2 (lower tiles only)
+                u.C = A + (long)(k + 2) * NB * ld + (long)(k + 2) * NB; u.ldc = ld;
+                u.A = panel + (size_t)NB * NB; u.lda = NB;
+                u.B = panel + (size_t)NB * NB; u.ldb = NB;
+                u.tiles_m = rest - 1; u.tiles_n = rest - 1; u.K = NB;
+                u.alpha = -1.0; u.beta = 1.0; u.lower_only = 1; u.kbegin_row = 0;
+                launch_gemm_nt(u, sm);
+                h->launches++;
+            }
         }
     }
+    // join: nothing is left running on the side stream that the main stream has not waited for (ev_panel of the
+    // last step), so work queued on the main stream after this call sees the complete factor
     return check_launch(h);
 }
 
@@ -194,7 +235,7 @@ int factor_and_solve(gpt_handle* h, double* ll, int* status) {
     const int Mp = h->Mp, M = h->M, nblk = Mp / NB;
     int rc;
     if ((rc = ensure(h, h->Inv, (size_t)nblk * NB * NB * sizeof(double)))) return rc;
-    if ((rc = ensure(h, h->P, (size_t)Mp * NB * sizeof(double)))) return rc;
+    if ((rc = ensure(h, h->P, (size_t)2 * Mp * NB * sizeof(double)))) return rc;
     if ((rc = ensure(h, h->Pres, (size_t)Mp * NB * sizeof(double)))) return rc;
     if ((rc = ensure(h, h->z, (size_t)Mp * sizeof(double)))) return rc;
     if ((rc = ensure(h, h->zt, (size_t)Mp * sizeof(double)))) return rc;
@@ -388,6 +429,12 @@ void gpt_destroy(gpt_handle* h) {
                      &h->cov, &h->Rt, &h->smp, &h->b_thetas, &h->b_y, &h->b_ll, &h->b_grad, &h->b_status,
                      &h->b_alpha, &h->b_ws, &h->b_counter};
     for (DevBuf* b : all) release(*b);
+    if (h->side_stream) {
+        cudaStreamSynchronize(h->side_stream);
+        cudaStreamDestroy(h->side_stream);
+        cudaEventDestroy(h->ev_col);
+        cudaEventDestroy(h->ev_panel);
+    }
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -899,7 +946,7 @@ int gpt_draw_sample(gpt_handle* h, int Ms, int S, const double* mean, const doub
     std::vector<double> hj(Ms, jitter);
     if ((rc = upload_padded(h, C, cov, Ms, Ms, Sp, Sp)) || (rc = upload(h, jit, hj.data(), sizeof(double) * Ms)) ||
         (rc = ensure(h, inv, sizeof(double) * (size_t)nblk * NB * NB)) ||
-        (rc = ensure(h, panel, sizeof(double) * (size_t)Sp * NB)) || (rc = ensure(h, resid, sizeof(double) * (size_t)Sp * NB)) ||
+        (rc = ensure(h, panel, sizeof(double) * (size_t)2 * Sp * NB)) || (rc = ensure(h, resid, sizeof(double) * (size_t)Sp * NB)) ||
         (rc = ensure(h, logdet, sizeof(double) * nblk)) ||
         (rc = ensure(h, info, sizeof(int))) || (rc = upload_padded(h, R, rand_vars, Ms, S, Sp, Rp)) ||
         (rc = ensure(h, Rt, sizeof(double) * (size_t)Rp * Sp)) || (rc = ensure(h, O, sizeof(double) * (size_t)Sp * Rp)) ||

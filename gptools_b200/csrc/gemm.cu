@@ -4,8 +4,10 @@
 // form the blocked Cholesky / trtri / lauum / T K T^T / triangular-solve paths need (symmetric
 // operands and pre-transposed inverses make every product NT).
 //
-// Tile 128x128x16, 256 threads = 8 warps (2 x 4), warp tile 64x32 = 8x4 DMMA.8x8x4 tiles,
-// 3-stage cp.async pipeline.  Shared rows are padded to 20 doubles: the fragment read
+// CTA tile 128x64x16, 128 threads = 4 warps (2 x 2), warp tile 64x32 = 8x4 DMMA.8x8x4 tiles,
+// 3-stage cp.async pipeline, TWO CTAs per SM: the read-modify-write epilogue of one CTA (an L2/HBM round trip with
+// the accumulators pinned in registers) overlaps the main loop of the other.  A 128x128 CTA alone on the SM
+// spent ~20% of a K=128 rank update in that epilogue (profiles/r01f_gemm_notes.txt).  Shared rows are padded to 20 doubles: the fragment read
 // A[g][k0+t] then maps the 16 lanes of a half-warp to 16 distinct 8-byte banks (g*20+t mod 16
 // = 4g+t), i.e. conflict-free LDS.64 for both operands.
 // Roofline: FP64 tensor pipe (measured cuBLAS Dgemm 35.5 TFLOP/s on this pool's B200).
@@ -14,14 +16,14 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 3, LDS_ = BK + 4;
-constexpr int THREADS = 256;
+constexpr int BM = 128, BN = 64, BK = 16, STAGES = 3, LDS_ = BK + 4;
+constexpr int THREADS = 128;
 constexpr size_t SMEM_BYTES = (size_t)STAGES * (BM + BN) * LDS_ * sizeof(double);
 
-__global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(GemmParams p) {
+__global__ void __launch_bounds__(THREADS, 2) gemm_nt_kernel(GemmParams p) {
     extern __shared__ __align__(16) double smem[];
     const int bm = blockIdx.y, bn = blockIdx.x;
-    if (p.lower_only && bn > bm) return;
+    if (p.lower_only && bn > 2 * bm + 1) return;  // bn counts 64-wide half tiles; diagonal 128-blocks are full
     const int kstart = p.kbegin_row ? bm * BM : 0;
     const int nk = (p.K - kstart) / BK;
     const double* __restrict__ Ag = p.A + (long)bm * BM * p.lda + kstart;
@@ -32,7 +34,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(GemmParams p) {
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int wm = warp >> 2, wn = warp & 3;
+    const int wm = warp >> 1, wn = warp & 1;
 
     auto load_stage = [&](int stage, int kc) {
         double* a_dst = sA + stage * BM * LDS_;
@@ -48,6 +50,16 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(GemmParams p) {
             cp_async16(b_dst + r * LDS_ + c, Bg + (long)r * p.ldb + kc * BK + c);
         }
     };
+
+    // The C tile is read only in the epilogue; all CTAs of a wave reach it together, which turns the 128 KB
+    // read-modify-write per tile into an HBM burst with the tensor pipe idle.  Pull the tile into L2 now so
+    // the fetch overlaps the main loop (the operands are L2 resident panels).
+    if (p.beta != 0.0) {
+        const char* cbase = reinterpret_cast<const char*>(p.C + (long)bm * BM * p.ldc + (long)bn * BN);
+#pragma unroll
+        for (int i = tid; i < BM * 4; i += THREADS)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(cbase + (long)(i >> 2) * p.ldc * 8 + (i & 3) * 128));
+    }
 
     double acc[8][4][2];
 #pragma unroll
@@ -86,21 +98,37 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(GemmParams p) {
     // epilogue: each lane owns C[g][2t], C[g][2t+1] of every 8x8 tile -> one 16-byte store
     const long row0 = (long)bm * BM + wm * 64 + g;
     const long col0 = (long)bn * BN + wn * 32 + 2 * t;
+    if (p.beta != 0.0) {
+        // read-modify-write in batches of 8 independent 16-byte loads per lane: issued back to back they cost one
+        // L2 round trip per batch instead of one per element (stores may alias the loads as far as nvcc knows)
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
+        for (int i0 = 0; i0 < 8; i0 += 2) {
+            double2 old[2][4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            double2* dst = reinterpret_cast<double2*>(p.C + (row0 + i * 8) * p.ldc + col0 + j * 8);
-            double2 v;
-            v.x = p.alpha * acc[i][j][0];
-            v.y = p.alpha * acc[i][j][1];
-            if (p.beta != 0.0) {
-                const double2 old = *dst;
-                v.x += p.beta * old.x;
-                v.y += p.beta * old.y;
-            }
-            *dst = v;
+            for (int ii = 0; ii < 2; ii++)
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    old[ii][j] = __ldcg(reinterpret_cast<const double2*>(p.C + (row0 + (i0 + ii) * 8) * p.ldc + col0 + j * 8));
+#pragma unroll
+            for (int ii = 0; ii < 2; ii++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    double2 v;
+                    v.x = p.alpha * acc[i0 + ii][j][0] + p.beta * old[ii][j].x;
+                    v.y = p.alpha * acc[i0 + ii][j][1] + p.beta * old[ii][j].y;
+                    *reinterpret_cast<double2*>(p.C + (row0 + (i0 + ii) * 8) * p.ldc + col0 + j * 8) = v;
+                }
         }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                double2 v;
+                v.x = p.alpha * acc[i][j][0];
+                v.y = p.alpha * acc[i][j][1];
+                *reinterpret_cast<double2*>(p.C + (row0 + i * 8) * p.ldc + col0 + j * 8) = v;
+            }
     }
 }
 
@@ -109,6 +137,6 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_nt_kernel(GemmParams p) {
 void launch_gemm_nt(const GemmParams& p, cudaStream_t s) {
     cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (p.tiles_m <= 0 || p.tiles_n <= 0) return;
-    dim3 grid(p.tiles_n, p.tiles_m);
+    dim3 grid(p.tiles_n * (128 / BN), p.tiles_m);
     gemm_nt_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(p);
 }
