@@ -12,105 +12,196 @@
 namespace {
 
 constexpr int NB = GPT_NB;
-constexpr int LDB = NB + 1;
-constexpr size_t POTRF_SMEM = ((size_t)NB * LDB + 3 * NB) * sizeof(double);
+constexpr int LDB = NB + 4;  // stride == 4 (mod 16): conflict-free DMMA fragment loads from the block
+constexpr int NBLK = NB / 8;
+constexpr size_t POTRF_SMEM = ((size_t)NB * LDB + 2 * NB) * sizeof(double);
+
+// ---- 128x128 diagonal block: blocked in-place Gauss-Jordan sweep on 8x8 sub-blocks ------------------------------
+// The first version of this kernel eliminated one column per __syncthreads with scalar FP64 (207 us per block,
+// and it sits on the critical path of the blocked Cholesky: 13% of an M = 24576 factorisation, all of an M = 4000
+// one).  Here everything except the sixteen 8x8 pivot factorisations is an 8x8x8 product = two DMMA.8x8x4
+// (same scheme as batched4.cu::potrf_inv_tile, tools/tile_model.py: blocked_gj_inverse_factor).
+// In-place layout of V while pivot block J is processed:
+//   (I,K), K > J : Schur complement;  (I,J): panel L_IJ (also written to A), later Y_IJ = -L_IJ Xp_J;
+//   K < J: Y_IK (rows > J) / X_JK (rows <= J, final inverse).
+__device__ __forceinline__ double* blk8(double* V, int I, int K) { return V + (8 * I) * LDB + 8 * K; }
+
+// C (8x8, in place) = sc * C + sa * A * B^T (nt) or sc * C + sa * A * B (nn); one warp.  G != null: also to global.
+template <bool NN>
+__device__ __forceinline__ void blk_mma(double* C, const double* A, const double* B, double sa, double sc, int g,
+                                        int t, double* G = nullptr, long ldg = 0) {
+    const double a0 = sa * A[g * LDB + t], a1 = sa * A[g * LDB + 4 + t];
+    double b0, b1;
+    if (NN) {
+        b0 = B[t * LDB + g];
+        b1 = B[(4 + t) * LDB + g];
+    } else {
+        b0 = B[g * LDB + t];
+        b1 = B[g * LDB + 4 + t];
+    }
+    double2 c = make_double2(0.0, 0.0);
+    if (sc != 0.0) {
+        c = *reinterpret_cast<const double2*>(C + g * LDB + 2 * t);
+        c.x *= sc;
+        c.y *= sc;
+    }
+    dmma884(c.x, c.y, a0, b0);
+    dmma884(c.x, c.y, a1, b1);
+    *reinterpret_cast<double2*>(C + g * LDB + 2 * t) = c;
+    if (G) *reinterpret_cast<double2*>(G + g * ldg + 2 * t) = c;
+}
+
+// Pivot block P (8x8 SPD, lower valid): in place -> chol(P)^{-1} (zeros above the diagonal); chol(P) itself goes
+// to the global block G (zeros above).  Every lane of one warp redundantly, fully unrolled in registers.
+// Returns sum(log L_ii).
+__device__ __forceinline__ double pivot8(double* P, double* G, long ldg, int lane, int row0, int* s_info) {
+    double p[8][8], lc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) p[i][j] = P[i * LDB + j];
+    double dsave[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        double d = p[j][j];
+        if (!(d > 0.0)) {
+            if (lane == 0 && *s_info == 0) *s_info = row0 + j + 1;
+            d = 1.0;
+        }
+        dsave[j] = d;
+        const double rinv = __drcp_rn(d);
+        double w[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) w[c] = (c > j) ? p[c][j] : ((c < j) ? p[j][c] : 0.0);
+#pragma unroll
+        for (int r = j + 1; r < 8; r++) lc[r][j] = w[r];  // unscaled column j of the Cholesky factor
+#pragma unroll
+        for (int r = j + 1; r < 8; r++) {
+            const double mult = w[r] * rinv;
+#pragma unroll
+            for (int c = 0; c <= r; c++) {
+                if (c == j) p[r][c] = -mult;
+                else p[r][c] -= mult * w[c];
+            }
+        }
+    }
+    double rs[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) rs[i] = 1.0 / sqrt(dsave[i]);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const double xval = (j < i) ? p[i][j] * rs[i] : ((j == i) ? rs[i] : 0.0);
+            const double lval = (j < i) ? lc[i][j] * rs[j] : ((j == i) ? dsave[i] * rs[i] : 0.0);
+            if (lane == ((i * 8 + j) & 31)) {
+                P[i * LDB + j] = xval;
+                G[i * ldg + j] = lval;
+            }
+        }
+    }
+    // one log per lane (lanes 0..7), summed over the warp: sum(log L_ii) = 1/2 sum(log d_i)
+    double mine = 1.0;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        if (lane == i) mine = dsave[i];
+    return 0.5 * warp_sum(log(mine));
+}
 
 __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__ A, long lda, double* __restrict__ inv,
                                                             double* __restrict__ yk, double* __restrict__ logdet_part,
                                                             int* __restrict__ info, int row0) {
     extern __shared__ __align__(16) double sm[];
-    double* Lb = sm;                 // NB x LDB; lower: L, strict upper: (L^{-1})^T
-    double* dvec = sm + NB * LDB;    // pivots d_j, then sqrt(d_j)
-    double* xdiag = dvec + NB;       // 1 / L_jj
-    double* yv = xdiag + NB;
+    double* V = sm;                  // NB x LDB
+    double* yv = sm + NB * LDB;      // right-hand side block
     __shared__ int s_info;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
 
     for (int idx = tid; idx < NB * NB; idx += 256) {
         const int r = idx >> 7, c = idx & (NB - 1);
-        Lb[r * LDB + c] = (c <= r) ? A[(long)r * lda + c] : 0.0;
+        V[r * LDB + c] = (c <= r) ? A[(long)r * lda + c] : 0.0;
     }
+    if (tid < NB && yk != nullptr) yv[tid] = yk[tid];
     if (tid == 0) s_info = 0;
     __syncthreads();
+    // the factor is a GEMM operand later: the blocks above the block diagonal must be clean zeros
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+        const int r = idx >> 7, c = idx & (NB - 1);
+        if ((c >> 3) > (r >> 3)) A[(long)r * lda + c] = 0.0;
+    }
+    double logacc = 0.0;  // warp 7
+    if (warp == 7) logacc = pivot8(blk8(V, 0, 0), A, lda, lane, row0, &s_info);
+    __syncthreads();
 
-    // right-looking elimination on the unscaled columns: a_ic -= a_ij a_cj / d_j  (i >= c > j)
-    const int ta = tid >> 4, tb = tid & 15;
-    for (int j = 0; j < NB - 1; j++) {
-        double d = Lb[j * LDB + j];
-        if (!(d > 0.0)) {
-            if (tid == 0 && s_info == 0) s_info = row0 + j + 1;
-            d = 1.0;
+#pragma unroll 1
+    for (int J = 0; J < NBLK; J++) {
+        const double* Xp = blk8(V, J, J);
+        // ---- phase A: multiply by the pivot inverses.  Items:
+        //   [0, J)            : X_JK = Xp_J Y_JK (K < J); for K = J-1 first Y_{J,J-1} = -L_{J,J-1} Xp_{J-1}
+        //   [J, J+n)          : L_IJ = V_IJ Xp_J^T (I > J), the final factor -> also to A
+        //   [J+n, J+2n)       : Y_{I,J-1} = -L_{I,J-1} Xp_{J-1} (I > J), the deferred last stage of step J-1
+        const int n = NBLK - 1 - J;
+        const int nitems = J + n + (J > 0 ? n : 0);
+        for (int item = warp; item < nitems; item += 8) {
+            if (item < J) {
+                const int K = item;
+                if (K == J - 1) {
+                    blk_mma<true>(blk8(V, J, K), blk8(V, J, K), blk8(V, J - 1, J - 1), -1.0, 0.0, g, t);
+                    __syncwarp();
+                }
+                blk_mma<true>(blk8(V, J, K), Xp, blk8(V, J, K), 1.0, 0.0, g, t);
+            } else if (item < J + n) {
+                const int I = J + 1 + (item - J);
+                blk_mma<false>(blk8(V, I, J), blk8(V, I, J), Xp, 1.0, 0.0, g, t, A + (long)(8 * I) * lda + 8 * J, lda);
+            } else {
+                const int I = J + 1 + (item - J - n);
+                blk_mma<true>(blk8(V, I, J - 1), blk8(V, I, J - 1), blk8(V, J - 1, J - 1), -1.0, 0.0, g, t);
+            }
         }
-        const double invd = 1.0 / d;
-        for (int i = j + 1 + ta; i < NB; i += 16) {
-            const double lij = Lb[i * LDB + j] * invd;
-            for (int c = j + 1 + tb; c <= i; c += 16) Lb[i * LDB + c] -= lij * Lb[c * LDB + j];
+        __syncthreads();
+        if (J + 1 == NBLK) break;
+        // ---- phase B: warp 7 finalises and factors the next pivot block while the others apply the rank-8 update
+        if (warp == 7) {
+            blk_mma<false>(blk8(V, J + 1, J + 1), blk8(V, J + 1, J), blk8(V, J + 1, J), -1.0, 1.0, g, t);
+            __syncwarp();
+            logacc += pivot8(blk8(V, J + 1, J + 1), A + (long)(8 * (J + 1)) * lda + 8 * (J + 1), lda, lane,
+                             row0 + 8 * (J + 1), &s_info);
+        } else {
+            int cnt = 0;
+            for (int I = J + 1; I < NBLK; I++) {
+                for (int K = J + 1; K <= I; K++) {
+                    if (I == J + 1) continue;  // (J+1, J+1) belongs to warp 7
+                    if ((cnt++ % 7) == warp)
+                        blk_mma<false>(blk8(V, I, K), blk8(V, I, J), blk8(V, K, J), -1.0, 1.0, g, t);
+                }
+                for (int K = 0; K < J; K++)
+                    if ((cnt++ % 7) == warp)
+                        blk_mma<true>(blk8(V, I, K), blk8(V, I, J), blk8(V, J, K), -1.0, 1.0, g, t);
+            }
         }
         __syncthreads();
     }
-    if (tid < NB) {
-        double d = Lb[tid * LDB + tid];
-        if (!(d > 0.0)) {
-            // pivots j < NB-1 were already flagged (in order) inside the loop; only the last is new here
-            if (tid == NB - 1 && s_info == 0) s_info = row0 + NB;
-            d = 1.0;
-        }
-        dvec[tid] = sqrt(d);
-        xdiag[tid] = 1.0 / dvec[tid];
-    }
-    __syncthreads();
-    for (int idx = tid; idx < NB * NB; idx += 256) {
-        const int r = idx >> 7, c = idx & (NB - 1);
-        if (c < r) Lb[r * LDB + c] *= xdiag[c];
-        else if (c == r) Lb[r * LDB + c] = dvec[r];
-    }
-    __syncthreads();
-    for (int idx = tid; idx < NB * NB; idx += 256) {
-        const int r = idx >> 7, c = idx & (NB - 1);
-        A[(long)r * lda + c] = (c <= r) ? Lb[r * LDB + c] : 0.0;  // clean lower-triangular block (a GEMM operand later)
-    }
-    if (tid < 32) {
-        double s = 0.0;
-        for (int j = tid; j < NB; j += 32) s += log(dvec[j]);
-        s = warp_sum(s);
-        if (tid == 0) {
-            *logdet_part = s;
-            if (s_info != 0) atomicCAS(info, 0, s_info);
-        }
-    }
 
-    // X = L^{-1}, column j owned by the lane pair (2j, 2j+1); X^T kept in the strict upper triangle.
-    {
-        const int j = tid >> 1, h = tid & 1;
-        const double xjj = xdiag[j];
-        for (int i = 1; i < NB; i++) {
-            double s = 0.0;
-            if (i > j) {
-                for (int m = j + h; m < i; m += 2) {
-                    const double x = (m == j) ? xjj : Lb[j * LDB + m];
-                    s += Lb[i * LDB + m] * x;
-                }
-            }
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            if (i > j && h == 0) Lb[j * LDB + i] = -s * xdiag[i];
-            __syncwarp();
-        }
-    }
-    __syncthreads();
+    // V now holds X = L^{-1} in its lower block triangle (diagonal blocks carry their own zeros)
     for (int idx = tid; idx < NB * NB; idx += 256) {
         const int r = idx >> 7, c = idx & (NB - 1);
-        inv[r * NB + c] = (c < r) ? Lb[c * LDB + r] : ((c == r) ? xdiag[r] : 0.0);
+        inv[r * NB + c] = ((c >> 3) <= (r >> 3)) ? V[r * LDB + c] : 0.0;
     }
     if (yk != nullptr) {
-        if (tid < NB) yv[tid] = yk[tid];
-        __syncthreads();
-        if (tid < NB) {
-            double s = xdiag[tid] * yv[tid];
-            for (int c = 0; c < tid; c++) s += Lb[c * LDB + tid] * yv[c];
-            yk[tid] = s;
-        }
+        // z_k = X y_k : two lanes per row
+        const int r = tid >> 1, h = tid & 1;
+        double sacc = 0.0;
+        for (int c = h; c <= r; c += 2) sacc += V[r * LDB + c] * yv[c];
+        sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+        if (h == 0) yk[r] = sacc;
+    }
+    if (tid == 7 * 32) {
+        *logdet_part = logacc;
+        if (s_info != 0) atomicCAS(info, 0, s_info);
     }
 }
+
 
 __global__ void __launch_bounds__(256) panel_gemv_kernel(const double* __restrict__ P, int rows,
                                                          const double* __restrict__ zk, double* __restrict__ y) {
