@@ -335,13 +335,13 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": "config 3: batched ll+grad, SE 2-D kernel, M=512 obs (256 values + 2x128 first "
                                    "derivatives), P=3 free params",
                        "thetas_per_gpu": B, "global_batch": B * world, "parallelism": "theta-sharded x%d" % world,
-                       "l2": "per-CTA factor workspace 296 x 1.44 MB = 427 MB > 126 MB L2 (no flush needed)",
+                       "l2": "per-CTA factor workspace 592 x 1.44 MB = 853 MB > 126 MB L2 (no flush needed)",
                        "results_ok": ok},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
                          "frac": achieved / peak_tflops if peak_tflops else None, "traffic": traffic,
-                         "kernel": "ll_batched_kernel", "kernel_ms": kernel_ms,
+                         "kernel": "ll_batched4_kernel", "kernel_ms": kernel_ms,
                          "flop_per_launch": B * FLOP_PER_EVAL,
                          "peak_source": "cuBLAS Dgemm 8192^3 fp64 measured live in this run (MEASURED_PEAKS.json "
                                         "has no FP64 entry); DMMA issue peak 37.1 TFLOP/s (profiles/r01_fp64_peak_microbench.txt)"},
