@@ -532,7 +532,8 @@ int gpt_cov_pairs(gpt_handle* h, int kernel_id, int D, int nparams, const double
                   double* out) {
     if (!h || !params || npairs < 0) return fail(h, GPT_ERR_USAGE, "gpt_cov_pairs: bad arguments");
     if (!supported_kernel(kernel_id, D, nparams)) return fail(h, GPT_ERR_UNSUPPORTED, "gpt_cov_pairs: unsupported kernel");
-    if (hyper_deriv >= 0 && kernel_id != GPT_SE) return fail(h, GPT_ERR_UNSUPPORTED, "hyper_deriv: SE only");
+    if (hyper_deriv >= nparams || (hyper_deriv == 1 && kernel_id == GPT_KERNEL_MATERN))
+        return fail(h, GPT_ERR_UNSUPPORTED, "hyper_deriv: index out of range, or d/dnu of the Matern kernel");
     if (npairs == 0) return 0;
     CUDA_OK(h, cudaSetDevice(h->device));
     CovParams cp;
@@ -560,7 +561,8 @@ int gpt_compute_Kij(gpt_handle* h, int kernel_id, int D, int nparams, const doub
                     double* K_out) {
     if (!h || !params || Mi < 1 || !Xi || !ni || !K_out) return fail(h, GPT_ERR_USAGE, "gpt_compute_Kij: bad arguments");
     if (!supported_kernel(kernel_id, D, nparams)) return fail(h, GPT_ERR_UNSUPPORTED, "gpt_compute_Kij: unsupported kernel");
-    if (hyper_deriv >= 0 && kernel_id != GPT_SE) return fail(h, GPT_ERR_UNSUPPORTED, "hyper_deriv: SE only");
+    if (hyper_deriv >= nparams || (hyper_deriv == 1 && kernel_id == GPT_KERNEL_MATERN))
+        return fail(h, GPT_ERR_UNSUPPORTED, "hyper_deriv: index out of range, or d/dnu of the Matern kernel");
     CUDA_OK(h, cudaSetDevice(h->device));
     const bool sym = (Xj == nullptr);
     if (sym) Mj = Mi;
@@ -605,8 +607,8 @@ int gpt_ll(gpt_handle* h, const double* params, double noise_sigma, double* ll, 
         if (P > GPT_MAX_PARAMS || !grad_idx) return fail(h, GPT_ERR_USAGE, "gpt_ll: bad gradient request");
         for (int q = 0; q < P; q++) {
             if (grad_idx[q] < 0 || grad_idx[q] > h->nparams) return fail(h, GPT_ERR_USAGE, "gpt_ll: bad grad_idx");
-            if (grad_idx[q] < h->nparams && h->kid != GPT_SE)
-                return fail(h, GPT_ERR_UNSUPPORTED, "hyper-parameter derivatives: SquaredExponentialKernel only");
+            if (grad_idx[q] == 1 && h->kid == GPT_KERNEL_MATERN)
+                return fail(h, GPT_ERR_UNSUPPORTED, "hyper-parameter derivatives: d/dnu of the Matern kernel is not available");
         }
     }
     CUDA_OK(h, cudaSetDevice(h->device));
@@ -1010,14 +1012,17 @@ static int batched_common(gpt_handle* h, int B, const double* d_thetas, const do
     bp.nidx = (d_grad && P > 0) ? P : 0;
     for (int q = 0; q < bp.nidx; q++) {
         if (grad_idx[q] < 0 || grad_idx[q] > h->nparams) return fail(h, GPT_ERR_USAGE, "gpt_ll_batched: bad grad_idx");
-        if (grad_idx[q] < h->nparams && h->kid != GPT_SE)
-            return fail(h, GPT_ERR_UNSUPPORTED, "hyper-parameter derivatives: SquaredExponentialKernel only");
+        if (grad_idx[q] == 1 && h->kid == GPT_KERNEL_MATERN)
+            return fail(h, GPT_ERR_UNSUPPORTED, "hyper-parameter derivatives: d/dnu of the Matern kernel is not available");
+        if (h->kid != GPT_KERNEL_SE && grad_idx[q] < h->nparams && grad_idx[q] >= 1 + GPT_MAX_DIM)
+            return fail(h, GPT_ERR_UNSUPPORTED, "gpt_ll_batched: hyper-parameter index beyond the batched gradient slots");
         bp.idx[q] = grad_idx[q];
     }
     bp.ll = d_ll; bp.grad = d_grad; bp.status = d_status; bp.alpha_out = d_alpha;
     // GPT_BATCHED_IMPL=2 selects the first-generation kernel (2 CTAs x 8 warps per SM) for A/B comparisons
     bool gen4 = true;
     if (const char* e = getenv("GPT_BATCHED_IMPL")) gen4 = (atoi(e) != 2);
+    if (h->kid != GPT_KERNEL_SE && bp.nidx > 0) gen4 = true;  // Matern / Gibbs hyper-derivatives exist in batched4.cu only
     int ctas;
     if (gen4) {
         int sms = 148;

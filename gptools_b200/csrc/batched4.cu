@@ -339,6 +339,9 @@ __device__ __forceinline__ void gen_ktot_tile(const Smem& sm, const BatchedParam
     const int c = tid & (TB - 1);
     const int gj = Jc * TB + c;
     if constexpr (FD == 0) {
+        unsigned want = 0;  // requested kernel parameters (bit q), gall has 1 + GPT_MAX_DIM slots
+        for (int q = 0; q < p.nidx; q++)
+            if (p.idx[q] < p.nparams && p.idx[q] < 1 + GPT_MAX_DIM) want |= 1u << p.idx[q];
 #pragma unroll 1
         for (int u = 0; u < 32; u++) {
             const int r = (tid >> 6) + 2 * u;
@@ -395,6 +398,9 @@ __device__ __forceinline__ void grad_tile(const Smem& sm, const BatchedParams& p
     if (gj >= p.M) return;
     const double aj = avec[gj];
     if constexpr (FD == 0) {
+        unsigned want = 0;  // requested kernel parameters (bit q), gall has 1 + GPT_MAX_DIM slots
+        for (int q = 0; q < p.nidx; q++)
+            if (p.idx[q] < p.nparams && p.idx[q] < 1 + GPT_MAX_DIM) want |= 1u << p.idx[q];
 #pragma unroll 1
         for (int u = 0; u < 32; u++) {
             const int r = (tid >> 6) + 2 * u;
@@ -406,12 +412,21 @@ __device__ __forceinline__ void grad_tile(const Smem& sm, const BatchedParams& p
                 tr_kinv += kinv;
                 w *= 0.5;
             }
-            double dk[2 + GPT_MAX_DIM];
-            se_cov_all(sm.cp, p.X + (size_t)gi * p.D, p.n + (size_t)gi * p.D, p.X + (size_t)gj * p.D,
-                       p.n + (size_t)gj * p.D, dk);
+            if (sm.cp.kid == GPT_KERNEL_SE) {
+                double dk[2 + GPT_MAX_DIM];
+                se_cov_all(sm.cp, p.X + (size_t)gi * p.D, p.n + (size_t)gi * p.D, p.X + (size_t)gj * p.D,
+                           p.n + (size_t)gj * p.D, dk);
 #pragma unroll
-            for (int q = 0; q < 1 + GPT_MAX_DIM; q++)
-                if (q <= p.D) gall[q] += w * dk[1 + q];
+                for (int q = 0; q < 1 + GPT_MAX_DIM; q++)
+                    if (q <= p.D) gall[q] += w * dk[1 + q];
+            } else {
+                // Matern / Gibbs: dual-number closed forms (covfn_hyper.cuh), only the requested parameters
+#pragma unroll
+                for (int q = 0; q < 1 + GPT_MAX_DIM; q++)
+                    if ((want >> q) & 1u)
+                        gall[q] += w * cov_hyper_eval(sm.cp, p.X + (size_t)gi * p.D, p.n + (size_t)gi * p.D,
+                                                      p.X + (size_t)gj * p.D, p.n + (size_t)gj * p.D, q);
+            }
         }
     } else {
         const SEHoist<FD> h = se_hoist<FD>(sm.cp);

@@ -478,11 +478,14 @@ GPT_HD double gibbs_cov(const CovParams& cp, const double* xi, const int32_t* ni
     return gibbs_cov_l(cp, xi[0], lx, lx1, ni[0], xj[0], ly, ly1, nj[0]);
 }
 
+#include "covfn_hyper.cuh"
+
 // ------------------------------------------------------------------------------------------
 // dispatch
 // ------------------------------------------------------------------------------------------
 GPT_HD double cov_eval(const CovParams& cp, const double* xi, const int32_t* ni, const double* xj,
                        const int32_t* nj, int hyper_deriv) {
+    if (hyper_deriv >= 0 && cp.kid != GPT_KERNEL_SE) return cov_hyper_eval(cp, xi, ni, xj, nj, hyper_deriv);
     switch (cp.kid) {
         case GPT_KERNEL_SE: return se_cov(cp, xi, ni, xj, nj, hyper_deriv);
         case GPT_KERNEL_MATERN52: return matern52_cov(cp, xi, ni, xj, nj);

@@ -16,6 +16,27 @@ int gpt_hostcheck_cov_pairs(int kid, int D, int nparams, const double* params, i
     return 0;
 }
 
+// dual-number evaluation of the non-SE kernels: value component (must equal the value path bit for bit) and
+// derivative component with respect to params[hyper_deriv]
+int gpt_hostcheck_cov_dual(int kid, int D, int nparams, const double* params, int hyper_deriv, long npairs,
+                           const double* Xi, const double* Xj, const int32_t* ni, const int32_t* nj, double* out_v,
+                           double* out_d) {
+    if (D > GPT_MAX_DIM || nparams > GPT_MAX_PARAMS || kid == GPT_KERNEL_SE) return -1;
+    CovParams cp;
+    cov_params_init(cp, kid, D, nparams, params);
+    for (long p = 0; p < npairs; p++) {
+        const double *xi = Xi + p * D, *xj = Xj + p * D;
+        const int32_t *mi = ni + p * D, *mj = nj + p * D;
+        GptDual r;
+        if (kid == GPT_KERNEL_MATERN52) r = matern52_cov_dual(cp, xi, mi, xj, mj, hyper_deriv);
+        else if (kid == GPT_KERNEL_MATERN) r = matern_cov_dual(cp, xi, mi, xj, mj, hyper_deriv);
+        else r = gibbs_cov_dual(cp, xi, mi, xj, mj, hyper_deriv);
+        out_v[p] = r.v;
+        out_d[p] = r.d;
+    }
+    return 0;
+}
+
 // out is (npairs, 2 + D): value, d/dsigma, d/dl_1..d/dl_D
 int gpt_hostcheck_se_all(int D, const double* params, long npairs, const double* Xi, const double* Xj,
                          const int32_t* ni, const int32_t* nj, double* out) {

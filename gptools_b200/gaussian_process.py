@@ -389,8 +389,8 @@ class GaussianProcess(object):
         ni = np.atleast_2d(np.asarray(ni, dtype=int))
         desc = k.device_descriptor()
         if desc is not None:
-            if hyper_deriv is not None and not k.supports_hyper_deriv:
-                raise NotImplementedError("Hyperparameter derivatives have not been implemented!")
+            if hyper_deriv is not None:
+                k.check_hyper_deriv([int(hyper_deriv)])
             k._check_orders(ni, ni if nj is None else np.atleast_2d(np.asarray(nj, dtype=int)))
             if Xj is None:
                 return self._dev().compute_Kij(desc[0], desc[1], Xi, ni, hyper_deriv=hyper_deriv)
@@ -431,8 +431,7 @@ class GaussianProcess(object):
             kid, kparams = self.k.device_descriptor()
             grad_idx = None
             if want_grad:
-                if not self.k.supports_hyper_deriv and nk_free > 0:
-                    raise NotImplementedError("Hyperparameter derivatives have not been implemented!")
+                self.k.check_hyper_deriv(list(self.k.free_param_idxs))
                 grad_idx = list(self.k.free_param_idxs)
                 if nn_free > 0:
                     grad_idx.append(len(kparams))
@@ -583,8 +582,7 @@ class GaussianProcess(object):
                 self.mu.params[:] = saved
         grad_idx = None
         if with_deriv:
-            if not self.k.supports_hyper_deriv and nk > 0:
-                raise NotImplementedError("Hyperparameter derivatives have not been implemented!")
+            self.k.check_hyper_deriv(list(kfree))
             grad_idx = list(kfree) + ([nparams] if nn > 0 else [])
         need_alpha = with_deriv and self.mu is not None and self.mu.num_free_params > 0
         full_eval = np.where(ok[:, None], full, np.tile(np.concatenate([kparams, [self._noise_sigma()]]), (B, 1)))

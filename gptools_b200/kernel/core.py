@@ -81,9 +81,15 @@ class DeviceKernel(Kernel):
     def _check_orders(self, ni, nj):
         pass
 
-    def __call__(self, Xi, Xj, ni, nj, hyper_deriv=None, symmetric=False):
-        if hyper_deriv is not None and not self.supports_hyper_deriv:
+    def check_hyper_deriv(self, idxs):
+        """Raise NotImplementedError (the reference's exception, kernel/core.py:723) when the derivative with
+        respect to any of the parameter indices ``idxs`` is not available on the device."""
+        if len(idxs) > 0 and not self.supports_hyper_deriv:
             raise NotImplementedError("Hyperparameter derivatives have not been implemented!")
+
+    def __call__(self, Xi, Xj, ni, nj, hyper_deriv=None, symmetric=False):
+        if hyper_deriv is not None:
+            self.check_hyper_deriv([int(hyper_deriv)])
         Xi = np.atleast_2d(np.asarray(Xi, dtype=float))
         Xj = np.atleast_2d(np.asarray(Xj, dtype=float))
         ni = np.atleast_2d(np.asarray(ni, dtype=int))

@@ -18,9 +18,12 @@ def tanh_warp(x, n, l1, l2, lw, x0):
 
 class GibbsKernel1dTanh(DeviceKernel):
     r"""k = sigma_f^2 sqrt(2 l(x) l(x') / (l(x)^2 + l(x')^2)) exp(-(x - x')^2 / (l(x)^2 + l(x')^2));
-    params = [sigma_f, l1, l2, lw, x0] (kernel/gibbs.py:244-505).  Derivative orders up to (1, 1)."""
+    params = [sigma_f, l1, l2, lw, x0] (kernel/gibbs.py:244-505).  Derivative orders up to (1, 1).
+    ``hyper_deriv`` is supported for all five parameters (the reference raises NotImplementedError,
+    kernel/gibbs.py:319): dual-number closed forms on the device (csrc/covfn_hyper.cuh)."""
 
     kernel_id = 3
+    supports_hyper_deriv = True
 
     def __init__(self, **kwargs):
         if kwargs.get('num_dim', 1) != 1:

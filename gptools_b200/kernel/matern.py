@@ -8,9 +8,13 @@ __all__ = ["Matern52Kernel", "MaternKernel"]
 
 class Matern52Kernel(DeviceKernel):
     r"""Matern nu = 5/2, value and first derivatives only; params = [sigma_f, l_1, ..., l_D]
-    (kernel/matern.py:468-555; closed forms of kernel/src/matern.c:61-186 in ``matern52_cov``)."""
+    (kernel/matern.py:468-555; closed forms of kernel/src/matern.c:61-186 in ``matern52_cov``).
+
+    ``hyper_deriv`` is supported (the reference raises NotImplementedError, kernel/matern.py:543): the closed
+    forms are re-evaluated in dual numbers on the device (csrc/covfn_hyper.cuh)."""
 
     kernel_id = 1
+    supports_hyper_deriv = True
 
     def __init__(self, num_dim=1, **kwargs):
         names = [r'\sigma_f'] + ['l_{:d}'.format(i + 1) for i in range(num_dim)]
@@ -28,9 +32,16 @@ class MaternKernel(DeviceKernel):
     The device function ``matern_cov`` reproduces the reference's behaviour -- including its one-term
     power series for derivative orders >= 1 when 0 < 2 nu r^2 <= 5e-4 (utils.py:1493-1516) and the origin
     limits (kernel/matern.py:444-457) -- for half-integer nu and total derivative order <= 2 per pair,
-    which covers value + first-derivative observations and predictions."""
+    which covers value + first-derivative observations and predictions.  ``hyper_deriv`` is supported for
+    sigma_f and the length scales (dual numbers, csrc/covfn_hyper.cuh); nu must be a fixed parameter then."""
 
     kernel_id = 2
+    supports_hyper_deriv = True
+
+    def check_hyper_deriv(self, idxs):
+        if 1 in [int(i) for i in idxs]:
+            raise NotImplementedError("The derivative with respect to nu is not available: fix nu "
+                                      "(fixed_params=[False, True, ...]) to use hyperparameter derivatives")
 
     def __init__(self, num_dim=1, **kwargs):
         names = [r'\sigma_f', r'\nu'] + ['l_{:d}'.format(i + 1) for i in range(num_dim)]

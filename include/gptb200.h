@@ -61,7 +61,8 @@ int gpt_set_y(gpt_handle* h, const double* y);
 int gpt_set_kernel(gpt_handle* h, int kernel_id, int nparams, double diag_factor);
 
 /* Kernel.__call__ on flattened pair lists (kernel/core.py:220-257): out[p] = k(Xi[p], Xj[p]; ni[p], nj[p]).
- * hyper_deriv = -1 for the value, else the index into params (SE only). Independent of set_data. */
+ * hyper_deriv = -1 for the value, else the index into params (every kernel; d/dnu of
+ * the generic Matern kernel is GPT_ERR_UNSUPPORTED). Independent of set_data. */
 int gpt_cov_pairs(gpt_handle* h, int kernel_id, int D, int nparams, const double* params, int hyper_deriv,
                   int64_t npairs, const double* Xi, const double* Xj, const int32_t* ni, const int32_t* nj,
                   double* out);

@@ -352,14 +352,106 @@ def case_noise():
     save("se_diagnoise", params=k.params.copy(), noise_sigma=nk.params.copy(), **gp_state(gp), **out)
 
 
+# ---------------------------------------------------------------- hyper-derivative oracle
+def _fd(f, theta, i, h):
+    """Central difference with one Richardson step: (4 D(h/2) - D(h)) / 3, error O(h^4)."""
+    def D(hh):
+        tp, tm = theta.copy(), theta.copy()
+        tp[i] += hh
+        tm[i] -= hh
+        return (f(tp) - f(tm)) / (2.0 * hh)
+    return (4.0 * D(h / 2.0) - D(h)) / 3.0
+
+
+def _hyperfd(name, gp, idx, rel_h):
+    """The reference raises NotImplementedError for hyper_deriv of these kernels (kernel/matern.py:543,
+    kernel/core.py:723, kernel/gibbs.py:319), so the golden gradient is the finite difference of the
+    reference's own ll (compute_K_L_alpha_ll, hyperprior included -- uniform here, so constant) and K."""
+    k = gp.k
+    theta0 = np.array(k.params, dtype=float)
+
+    def set_theta(th):
+        k.params[:] = th
+        gp.K_up_to_date = False
+
+    def ll(th):
+        set_theta(th)
+        gp.compute_K_L_alpha_ll()
+        return float(gp.ll)
+
+    def Kmat(th):
+        set_theta(th)
+        return np.array(gp.compute_Kij(gp.X, None, gp.n, None))
+
+    grad = np.array([_fd(ll, theta0, i, rel_h * abs(theta0[i])) for i in idx])
+    dK = np.array([_fd(Kmat, theta0, i, rel_h * abs(theta0[i])) for i in idx])
+    set_theta(theta0)
+    gp.compute_K_L_alpha_ll()
+    save(name, params=theta0, idx=np.array(idx, dtype=int), ll=gp.ll, ll_grad_fd=grad, dK_fd=dK,
+         rel_h=rel_h, **gp_state(gp))
+
+
+def case_hyperfd():
+    # Matern 5/2, 1-D, values + derivatives (inputs of matern52_kat2)
+    rs = RandomState(1)
+    X = np.sort(rs.rand(8))
+    k = g.Matern52Kernel(num_dim=1, initial_params=[2.0, 0.4], param_bounds=[(0, 10)] * 2)
+    gp = g.GaussianProcess(k)
+    gp.add_data(X, np.sin(5 * X), err_y=0.02)
+    gp.add_data(X[::2], 5 * np.cos(5 * X[::2]), n=1, err_y=0.05)
+    _hyperfd("hyperfd_matern52_1d", gp, [0, 1], 1e-3)
+    # Matern 5/2, 2-D, value + both gradient components (inputs of matern52_2d_testshape)
+    rs = RandomState(0)
+    X2 = rs.randn(5, 2)
+    ls = np.exp(RandomState(5).randn(2) * 0.5)
+    k2 = g.Matern52Kernel(num_dim=2, initial_params=[1.0, ls[0], ls[1]], param_bounds=[(0, 10)] * 3)
+    gp2 = g.GaussianProcess(k2)
+    gp2.add_data(X2, rs.randn(5), err_y=0.1)
+    gp2.add_data(X2, rs.randn(5), n=np.tile([1, 0], (5, 1)), err_y=0.1)
+    gp2.add_data(X2, rs.randn(5), n=np.tile([0, 1], (5, 1)), err_y=0.1)
+    _hyperfd("hyperfd_matern52_2d", gp2, [0, 1, 2], 1e-3)
+    # generic Matern (nu fixed), smooth inputs (no series-zone pairs: the reference's kvp round-off would
+    # dominate a finite difference there), values + derivatives where nu allows
+    rs = RandomState(3)
+    X = np.sort(rs.rand(14)) * 3.0
+    for nu in (2.5, 3.5, 1.5):
+        k = g.MaternKernel(num_dim=1, initial_params=[1.4, nu, 0.6], param_bounds=[(0, 10)] * 3)
+        gp = g.GaussianProcess(k)
+        gp.add_data(X, np.sin(2 * X), err_y=0.05)
+        if nu > 2:
+            gp.add_data(X[::3], 2 * np.cos(2 * X[::3]), n=1, err_y=0.05)
+        _hyperfd("hyperfd_matern_generic_nu%s" % str(nu).replace(".", "p"), gp, [0, 2], 4e-3)
+    rs = RandomState(4)
+    X2 = rs.rand(8, 2)
+    k = g.MaternKernel(num_dim=2, initial_params=[0.9, 2.5, 0.5, 0.8], param_bounds=[(0, 10)] * 4)
+    gp = g.GaussianProcess(k)
+    gp.add_data(X2, np.sin(X2).sum(1), err_y=0.05)
+    gp.add_data(X2, np.cos(X2[:, 0]), n=np.tile([1, 0], (8, 1)), err_y=0.05)
+    _hyperfd("hyperfd_matern_generic_2d", gp, [0, 2, 3], 4e-3)
+    # Gibbs-tanh: direct observations incl. a derivative, and the T path (inputs of gibbs_kat3)
+    k = g.GibbsKernel1dTanh(initial_params=[1.5, 0.6, 0.1, 0.05, 0.9],
+                            param_bounds=[(0, 10), (0, 5), (0, 5), (0, 1), (0, 2)])
+    Xd = np.linspace(0.05, 1.05, 11)
+    gp = g.GaussianProcess(k)
+    gp.add_data(Xd, 2.5 - 1.5 * np.tanh((Xd - 0.9) / 0.1), err_y=0.05)
+    gp.add_data(Xd[::4], -1.0 * np.ones(3), n=1, err_y=0.3)
+    gp.add_data(0, 0, n=1)
+    _hyperfd("hyperfd_gibbs_direct", gp, [0, 1, 2, 3, 4], 1e-3)
+    k = g.GibbsKernel1dTanh(initial_params=[1.5, 0.6, 0.1, 0.05, 0.9],
+                            param_bounds=[(0, 10), (0, 5), (0, 5), (0, 1), (0, 2)])
+    Xq = np.linspace(0, 1.1, 12)
+    T = np.zeros((3, 12))
+    T[0, :6] = T[1, 3:9] = T[2, 6:] = 1 / 6.0
+    gp = g.GaussianProcess(k)
+    gp.add_data(Xq, [2.5, 2.0, 1.0], err_y=0.05, T=T)
+    gp.add_data(0, 0, n=1)
+    _hyperfd("hyperfd_gibbs_T", gp, [0, 1, 2, 3, 4], 1e-3)
+
+
 if __name__ == "__main__":
-    case_se2d()
-    case_se_pairs()
-    case_matern52()
-    case_matern_generic()
-    case_gibbs()
-    case_c5_full()
-    case_demo()
-    case_c3()
-    case_c2()
-    case_noise()
+    cases = [case_se2d, case_se_pairs, case_matern52, case_matern_generic, case_gibbs, case_c5_full, case_demo,
+             case_c3, case_c2, case_noise, case_hyperfd]
+    only = set(sys.argv[1:])          # e.g. `make_golden.py case_hyperfd` regenerates one family
+    for c in cases:
+        if not only or c.__name__ in only:
+            c()

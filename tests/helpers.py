@@ -53,3 +53,20 @@ def var_tol(cov_diag_prior, rtol=1e-9):
     """predictive variance is a cancellation K** - |v|^2; agreement is bounded by
     rtol * K** (the prior variance), not by rtol * var."""
     return rtol * np.maximum(np.abs(cov_diag_prior), 1e-300)
+
+
+# hyper-derivative goldens: Richardson finite differences of the reference's ll and K (make_golden.py: case_hyperfd)
+HYPERFD_KERNEL = {"hyperfd_matern52_1d": KERNEL_MATERN52, "hyperfd_matern52_2d": KERNEL_MATERN52,
+                  "hyperfd_matern_generic_nu2p5": KERNEL_MATERN, "hyperfd_matern_generic_nu3p5": KERNEL_MATERN,
+                  "hyperfd_matern_generic_nu1p5": KERNEL_MATERN, "hyperfd_matern_generic_2d": KERNEL_MATERN,
+                  "hyperfd_gibbs_direct": KERNEL_GIBBS_TANH, "hyperfd_gibbs_T": KERNEL_GIBBS_TANH}
+
+
+def richardson_fd(f, theta, i, h):
+    """(4 D(h/2) - D(h)) / 3 with D the central difference of f along theta[i]."""
+    def D(hh):
+        tp, tm = np.array(theta, dtype=float), np.array(theta, dtype=float)
+        tp[i] += hh
+        tm[i] -= hh
+        return (f(tp) - f(tm)) / (2.0 * hh)
+    return (4.0 * D(h / 2.0) - D(h)) / 3.0

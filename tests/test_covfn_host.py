@@ -17,13 +17,14 @@ CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
 def lib():
     so = os.path.join(CSRC, "libgptb200_hostcheck.so")
     src = os.path.join(CSRC, "hostcheck.cpp")
-    hdr = os.path.join(CSRC, "covfn.cuh")
-    if (not os.path.exists(so)) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    hdrs = [os.path.join(CSRC, "covfn.cuh"), os.path.join(CSRC, "covfn_hyper.cuh")]
+    if (not os.path.exists(so)) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in [src] + hdrs):
         subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-x", "c++", "-o", so, src, "-lm"])
     L = ctypes.CDLL(so)
     dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int32)
     L.gpt_hostcheck_cov_pairs.argtypes = [ctypes.c_int] * 3 + [dp, ctypes.c_int, ctypes.c_long, dp, dp, ip, ip, dp]
     L.gpt_hostcheck_se_all.argtypes = [ctypes.c_int, dp, ctypes.c_long, dp, dp, ip, ip, dp]
+    L.gpt_hostcheck_cov_dual.argtypes = [ctypes.c_int] * 3 + [dp, ctypes.c_int, ctypes.c_long, dp, dp, ip, ip, dp, dp]
     return L
 
 
@@ -117,3 +118,48 @@ def test_matern_generic_series_zone_is_emulated(lib):
     zone = np.repeat((y > 0) & (y <= 5e-4), 4) & ((ni + nj)[:, 0] == 2)
     assert zone.any() and np.abs(got - k52)[zone].max() > 1e-4      # the series zone really differs
     assert np.abs(got - k52)[~np.repeat((y > 0) & (y <= 5e-4), 4)].max() < 1e-9
+
+
+# ---- hyper-parameter derivatives of the Matern / Gibbs kernels (csrc/covfn_hyper.cuh) ----------
+HYPERFD = {"hyperfd_matern52_1d": 1, "hyperfd_matern52_2d": 1, "hyperfd_matern_generic_nu2p5": 2,
+           "hyperfd_matern_generic_nu3p5": 2, "hyperfd_matern_generic_nu1p5": 2, "hyperfd_matern_generic_2d": 2,
+           "hyperfd_gibbs_direct": 3, "hyperfd_gibbs_T": 3}
+
+
+def dual(lib, kid, params, X, n, hyper_deriv):
+    M, D = X.shape
+    Xi = np.ascontiguousarray(np.repeat(X, M, axis=0), dtype=np.float64)
+    Xj = np.ascontiguousarray(np.tile(X, (M, 1)), dtype=np.float64)
+    ni = np.ascontiguousarray(np.repeat(n, M, axis=0), dtype=np.int32)
+    nj = np.ascontiguousarray(np.tile(n, (M, 1)), dtype=np.int32)
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    v, d = np.empty(M * M), np.empty(M * M)
+    rc = lib.gpt_hostcheck_cov_dual(kid, D, len(params), _ptr(params, ctypes.c_double), hyper_deriv, M * M,
+                                    _ptr(Xi, ctypes.c_double), _ptr(Xj, ctypes.c_double), _ptr(ni, ctypes.c_int32),
+                                    _ptr(nj, ctypes.c_int32), _ptr(v, ctypes.c_double), _ptr(d, ctypes.c_double))
+    assert rc == 0
+    return v.reshape(M, M), d.reshape(M, M)
+
+
+@pytest.mark.parametrize("case", sorted(HYPERFD))
+def test_hyper_derivative_closed_forms_match_reference_finite_differences(lib, case):
+    """dk/dtheta from the dual-number closed forms against the Richardson central difference of the
+    reference's own compute_Kij (the reference has no analytic form to compare with).  Tolerance: 1e-6 of
+    the largest entry -- the finite difference, not the closed form, is the limiting side."""
+    gd = load_golden(case)
+    kid, X, n = HYPERFD[case], gd["X"], gd["n"].astype(np.int32)
+    for q, p in enumerate(gd["idx"]):
+        dK = Kmat(lib, kid, gd["params"], X, n, hyper_deriv=int(p))
+        ref = gd["dK_fd"][q]
+        assert_close(dK, ref, rtol=0.0, atol=1e-6 * np.abs(ref).max(), what="%s dK/dtheta_%d" % (case, p))
+
+
+@pytest.mark.parametrize("case", sorted(HYPERFD))
+def test_dual_value_component_is_the_value_path(lib, case):
+    gd = load_golden(case)
+    kid, X, n = HYPERFD[case], gd["X"], gd["n"].astype(np.int32)
+    K = Kmat(lib, kid, gd["params"], X, n)
+    for p in gd["idx"]:
+        v, d = dual(lib, kid, gd["params"], X, n, int(p))
+        assert_close(v, K, rtol=1e-14, atol=1e-300, what="%s dual value (seed %d)" % (case, p))
+        assert np.array_equal(d, Kmat(lib, kid, gd["params"], X, n, hyper_deriv=int(p)))
