@@ -256,28 +256,45 @@ __device__ void potrf_inv_tile(Smem& sm, const Lane& L, double* V, int row0) {
 #pragma unroll 1
     for (int J = 0; J < 8; J++) {
         const double* Xp = blk8(V, J, J);
-        // S1: row block J of the result (X_JK = Xp Y_JK, K < J) and the panel (L_IJ = V_IJ Xp^T, I > J)
-        for (int item = L.warp; item < 7; item += 4) {
-            if (item < J) blk_mma<true>(blk8(V, J, item), Xp, blk8(V, J, item), 1.0, 0.0, g, t);
-            else blk_mma<false>(blk8(V, item + 1, J), blk8(V, item + 1, J), Xp, 1.0, 0.0, g, t);
-        }
-        __syncthreads();
-        // S2: trailing update V_IK -= L_IJ L_KJ^T (J < K <= I) and inverse part Y_IK -= L_IJ X_JK (K < J < I)
-        {
-            int cnt = 0;
-            for (int I = J + 1; I < 8; I++) {
-                for (int K = J + 1; K <= I; K++)
-                    if ((cnt++ & 3) == L.warp) blk_mma<false>(blk8(V, I, K), blk8(V, I, J), blk8(V, K, J), -1.0, 1.0, g, t);
-                for (int K = 0; K < J; K++)
-                    if ((cnt++ & 3) == L.warp) blk_mma<true>(blk8(V, I, K), blk8(V, I, J), blk8(V, J, K), -1.0, 1.0, g, t);
+        // phase A: multiply by the pivot inverses.  Items:
+        //   [0, J)      : X_JK = Xp_J Y_JK (K < J); for K = J-1 first Y_{J,J-1} = -L_{J,J-1} Xp_{J-1}
+        //   [J, J+n)    : L_IJ = V_IJ Xp_J^T (I > J)
+        //   [J+n, J+2n) : Y_{I,J-1} = -L_{I,J-1} Xp_{J-1} (I > J), the deferred last stage of step J-1
+        const int n = 7 - J;
+        const int nitems = J + n + (J > 0 ? n : 0);
+        for (int item = L.warp; item < nitems; item += 4) {
+            if (item < J) {
+                if (item == J - 1) {
+                    blk_mma<true>(blk8(V, J, item), blk8(V, J, item), blk8(V, J - 1, J - 1), -1.0, 0.0, g, t);
+                    __syncwarp();
+                }
+                blk_mma<true>(blk8(V, J, item), Xp, blk8(V, J, item), 1.0, 0.0, g, t);
+            } else if (item < J + n) {
+                const int I = J + 1 + (item - J);
+                blk_mma<false>(blk8(V, I, J), blk8(V, I, J), Xp, 1.0, 0.0, g, t);
+            } else {
+                const int I = J + 1 + (item - J - n);
+                blk_mma<true>(blk8(V, I, J - 1), blk8(V, I, J - 1), blk8(V, J - 1, J - 1), -1.0, 0.0, g, t);
             }
         }
         __syncthreads();
-        // S3: Y_IJ = -L_IJ Xp (warps 0..2) while warp 3 factors the next pivot block
+        if (J == 7) break;
+        // phase B: warp 3 finalises and factors the NEXT pivot block (the serial scalar chain) while warps 0..2
+        // apply the rest of the rank-8 update: V_IK -= L_IJ L_KJ^T (J < K <= I), Y_IK -= L_IJ X_JK (K < J < I)
         if (L.warp == 3) {
-            if (J + 1 < 8) logacc += 0.5 * log(diag8(sm, blk8(V, J + 1, J + 1), L.lane, row0 + 8 * (J + 1)));
+            blk_mma<false>(blk8(V, J + 1, J + 1), blk8(V, J + 1, J), blk8(V, J + 1, J), -1.0, 1.0, g, t);
+            __syncwarp();
+            logacc += 0.5 * log(diag8(sm, blk8(V, J + 1, J + 1), L.lane, row0 + 8 * (J + 1)));
         } else {
-            for (int I = J + 1 + L.warp; I < 8; I += 3) blk_mma<true>(blk8(V, I, J), blk8(V, I, J), Xp, -1.0, 0.0, g, t);
+            int cnt = 0;
+            for (int I = J + 1; I < 8; I++) {
+                for (int K = J + 1; K <= I; K++) {
+                    if (I == J + 1) continue;  // (J+1, J+1) belongs to warp 3
+                    if ((cnt++ % 3) == L.warp) blk_mma<false>(blk8(V, I, K), blk8(V, I, J), blk8(V, K, J), -1.0, 1.0, g, t);
+                }
+                for (int K = 0; K < J; K++)
+                    if ((cnt++ % 3) == L.warp) blk_mma<true>(blk8(V, I, K), blk8(V, I, J), blk8(V, J, K), -1.0, 1.0, g, t);
+            }
         }
         __syncthreads();
     }
