@@ -802,6 +802,7 @@ int gpt_get_K(gpt_handle* h, double* K) {
 }
 
 int gpt_predict(gpt_handle* h, int Ms, const double* Xs, const int32_t* ns, double* mean, double* var, double* cov) {
+    if (h && Ms == 0) return 0;  // empty test set: nothing to write
     if (!h || Ms < 1 || !Xs || !ns || !mean) return fail(h, GPT_ERR_USAGE, "gpt_predict: bad arguments");
     if (!h->factor_valid || h->cp.kid < 0) return fail(h, GPT_ERR_USAGE, "gpt_predict: no valid factorisation (call gpt_ll)");
     CUDA_OK(h, cudaSetDevice(h->device));
@@ -1066,6 +1067,7 @@ static int batched_common(gpt_handle* h, int B, const double* d_thetas, const do
 
 int gpt_ll_batched_dev(gpt_handle* h, int B, const double* d_thetas, const double* d_y_batch, double* d_ll,
                        double* d_grad, const int32_t* grad_idx, int P, int* d_status, double* d_alpha_out) {
+    if (h && B == 0) return 0;  // empty batch
     if (!h || B < 1 || !d_thetas || !d_ll || !d_status) return fail(h, GPT_ERR_USAGE, "gpt_ll_batched_dev: bad arguments");
     if (h->M < 1 || h->kid < 0) return fail(h, GPT_ERR_USAGE, "gpt_ll_batched: set_data / set_kernel first");
     CUDA_OK(h, cudaSetDevice(h->device));
@@ -1074,6 +1076,7 @@ int gpt_ll_batched_dev(gpt_handle* h, int B, const double* d_thetas, const doubl
 
 int gpt_ll_batched(gpt_handle* h, int B, const double* thetas, const double* y_batch, double* ll, double* grad,
                    const int32_t* grad_idx, int P, int* status, double* alpha_out) {
+    if (h && B == 0) return 0;  // empty batch
     if (!h || B < 1 || !thetas || !ll || !status) return fail(h, GPT_ERR_USAGE, "gpt_ll_batched: bad arguments");
     if (h->M < 1 || h->kid < 0) return fail(h, GPT_ERR_USAGE, "gpt_ll_batched: set_data / set_kernel first");
     CUDA_OK(h, cudaSetDevice(h->device));

@@ -220,7 +220,7 @@ __device__ __forceinline__ double diag8(Smem& sm, double* P, int lane, int row0)
         }
         dsave[j] = d;
         dprod *= d;
-        const double rinv = __drcp_rn(d);
+        const double rinv = fast_rcp_pos(d);
         double w[8];
 #pragma unroll
         for (int c = 0; c < 8; c++) w[c] = (c > j) ? p[c][j] : ((c < j) ? p[j][c] : 0.0);
@@ -234,15 +234,15 @@ __device__ __forceinline__ double diag8(Smem& sm, double* P, int lane, int row0)
             }
         }
     }
+    // every lane holds every value: uniform (same address, same data) shared-memory stores; 64 lane-predicated
+    // branches here cost several times the elimination itself
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        const double rs = 1.0 / sqrt(dsave[i]);
+        const double rs = fast_rsqrt_pos(dsave[i]);
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const double val = (j < i) ? p[i][j] * rs : ((j == i) ? rs : 0.0);
-            if (lane == ((i * 8 + j) & 31)) P[i * LDT + j] = val;
-        }
+        for (int j = 0; j < 8; j++) P[i * LDT + j] = (j < i) ? p[i][j] * rs : ((j == i) ? rs : 0.0);
     }
+    __syncwarp();
     return dprod;
 }
 
@@ -286,14 +286,20 @@ __device__ void potrf_inv_tile(Smem& sm, const Lane& L, double* V, int row0) {
             __syncwarp();
             logacc += 0.5 * log(diag8(sm, blk8(V, J + 1, J + 1), L.lane, row0 + 8 * (J + 1)));
         } else {
-            int cnt = 0;
-            for (int I = J + 1; I < 8; I++) {
-                for (int K = J + 1; K <= I; K++) {
-                    if (I == J + 1) continue;  // (J+1, J+1) belongs to warp 3
-                    if ((cnt++ % 3) == L.warp) blk_mma<false>(blk8(V, I, K), blk8(V, I, J), blk8(V, K, J), -1.0, 1.0, g, t);
+            // row I > J carries I items: K in [0, I] without K == J; warp w takes items w, w + 3, ... of the
+            // row-major list ((J+1, J+1) is warp 3's)
+            int I = J + 1, q = L.warp;
+            for (;;) {
+                while (I < 8 && q >= I) {
+                    q -= I;
+                    I++;
                 }
-                for (int K = 0; K < J; K++)
-                    if ((cnt++ % 3) == L.warp) blk_mma<true>(blk8(V, I, K), blk8(V, I, J), blk8(V, J, K), -1.0, 1.0, g, t);
+                if (I >= 8) break;
+                const int K = (q < J) ? q : q + 1;
+                if (K < J) blk_mma<true>(blk8(V, I, K), blk8(V, I, J), blk8(V, J, K), -1.0, 1.0, g, t);
+                else if (!(I == J + 1 && K == J + 1))
+                    blk_mma<false>(blk8(V, I, K), blk8(V, I, J), blk8(V, K, J), -1.0, 1.0, g, t);
+                q += 3;
             }
         }
         __syncthreads();

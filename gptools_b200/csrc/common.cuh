@@ -29,4 +29,25 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// 1/d and 1/sqrt(d) for normal positive d: hardware seed (MUFU.RCP64H / MUFU.RSQ64H, ~2^-23) plus two Newton steps,
+// all inline -- the library versions (__drcp_rn, 1.0 / sqrt) add slow-path calls to the serial pivot chains of the
+// in-tile factorizations.  Relative error ~2e-16 (not correctly rounded).
+__device__ __forceinline__ double fast_rcp_pos(double d) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    double e = fma(-d, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-d, x, 1.0);
+    return fma(x, e, x);
+}
+__device__ __forceinline__ double fast_rsqrt_pos(double d) {
+    double x;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    const double hd = 0.5 * d;
+    double e = fma(-hd * x, x, 0.5);
+    x = fma(x, e, x);
+    e = fma(-hd * x, x, 0.5);
+    return fma(x, e, x);
+}
+
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }

@@ -6,6 +6,7 @@
 //   backsolve    : alpha = L^{-T} z, one block per launch
 //   grad_reduce  : 1/2 tr((a a^T - S) dK_p) with the dK tiles regenerated on the fly (never stored)
 // Replaces scipy.linalg.cholesky / cho_solve in compute_K_L_alpha_ll (gaussian_process.py:1452-1504).
+#include <cstdio>
 #include "common.cuh"
 #include "internal.h"
 
@@ -26,40 +27,72 @@ constexpr size_t POTRF_SMEM = ((size_t)NB * LDB + 2 * NB) * sizeof(double);
 //   K < J: Y_IK (rows > J) / X_JK (rows <= J, final inverse).
 __device__ __forceinline__ double* blk8(double* V, int I, int K) { return V + (8 * I) * LDB + 8 * K; }
 
-// C (8x8, in place) = sc * C + sa * A * B^T (nt) or sc * C + sa * A * B (nn); one warp.  G != null: also to global.
-template <bool NN>
-__device__ __forceinline__ void blk_mma(double* C, const double* A, const double* B, double sa, double sc, int g,
-                                        int t, double* G = nullptr, long ldg = 0) {
-    const double a0 = sa * A[g * LDB + t], a1 = sa * A[g * LDB + 4 + t];
-    double b0, b1;
-    if (NN) {
-        b0 = B[t * LDB + g];
-        b1 = B[(4 + t) * LDB + g];
-    } else {
-        b0 = B[g * LDB + t];
-        b1 = B[g * LDB + 4 + t];
+// One 8x8x8 block product: C (in place) = sc * C + sa * A * B^T (nt) or sc * C + sa * A * B (nn), G != null: also
+// stored to global.  A warp runs up to FOUR independent products at a time (loads of all four, then the DMMAs
+// interleaved, then the stores) -- the products are latency chains (LDS -> DMMA -> DMMA -> STS), and the kernel is
+// a single CTA on the critical path of the blocked Cholesky, so instruction-level parallelism is all there is.
+struct BlkItem {
+    double* C;
+    const double* A;
+    const double* B;
+    double* G;
+    int nn;
+    bool valid;
+};
+
+__device__ __forceinline__ void blk_batch(const BlkItem (&it)[4], double sa, double sc, long ldg, int g, int t) {
+    double a0[4], a1[4], b0[4], b1[4];
+    double2 c[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        if (it[u].valid) {
+            const int ob0 = it[u].nn ? t * LDB + g : g * LDB + t;
+            const int ob1 = it[u].nn ? (4 + t) * LDB + g : g * LDB + 4 + t;
+            a0[u] = it[u].A[g * LDB + t];
+            a1[u] = it[u].A[g * LDB + 4 + t];
+            b0[u] = it[u].B[ob0];
+            b1[u] = it[u].B[ob1];
+            c[u] = (sc != 0.0) ? *reinterpret_cast<const double2*>(it[u].C + g * LDB + 2 * t) : make_double2(0.0, 0.0);
+        }
     }
-    double2 c = make_double2(0.0, 0.0);
-    if (sc != 0.0) {
-        c = *reinterpret_cast<const double2*>(C + g * LDB + 2 * t);
-        c.x *= sc;
-        c.y *= sc;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        if (it[u].valid) {
+            a0[u] *= sa;
+            a1[u] *= sa;
+            c[u].x *= sc;
+            c[u].y *= sc;
+            dmma884(c[u].x, c[u].y, a0[u], b0[u]);
+        }
     }
-    dmma884(c.x, c.y, a0, b0);
-    dmma884(c.x, c.y, a1, b1);
-    *reinterpret_cast<double2*>(C + g * LDB + 2 * t) = c;
-    if (G) *reinterpret_cast<double2*>(G + g * ldg + 2 * t) = c;
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+        if (it[u].valid) dmma884(c[u].x, c[u].y, a1[u], b1[u]);
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        if (it[u].valid) {
+            *reinterpret_cast<double2*>(it[u].C + g * LDB + 2 * t) = c[u];
+            if (it[u].G) *reinterpret_cast<double2*>(it[u].G + g * ldg + 2 * t) = c[u];
+        }
+    }
 }
 
 // Pivot block P (8x8 SPD, lower valid): in place -> chol(P)^{-1} (zeros above the diagonal); chol(P) itself goes
-// to the global block G (zeros above).  Every lane of one warp redundantly, fully unrolled in registers.
-// Returns sum(log L_ii).
-__device__ __forceinline__ double pivot8(double* P, double* G, long ldg, int lane, int row0, int* s_info) {
+// to the global block G (zeros above); the eight pivots go to dsm (their logs are taken in parallel at the end).
+// Every lane of one warp redundantly, fully unrolled in registers.
+__device__ __forceinline__ void pivot8(double* P, double* G, long ldg, double* dsm, double* lsm, int lane, int row0,
+                                       int* s_info) {
     double p[8][8], lc[8][8];
+#ifdef GPT_POTRF_TIMING
+    long long c0 = clock64();
+#endif
 #pragma unroll
     for (int i = 0; i < 8; i++)
 #pragma unroll
         for (int j = 0; j <= i; j++) p[i][j] = P[i * LDB + j];
+#ifdef GPT_POTRF_TIMING
+    long long c1 = clock64();
+#endif
     double dsave[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) {
@@ -69,7 +102,7 @@ __device__ __forceinline__ double pivot8(double* P, double* G, long ldg, int lan
             d = 1.0;
         }
         dsave[j] = d;
-        const double rinv = __drcp_rn(d);
+        const double rinv = fast_rcp_pos(d);
         double w[8];
 #pragma unroll
         for (int c = 0; c < 8; c++) w[c] = (c > j) ? p[c][j] : ((c < j) ? p[j][c] : 0.0);
@@ -85,27 +118,35 @@ __device__ __forceinline__ double pivot8(double* P, double* G, long ldg, int lan
             }
         }
     }
+#ifdef GPT_POTRF_TIMING
+    long long c2 = clock64();
+#endif
     double rs[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) rs[i] = 1.0 / sqrt(dsave[i]);
+    for (int i = 0; i < 8; i++) rs[i] = fast_rsqrt_pos(dsave[i]);
+#ifdef GPT_POTRF_TIMING
+    long long c3 = clock64();
+#endif
+    // Every lane holds every value: store them with uniform (same address, same data) shared-memory writes --
+    // 64 lane-predicated branches cost ~7000 cycles here, five times the elimination itself.  The factor goes
+    // through the scratch block lsm and is copied to global by all lanes.
 #pragma unroll
     for (int i = 0; i < 8; i++) {
+        dsm[i] = dsave[i];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const double xval = (j < i) ? p[i][j] * rs[i] : ((j == i) ? rs[i] : 0.0);
-            const double lval = (j < i) ? lc[i][j] * rs[j] : ((j == i) ? dsave[i] * rs[i] : 0.0);
-            if (lane == ((i * 8 + j) & 31)) {
-                P[i * LDB + j] = xval;
-                G[i * ldg + j] = lval;
-            }
+            P[i * LDB + j] = (j < i) ? p[i][j] * rs[i] : ((j == i) ? rs[i] : 0.0);
+            lsm[i * 8 + j] = (j < i) ? lc[i][j] * rs[j] : ((j == i) ? dsave[i] * rs[i] : 0.0);
         }
     }
-    // one log per lane (lanes 0..7), summed over the warp: sum(log L_ii) = 1/2 sum(log d_i)
-    double mine = 1.0;
-#pragma unroll
-    for (int i = 0; i < 8; i++)
-        if (lane == i) mine = dsave[i];
-    return 0.5 * warp_sum(log(mine));
+    __syncwarp();
+    G[(lane >> 3) * ldg + (lane & 7)] = lsm[lane];
+    G[((lane >> 3) + 4) * ldg + (lane & 7)] = lsm[lane + 32];
+    __syncwarp();
+#ifdef GPT_POTRF_TIMING
+    long long c4 = clock64();
+    if (lane == 0 && row0 == 24) printf("pivot8: load %lld elim %lld rsqrt %lld store %lld\n", c1 - c0, c2 - c1, c3 - c2, c4 - c3);
+#endif
 }
 
 __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__ A, long lda, double* __restrict__ inv,
@@ -114,7 +155,9 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
     extern __shared__ __align__(16) double sm[];
     double* V = sm;                  // NB x LDB
     double* yv = sm + NB * LDB;      // right-hand side block
+    double* dsm = yv + NB;           // the NB pivots
     __shared__ int s_info;
+    __shared__ double lsm[64];       // pivot8 scratch: one 8x8 block of the factor
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
 
@@ -130,56 +173,113 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
         const int r = idx >> 7, c = idx & (NB - 1);
         if ((c >> 3) > (r >> 3)) A[(long)r * lda + c] = 0.0;
     }
-    double logacc = 0.0;  // warp 7
-    if (warp == 7) logacc = pivot8(blk8(V, 0, 0), A, lda, lane, row0, &s_info);
+    if (warp == 7) pivot8(blk8(V, 0, 0), A, lda, dsm, lsm, lane, row0, &s_info);
     __syncthreads();
 
 #pragma unroll 1
     for (int J = 0; J < NBLK; J++) {
-        const double* Xp = blk8(V, J, J);
-        // ---- phase A: multiply by the pivot inverses.  Items:
-        //   [0, J)            : X_JK = Xp_J Y_JK (K < J); for K = J-1 first Y_{J,J-1} = -L_{J,J-1} Xp_{J-1}
-        //   [J, J+n)          : L_IJ = V_IJ Xp_J^T (I > J), the final factor -> also to A
-        //   [J+n, J+2n)       : Y_{I,J-1} = -L_{I,J-1} Xp_{J-1} (I > J), the deferred last stage of step J-1
+        double* Xp = blk8(V, J, J);
+#ifdef GPT_POTRF_TIMING
+        long long tA0 = clock64();
+#endif
+        // ---- phase A: multiply by the pivot inverses.
+        //   chain (J > 0, warp 0) : Y_{J,J-1} = -L_{J,J-1} Xp_{J-1}, then X_{J,J-1} = Xp_J Y_{J,J-1}
+        //   a [0, na)             : X_JK = Xp_J Y_JK, K < J-1                               (nn, sa = +1)
+        //   b [na, na+n)          : L_IJ = V_IJ Xp_J^T, I > J, the final factor -> also to A (nt, sa = +1)
+        //   c [na+n, na+2n)       : Y_{I,J-1} = -L_{I,J-1} Xp_{J-1}, I > J (deferred from step J-1) (nn, sa = -1)
         const int n = NBLK - 1 - J;
-        const int nitems = J + n + (J > 0 ? n : 0);
-        for (int item = warp; item < nitems; item += 8) {
-            if (item < J) {
-                const int K = item;
-                if (K == J - 1) {
-                    blk_mma<true>(blk8(V, J, K), blk8(V, J, K), blk8(V, J - 1, J - 1), -1.0, 0.0, g, t);
-                    __syncwarp();
+        const int na = (J > 0) ? J - 1 : 0;
+        if (J > 0 && warp == 0) {
+            BlkItem it[4];
+            it[0].C = blk8(V, J, J - 1); it[0].A = blk8(V, J, J - 1); it[0].B = blk8(V, J - 1, J - 1);
+            it[0].G = nullptr; it[0].nn = 1; it[0].valid = true;
+            it[1].valid = it[2].valid = it[3].valid = false;
+            blk_batch(it, -1.0, 0.0, lda, g, t);
+            __syncwarp();
+            it[0].A = Xp; it[0].B = blk8(V, J, J - 1);
+            blk_batch(it, 1.0, 0.0, lda, g, t);
+        }
+        for (int base = warp; base < na + n; base += 32) {  // sa = +1 items
+            BlkItem it[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int item = base + 8 * u;
+                it[u].valid = item < na + n;
+                if (item < na) {
+                    it[u].C = blk8(V, J, item); it[u].A = Xp; it[u].B = blk8(V, J, item); it[u].G = nullptr; it[u].nn = 1;
+                } else {
+                    const int I = J + 1 + (item - na);
+                    it[u].C = blk8(V, I, J); it[u].A = blk8(V, I, J); it[u].B = Xp;
+                    it[u].G = A + (long)(8 * I) * lda + 8 * J; it[u].nn = 0;
                 }
-                blk_mma<true>(blk8(V, J, K), Xp, blk8(V, J, K), 1.0, 0.0, g, t);
-            } else if (item < J + n) {
-                const int I = J + 1 + (item - J);
-                blk_mma<false>(blk8(V, I, J), blk8(V, I, J), Xp, 1.0, 0.0, g, t, A + (long)(8 * I) * lda + 8 * J, lda);
-            } else {
-                const int I = J + 1 + (item - J - n);
-                blk_mma<true>(blk8(V, I, J - 1), blk8(V, I, J - 1), blk8(V, J - 1, J - 1), -1.0, 0.0, g, t);
+            }
+            blk_batch(it, 1.0, 0.0, lda, g, t);
+        }
+        if (J > 0) {
+            for (int base = warp; base < n; base += 32) {  // sa = -1 items
+                BlkItem it[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int I = J + 1 + base + 8 * u;
+                    it[u].valid = (base + 8 * u) < n;
+                    it[u].C = blk8(V, I, J - 1); it[u].A = blk8(V, I, J - 1); it[u].B = blk8(V, J - 1, J - 1);
+                    it[u].G = nullptr; it[u].nn = 1;
+                }
+                blk_batch(it, -1.0, 0.0, lda, g, t);
             }
         }
+#ifdef GPT_POTRF_TIMING
+        long long tA1 = clock64();
+#endif
         __syncthreads();
         if (J + 1 == NBLK) break;
+#ifdef GPT_POTRF_TIMING
+        long long tB0 = clock64();
+#endif
         // ---- phase B: warp 7 finalises and factors the next pivot block while the others apply the rank-8 update
         if (warp == 7) {
-            blk_mma<false>(blk8(V, J + 1, J + 1), blk8(V, J + 1, J), blk8(V, J + 1, J), -1.0, 1.0, g, t);
+            BlkItem it[4];
+            it[0].C = blk8(V, J + 1, J + 1); it[0].A = blk8(V, J + 1, J); it[0].B = blk8(V, J + 1, J);
+            it[0].G = nullptr; it[0].nn = 0; it[0].valid = true;
+            it[1].valid = it[2].valid = it[3].valid = false;
+            blk_batch(it, -1.0, 1.0, lda, g, t);
             __syncwarp();
-            logacc += pivot8(blk8(V, J + 1, J + 1), A + (long)(8 * (J + 1)) * lda + 8 * (J + 1), lda, lane,
-                             row0 + 8 * (J + 1), &s_info);
+            pivot8(blk8(V, J + 1, J + 1), A + (long)(8 * (J + 1)) * lda + 8 * (J + 1), lda, dsm + 8 * (J + 1), lsm, lane,
+                   row0 + 8 * (J + 1), &s_info);
         } else {
-            int cnt = 0;
-            for (int I = J + 1; I < NBLK; I++) {
-                for (int K = J + 1; K <= I; K++) {
-                    if (I == J + 1) continue;  // (J+1, J+1) belongs to warp 7
-                    if ((cnt++ % 7) == warp)
-                        blk_mma<false>(blk8(V, I, K), blk8(V, I, J), blk8(V, K, J), -1.0, 1.0, g, t);
+            // Row I > J carries I items: K in [0, I] without K == J (K < J: inverse part Y_IK -= L_IJ X_JK,
+            // K > J: trailing part V_IK -= L_IJ L_KJ^T).  Warp w takes the items w, w + 7, ... of the row-major
+            // list; (J+1, J+1) is warp 7's.
+            int I = J + 1, q = warp;
+            bool more = true;
+            while (more) {
+                BlkItem it[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    while (I < NBLK && q >= I) {
+                        q -= I;
+                        I++;
+                    }
+                    const bool in = I < NBLK;
+                    const int K = (q < J) ? q : q + 1;
+                    it[u].valid = in && !(I == J + 1 && K == J + 1);
+                    const int Ic = in ? I : J + 1, Kc = in ? K : 0;
+                    it[u].C = blk8(V, Ic, Kc);
+                    it[u].A = blk8(V, Ic, J);
+                    it[u].nn = (Kc < J) ? 1 : 0;
+                    it[u].B = (Kc < J) ? blk8(V, J, Kc) : blk8(V, Kc, J);
+                    it[u].G = nullptr;
+                    q += 7;
+                    more = in;
                 }
-                for (int K = 0; K < J; K++)
-                    if ((cnt++ % 7) == warp)
-                        blk_mma<true>(blk8(V, I, K), blk8(V, I, J), blk8(V, J, K), -1.0, 1.0, g, t);
+                blk_batch(it, -1.0, 1.0, lda, g, t);
             }
         }
+#ifdef GPT_POTRF_TIMING
+        long long tB1 = clock64();
+        if (lane == 0 && (warp == 0 || warp == 7) && row0 == 0)
+            printf("J=%d warp=%d phaseA %lld  barrier %lld  phaseB %lld\n", J, warp, tA1 - tA0, tB0 - tA1, tB1 - tB0);
+#endif
         __syncthreads();
     }
 
@@ -196,8 +296,14 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
         sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
         if (h == 0) yk[r] = sacc;
     }
-    if (tid == 7 * 32) {
-        *logdet_part = logacc;
+    __shared__ double red[4];
+    if (warp < 4) {  // sum(log L_ii) = 1/2 sum(log d_i), one pivot per thread
+        const double lg = warp_sum(log(dsm[tid]));
+        if (lane == 0) red[warp] = lg;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        *logdet_part = 0.5 * ((red[0] + red[1]) + (red[2] + red[3]));
         if (s_info != 0) atomicCAS(info, 0, s_info);
     }
 }
@@ -218,23 +324,44 @@ __global__ void __launch_bounds__(256) panel_gemv_kernel(const double* __restric
 __global__ void __launch_bounds__(256) backsolve_step_kernel(const double* __restrict__ L, long ld, int k,
                                                              const double* __restrict__ inv_k,
                                                              double* __restrict__ z, double* __restrict__ alpha) {
+    // alpha_k = Inv_k^T z_k (every CTA redundantly), then 64 columns of z[0 : k*128] -= L_k^T alpha_k per CTA.
+    // Both contractions are split four ways over the row index and reduced through shared memory: the loads of
+    // one thread are independent, so the chain is 32 deep instead of 128.
     __shared__ double ak[NB];
+    __shared__ double part[4][NB];
     const int tid = threadIdx.x;
+    {
+        const int o = tid & (NB - 1), h = tid >> 7;  // output, half of the rows
+        double s0 = 0.0, s1 = 0.0;
+        const int i0 = h * 64;
+#pragma unroll 8
+        for (int i = i0; i < i0 + 64; i += 2) {
+            s0 += (i >= o) ? inv_k[i * NB + o] * z[k * NB + i] : 0.0;
+            s1 += (i + 1 >= o) ? inv_k[(i + 1) * NB + o] * z[k * NB + i + 1] : 0.0;
+        }
+        part[h][o] = s0 + s1;
+    }
+    __syncthreads();
     if (tid < NB) {
-        double s = 0.0;
-        for (int i = tid; i < NB; i++) s += inv_k[i * NB + tid] * z[k * NB + i];
+        const double s = part[0][tid] + part[1][tid];
         ak[tid] = s;
         if (blockIdx.x == 0) alpha[k * NB + tid] = s;
     }
     __syncthreads();
-    const int c = blockIdx.x * 256 + tid;
+    const int cl = tid & 63, grp = tid >> 6;
+    const int c = blockIdx.x * 64 + cl;
+    double s0 = 0.0, s1 = 0.0;
     if (c < k * NB) {
-        const double* col = L + (long)k * NB * ld + c;
-        double s = 0.0;
-#pragma unroll 4
-        for (int r = 0; r < NB; r++) s += col[(long)r * ld] * ak[r];
-        z[c] -= s;
+        const double* col = L + ((long)k * NB + grp * 32) * ld + c;
+#pragma unroll 8
+        for (int r = 0; r < 32; r += 2) {
+            s0 += col[(long)r * ld] * ak[grp * 32 + r];
+            s1 += col[(long)(r + 1) * ld] * ak[grp * 32 + r + 1];
+        }
     }
+    part[grp][cl] = s0 + s1;
+    __syncthreads();
+    if (tid < 64 && c < k * NB) z[c] -= (part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]);
 }
 
 __global__ void transpose_kernel(double* __restrict__ out, long ldo, const double* __restrict__ in, long ldi,
@@ -391,7 +518,7 @@ void launch_panel_gemv(const double* P, int rows, const double* zk, double* y, c
 
 void launch_backsolve_step(const double* L, long ld, int k, const double* inv_k, double* z, double* alpha,
                            cudaStream_t s) {
-    int grid = (k * NB + 255) / 256;
+    int grid = (k * NB + 63) / 64;
     if (grid < 1) grid = 1;
     backsolve_step_kernel<<<grid, 256, 0, s>>>(L, ld, k, inv_k, z, alpha);
 }

@@ -319,3 +319,40 @@ def test_hyper_gradient_c2_shape_vs_oracle_fd(dev):
     assert_close(gB[0], grad, rtol=1e-8, atol=1e-9 * np.abs(grad).max(), what="batched gradient")
     fd1 = np.array([richardson_fd(ll_of, ths[1, :2], i, 2e-3 * ths[1, i]) for i in range(2)])
     assert_close(gB[1], fd1, rtol=0.0, atol=1e-6 * np.abs(fd1).max(), what="batched gradient, theta 1")
+
+
+@pytest.mark.parametrize("M", [1, 2, 63, 64, 65, 127, 129])
+def test_tiny_and_ragged_sizes_all_paths(dev, M):
+    """Sizes around the 64-row batched tile and the 128-row block of the single path, down to one observation:
+    ll, gradient, alpha, predictive mean and variance against the pinned oracle; empty inputs are no-ops."""
+    from oracle import gp_oracle as orc
+    rs = np.random.RandomState(M)
+    X = rs.rand(M, 1)
+    n = np.zeros((M, 1), dtype=int)
+    y = np.sin(3 * X[:, 0])
+    err = np.full(M, 0.1)
+    th = np.array([1.0, 0.4])
+    ref = orc.compute_K_L_alpha_ll(orc.KERNEL_SE, th, X, n, y, err, None, 0.0, 1e2, grad_idx=[0, 1])
+    dev.set_data(X, n, y, err)
+    dev.set_kernel(KERNEL_SE, 2, 1e2)
+    ll, g, st = dev.ll(th, 0.0, grad_idx=[0, 1])
+    assert st == 0
+    assert_close(ll, ref["ll"], rtol=1e-9, what="ll")
+    assert_close(g, ref["ll_deriv"], rtol=1e-9, atol=1e-9 * np.abs(ref["ll_deriv"]).max(), what="grad")
+    assert_close(dev.get_alpha(), np.ravel(ref["alpha"]), rtol=1e-9, atol=1e-9 * np.abs(ref["alpha"]).max(), what="alpha")
+    llb, gb, stb = dev.ll_batched(np.array([[1.0, 0.4, 0.0]] * 3), grad_idx=[0, 1])
+    assert (stb == 0).all()
+    assert_close(llb, np.full(3, ref["ll"]), rtol=1e-9, what="batched ll")
+    assert_close(gb[2], ref["ll_deriv"], rtol=1e-9, atol=1e-9 * np.abs(ref["ll_deriv"]).max(), what="batched grad")
+    Xs = rs.rand(5, 1)
+    ns = np.zeros((5, 1), dtype=int)
+    dev.ll(th, 0.0)
+    mean, var, _ = dev.predict(Xs, ns, want_var=True)
+    pm, ps, pc = orc.predict(orc.KERNEL_SE, th, X, n, ref["L"], ref["alpha"], Xs, ns)
+    assert_close(mean, pm, rtol=1e-9, atol=1e-9, what="mean")
+    assert np.all(np.abs(var - np.diag(pc)) <= 1e-9 * th[0] ** 2)
+    # empty test set / empty batch: accepted, nothing written
+    m0, v0, _ = dev.predict(np.zeros((0, 1)), np.zeros((0, 1), dtype=int), want_var=True)
+    assert m0.shape == (0,) and v0.shape == (0,)
+    l0, g0, s0 = dev.ll_batched(np.zeros((0, 3)), grad_idx=[0, 1])
+    assert l0.shape == (0,) and g0.shape == (0, 2) and s0.shape == (0,)
