@@ -38,7 +38,7 @@ constexpr int PTS_ORD = 192;
 
 struct Smem {
     double R[R_D];
-    double wA[2 * TB], wB[2 * TB];  // pivot row/column vectors of the sweep, stored twice (index wrap-around)
+    double piv[8];  // product of the 8 pivots of each 8x8 pivot block of the tile being factored
     double rk[TB], zk[TB];
     double red[4][GPT_MAX_PARAMS + 2];
     const double* a[MAXT];
@@ -250,8 +250,10 @@ __device__ __forceinline__ double diag8(Smem& sm, double* P, int lane, int row0)
 // sum log L_ii in sm.red[0][0]; sm.info on a non-positive pivot.
 __device__ void potrf_inv_tile(Smem& sm, const Lane& L, double* V, int row0) {
     const int g = L.g, t = L.t;
-    double logacc = 0.0;  // warp 3, all lanes
-    if (L.warp == 3) logacc += 0.5 * log(diag8(sm, blk8(V, 0, 0), L.lane, row0));
+    if (L.warp == 3) {
+        const double dp = diag8(sm, blk8(V, 0, 0), L.lane, row0);
+        if (L.lane == 0) sm.piv[0] = dp;
+    }
     __syncthreads();
 #pragma unroll 1
     for (int J = 0; J < 8; J++) {
@@ -284,7 +286,8 @@ __device__ void potrf_inv_tile(Smem& sm, const Lane& L, double* V, int row0) {
         if (L.warp == 3) {
             blk_mma<false>(blk8(V, J + 1, J + 1), blk8(V, J + 1, J), blk8(V, J + 1, J), -1.0, 1.0, g, t);
             __syncwarp();
-            logacc += 0.5 * log(diag8(sm, blk8(V, J + 1, J + 1), L.lane, row0 + 8 * (J + 1)));
+            const double dp = diag8(sm, blk8(V, J + 1, J + 1), L.lane, row0 + 8 * (J + 1));
+            if (L.lane == 0) sm.piv[J + 1] = dp;
         } else {
             // row I > J carries I items: K in [0, I] without K == J; warp w takes items w, w + 3, ... of the
             // row-major list ((J+1, J+1) is warp 3's)
@@ -309,7 +312,11 @@ __device__ void potrf_inv_tile(Smem& sm, const Lane& L, double* V, int row0) {
         const int r = idx >> 6, c = idx & (TB - 1);
         if ((c >> 3) > (r >> 3)) V[r * LDT + c] = 0.0;
     }
-    if (L.tid == 96) sm.red[0][0] = logacc;  // lane 0 of warp 3
+    __syncthreads();
+    if (L.warp == 0) {  // sum log L_ii = 1/2 sum log(pivot products): one log per lane, off the pivot chain
+        const double lg = warp_sum(L.lane < 8 ? log(sm.piv[L.lane]) : 0.0);
+        if (L.lane == 0) sm.red[0][0] = 0.5 * lg;
+    }
     __syncthreads();
 }
 
