@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(CSRC, "libgptb200.so")
 HOSTCHECK = os.path.join(CSRC, "libgptb200_hostcheck.so")
-SOURCES = ["api.cu", "assemble.cu", "gemm.cu", "factor.cu", "predict.cu", "batched.cu", "batched4.cu"]
+SOURCES = ["api.cu", "assemble.cu", "gemm.cu", "factor.cu", "predict.cu", "batched4.cu"]
 HEADERS = ["common.cuh", "covfn.cuh", "internal.h", "se_fast.cuh", os.path.join(INCLUDE, "gptb200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]

@@ -1020,18 +1020,9 @@ static int batched_common(gpt_handle* h, int B, const double* d_thetas, const do
         bp.idx[q] = grad_idx[q];
     }
     bp.ll = d_ll; bp.grad = d_grad; bp.status = d_status; bp.alpha_out = d_alpha;
-    // GPT_BATCHED_IMPL=2 selects the first-generation kernel (2 CTAs x 8 warps per SM) for A/B comparisons
-    bool gen4 = true;
-    if (const char* e = getenv("GPT_BATCHED_IMPL")) gen4 = (atoi(e) != 2);
-    if (h->kid != GPT_KERNEL_SE && bp.nidx > 0) gen4 = true;  // Matern / Gibbs hyper-derivatives exist in batched4.cu only
-    int ctas;
-    if (gen4) {
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-        ctas = sms * batched4_ctas_per_sm();
-    } else {
-        ctas = batched_max_ctas(h->device);
-    }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    int ctas = sms * batched4_ctas_per_sm();
     if (ctas > B) ctas = B;
     bp.ws_per_cta = batched_ws_doubles_per_cta(bp.nT);
     int rc;
@@ -1046,8 +1037,7 @@ static int batched_common(gpt_handle* h, int B, const double* d_thetas, const do
     bp.phase_cycles = ptr<long long>(h->scal);
 #endif
     CUDA_OK(h, cudaMemsetAsync(bp.counter, 0, sizeof(int), h->stream));
-    if (gen4) launch_ll_batched4(bp, ctas, h->stream);
-    else launch_ll_batched(bp, ctas, h->stream);
+    launch_ll_batched4(bp, ctas, h->stream);
     h->launches++;
 #ifdef GPT_PHASE_TIMING
     {

@@ -1,9 +1,9 @@
-// Batched ll + gradient, second generation: FOUR independent theta streams per SM.
+// Batched ll + gradient: FOUR independent theta streams per SM.
 //
-// Same algorithm and tile conventions as batched.cu (phase 1 left-looking Cholesky with generated K tiles and
-// inverted diagonal tiles, back substitution, phase 2 XT = L^{-T} in place, phase 3 K^{-1} tiles contracted with
-// regenerated dK tiles), re-cut for latency tolerance.  Measurements on the first kernel (profiles/r01b_*,
-// phase timing): the FP64 pipe -- which DMMA and scalar DFMA share on B200 (profiles/microbench/fp64_overlap.cu)
+// One persistent CTA per theta: phase 1 left-looking Cholesky with generated K tiles and inverted diagonal tiles,
+// back substitution, phase 2 XT = L^{-T} in place, phase 3 K^{-1} tiles contracted with regenerated dK tiles
+// (tools/tile_model.py is the numpy model of the tile recurrences).  Cut for latency tolerance: measurements on
+// the first-generation kernel (256 threads, 2 CTAs/SM; git history, profiles/r01a_*): the FP64 pipe -- which DMMA and scalar DFMA share on B200 (profiles/microbench/fp64_overlap.cu)
 // -- was only ~63% busy because each CTA spends half of its time in latency-bound non-GEMM phases and only two
 // CTAs (= two thetas) fit on an SM.  Here a CTA is 4 warps / 128 threads with a ~53 KB footprint, so four CTAs
 // (four thetas) share an SM and the chance that nobody feeds the tensor pipe drops from ~29% to ~8%:
@@ -23,13 +23,20 @@ using namespace sefast;
 
 constexpr int TB = 64;
 constexpr int BK = 16;
-constexpr int STAGES = 3;
+#ifndef GPT_B4_STAGES
+#define GPT_B4_STAGES 3
+#endif
+#ifndef GPT_B4_MINB
+#define GPT_B4_MINB 4
+#endif
+constexpr int STAGES = GPT_B4_STAGES;
 constexpr int THREADS = 128;
 constexpr int CHUNK = TB * BK;         // doubles per operand chunk
 constexpr int STAGE_D = 2 * CHUNK;     // A, B
-constexpr int R_D = STAGES * STAGE_D;  // 6144 doubles = 48 KB ring; also staging tile (64 x 68) + staged row points
 constexpr int LDT = 68;
 constexpr int ST_D = TB * LDT;         // 4352
+// ring (3 stages: 6144 doubles = 48 KB); the same storage is the staging tile (64 x 68) + staged row points
+constexpr int R_D = (STAGES * STAGE_D > ST_D + 256) ? STAGES * STAGE_D : ST_D + 256;
 constexpr int MAXT = 32;
 constexpr int TILE = TB * TB;
 constexpr int PTS_OFF = ST_D;          // staged rows behind the staging tile: x[64][FD] (<= 128), alpha[64], orders
@@ -518,7 +525,7 @@ __device__ __forceinline__ void grad_tile(const Smem& sm, const BatchedParams& p
 }
 
 template <int FD>
-__global__ void __launch_bounds__(THREADS, 4) ll_batched4_kernel(BatchedParams p) {
+__global__ void __launch_bounds__(THREADS, GPT_B4_MINB) ll_batched4_kernel(BatchedParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     Lane L;
@@ -811,12 +818,16 @@ void launch_t(const BatchedParams& p, int num_ctas, cudaStream_t s) {
 
 }  // namespace
 
+size_t batched_ws_doubles_per_cta(int nT) {
+    return (size_t)(nT * (nT + 1) / 2 + nT) * TILE + (size_t)3 * nT * TB;
+}
+
 int batched4_ctas_per_sm() {
     if (const char* e = getenv("GPT_B4_CTAS_PER_SM")) {
         const int v = atoi(e);
-        if (v == 2 || v == 3) return v;
+        if (v >= 2 && v <= GPT_B4_MINB) return v;
     }
-    return 4;
+    return GPT_B4_MINB;
 }
 
 void launch_ll_batched4(const BatchedParams& p, int num_ctas, cudaStream_t s) {

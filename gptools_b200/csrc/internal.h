@@ -97,7 +97,7 @@ void launch_predict_mean_fused(const CovParams& cp, const double* X, const int32
 // kss[s] = k(x*_s, x*_s) with orders ns
 void launch_prior_diag(const CovParams& cp, const double* Xs, const int32_t* ns, int rows, double* kss, cudaStream_t s);
 
-// ---- batched.cu : many-theta persistent kernel ---------------------------------------------------
+// ---- batched4.cu : many-theta persistent kernel, 4 CTAs (= 4 thetas) per SM --------------------------
 struct BatchedParams {
     int kid, D, nparams;
     int M;                 // observations (= latent points; no T on this path)
@@ -122,8 +122,5 @@ struct BatchedParams {
     long long* phase_cycles;  // optional (8): per-phase cycle sums, only with -DGPT_PHASE_TIMING
 };
 size_t batched_ws_doubles_per_cta(int nT);
-int batched_max_ctas(int device);
-void launch_ll_batched(const BatchedParams& p, int num_ctas, cudaStream_t s);
-// batched4.cu : second-generation kernel, 4 CTAs (= 4 thetas) per SM
 int batched4_ctas_per_sm();
 void launch_ll_batched4(const BatchedParams& p, int num_ctas, cudaStream_t s);

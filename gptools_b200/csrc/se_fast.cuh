@@ -1,4 +1,4 @@
-// Register-resident squared-exponential evaluators shared by the batched kernels (batched.cu, batched4.cu),
+// Register-resident squared-exponential evaluators shared by the batched kernel (batched4.cu) and the fused predictive mean (predict.cu),
 // plus the per-phase cycle-accounting macros of the development build (-DGPT_PHASE_TIMING).
 #pragma once
 #include "common.cuh"

@@ -1,4 +1,4 @@
-"""Numpy model of the batched kernel's tile algorithm (gptools_b200/csrc/batched.cu), used to validate the
+"""Numpy model of the batched kernel's tile algorithm (gptools_b200/csrc/batched4.cu), used to validate the
 slot / in-place conventions before writing CUDA.  Phase 1: left-looking Cholesky with inverted diagonal
 tiles; phase 2: XT = L^{-T} by block substitution, in place; phase 3: K^{-1} tiles = sum XT XT^T."""
 import numpy as np
@@ -92,7 +92,7 @@ if __name__ == "__main__":
 
 
 def gj_inverse_factor(A):
-    """Model of potrf_inv_tile (batched.cu): in-place sweep returning X = chol(A)^{-1} and the pivots d.
+    """Model of potrf_inv_tile (batched4.cu): in-place sweep returning X = chol(A)^{-1} and the pivots d.
     Position (r, c): for c > j still holds the Schur complement a_rc, for c <= j holds e_rc = (L_unit^{-1})_rc."""
     n = A.shape[0]
     V = np.tril(A).copy()
