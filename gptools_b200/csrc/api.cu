@@ -55,6 +55,7 @@ struct gpt_handle {
     DevBuf Xs, ns, Kst, Kso, kss, mean, var, cov, Rt, smp;
     // batched
     DevBuf b_thetas, b_y, b_ll, b_grad, b_status, b_alpha, b_ws, b_counter;
+    DevBuf Vtmp;  // predict: one 128-column block of V^T (out-of-place multiply by the block inverse)
 };
 
 namespace {
@@ -427,7 +428,7 @@ void gpt_destroy(gpt_handle* h) {
                      &h->zt, &h->alpha, &h->logdet, &h->info, &h->scal, &h->XT, &h->Kinv, &h->S, &h->partials,
                      &h->gout, &h->u, &h->Sg, &h->Yt, &h->Xs, &h->ns, &h->Kst, &h->Kso, &h->kss, &h->mean, &h->var,
                      &h->cov, &h->Rt, &h->smp, &h->b_thetas, &h->b_y, &h->b_ll, &h->b_grad, &h->b_status,
-                     &h->b_alpha, &h->b_ws, &h->b_counter};
+                     &h->b_alpha, &h->b_ws, &h->b_counter, &h->Vtmp};
     for (DevBuf* b : all) release(*b);
     if (h->side_stream) {
         cudaStreamSynchronize(h->side_stream);
@@ -810,9 +811,24 @@ int gpt_predict(gpt_handle* h, int Ms, const double* Xs, const int32_t* ns, doub
     const int D = h->D, N = h->N, M = h->M, Np = h->Np, Mp = h->Mp, nblk = Mp / NB;
     int rc;
     // chunk of test points; the full covariance needs every test point in one chunk
-    int CH = cov ? round_up(Ms, NB) : round_up(Ms < 16384 ? Ms : 16384, NB);
-    // bound the chunk buffers to ~8 GB
-    while (!cov && CH > NB && (size_t)CH * (Np + Mp) * sizeof(double) > ((size_t)8 << 30)) CH = round_up(CH / 2, NB);
+    // otherwise: whole waves of the solve GEMMs (row tiles = a multiple of the SM count; a 8192-row chunk filled
+    // 43% of the machine), as many as fit a third of the free device memory (capped at 48 GB)
+    int CH = round_up(Ms, NB);
+    if (!cov) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        size_t budget = free_b / 3;
+        if (budget > ((size_t)48 << 30)) budget = (size_t)48 << 30;
+        const size_t per_row = (size_t)(Np + (h->hasT ? Mp : 0) + NB) * sizeof(double);
+        const long wave = (long)sms * NB;
+        long fit = (long)(budget / per_row);
+        if (fit >= wave) fit = fit / wave * wave;
+        else fit = fit / NB * NB;
+        if (fit < NB) fit = NB;
+        if (CH > fit) CH = (int)fit;
+    }
     if ((rc = upload(h, h->Xs, Xs, sizeof(double) * (size_t)Ms * D))) return rc;
     if ((rc = upload(h, h->ns, ns, sizeof(int32_t) * (size_t)Ms * D))) return rc;
     if (!var && !cov) {
@@ -842,6 +858,7 @@ int gpt_predict(gpt_handle* h, int Ms, const double* Xs, const int32_t* ns, doub
     if (h->hasT && (rc = ensure(h, h->Kso, sizeof(double) * (size_t)CH * Mp))) return rc;
     if ((rc = ensure(h, h->mean, sizeof(double) * (size_t)round_up(Ms, NB)))) return rc;
     if (var || cov) {
+        if ((rc = ensure(h, h->Vtmp, sizeof(double) * (size_t)CH * NB))) return rc;
         if ((rc = ensure(h, h->kss, sizeof(double) * (size_t)round_up(Ms, NB)))) return rc;
         if ((rc = ensure(h, h->var, sizeof(double) * (size_t)round_up(Ms, NB)))) return rc;
     }
@@ -887,14 +904,16 @@ int gpt_predict(gpt_handle* h, int Ms, const double* Xs, const int32_t* ns, doub
                     launch_gemm_nt(g, s);
                     h->launches++;
                 }
+                // V_I = W_I Inv_I^T, out of place (two CTAs share the rows of W_I: in place would race), then back
                 GemmParams g2;
-                g2.C = Ko + (long)I * NB; g2.ldc = ldk;
+                g2.C = ptr<double>(h->Vtmp); g2.ldc = NB;
                 g2.A = Ko + (long)I * NB; g2.lda = ldk;
                 g2.B = ptr<double>(h->Inv) + (size_t)I * NB * NB; g2.ldb = NB;
                 g2.tiles_m = rows_pad / NB; g2.tiles_n = 1; g2.K = NB;
                 g2.alpha = 1.0; g2.beta = 0.0; g2.lower_only = 0; g2.kbegin_row = 0;
                 launch_gemm_nt(g2, s);
-                h->launches++;
+                launch_copy2d(Ko + (long)I * NB, ldk, ptr<double>(h->Vtmp), NB, rows_pad, NB, s);
+                h->launches += 2;
             }
             launch_prior_diag(h->cp, ptr<double>(h->Xs) + (size_t)s0 * D, ptr<int32_t>(h->ns) + (size_t)s0 * D, rows,
                               ptr<double>(h->kss) + s0, s);

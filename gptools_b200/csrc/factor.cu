@@ -381,9 +381,12 @@ __global__ void transpose_kernel(double* __restrict__ out, long ldo, const doubl
 
 __global__ void copy2d_kernel(double* __restrict__ out, long ldo, const double* __restrict__ in, long ldi,
                               int rows, int cols) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = blockIdx.y;
-    if (c < cols && r < rows) out[(long)r * ldo + c] = in[(long)r * ldi + c];
+    // 8 rows per CTA (a warp per row, lanes stride the columns); rows live in grid.x, which has no 65535 limit
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const double* src = in + (long)r * ldi;
+    double* dst = out + (long)r * ldo;
+    for (int c = threadIdx.x & 31; c < cols; c += 32) dst[c] = src[c];
 }
 
 __global__ void add_diag_kernel(double* __restrict__ A, long lda, const double* __restrict__ d, int n) {
@@ -397,10 +400,11 @@ __global__ void fill_kernel(double* __restrict__ p, long n, double v) {
 
 __global__ void identity_pad_kernel(double* __restrict__ A, long lda, int n_valid, int n_pad) {
     // rows/cols >= n_valid: zero, with ones on the diagonal
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = blockIdx.y;
-    if (c >= n_pad || r >= n_pad) return;
-    if (r >= n_valid || c >= n_valid) A[(long)r * lda + c] = (r == c) ? 1.0 : 0.0;
+    // only the padding is touched: full rows r >= n_valid, and the column strip c >= n_valid of the other rows
+    const int r = blockIdx.x;  // rows in grid.x (no 65535 limit)
+    if (r >= n_pad) return;
+    const int c0 = (r >= n_valid) ? 0 : n_valid;
+    for (int c = c0 + threadIdx.x; c < n_pad; c += blockDim.x) A[(long)r * lda + c] = (r == c) ? 1.0 : 0.0;
 }
 
 constexpr int GT = 64;
@@ -530,8 +534,7 @@ void launch_transpose(double* out, long ldo, const double* in, long ldi, int row
 
 void launch_copy2d(double* out, long ldo, const double* in, long ldi, int rows, int cols, cudaStream_t s) {
     if (rows <= 0 || cols <= 0) return;
-    dim3 grid((cols + 255) / 256, rows);
-    copy2d_kernel<<<grid, 256, 0, s>>>(out, ldo, in, ldi, rows, cols);
+    copy2d_kernel<<<(rows + 7) / 8, 256, 0, s>>>(out, ldo, in, ldi, rows, cols);
 }
 
 void launch_add_diag(double* A, long lda, const double* d, int n, cudaStream_t s) {
@@ -546,8 +549,8 @@ void launch_fill(double* p, long n, double v, cudaStream_t s) {
 }
 
 void launch_set_identity_pad(double* A, long lda, int n_valid, int n_pad, cudaStream_t s) {
-    dim3 grid((n_pad + 255) / 256, n_pad);
-    identity_pad_kernel<<<grid, 256, 0, s>>>(A, lda, n_valid, n_pad);
+    if (n_pad <= n_valid) return;
+    identity_pad_kernel<<<n_pad, 128, 0, s>>>(A, lda, n_valid, n_pad);
 }
 
 void launch_grad_reduce(const GradReduceParams& p, cudaStream_t s) {
