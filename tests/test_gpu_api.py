@@ -334,3 +334,41 @@ def test_matern_and_gibbs_optimise_with_device_gradient():
     f, df = gpg.update_hyperparameters(gg["params"])
     assert_close(-f, gg["ll"], rtol=1e-9)
     assert_close(-df, gg["ll_grad_fd"], rtol=0.0, atol=1e-6 * np.abs(gg["ll_grad_fd"]).max())
+
+
+@pytest.mark.parametrize("kernel", ["matern52", "matern_generic"])
+def test_c2_full_size_against_oracle(kernel):
+    """Config 2 at full size (2000 locations x (value, derivative) = 4000 observations, Matern nu = 5/2 in both of
+    the reference's implementations): ll, alpha and the predictive mean / std on a slice of the 1e5-point grid
+    against the pinned oracle (which takes ~10 s here); the full 1e5-point prediction is checked for consistency
+    with the slice and for the size-independent properties (std >= 0, bounded by the prior)."""
+    from oracle import gp_oracle as orc
+    rs = np.random.RandomState(0)
+    X = np.sort(rs.rand(2000)) * 10
+    yv = np.sin(X) + 0.05 * rs.randn(2000)
+    yd = np.cos(X) + 0.05 * rs.randn(2000)
+    if kernel == "matern52":
+        k = g.Matern52Kernel(num_dim=1, initial_params=[1.0, 0.8], param_bounds=[(0, 10)] * 2)
+        kid = orc.KERNEL_MATERN52
+    else:
+        k = g.MaternKernel(num_dim=1, initial_params=[1.0, 2.5, 0.8], param_bounds=[(0, 10)] * 3)
+        kid = orc.KERNEL_MATERN
+    gp = g.GaussianProcess(k)
+    gp.add_data(X, yv, err_y=0.05)
+    gp.add_data(X, yd, err_y=0.05, n=1)
+    gp.compute_K_L_alpha_ll()
+    ref = orc.compute_K_L_alpha_ll(kid, np.array(k.params), gp.X, gp.n, gp.y, gp.err_y, None, 0.0, 1e2)
+    assert_close(gp.ll - gp.hyperprior(gp.params), ref["ll"], rtol=1e-9, what="ll")
+    tol = 2e-6 if kernel == "matern_generic" else 1e-8   # generic Matern: the oracle mirrors the reference's kvp round-off
+    assert_close(gp.alpha.ravel(), np.ravel(ref["alpha"]), rtol=0.0, atol=tol * np.abs(ref["alpha"]).max(), what="alpha")
+    Xs = np.linspace(0, 10, 100000)
+    mean, std = gp.predict(Xs)
+    sl = slice(0, 100000, 97)
+    pm, ps, _ = orc.predict(kid, np.array(k.params), gp.X, gp.n, ref["L"], ref["alpha"], Xs[sl][:, None],
+                            np.zeros((len(Xs[sl]), 1), dtype=int))
+    assert_close(mean[sl], pm, rtol=0.0, atol=1e-7 if kernel == "matern_generic" else 1e-9, what="mean")
+    assert np.all(np.abs(std[sl] ** 2 - ps ** 2) <= (1e-7 if kernel == "matern_generic" else 1e-9) * k.params[0] ** 2)
+    assert np.all(std >= 0) and np.all(std <= k.params[0] * (1 + 1e-12))
+    m2, s2 = gp.predict(Xs[sl])
+    assert_close(m2, mean[sl], rtol=1e-12, atol=1e-13, what="chunking independence (mean)")
+    assert_close(s2, std[sl], rtol=1e-9, atol=1e-12, what="chunking independence (std)")
