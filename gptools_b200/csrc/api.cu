@@ -48,13 +48,14 @@ struct gpt_handle {
     bool factor_valid = false;
     CovParams cp;
     double noise_sigma = 0.0;
-    DevBuf A, Klat, W, Inv, P, Pres, z, zt, alpha, logdet, info, scal;
+    DevBuf A, Klat, W, Inv, P, z, zt, alpha, logdet, info, scal;
     // gradient workspaces
     DevBuf XT, Kinv, S, partials, gout, u, Sg, Yt;
     // predict workspaces
     DevBuf Xs, ns, Kst, Kso, kss, mean, var, cov, Rt, smp;
     // batched
     DevBuf b_thetas, b_y, b_ll, b_grad, b_status, b_alpha, b_ws, b_counter;
+    DevBuf ds_C, ds_inv, ds_panel, ds_logdet, ds_info, ds_R, ds_Rt, ds_O, ds_mu, ds_jit;  // draw_sample scratch
     DevBuf Vtmp;  // predict: one 128-column block of V^T (out-of-place multiply by the block inverse)
 };
 
@@ -117,11 +118,11 @@ int supported_kernel(int kid, int D, int nparams) {
 // Blocked right-looking Cholesky of the nblk*128 square matrix A (lower), in place, with one-block LOOKAHEAD:
 // the trailing update of step k is split into the strip that finalises block column k+1 and the rest; the
 // (serial) diagonal-block factorisation and the panel of step k+1 run on a side stream while the rest of the
-// step-k update keeps the machine busy.  panel / resid hold TWO panels (double buffered).  Writes the inverses of
+// step-k update keeps the machine busy.  panel2 holds TWO panels (double buffered).  Writes the inverses of
 // the diagonal blocks to inv (nblk x 128 x 128), per-block log-det shares, info, and (optionally) overwrites rhs
 // with L^{-1} rhs.  All heavy work is DMMA GEMM (gemm.cu).
-int blocked_potrf(gpt_handle* h, double* A, long ld, int nblk, double* inv, double* panel2, double* resid,
-                  double* rhs, double* logdet, int* info) {
+int blocked_potrf(gpt_handle* h, double* A, long ld, int nblk, double* inv, double* panel2, double* rhs, double* logdet,
+                  int* info) {
     cudaStream_t sm = h->stream;
     if (!h->side_stream) {
         // highest priority: its few CTAs are placed as soon as an SM frees up, ahead of the queued update tiles
@@ -146,32 +147,11 @@ int blocked_potrf(gpt_handle* h, double* A, long ld, int nblk, double* inv, doub
         h->launches++;
         if (rest > 0) {
             double* A21 = A + (long)(k + 1) * NB * ld + (long)k * NB;
-            // panel P = A21 L11^{-T} through the explicit block inverse (a DMMA GEMM) ...
-            GemmParams g;
-            g.C = panel; g.ldc = NB;
-            g.A = A21; g.lda = ld;
-            g.B = inv_k; g.ldb = NB;
-            g.tiles_m = rest; g.tiles_n = 1; g.K = NB;
-            g.alpha = 1.0; g.beta = 0.0; g.lower_only = 0; g.kbegin_row = 0;
-            launch_gemm_nt(g, ss);
-            // ... plus one step of iterative refinement, P += (A21 - P L11^T) L11^{-T}: multiplying by an explicit
-            // inverse alone loses cond(L11)*eps, which matters for the nearly singular covariances draw_sample factors
-            launch_copy2d(resid, NB, A21, ld, rest * NB, NB, ss);
-            GemmParams r1 = g;
-            r1.C = resid; r1.ldc = NB;
-            r1.A = panel; r1.lda = NB;
-            r1.B = Akk; r1.ldb = ld;
-            r1.alpha = -1.0; r1.beta = 1.0;
-            launch_gemm_nt(r1, ss);
-            GemmParams r2 = g;
-            r2.C = panel; r2.ldc = NB;
-            r2.A = resid; r2.lda = NB;
-            r2.B = inv_k; r2.ldb = NB;
-            r2.alpha = 1.0; r2.beta = 1.0;
-            launch_gemm_nt(r2, ss);
-            launch_copy2d(A21, ld, panel, NB, rest * NB, NB, ss);
-            if (rhs) launch_panel_gemv(panel, rest * NB, rhs + (long)k * NB, rhs + (long)(k + 1) * NB, ss);
-            h->launches += rhs ? 6 : 5;
+            // panel P = A21 L11^{-T}: one-pass blocked substitution (factor.cu: panel_trsm_kernel), in place, plus the
+            // contiguous copy the rank-128 update reads and the right-hand-side update
+            launch_panel_trsm(A21, ld, Akk, ld, inv_k, panel, rest * NB, rhs ? rhs + (long)k * NB : nullptr,
+                              rhs ? rhs + (long)(k + 1) * NB : nullptr, ss);
+            h->launches++;
         }
         CUDA_OK(h, cudaEventRecord(h->ev_panel, ss));
         // ---- main stream: trailing update of step k, next block column first ----
@@ -237,7 +217,6 @@ int factor_and_solve(gpt_handle* h, double* ll, int* status) {
     int rc;
     if ((rc = ensure(h, h->Inv, (size_t)nblk * NB * NB * sizeof(double)))) return rc;
     if ((rc = ensure(h, h->P, (size_t)2 * Mp * NB * sizeof(double)))) return rc;
-    if ((rc = ensure(h, h->Pres, (size_t)Mp * NB * sizeof(double)))) return rc;
     if ((rc = ensure(h, h->z, (size_t)Mp * sizeof(double)))) return rc;
     if ((rc = ensure(h, h->zt, (size_t)Mp * sizeof(double)))) return rc;
     if ((rc = ensure(h, h->alpha, (size_t)Mp * sizeof(double)))) return rc;
@@ -246,7 +225,7 @@ int factor_and_solve(gpt_handle* h, double* ll, int* status) {
     CUDA_OK(h, cudaMemsetAsync(h->z.p, 0, (size_t)Mp * sizeof(double), s));
     CUDA_OK(h, cudaMemcpyAsync(h->z.p, h->y.p, (size_t)M * sizeof(double), cudaMemcpyDeviceToDevice, s));
     if ((rc = blocked_potrf(h, ptr<double>(h->A), Mp, nblk, ptr<double>(h->Inv), ptr<double>(h->P),
-                            ptr<double>(h->Pres), ptr<double>(h->z), ptr<double>(h->logdet), ptr<int>(h->info))))
+                            ptr<double>(h->z), ptr<double>(h->logdet), ptr<int>(h->info))))
         return rc;
     CUDA_OK(h, cudaMemcpyAsync(h->zt.p, h->z.p, (size_t)Mp * sizeof(double), cudaMemcpyDeviceToDevice, s));
     for (int k = nblk - 1; k >= 0; k--) {
@@ -424,11 +403,12 @@ void gpt_destroy(gpt_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf* all[] = {&h->X, &h->n, &h->y, &h->diag, &h->T, &h->Tt, &h->A, &h->Klat, &h->W, &h->Inv, &h->P, &h->Pres, &h->z,
+    DevBuf* all[] = {&h->X, &h->n, &h->y, &h->diag, &h->T, &h->Tt, &h->A, &h->Klat, &h->W, &h->Inv, &h->P, &h->z,
                      &h->zt, &h->alpha, &h->logdet, &h->info, &h->scal, &h->XT, &h->Kinv, &h->S, &h->partials,
                      &h->gout, &h->u, &h->Sg, &h->Yt, &h->Xs, &h->ns, &h->Kst, &h->Kso, &h->kss, &h->mean, &h->var,
                      &h->cov, &h->Rt, &h->smp, &h->b_thetas, &h->b_y, &h->b_ll, &h->b_grad, &h->b_status,
-                     &h->b_alpha, &h->b_ws, &h->b_counter, &h->Vtmp};
+                     &h->b_alpha, &h->b_ws, &h->b_counter, &h->Vtmp, &h->ds_C, &h->ds_inv, &h->ds_panel, &h->ds_logdet,
+                     &h->ds_info, &h->ds_R, &h->ds_Rt, &h->ds_O, &h->ds_mu, &h->ds_jit};
     for (DevBuf* b : all) release(*b);
     if (h->side_stream) {
         cudaStreamSynchronize(h->side_stream);
@@ -962,13 +942,15 @@ int gpt_draw_sample(gpt_handle* h, int Ms, int S, const double* mean, const doub
     cudaStream_t s = h->stream;
     const int Sp = round_up(Ms, NB), nblk = Sp / NB, Rp = round_up(S, NB);
     int rc;
-    DevBuf C, inv, panel, resid, logdet, info, R, Rt, O, mu, jit;
-    auto cleanup = [&]() { release(C); release(inv); release(panel); release(resid); release(logdet); release(info); release(R);
-                           release(Rt); release(O); release(mu); release(jit); };
+    // scratch lives in the handle (grown on demand, freed by gpt_destroy): cudaMalloc / cudaFree per call cost more than
+    // the factorisation itself at config-5 sizes
+    DevBuf &C = h->ds_C, &inv = h->ds_inv, &panel = h->ds_panel, &logdet = h->ds_logdet, &info = h->ds_info, &R = h->ds_R,
+           &Rt = h->ds_Rt, &O = h->ds_O, &mu = h->ds_mu, &jit = h->ds_jit;
+    auto cleanup = [&]() {};
     std::vector<double> hj(Ms, jitter);
     if ((rc = upload_padded(h, C, cov, Ms, Ms, Sp, Sp)) || (rc = upload(h, jit, hj.data(), sizeof(double) * Ms)) ||
         (rc = ensure(h, inv, sizeof(double) * (size_t)nblk * NB * NB)) ||
-        (rc = ensure(h, panel, sizeof(double) * (size_t)2 * Sp * NB)) || (rc = ensure(h, resid, sizeof(double) * (size_t)Sp * NB)) ||
+        (rc = ensure(h, panel, sizeof(double) * (size_t)2 * Sp * NB)) ||
         (rc = ensure(h, logdet, sizeof(double) * nblk)) ||
         (rc = ensure(h, info, sizeof(int))) || (rc = upload_padded(h, R, rand_vars, Ms, S, Sp, Rp)) ||
         (rc = ensure(h, Rt, sizeof(double) * (size_t)Rp * Sp)) || (rc = ensure(h, O, sizeof(double) * (size_t)Sp * Rp)) ||
@@ -978,8 +960,8 @@ int gpt_draw_sample(gpt_handle* h, int Ms, int S, const double* mean, const doub
     }
     launch_add_diag(ptr<double>(C), Sp, ptr<double>(jit), Ms, s);
     launch_set_identity_pad(ptr<double>(C), Sp, Ms, Sp, s);
-    rc = blocked_potrf(h, ptr<double>(C), Sp, nblk, ptr<double>(inv), ptr<double>(panel), ptr<double>(resid), nullptr,
-                       ptr<double>(logdet), ptr<int>(info));
+    rc = blocked_potrf(h, ptr<double>(C), Sp, nblk, ptr<double>(inv), ptr<double>(panel), nullptr, ptr<double>(logdet),
+                       ptr<int>(info));
     if (!rc) {
         dim3 tg((Sp + 255) / 256, Sp);
         tril_kernel<<<tg, 256, 0, s>>>(ptr<double>(C), Sp, Sp);

@@ -309,6 +309,98 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
 }
 
 
+// ---- panel solve: P = A21 L11^{-T}, one pass, in place -----------------------------------------------------------
+// Blocked forward substitution on 8-column blocks, each warp owning 8 rows of the panel with the whole 8 x 128 row
+// slab in accumulator registers (16 DMMA C-fragments): for J = 0..15: P_J = A_J Xp_J^T (Xp_J = the 8x8 diagonal
+// block inverse, i.e. the diagonal block of Inv), then A_K -= P_J L_KJ^T for K > J.  Warps never synchronise with
+// each other after the operand load.  Replaces "multiply by the explicit 128x128 inverse + one refinement step"
+// (3 GEMM launches + 2 copies + the rhs update, ~75 us on the critical path of the blocked Cholesky) by one ~10 us
+// launch that is backward stable at the 8x8 block level.  Also writes the panel copy the rank-128 update reads and
+// applies the right-hand-side update y -= P z_k.
+constexpr int TR_ROWS = 64;
+constexpr size_t TRSM_SMEM = ((size_t)NB * LDB + (size_t)TR_ROWS * LDB + NBLK * 64) * sizeof(double);
+
+__global__ void __launch_bounds__(256, 1) panel_trsm_kernel(double* __restrict__ A21, long lda,
+                                                            const double* __restrict__ L11, long ldl,
+                                                            const double* __restrict__ inv_k, double* __restrict__ panel,
+                                                            int rows, const double* __restrict__ zk,
+                                                            double* __restrict__ y) {
+    extern __shared__ __align__(16) double sm[];
+    double* Ls = sm;                       // NB x LDB: L11 (lower; the zeros above are loaded too)
+    double* As = Ls + NB * LDB;            // TR_ROWS x LDB: the row slab, A21 on entry, P on exit
+    double* Xs = As + TR_ROWS * LDB;       // NBLK blocks of 8 x 8: diagonal blocks of Inv
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int r0 = blockIdx.x * TR_ROWS;
+
+    for (int idx = tid; idx < NB * 64; idx += 256) {
+        const int r = idx >> 6, c2 = (idx & 63) * 2;
+        cp_async16(Ls + r * LDB + c2, L11 + (long)r * ldl + c2);
+    }
+    for (int idx = tid; idx < TR_ROWS * 64; idx += 256) {
+        const int r = idx >> 6, c2 = (idx & 63) * 2;
+        if (r0 + r < rows) cp_async16(As + r * LDB + c2, A21 + (long)(r0 + r) * lda + c2);
+        else As[r * LDB + c2] = As[r * LDB + c2 + 1] = 0.0;
+    }
+    for (int idx = tid; idx < NBLK * 32; idx += 256) {
+        const int J = idx >> 5, rr = (idx >> 2) & 7, cc = (idx & 3) * 2;
+        cp_async16(Xs + J * 64 + rr * 8 + cc, inv_k + (long)(8 * J + rr) * NB + 8 * J + cc);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+
+    double* Aw = As + (warp * 8 + g) * LDB;  // this lane's row of the warp's 8-row slab
+    double2 acc[NBLK];
+#pragma unroll
+    for (int K = 0; K < NBLK; K++) acc[K] = *reinterpret_cast<const double2*>(Aw + 8 * K + 2 * t);
+#pragma unroll
+    for (int J = 0; J < NBLK; J++) {
+        // A_J (C-fragment layout) -> A-fragment layout through the slab
+        *reinterpret_cast<double2*>(Aw + 8 * J + 2 * t) = acc[J];
+        __syncwarp();
+        const double a0 = Aw[8 * J + t], a1 = Aw[8 * J + 4 + t];
+        const double x0 = Xs[J * 64 + g * 8 + t], x1 = Xs[J * 64 + g * 8 + 4 + t];
+        double2 pj = make_double2(0.0, 0.0);
+        dmma884(pj.x, pj.y, a0, x0);
+        dmma884(pj.x, pj.y, a1, x1);
+        __syncwarp();
+        *reinterpret_cast<double2*>(Aw + 8 * J + 2 * t) = pj;  // final P_J
+        __syncwarp();
+        const double n0 = -Aw[8 * J + t], n1 = -Aw[8 * J + 4 + t];
+#pragma unroll
+        for (int K = 0; K < NBLK; K++) {
+            if (K > J) {
+                const double b0 = Ls[(8 * K + g) * LDB + 8 * J + t], b1 = Ls[(8 * K + g) * LDB + 8 * J + 4 + t];
+                dmma884(acc[K].x, acc[K].y, n0, b0);
+                dmma884(acc[K].x, acc[K].y, n1, b1);
+            }
+        }
+    }
+    __syncwarp();
+    // write P to the panel buffer and back into A21; y -= P z_k
+    double2 za = make_double2(0.0, 0.0), zb = za;
+    if (y != nullptr) {
+        za = *reinterpret_cast<const double2*>(zk + lane * 4);
+        zb = *reinterpret_cast<const double2*>(zk + lane * 4 + 2);
+    }
+#pragma unroll
+    for (int rr = 0; rr < 8; rr++) {
+        const int row = r0 + warp * 8 + rr;
+        const double2 va = *reinterpret_cast<const double2*>(As + (warp * 8 + rr) * LDB + lane * 4);
+        const double2 vb = *reinterpret_cast<const double2*>(As + (warp * 8 + rr) * LDB + lane * 4 + 2);
+        double sdot = (va.x * za.x + va.y * za.y) + (vb.x * zb.x + vb.y * zb.y);
+        sdot = warp_sum(sdot);
+        if (row < rows) {
+            *reinterpret_cast<double2*>(panel + (long)row * NB + lane * 4) = va;
+            *reinterpret_cast<double2*>(panel + (long)row * NB + lane * 4 + 2) = vb;
+            *reinterpret_cast<double2*>(A21 + (long)row * lda + lane * 4) = va;
+            *reinterpret_cast<double2*>(A21 + (long)row * lda + lane * 4 + 2) = vb;
+            if (lane == 0 && y != nullptr) y[row] -= sdot;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) panel_gemv_kernel(const double* __restrict__ P, int rows,
                                                          const double* __restrict__ zk, double* __restrict__ y) {
     const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -513,6 +605,17 @@ void launch_potrf_diag(double* Ablk, long lda, double* inv, double* yk, double* 
                        int /*nvalid*/, cudaStream_t s) {
     cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM);
     potrf_diag_kernel<<<1, 256, POTRF_SMEM, s>>>(Ablk, lda, inv, yk, logdet_part, info, row0);
+}
+
+void launch_panel_trsm(double* A21, long lda, const double* L11, long ldl, const double* inv_k, double* panel, int rows,
+                       const double* zk, double* y, cudaStream_t s) {
+    if (rows <= 0) return;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(panel_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSM_SMEM);
+        attr_set = true;
+    }
+    panel_trsm_kernel<<<(rows + TR_ROWS - 1) / TR_ROWS, 256, TRSM_SMEM, s>>>(A21, lda, L11, ldl, inv_k, panel, rows, zk, y);
 }
 
 void launch_panel_gemv(const double* P, int rows, const double* zk, double* y, cudaStream_t s) {

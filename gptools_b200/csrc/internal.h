@@ -53,6 +53,10 @@ void launch_cov_pairs(const CovParams& cp, int hyper_deriv, long npairs, const d
 // inv, optionally z_k = inv * y_k (in place on y), accumulate sum(log diag) and the LAPACK-style info.
 void launch_potrf_diag(double* Ablk, long lda, double* inv, double* yk, double* logdet_part, int* info,
                        int row0, int nvalid, cudaStream_t s);
+// panel solve in place: A21 (rows x 128, ld lda) <- A21 L11^{-T}; copy to panel (ld 128); y -= P zk when y != NULL.
+// inv_k supplies the 8x8 diagonal-block inverses of L11 (its own diagonal blocks).
+void launch_panel_trsm(double* A21, long lda, const double* L11, long ldl, const double* inv_k, double* panel, int rows,
+                       const double* zk, double* y, cudaStream_t s);
 // y[r] -= sum_c P[r][c] * zk[c], r < rows (P is rows x 128, ld 128)
 void launch_panel_gemv(const double* P, int rows, const double* zk, double* y, cudaStream_t s);
 // back substitution step k: alpha_k = inv_k^T z_k ; z[0 : k*128] -= L[k-block rows, 0 : k*128]^T alpha_k
