@@ -48,7 +48,7 @@ struct gpt_handle {
     bool factor_valid = false;
     CovParams cp;
     double noise_sigma = 0.0;
-    DevBuf A, Klat, W, Inv, P, z, zt, alpha, logdet, info, scal;
+    DevBuf A, Klat, W, Inv, P, z, alpha, logdet, info, scal;
     // gradient workspaces
     DevBuf XT, Kinv, S, partials, gout, u, Sg, Yt;
     // predict workspaces
@@ -56,6 +56,7 @@ struct gpt_handle {
     // batched
     DevBuf b_thetas, b_y, b_ll, b_grad, b_status, b_alpha, b_ws, b_counter;
     DevBuf ds_C, ds_inv, ds_panel, ds_logdet, ds_info, ds_R, ds_Rt, ds_O, ds_mu, ds_jit;  // draw_sample scratch
+    DevBuf flags;  // backsolve chain: one int per 128-row block
     DevBuf Vtmp;  // predict: one 128-column block of V^T (out-of-place multiply by the block inverse)
 };
 
@@ -218,7 +219,6 @@ int factor_and_solve(gpt_handle* h, double* ll, int* status) {
     if ((rc = ensure(h, h->Inv, (size_t)nblk * NB * NB * sizeof(double)))) return rc;
     if ((rc = ensure(h, h->P, (size_t)2 * Mp * NB * sizeof(double)))) return rc;
     if ((rc = ensure(h, h->z, (size_t)Mp * sizeof(double)))) return rc;
-    if ((rc = ensure(h, h->zt, (size_t)Mp * sizeof(double)))) return rc;
     if ((rc = ensure(h, h->alpha, (size_t)Mp * sizeof(double)))) return rc;
     if ((rc = ensure(h, h->logdet, (size_t)nblk * sizeof(double)))) return rc;
     if ((rc = ensure(h, h->info, sizeof(int)))) return rc;
@@ -227,12 +227,10 @@ int factor_and_solve(gpt_handle* h, double* ll, int* status) {
     if ((rc = blocked_potrf(h, ptr<double>(h->A), Mp, nblk, ptr<double>(h->Inv), ptr<double>(h->P),
                             ptr<double>(h->z), ptr<double>(h->logdet), ptr<int>(h->info))))
         return rc;
-    CUDA_OK(h, cudaMemcpyAsync(h->zt.p, h->z.p, (size_t)Mp * sizeof(double), cudaMemcpyDeviceToDevice, s));
-    for (int k = nblk - 1; k >= 0; k--) {
-        launch_backsolve_step(ptr<double>(h->A), Mp, k, ptr<double>(h->Inv) + (size_t)k * NB * NB,
-                              ptr<double>(h->zt), ptr<double>(h->alpha), s);
-        h->launches++;
-    }
+    if ((rc = ensure(h, h->flags, sizeof(int) * nblk))) return rc;
+    launch_backsolve_chain(ptr<double>(h->A), Mp, nblk, ptr<double>(h->Inv), ptr<double>(h->z), ptr<double>(h->alpha),
+                           ptr<int>(h->flags), s);
+    h->launches++;
     if ((rc = check_launch(h))) return rc;
     std::vector<double> hz(M), hl(nblk);
     int hinfo = 0;
@@ -404,10 +402,10 @@ void gpt_destroy(gpt_handle* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     DevBuf* all[] = {&h->X, &h->n, &h->y, &h->diag, &h->T, &h->Tt, &h->A, &h->Klat, &h->W, &h->Inv, &h->P, &h->z,
-                     &h->zt, &h->alpha, &h->logdet, &h->info, &h->scal, &h->XT, &h->Kinv, &h->S, &h->partials,
+                     &h->alpha, &h->logdet, &h->info, &h->scal, &h->XT, &h->Kinv, &h->S, &h->partials,
                      &h->gout, &h->u, &h->Sg, &h->Yt, &h->Xs, &h->ns, &h->Kst, &h->Kso, &h->kss, &h->mean, &h->var,
                      &h->cov, &h->Rt, &h->smp, &h->b_thetas, &h->b_y, &h->b_ll, &h->b_grad, &h->b_status,
-                     &h->b_alpha, &h->b_ws, &h->b_counter, &h->Vtmp, &h->ds_C, &h->ds_inv, &h->ds_panel, &h->ds_logdet,
+                     &h->b_alpha, &h->b_ws, &h->b_counter, &h->Vtmp, &h->flags, &h->ds_C, &h->ds_inv, &h->ds_panel, &h->ds_logdet,
                      &h->ds_info, &h->ds_R, &h->ds_Rt, &h->ds_O, &h->ds_mu, &h->ds_jit};
     for (DevBuf* b : all) release(*b);
     if (h->side_stream) {

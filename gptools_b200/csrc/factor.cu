@@ -2,11 +2,10 @@
 //   potrf_diag   : 128x128 diagonal block factorisation + explicit inverse of the block (so that the
 //                  panel solve, the triangular solves of predict and trtri all become DMMA GEMMs),
 //                  the block's share of z = L^{-1} y, its log-determinant share and LAPACK-style info
-//   panel_gemv   : right-looking update of the remaining right-hand side
-//   backsolve    : alpha = L^{-T} z, one block per launch
+//   panel_trsm   : one-pass panel solve P = A21 L11^{-T} (+ panel copy, right-hand-side update)
+//   backsolve    : alpha = L^{-T} z, one launch (chain of CTAs)
 //   grad_reduce  : 1/2 tr((a a^T - S) dK_p) with the dK tiles regenerated on the fly (never stored)
 // Replaces scipy.linalg.cholesky / cho_solve in compute_K_L_alpha_ll (gaussian_process.py:1452-1504).
-#include <cstdio>
 #include "common.cuh"
 #include "internal.h"
 
@@ -83,16 +82,10 @@ __device__ __forceinline__ void blk_batch(const BlkItem (&it)[4], double sa, dou
 __device__ __forceinline__ void pivot8(double* P, double* G, long ldg, double* dsm, double* lsm, int lane, int row0,
                                        int* s_info) {
     double p[8][8], lc[8][8];
-#ifdef GPT_POTRF_TIMING
-    long long c0 = clock64();
-#endif
 #pragma unroll
     for (int i = 0; i < 8; i++)
 #pragma unroll
         for (int j = 0; j <= i; j++) p[i][j] = P[i * LDB + j];
-#ifdef GPT_POTRF_TIMING
-    long long c1 = clock64();
-#endif
     double dsave[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) {
@@ -118,15 +111,9 @@ __device__ __forceinline__ void pivot8(double* P, double* G, long ldg, double* d
             }
         }
     }
-#ifdef GPT_POTRF_TIMING
-    long long c2 = clock64();
-#endif
     double rs[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) rs[i] = fast_rsqrt_pos(dsave[i]);
-#ifdef GPT_POTRF_TIMING
-    long long c3 = clock64();
-#endif
     // Every lane holds every value: store them with uniform (same address, same data) shared-memory writes --
     // 64 lane-predicated branches cost ~7000 cycles here, five times the elimination itself.  The factor goes
     // through the scratch block lsm and is copied to global by all lanes.
@@ -143,10 +130,6 @@ __device__ __forceinline__ void pivot8(double* P, double* G, long ldg, double* d
     G[(lane >> 3) * ldg + (lane & 7)] = lsm[lane];
     G[((lane >> 3) + 4) * ldg + (lane & 7)] = lsm[lane + 32];
     __syncwarp();
-#ifdef GPT_POTRF_TIMING
-    long long c4 = clock64();
-    if (lane == 0 && row0 == 24) printf("pivot8: load %lld elim %lld rsqrt %lld store %lld\n", c1 - c0, c2 - c1, c3 - c2, c4 - c3);
-#endif
 }
 
 __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__ A, long lda, double* __restrict__ inv,
@@ -179,9 +162,6 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
 #pragma unroll 1
     for (int J = 0; J < NBLK; J++) {
         double* Xp = blk8(V, J, J);
-#ifdef GPT_POTRF_TIMING
-        long long tA0 = clock64();
-#endif
         // ---- phase A: multiply by the pivot inverses.
         //   chain (J > 0, warp 0) : Y_{J,J-1} = -L_{J,J-1} Xp_{J-1}, then X_{J,J-1} = Xp_J Y_{J,J-1}
         //   a [0, na)             : X_JK = Xp_J Y_JK, K < J-1                               (nn, sa = +1)
@@ -228,14 +208,8 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
                 blk_batch(it, -1.0, 0.0, lda, g, t);
             }
         }
-#ifdef GPT_POTRF_TIMING
-        long long tA1 = clock64();
-#endif
         __syncthreads();
         if (J + 1 == NBLK) break;
-#ifdef GPT_POTRF_TIMING
-        long long tB0 = clock64();
-#endif
         // ---- phase B: warp 7 finalises and factors the next pivot block while the others apply the rank-8 update
         if (warp == 7) {
             BlkItem it[4];
@@ -275,11 +249,6 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
                 blk_batch(it, -1.0, 1.0, lda, g, t);
             }
         }
-#ifdef GPT_POTRF_TIMING
-        long long tB1 = clock64();
-        if (lane == 0 && (warp == 0 || warp == 7) && row0 == 0)
-            printf("J=%d warp=%d phaseA %lld  barrier %lld  phaseB %lld\n", J, warp, tA1 - tA0, tB0 - tA1, tB1 - tB0);
-#endif
         __syncthreads();
     }
 
@@ -307,7 +276,6 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
         if (s_info != 0) atomicCAS(info, 0, s_info);
     }
 }
-
 
 // ---- panel solve: P = A21 L11^{-T}, one pass, in place -----------------------------------------------------------
 // Blocked forward substitution on 8-column blocks, each warp owning 8 rows of the panel with the whole 8 x 128 row
@@ -399,61 +367,6 @@ __global__ void __launch_bounds__(256, 1) panel_trsm_kernel(double* __restrict__
             if (lane == 0 && y != nullptr) y[row] -= sdot;
         }
     }
-}
-
-__global__ void __launch_bounds__(256) panel_gemv_kernel(const double* __restrict__ P, int rows,
-                                                         const double* __restrict__ zk, double* __restrict__ y) {
-    const int warp = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= rows) return;
-    const double* row = P + (long)warp * NB;
-    double s = 0.0;
-#pragma unroll
-    for (int c = lane; c < NB; c += 32) s += row[c] * zk[c];
-    s = warp_sum(s);
-    if (lane == 0) y[warp] -= s;
-}
-
-__global__ void __launch_bounds__(256) backsolve_step_kernel(const double* __restrict__ L, long ld, int k,
-                                                             const double* __restrict__ inv_k,
-                                                             double* __restrict__ z, double* __restrict__ alpha) {
-    // alpha_k = Inv_k^T z_k (every CTA redundantly), then 64 columns of z[0 : k*128] -= L_k^T alpha_k per CTA.
-    // Both contractions are split four ways over the row index and reduced through shared memory: the loads of
-    // one thread are independent, so the chain is 32 deep instead of 128.
-    __shared__ double ak[NB];
-    __shared__ double part[4][NB];
-    const int tid = threadIdx.x;
-    {
-        const int o = tid & (NB - 1), h = tid >> 7;  // output, half of the rows
-        double s0 = 0.0, s1 = 0.0;
-        const int i0 = h * 64;
-#pragma unroll 8
-        for (int i = i0; i < i0 + 64; i += 2) {
-            s0 += (i >= o) ? inv_k[i * NB + o] * z[k * NB + i] : 0.0;
-            s1 += (i + 1 >= o) ? inv_k[(i + 1) * NB + o] * z[k * NB + i + 1] : 0.0;
-        }
-        part[h][o] = s0 + s1;
-    }
-    __syncthreads();
-    if (tid < NB) {
-        const double s = part[0][tid] + part[1][tid];
-        ak[tid] = s;
-        if (blockIdx.x == 0) alpha[k * NB + tid] = s;
-    }
-    __syncthreads();
-    const int cl = tid & 63, grp = tid >> 6;
-    const int c = blockIdx.x * 64 + cl;
-    double s0 = 0.0, s1 = 0.0;
-    if (c < k * NB) {
-        const double* col = L + ((long)k * NB + grp * 32) * ld + c;
-#pragma unroll 8
-        for (int r = 0; r < 32; r += 2) {
-            s0 += col[(long)r * ld] * ak[grp * 32 + r];
-            s1 += col[(long)(r + 1) * ld] * ak[grp * 32 + r + 1];
-        }
-    }
-    part[grp][cl] = s0 + s1;
-    __syncthreads();
-    if (tid < 64 && c < k * NB) z[c] -= (part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]);
 }
 
 __global__ void transpose_kernel(double* __restrict__ out, long ldo, const double* __restrict__ in, long ldi,
@@ -618,16 +531,94 @@ void launch_panel_trsm(double* A21, long lda, const double* L11, long ldl, const
     panel_trsm_kernel<<<(rows + TR_ROWS - 1) / TR_ROWS, 256, TRSM_SMEM, s>>>(A21, lda, L11, ldl, inv_k, panel, rows, zk, y);
 }
 
-void launch_panel_gemv(const double* P, int rows, const double* zk, double* y, cudaStream_t s) {
-    if (rows <= 0) return;
-    panel_gemv_kernel<<<(rows + 7) / 8, 256, 0, s>>>(P, rows, zk, y);
+// ---- alpha = L^{-T} z in ONE launch: a chain of CTAs, one per 128-row block ----------------------------------------
+// CTA i owns block b = nblk-1-i of the solution (so it only ever waits for CTAs dispatched before it).  It folds
+// z_b -= L[k, b]^T alpha_k for k = nblk-1 .. b+1 as the alpha_k are published, then alpha_b = Inv_b^T z_b.  The two
+// operands on the critical path -- the tile L[b+1, b] needed last and Inv_b -- are fetched before the wait (into
+// registers and shared memory), so a link of the chain costs a flag poll + ~130 FMAs per thread, not a kernel
+// launch plus two cold 128 KB reads (the per-block launches took 29 us each: 15% of an M = 4000 factorisation).
+constexpr size_t BSC_SMEM = ((size_t)NB * NB + 6 * NB) * sizeof(double);
+
+__global__ void __launch_bounds__(256, 1) backsolve_chain_kernel(const double* __restrict__ L, long ld, int nblk,
+                                                                 const double* __restrict__ inv,
+                                                                 const double* __restrict__ z, double* alpha,
+                                                                 int* flags) {
+    extern __shared__ __align__(16) double sm[];
+    double* invs = sm;                 // Inv_b, NB x NB
+    double* zs = sm + NB * NB;         // z_b
+    double* ak = zs + NB;              // alpha_k
+    double* part = ak + NB;            // 4 x NB partial sums
+    const int tid = threadIdx.x;
+    const int b = nblk - 1 - blockIdx.x;
+    const int c = tid & (NB - 1), hh = tid >> 7;  // column, half of the rows
+
+    const double* invb = inv + (size_t)b * NB * NB;
+    for (int idx = tid; idx < NB * NB / 2; idx += 256) cp_async16(invs + 2 * idx, invb + 2 * idx);
+    cp_async_commit();
+    if (tid < NB) zs[tid] = z[b * NB + tid];
+    // the tile needed last, L[b+1, b]: rows hh*64 .. +63 of column c, in registers
+    double last[64];
+    if (b + 1 < nblk) {
+        const double* tile = L + ((long)(b + 1) * NB + hh * 64) * ld + (long)b * NB + c;
+#pragma unroll
+        for (int r = 0; r < 64; r++) last[r] = tile[(long)r * ld];
+    }
+    __syncthreads();
+
+    for (int k = nblk - 1; k > b; k--) {
+        if (tid == 0) {
+            while (atomicAdd(flags + k, 0) == 0) __nanosleep(64);
+            __threadfence();
+        }
+        __syncthreads();
+        if (tid < NB) ak[tid] = __ldcg(alpha + (long)k * NB + tid);
+        __syncthreads();
+        double s0 = 0.0, s1 = 0.0;
+        if (k == b + 1) {
+#pragma unroll
+            for (int r = 0; r < 64; r += 2) {
+                s0 = fma(last[r], ak[hh * 64 + r], s0);
+                s1 = fma(last[r + 1], ak[hh * 64 + r + 1], s1);
+            }
+        } else {
+            const double* tile = L + ((long)k * NB + hh * 64) * ld + (long)b * NB + c;
+#pragma unroll 16
+            for (int r = 0; r < 64; r += 2) {
+                s0 = fma(tile[(long)r * ld], ak[hh * 64 + r], s0);
+                s1 = fma(tile[(long)(r + 1) * ld], ak[hh * 64 + r + 1], s1);
+            }
+        }
+        part[hh * NB + c] = s0 + s1;
+        __syncthreads();
+        if (tid < NB) zs[tid] -= part[tid] + part[NB + tid];
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    {   // alpha_b = Inv_b^T z_b: output c, rows i >= c only (Inv is lower triangular), split two ways
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll 8
+        for (int i = hh * 64; i < hh * 64 + 64; i += 2) {
+            s0 = fma(invs[i * NB + c], zs[i], s0);
+            s1 = fma(invs[(i + 1) * NB + c], zs[i + 1], s1);
+        }
+        part[hh * NB + c] = s0 + s1;
+    }
+    __syncthreads();
+    if (tid < NB) alpha[(long)b * NB + tid] = part[tid] + part[NB + tid];
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) atomicExch(flags + b, 1);
 }
 
-void launch_backsolve_step(const double* L, long ld, int k, const double* inv_k, double* z, double* alpha,
-                           cudaStream_t s) {
-    int grid = (k * NB + 63) / 64;
-    if (grid < 1) grid = 1;
-    backsolve_step_kernel<<<grid, 256, 0, s>>>(L, ld, k, inv_k, z, alpha);
+void launch_backsolve_chain(const double* L, long ld, int nblk, const double* inv, const double* z, double* alpha,
+                            int* flags, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(backsolve_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BSC_SMEM);
+        attr_set = true;
+    }
+    cudaMemsetAsync(flags, 0, sizeof(int) * nblk, s);
+    backsolve_chain_kernel<<<nblk, 256, BSC_SMEM, s>>>(L, ld, nblk, inv, z, alpha, flags);
 }
 
 void launch_transpose(double* out, long ldo, const double* in, long ldi, int rows, int cols, cudaStream_t s) {

@@ -57,11 +57,9 @@ void launch_potrf_diag(double* Ablk, long lda, double* inv, double* yk, double* 
 // inv_k supplies the 8x8 diagonal-block inverses of L11 (its own diagonal blocks).
 void launch_panel_trsm(double* A21, long lda, const double* L11, long ldl, const double* inv_k, double* panel, int rows,
                        const double* zk, double* y, cudaStream_t s);
-// y[r] -= sum_c P[r][c] * zk[c], r < rows (P is rows x 128, ld 128)
-void launch_panel_gemv(const double* P, int rows, const double* zk, double* y, cudaStream_t s);
-// back substitution step k: alpha_k = inv_k^T z_k ; z[0 : k*128] -= L[k-block rows, 0 : k*128]^T alpha_k
-void launch_backsolve_step(const double* L, long ld, int k, const double* inv_k, double* z, double* alpha,
-                           cudaStream_t s);
+// alpha = L^{-T} z in one launch (chain of CTAs, flags: nblk ints of scratch)
+void launch_backsolve_chain(const double* L, long ld, int nblk, const double* inv, const double* z, double* alpha,
+                            int* flags, cudaStream_t s);
 void launch_transpose(double* out, long ldo, const double* in, long ldi, int rows, int cols, cudaStream_t s);
 void launch_copy2d(double* out, long ldo, const double* in, long ldi, int rows, int cols, cudaStream_t s);
 void launch_add_diag(double* A, long lda, const double* d, int n, cudaStream_t s);
