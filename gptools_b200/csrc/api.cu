@@ -29,7 +29,7 @@ struct gpt_handle {
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
     cudaStream_t side_stream = nullptr;  // lookahead stream of the blocked Cholesky
-    cudaEvent_t ev_col = nullptr, ev_panel = nullptr;
+    cudaEvent_t ev_col = nullptr, ev_panel = nullptr, ev_rest[2] = {nullptr, nullptr};
     std::string err;
     int64_t launches = 0;
 
@@ -132,22 +132,30 @@ int blocked_potrf(gpt_handle* h, double* A, long ld, int nblk, double* inv, doub
         CUDA_OK(h, cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, prio_hi));
         CUDA_OK(h, cudaEventCreateWithFlags(&h->ev_col, cudaEventDisableTiming));
         CUDA_OK(h, cudaEventCreateWithFlags(&h->ev_panel, cudaEventDisableTiming));
+        CUDA_OK(h, cudaEventCreateWithFlags(&h->ev_rest[0], cudaEventDisableTiming));
+        CUDA_OK(h, cudaEventCreateWithFlags(&h->ev_rest[1], cudaEventDisableTiming));
     }
     cudaStream_t ss = h->side_stream;
     CUDA_OK(h, cudaMemsetAsync(info, 0, sizeof(int), sm));
-    // the side stream starts after everything queued so far on the main stream (assembly, rhs set-up)
-    CUDA_OK(h, cudaEventRecord(h->ev_col, sm));
+    // Dependencies (block column c is final once strip(c-1) has run; rest(j) touches block columns >= j+2):
+    //   potrf_diag(k): rest(k-2) [ev_rest, alternating pair] + its own in-kernel update with panel(k-1)
+    //   trsm(k)      : strip(k-1) [ev_col]            strip(k), rest(k): trsm(k) [ev_panel], in main-stream order
+    CUDA_OK(h, cudaEventRecord(h->ev_col, sm));  // everything queued so far (assembly, rhs set-up)
     for (int k = 0; k < nblk; k++) {
         double* Akk = A + (long)k * NB * ld + (long)k * NB;
         double* inv_k = inv + (size_t)k * NB * NB;
         double* panel = panel2 + (size_t)(k & 1) * (size_t)nblk * NB * NB;
+        const double* panel_prev = panel2 + (size_t)((k - 1) & 1) * (size_t)nblk * NB * NB;
         const int rest = nblk - k - 1;
-        // ---- side stream: diagonal block + panel of step k (needs block column k final: ev_col) ----
-        CUDA_OK(h, cudaStreamWaitEvent(ss, h->ev_col, 0));
-        launch_potrf_diag(Akk, ld, inv_k, rhs ? rhs + (long)k * NB : nullptr, logdet + k, info, k * NB, NB, ss);
+        // ---- side stream: diagonal block + panel of step k ----
+        if (k == 0) CUDA_OK(h, cudaStreamWaitEvent(ss, h->ev_col, 0));
+        if (k >= 2) CUDA_OK(h, cudaStreamWaitEvent(ss, h->ev_rest[k & 1], 0));
+        launch_potrf_diag(Akk, ld, inv_k, rhs ? rhs + (long)k * NB : nullptr, logdet + k, info, k * NB,
+                          k > 0 ? panel_prev : nullptr, ss);
         h->launches++;
         if (rest > 0) {
             double* A21 = A + (long)(k + 1) * NB * ld + (long)k * NB;
+            if (k > 0) CUDA_OK(h, cudaStreamWaitEvent(ss, h->ev_col, 0));
             // panel P = A21 L11^{-T}: one-pass blocked substitution (factor.cu: panel_trsm_kernel), in place, plus the
             // contiguous copy the rank-128 update reads and the right-hand-side update
             launch_panel_trsm(A21, ld, Akk, ld, inv_k, panel, rest * NB, rhs ? rhs + (long)k * NB : nullptr,
@@ -158,15 +166,17 @@ int blocked_potrf(gpt_handle* h, double* A, long ld, int nblk, double* inv, doub
         // ---- main stream: trailing update of step k, next block column first ----
         CUDA_OK(h, cudaStreamWaitEvent(sm, h->ev_panel, 0));
         if (rest > 0) {
-            GemmParams c;  // strip: block column k+1, rows >= k+1
-            c.C = A + (long)(k + 1) * NB * ld + (long)(k + 1) * NB; c.ldc = ld;
-            c.A = panel; c.lda = NB;
-            c.B = panel; c.ldb = NB;
-            c.tiles_m = rest; c.tiles_n = 1; c.K = NB;
-            c.alpha = -1.0; c.beta = 1.0; c.lower_only = 0; c.kbegin_row = 0;
-            launch_gemm_nt(c, sm);
+            if (rest > 1) {
+                GemmParams c;  // strip: block column k+1, rows >= k+2 (the diagonal block is potrf_diag(k+1)'s)
+                c.C = A + (long)(k + 2) * NB * ld + (long)(k + 1) * NB; c.ldc = ld;
+                c.A = panel + (size_t)NB * NB; c.lda = NB;
+                c.B = panel; c.ldb = NB;
+                c.tiles_m = rest - 1; c.tiles_n = 1; c.K = NB;
+                c.alpha = -1.0; c.beta = 1.0; c.lower_only = 0; c.kbegin_row = 0;
+                launch_gemm_nt(c, sm);
+                h->launches++;
+            }
             CUDA_OK(h, cudaEventRecord(h->ev_col, sm));
-            h->launches++;
             if (rest > 1) {
                 GemmParams u;  // rest: block columns >= k+2 (lower tiles only)
                 u.C = A + (long)(k + 2) * NB * ld + (long)(k + 2) * NB; u.ldc = ld;
@@ -177,6 +187,7 @@ int blocked_potrf(gpt_handle* h, double* A, long ld, int nblk, double* inv, doub
                 launch_gemm_nt(u, sm);
                 h->launches++;
             }
+            CUDA_OK(h, cudaEventRecord(h->ev_rest[k & 1], sm));
         }
     }
     // join: nothing is left running on the side stream that the main stream has not waited for (ev_panel of the
@@ -413,6 +424,8 @@ void gpt_destroy(gpt_handle* h) {
         cudaStreamDestroy(h->side_stream);
         cudaEventDestroy(h->ev_col);
         cudaEventDestroy(h->ev_panel);
+        cudaEventDestroy(h->ev_rest[0]);
+        cudaEventDestroy(h->ev_rest[1]);
     }
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;

@@ -14,7 +14,8 @@ namespace {
 constexpr int NB = GPT_NB;
 constexpr int LDB = NB + 4;  // stride == 4 (mod 16): conflict-free DMMA fragment loads from the block
 constexpr int NBLK = NB / 8;
-constexpr size_t POTRF_SMEM = ((size_t)NB * LDB + 2 * NB) * sizeof(double);
+constexpr int PCH = NB * 20;  // one 128 x 16 chunk of the previous panel block, rows padded to 20
+constexpr size_t POTRF_SMEM = ((size_t)NB * LDB + 2 * NB + 2 * PCH) * sizeof(double);
 
 // ---- 128x128 diagonal block: blocked in-place Gauss-Jordan sweep on 8x8 sub-blocks ------------------------------
 // The first version of this kernel eliminated one column per __syncthreads with scalar FP64 (207 us per block,
@@ -132,9 +133,13 @@ __device__ __forceinline__ void pivot8(double* P, double* G, long ldg, double* d
     __syncwarp();
 }
 
+// Pprev != null: the block still lacks the rank-128 update of the previous step, A -= Pprev Pprev^T (Pprev = the
+// 128 x 128 block of the previous panel that sits beside this diagonal block); applying it here takes the strip
+// GEMM of the blocked Cholesky off the critical path.
 __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__ A, long lda, double* __restrict__ inv,
                                                             double* __restrict__ yk, double* __restrict__ logdet_part,
-                                                            int* __restrict__ info, int row0) {
+                                                            int* __restrict__ info, int row0,
+                                                            const double* __restrict__ Pprev) {
     extern __shared__ __align__(16) double sm[];
     double* V = sm;                  // NB x LDB
     double* yv = sm + NB * LDB;      // right-hand side block
@@ -151,6 +156,54 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
     if (tid < NB && yk != nullptr) yv[tid] = yk[tid];
     if (tid == 0) s_info = 0;
     __syncthreads();
+    if (Pprev != nullptr) {
+        // 136 lower 8x8 blocks, 17 per warp, accumulated over eight 16-wide chunks of Pprev (double-buffered)
+        double* Pc = dsm + NB;
+        double2 acc[17];
+        int offI[17], offK[17];
+#pragma unroll
+        for (int j = 0; j < 17; j++) {
+            const int q = warp + 8 * j;
+            int I = (int)((sqrtf(8.0f * (float)q + 1.0f) - 1.0f) * 0.5f);
+            while ((I + 1) * (I + 2) / 2 <= q) I++;
+            while (I * (I + 1) / 2 > q) I--;
+            const int K = q - I * (I + 1) / 2;
+            offI[j] = 8 * I;
+            offK[j] = 8 * K;
+            acc[j] = make_double2(0.0, 0.0);
+        }
+        auto load_chunk = [&](int st, int kc) {
+            for (int idx = tid; idx < NB * 8; idx += 256) {
+                const int r = idx >> 3, c2 = (idx & 7) * 2;
+                cp_async16(Pc + st * PCH + r * 20 + c2, Pprev + (long)r * NB + kc * 16 + c2);
+            }
+        };
+        load_chunk(0, 0);
+        cp_async_commit();
+        for (int kc = 0; kc < 8; kc++) {
+            if (kc + 1 < 8) load_chunk((kc + 1) & 1, kc + 1);
+            cp_async_commit();
+            cp_async_wait<1>();
+            __syncthreads();
+            const double* Ps = Pc + (kc & 1) * PCH;
+#pragma unroll
+            for (int j = 0; j < 17; j++) {
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++)
+                    dmma884(acc[j].x, acc[j].y, Ps[(offI[j] + g) * 20 + kk * 4 + t], Ps[(offK[j] + g) * 20 + kk * 4 + t]);
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int j = 0; j < 17; j++) {
+            double2* v = reinterpret_cast<double2*>(V + (offI[j] + g) * LDB + offK[j] + 2 * t);
+            double2 cur = *v;
+            cur.x -= acc[j].x;
+            cur.y -= acc[j].y;
+            *v = cur;
+        }
+        __syncthreads();
+    }
     // the factor is a GEMM operand later: the blocks above the block diagonal must be clean zeros
     for (int idx = tid; idx < NB * NB; idx += 256) {
         const int r = idx >> 7, c = idx & (NB - 1);
@@ -515,9 +568,13 @@ __global__ void trace_sumsq_kernel(const double* __restrict__ A, long lda, const
 }  // namespace
 
 void launch_potrf_diag(double* Ablk, long lda, double* inv, double* yk, double* logdet_part, int* info, int row0,
-                       int /*nvalid*/, cudaStream_t s) {
-    cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM);
-    potrf_diag_kernel<<<1, 256, POTRF_SMEM, s>>>(Ablk, lda, inv, yk, logdet_part, info, row0);
+                       const double* Pprev, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM);
+        attr_set = true;
+    }
+    potrf_diag_kernel<<<1, 256, POTRF_SMEM, s>>>(Ablk, lda, inv, yk, logdet_part, info, row0, Pprev);
 }
 
 void launch_panel_trsm(double* A21, long lda, const double* L11, long ldl, const double* inv_k, double* panel, int rows,

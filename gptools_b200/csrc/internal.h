@@ -51,8 +51,9 @@ void launch_cov_pairs(const CovParams& cp, int hyper_deriv, long npairs, const d
 // ---- factor.cu : blocked Cholesky pieces, solves, reductions -----------------------------------
 // Factor one 128x128 diagonal block in place (lower), write its inverse (lower, zero above) to
 // inv, optionally z_k = inv * y_k (in place on y), accumulate sum(log diag) and the LAPACK-style info.
+// Pprev (128 x 128, ld 128) or NULL: first apply the pending update Ablk -= Pprev Pprev^T.
 void launch_potrf_diag(double* Ablk, long lda, double* inv, double* yk, double* logdet_part, int* info,
-                       int row0, int nvalid, cudaStream_t s);
+                       int row0, const double* Pprev, cudaStream_t s);
 // panel solve in place: A21 (rows x 128, ld lda) <- A21 L11^{-T}; copy to panel (ld 128); y -= P zk when y != NULL.
 // inv_k supplies the 8x8 diagonal-block inverses of L11 (its own diagonal blocks).
 void launch_panel_trsm(double* A21, long lda, const double* L11, long ldl, const double* inv_k, double* panel, int rows,
