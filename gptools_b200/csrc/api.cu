@@ -802,8 +802,7 @@ int gpt_predict(gpt_handle* h, int Ms, const double* Xs, const int32_t* ns, doub
     const int D = h->D, N = h->N, M = h->M, Np = h->Np, Mp = h->Mp, nblk = Mp / NB;
     int rc;
     // chunk of test points; the full covariance needs every test point in one chunk
-    // otherwise: whole waves of the solve GEMMs (row tiles = a multiple of the SM count; a 8192-row chunk filled
-    // 43% of the machine), as many as fit a third of the free device memory (capped at 48 GB)
+    // otherwise: whole waves of the solve GEMMs (an 8192-row chunk filled 43% of the machine), as many as fit a third of the free device memory (capped at 48 GB)
     int CH = round_up(Ms, NB);
     if (!cov) {
         int sms = 148;
@@ -813,7 +812,7 @@ int gpt_predict(gpt_handle* h, int Ms, const double* Xs, const int32_t* ns, doub
         size_t budget = free_b / 3;
         if (budget > ((size_t)48 << 30)) budget = (size_t)48 << 30;
         const size_t per_row = (size_t)(Np + (h->hasT ? Mp : 0) + NB) * sizeof(double);
-        const long wave = (long)sms * NB;
+        const long wave = gemm_rows_per_wave_n128(sms);
         long fit = (long)(budget / per_row);
         if (fit >= wave) fit = fit / wave * wave;
         else fit = fit / NB * NB;

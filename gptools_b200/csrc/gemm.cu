@@ -5,9 +5,10 @@
 // operands and pre-transposed inverses make every product NT).
 //
 // CTA tile 128x64x16, 128 threads = 4 warps (2 x 2), warp tile 64x32 = 8x4 DMMA.8x8x4 tiles,
-// 3-stage cp.async pipeline, TWO CTAs per SM: the read-modify-write epilogue of one CTA (an L2/HBM round trip with
-// the accumulators pinned in registers) overlaps the main loop of the other.  A 128x128 CTA alone on the SM
-// spent ~20% of a K=128 rank update in that epilogue (profiles/r01f_gemm_notes.txt).  Shared rows are padded to 20 doubles: the fragment read
+// double-buffered cp.async pipeline (61 KB), 166 registers, THREE CTAs per SM: the read-modify-write epilogue of one
+// CTA (an L2/HBM round trip with the accumulators pinned in registers), its pipeline fill and its barriers overlap
+// the main loops of the other two.  A 128x128 CTA alone on the SM spent ~20% of a K=128 rank update in the
+// epilogue; thread-level parallelism across CTAs beat a deeper pipeline (profiles/r01f_gemm_notes.txt).  Shared rows are padded to 20 doubles: the fragment read
 // A[g][k0+t] then maps the 16 lanes of a half-warp to 16 distinct 8-byte banks (g*20+t mod 16
 // = 4g+t), i.e. conflict-free LDS.64 for both operands.
 // Roofline: FP64 tensor pipe (measured cuBLAS Dgemm 35.5 TFLOP/s on this pool's B200).
@@ -16,11 +17,11 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 64, BK = 16, STAGES = 3, LDS_ = BK + 4;
+constexpr int BM = 128, BN = 64, BK = 16, STAGES = 2, LDS_ = BK + 4;
 constexpr int THREADS = 128;
 constexpr size_t SMEM_BYTES = (size_t)STAGES * (BM + BN) * LDS_ * sizeof(double);
 
-__global__ void __launch_bounds__(THREADS, 2) gemm_nt_kernel(GemmParams p) {
+__global__ void __launch_bounds__(THREADS, 3) gemm_nt_kernel(GemmParams p) {
     extern __shared__ __align__(16) double smem[];
     const int bm = blockIdx.y, bn = blockIdx.x;
     if (p.lower_only && bn > 2 * bm + 1) return;  // bn counts 64-wide half tiles; diagonal 128-blocks are full
@@ -133,6 +134,9 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_nt_kernel(GemmParams p) {
 }
 
 }  // namespace
+
+// rows of a 128-column output (tiles_n == 1) that fill the machine with whole waves of CTAs
+long gemm_rows_per_wave_n128(int num_sms) { return (long)num_sms * 3 /* CTAs per SM */ * 128 / (128 / BN); }
 
 void launch_gemm_nt(const GemmParams& p, cudaStream_t s) {
     cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);

@@ -24,6 +24,7 @@ struct GemmParams {
     int kbegin_row;  // contraction starts at k = tile_m*128 (A upper block-triangular)
 };
 void launch_gemm_nt(const GemmParams& p, cudaStream_t s);
+long gemm_rows_per_wave_n128(int num_sms);
 
 // ---- assemble.cu : covariance tile generation ------------------------------------------------
 struct AssembleParams {

@@ -41,7 +41,7 @@ def c4(nloc):
         t, _ = timed(lambda: d.predict(Xs, ns, want_var=False))
         print("   predict mean only  M*=%d: %.3f s  %.3g points/s  (equivalent K* bytes %.0f GB/s)" % (
             Ms, t, Ms / t, 8.0 * M * Ms / t * 1e-9))
-    Ms = 100000 if M <= 24576 else 2 * 148 * 128   # whole waves of the solve GEMMs
+    Ms = 100000 if M <= 24576 else 28416   # one whole wave of the solve GEMMs (148 SMs x 3 CTAs x 64 rows)
     Xs = RandomState(2).rand(Ms, 2)
     ns = np.zeros((Ms, 2), dtype=int)
     t, _ = timed(lambda: d.predict(Xs, ns, want_var=True))
