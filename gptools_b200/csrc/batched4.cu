@@ -46,6 +46,7 @@ constexpr int PTS_ORD = 192;
 struct Smem {
     double R[R_D];
     double piv[8];  // product of the 8 pivots of each 8x8 pivot block of the tile being factored
+    double exptab[64];  // 2^(j/64), for exp_nonpos_tab
     double rk[TB], zk[TB];
     double red[4][GPT_MAX_PARAMS + 2];
     const double* a[MAXT];
@@ -386,7 +387,8 @@ __device__ __forceinline__ void gen_ktot_tile(const Smem& sm, const BatchedParam
             St[r * LDT + c] = ktot_entry(sm, p, I * TB + r, gj) - St[r * LDT + c];
         }
     } else {
-        const SEHoist<FD> h = se_hoist<FD>(sm.cp);
+        SEHoist<FD> h = se_hoist<FD>(sm.cp);
+        h.etab = sm.exptab;
         const bool col_ok = gj < p.M;
         const PointReg<FD> pj = load_point<FD>(p.X, p.n, col_ok ? gj : 0);
         const double dj = col_ok ? sm.noise2 + __ldg(p.diag + gj) : 0.0;
@@ -397,7 +399,7 @@ __device__ __forceinline__ void gen_ktot_tile(const Smem& sm, const BatchedParam
                 const int r = (tid >> 6) + 2 * u;
                 const int gi = I * TB + r;
                 const PointReg<FD> pi = staged_point<FD>(pts, r);
-                double v = se_value_low<FD>(h, pi, pj);
+                double v = se_value_low<FD, true>(h, pi, pj);
                 v = (gi == gj) ? v + dj : v;
                 const double pad = (gi == gj) ? 1.0 : 0.0;
                 v = (col_ok && gi < p.M) ? v : pad;
@@ -466,7 +468,8 @@ __device__ __forceinline__ void grad_tile(const Smem& sm, const BatchedParams& p
             }
         }
     } else {
-        const SEHoist<FD> h = se_hoist<FD>(sm.cp);
+        SEHoist<FD> h = se_hoist<FD>(sm.cp);
+        h.etab = sm.exptab;
         const PointReg<FD> pj = load_point<FD>(p.X, p.n, gj);
         const double* pts = sm.R + PTS_OFF;
         double wk = 0.0;
@@ -486,7 +489,7 @@ __device__ __forceinline__ void grad_tile(const Smem& sm, const BatchedParams& p
                 w = use ? w : 0.0;
                 trl += (use && on_diag) ? kinv : 0.0;
                 double K, dl[FD];
-                se_value_grad_low<FD>(h, pi, pj, K, dl);
+                se_value_grad_low<FD, true>(h, pi, pj, K, dl);
                 wk = fma(w, K, wk);
 #pragma unroll
                 for (int d = 0; d < FD; d++) gall[1 + d] = fma(w, dl[d], gall[1 + d]);
@@ -544,6 +547,7 @@ __global__ void __launch_bounds__(THREADS, GPT_B4_MINB) ll_batched4_kernel(Batch
     double* avec = rvec + (size_t)nT * TB;
     double* St = sm.R;
     double acc[4][4][2];
+    if (L.tid < 64) sm.exptab[L.tid] = GPT_EXP2_64[L.tid];  // published by the first barrier of the theta loop
 
     for (;;) {
         __syncthreads();

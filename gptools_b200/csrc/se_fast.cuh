@@ -28,6 +28,7 @@ template <int D>
 struct SEHoist {
     double sig2, sig;
     double il[D];
+    const double* etab;  // 2^(j/64) table in shared memory for the TAB variants of the low-order evaluators, or null
 };
 
 template <int D>
@@ -37,6 +38,7 @@ __device__ __forceinline__ SEHoist<D> se_hoist(const CovParams& cp) {
     h.sig = cp.p[0];
 #pragma unroll
     for (int d = 0; d < D; d++) h.il[d] = cp.inv_l[d];
+    h.etab = nullptr;
     return h;
 }
 
@@ -111,7 +113,13 @@ __device__ __forceinline__ void se_value_grad(const SEHoist<D>& h, const PointRe
 
 // Branch-free versions for derivative orders <= 1 on both sides (m_d <= 2): selects only, so that the compiler
 // can interleave the unrolled evaluations (a conditional branch per entry serialises them -- measured).
-template <int D>
+template <bool TAB, int D>
+__device__ __forceinline__ double exp_low(const SEHoist<D>& h, double x) {
+    if constexpr (TAB) return exp_nonpos_tab(x, h.etab);
+    else return exp_nonpos_nobranch(x);
+}
+
+template <int D, bool TAB = false>
 __device__ __forceinline__ double se_value_low(const SEHoist<D>& h, const PointReg<D>& a, const PointReg<D>& b) {
     double r2 = 0.0, prod = 1.0;
     int sj = 0;
@@ -123,11 +131,11 @@ __device__ __forceinline__ double se_value_low(const SEHoist<D>& h, const PointR
         sj += b.n[d];
         prod *= se_dim_value_low(tau, h.il[d], a.n[d] + b.n[d]);
     }
-    const double k = h.sig2 * exp_nonpos_nobranch(-0.5 * r2) * prod;
+    const double k = h.sig2 * exp_low<TAB>(h, -0.5 * r2) * prod;
     return (sj & 1) ? -k : k;
 }
 
-template <int D>
+template <int D, bool TAB = false>
 __device__ __forceinline__ void se_value_grad_low(const SEHoist<D>& h, const PointReg<D>& a, const PointReg<D>& b,
                                                   double& K, double (&dl)[D]) {
     double r2 = 0.0;
@@ -141,7 +149,7 @@ __device__ __forceinline__ void se_value_grad_low(const SEHoist<D>& h, const Poi
         sj += b.n[d];
         se_dim_factor_low(tau, h.il[d], a.n[d] + b.n[d], f[d], g[d]);
     }
-    double base = h.sig2 * exp_nonpos_nobranch(-0.5 * r2);
+    double base = h.sig2 * exp_low<TAB>(h, -0.5 * r2);
     base = (sj & 1) ? -base : base;
     double prod = 1.0;
 #pragma unroll
