@@ -5,10 +5,10 @@
 // (tools/tile_model.py is the numpy model of the tile recurrences).  Cut for latency tolerance: measurements on
 // the first-generation kernel (256 threads, 2 CTAs/SM; git history, profiles/r01a_*): the FP64 pipe -- which DMMA and scalar DFMA share on B200 (profiles/microbench/fp64_overlap.cu)
 // -- was only ~63% busy because each CTA spends half of its time in latency-bound non-GEMM phases and only two
-// CTAs (= two thetas) fit on an SM.  Here a CTA is 4 warps / 128 threads with a ~53 KB footprint, so four CTAs
+// CTAs (= two thetas) fit on an SM.  Here a CTA is 4 warps / 128 threads with a ~39 KB footprint, so four CTAs
 // (four thetas) share an SM and the chance that nobody feeds the tensor pipe drops from ~29% to ~8%:
 //   * one 64x64 output tile per job, 32x32 warp tiles (16 DMMA.8x8x4 per k-step, 64 accumulator registers);
-//   * operands stream through a 3-stage cp.async ring of 64x16 chunks (A, B) with the same XOR swizzle;
+//   * operands stream through a double-buffered cp.async ring of 64x16 chunks (A, B) with an XOR swizzle;
 //   * no dedicated diagonal-tile buffer: the Gauss-Jordan sweep runs in registers (32 entries per thread) and
 //     its result goes straight to the workspace; panel products take their B fragments directly from L2.
 // Algorithmic work: M^3 flop per theta; roofline = FP64 tensor pipe.
@@ -24,7 +24,7 @@ using namespace sefast;
 constexpr int TB = 64;
 constexpr int BK = 16;
 #ifndef GPT_B4_STAGES
-#define GPT_B4_STAGES 3
+#define GPT_B4_STAGES 2  // 2 stages = 39 KB per CTA: the smaller carve-out leaves ~90 KB of L1 per SM (measured +3% over 3)
 #endif
 #ifndef GPT_B4_MINB
 #define GPT_B4_MINB 4
@@ -35,7 +35,7 @@ constexpr int CHUNK = TB * BK;         // doubles per operand chunk
 constexpr int STAGE_D = 2 * CHUNK;     // A, B
 constexpr int LDT = 68;
 constexpr int ST_D = TB * LDT;         // 4352
-// ring (3 stages: 6144 doubles = 48 KB); the same storage is the staging tile (64 x 68) + staged row points
+// ring (2 stages: 4096 doubles = 32 KB); the same storage is the staging tile (64 x 68) + staged row points
 constexpr int R_D = (STAGES * STAGE_D > ST_D + 256) ? STAGES * STAGE_D : ST_D + 256;
 constexpr int MAXT = 32;
 constexpr int TILE = TB * TB;
