@@ -206,6 +206,7 @@ __device__ __forceinline__ void blk_mma(double* C, const double* A, const double
     }
     dmma884(c.x, c.y, a0, b0);
     dmma884(c.x, c.y, a1, b1);
+    __syncwarp();  // C may alias A or B (in-place products): every lane has read its fragments before any lane stores
     *reinterpret_cast<double2*>(C + g * LDT + 2 * t) = c;
 }
 
@@ -217,6 +218,7 @@ __device__ __forceinline__ double diag8(Smem& sm, double* P, int lane, int row0)
     for (int i = 0; i < 8; i++)
 #pragma unroll
         for (int j = 0; j <= i; j++) p[i][j] = P[i * LDT + j];
+    __syncwarp();  // the result overwrites P: all lanes have read it
     double dprod = 1.0;
     double dsave[8];
 #pragma unroll

@@ -68,6 +68,7 @@ __device__ __forceinline__ void blk_batch(const BlkItem (&it)[4], double sa, dou
 #pragma unroll
     for (int u = 0; u < 4; u++)
         if (it[u].valid) dmma884(c[u].x, c[u].y, a1[u], b1[u]);
+    __syncwarp();  // C may alias A or B (in-place products): every lane has read its fragments before any lane stores
 #pragma unroll
     for (int u = 0; u < 4; u++) {
         if (it[u].valid) {
@@ -87,6 +88,7 @@ __device__ __forceinline__ void pivot8(double* P, double* G, long ldg, double* d
     for (int i = 0; i < 8; i++)
 #pragma unroll
         for (int j = 0; j <= i; j++) p[i][j] = P[i * LDB + j];
+    __syncwarp();  // the result overwrites P: all lanes have read it
     double dsave[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) {
