@@ -60,6 +60,10 @@ def c2():
     for name, kid, th in (("Matern52", 1, [1.0, 0.8]), ("Matern(nu=5/2)", 2, [1.0, 2.5, 0.8])):
         d.set_kernel(kid, len(th), 1e2)
         t, (ll, _, st) = timed(lambda: d.ll(np.array(th), 0.0), 3)
+        gi = [0, 1] if kid == 1 else [0, 2]
+        tg, (_, g, _) = timed(lambda: d.ll(np.array(th), 0.0, grad_idx=gi), 3)
+        print("C2 %s M=4000: ll+grad %.4f s (grad %s)" % (name, tg, np.array2string(g, precision=6)))
+        d.ll(np.array(th), 0.0)
         Xs = np.linspace(0, 10, 100000)[:, None]
         tp, _ = timed(lambda: d.predict(Xs, np.zeros((100000, 1), int), want_var=True))
         tm, _ = timed(lambda: d.predict(Xs, np.zeros((100000, 1), int), want_var=False))
