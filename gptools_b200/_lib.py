@@ -49,6 +49,8 @@ SIGNATURES = {
     "gpt_ll_batched_dev": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp, _vp, _c_int32_p, ctypes.c_int, _vp, _vp]),
     "gpt_predict": (ctypes.c_int, [_vp, ctypes.c_int, _c_double_p, _c_int32_p, _c_double_p, _c_double_p,
                                    _c_double_p]),
+    "gpt_predict_from_Kstar": (ctypes.c_int, [_vp, ctypes.c_int, _c_double_p, _c_double_p, _c_double_p, _c_double_p,
+                                              _c_double_p, _c_double_p]),
     "gpt_draw_sample": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _c_double_p, _c_double_p, _c_double_p,
                                        ctypes.c_double, _c_double_p, _c_int_p]),
     "gpt_launch_count": (ctypes.c_int64, [_vp]),
@@ -292,6 +294,22 @@ class Device(object):
         var = np.empty(Ms, dtype=np.float64) if (want_var or want_cov) else None
         cov = np.empty((Ms, Ms), dtype=np.float64) if want_cov else None
         self._check(self._lib.gpt_predict(self._h, Ms, _dp(Xs), _ip(ns), _dp(mean), _dp(var), _dp(cov)), "gpt_predict")
+        return mean, var, cov
+
+    def predict_from_Kstar(self, Kstar, kss_diag=None, Kss=None, want_var=True, want_cov=False):
+        """Host-evaluated kernels: ``Kstar`` is the (N latent x Ms) cross-covariance of gaussian_process.py:966,
+        ``kss_diag`` / ``Kss`` the prior variance / covariance of the test points."""
+        KstarT = _f64(np.ascontiguousarray(np.asarray(Kstar, dtype=np.float64).T))
+        Ms = KstarT.shape[0]
+        if KstarT.shape[1] != self.N:
+            raise ValueError("Kstar must have one row per latent training point")
+        kd = _f64(kss_diag, (Ms,)) if kss_diag is not None else None
+        KS = _f64(Kss, (Ms, Ms)) if Kss is not None else None
+        mean = np.empty(Ms, dtype=np.float64)
+        var = np.empty(Ms, dtype=np.float64) if (want_var or want_cov) else None
+        cov = np.empty((Ms, Ms), dtype=np.float64) if want_cov else None
+        self._check(self._lib.gpt_predict_from_Kstar(self._h, Ms, _dp(KstarT), _dp(kd), _dp(KS), _dp(mean), _dp(var),
+                                                     _dp(cov)), "gpt_predict_from_Kstar")
         return mean, var, cov
 
     def draw_sample(self, mean, cov, rand_vars, jitter):

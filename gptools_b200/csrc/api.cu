@@ -793,6 +793,81 @@ int gpt_get_K(gpt_handle* h, double* K) {
     return 0;
 }
 
+// Shared by gpt_predict and gpt_predict_from_Kstar.  On entry h->Kst holds K*^T for `rows` test points (test points
+// as rows, ld Np, zero padded to rows_pad).  Applies T (when present), writes the predictive mean for these points
+// to h->mean + s0 and, when need_second, overwrites the chunk with V^T = K*^T L^{-T} (block forward substitution,
+// every step a DMMA GEMM; gaussian_process.py:983).  *Ko / *ldk: where the (transformed) chunk lives.
+static int predict_solve_chunk(gpt_handle* h, int s0, int rows, int rows_pad, bool need_second, double** Ko_out, long* ldk_out) {
+    cudaStream_t s = h->stream;
+    const int N = h->N, M = h->M, Np = h->Np, Mp = h->Mp, nblk = Mp / NB;
+    (void)N;
+    double* Ko = ptr<double>(h->Kst);
+    long ldk = Np;
+    if (h->hasT) {
+        GemmParams g;  // (K*^T) T^T
+        g.C = ptr<double>(h->Kso); g.ldc = Mp;
+        g.A = ptr<double>(h->Kst); g.lda = Np;
+        g.B = ptr<double>(h->T); g.ldb = Np;
+        g.tiles_m = rows_pad / NB; g.tiles_n = Mp / NB; g.K = Np;
+        g.alpha = 1.0; g.beta = 0.0; g.lower_only = 0; g.kbegin_row = 0;
+        launch_gemm_nt(g, s);
+        h->launches++;
+        Ko = ptr<double>(h->Kso);
+        ldk = Mp;
+    }
+    launch_rowdot(Ko, ldk, rows, M, ptr<double>(h->alpha), ptr<double>(h->mean) + s0, s);
+    h->launches++;
+    if (need_second) {
+        for (int I = 0; I < nblk; I++) {
+            if (I > 0) {
+                GemmParams g;
+                g.C = Ko + (long)I * NB; g.ldc = ldk;
+                g.A = Ko; g.lda = ldk;
+                g.B = ptr<double>(h->A) + (long)I * NB * Mp; g.ldb = Mp;
+                g.tiles_m = rows_pad / NB; g.tiles_n = 1; g.K = I * NB;
+                g.alpha = -1.0; g.beta = 1.0; g.lower_only = 0; g.kbegin_row = 0;
+                launch_gemm_nt(g, s);
+                h->launches++;
+            }
+            // V_I = W_I Inv_I^T, out of place (two CTAs share the rows of W_I: in place would race), then back
+            GemmParams g2;
+            g2.C = ptr<double>(h->Vtmp); g2.ldc = NB;
+            g2.A = Ko + (long)I * NB; g2.lda = ldk;
+            g2.B = ptr<double>(h->Inv) + (size_t)I * NB * NB; g2.ldb = NB;
+            g2.tiles_m = rows_pad / NB; g2.tiles_n = 1; g2.K = NB;
+            g2.alpha = 1.0; g2.beta = 0.0; g2.lower_only = 0; g2.kbegin_row = 0;
+            launch_gemm_nt(g2, s);
+            launch_copy2d(Ko + (long)I * NB, ldk, ptr<double>(h->Vtmp), NB, rows_pad, NB, s);
+            h->launches += 2;
+        }
+    }
+    *Ko_out = Ko;
+    *ldk_out = ldk;
+    return 0;
+}
+
+// Test-point chunk size: the full covariance needs every test point in one chunk; otherwise whole waves of the
+// solve GEMMs (an 8192-row chunk filled 43% of the machine), as many as fit a third of the free device memory
+// (capped at 48 GB).
+static int predict_chunk_rows(gpt_handle* h, int Ms, bool full_cov) {
+    int CH = round_up(Ms, NB);
+    if (full_cov) return CH;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    size_t budget = free_b / 3;
+    if (budget > ((size_t)48 << 30)) budget = (size_t)48 << 30;
+    const size_t per_row = (size_t)(h->Np + (h->hasT ? h->Mp : 0) + NB) * sizeof(double);
+    const long wave = gemm_rows_per_wave_n128(sms);
+    long fit = (long)(budget / per_row);
+    if (fit >= wave) fit = fit / wave * wave;
+    else fit = fit / NB * NB;
+    if (fit < NB) fit = NB;
+    if (CH > fit) CH = (int)fit;
+    return CH;
+}
+
 int gpt_predict(gpt_handle* h, int Ms, const double* Xs, const int32_t* ns, double* mean, double* var, double* cov) {
     if (h && Ms == 0) return 0;  // empty test set: nothing to write
     if (!h || Ms < 1 || !Xs || !ns || !mean) return fail(h, GPT_ERR_USAGE, "gpt_predict: bad arguments");
@@ -801,24 +876,7 @@ int gpt_predict(gpt_handle* h, int Ms, const double* Xs, const int32_t* ns, doub
     cudaStream_t s = h->stream;
     const int D = h->D, N = h->N, M = h->M, Np = h->Np, Mp = h->Mp, nblk = Mp / NB;
     int rc;
-    // chunk of test points; the full covariance needs every test point in one chunk
-    // otherwise: whole waves of the solve GEMMs (an 8192-row chunk filled 43% of the machine), as many as fit a third of the free device memory (capped at 48 GB)
-    int CH = round_up(Ms, NB);
-    if (!cov) {
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-        size_t free_b = 0, total_b = 0;
-        cudaMemGetInfo(&free_b, &total_b);
-        size_t budget = free_b / 3;
-        if (budget > ((size_t)48 << 30)) budget = (size_t)48 << 30;
-        const size_t per_row = (size_t)(Np + (h->hasT ? Mp : 0) + NB) * sizeof(double);
-        const long wave = gemm_rows_per_wave_n128(sms);
-        long fit = (long)(budget / per_row);
-        if (fit >= wave) fit = fit / wave * wave;
-        else fit = fit / NB * NB;
-        if (fit < NB) fit = NB;
-        if (CH > fit) CH = (int)fit;
-    }
+    const int CH = predict_chunk_rows(h, Ms, cov != nullptr);
     if ((rc = upload(h, h->Xs, Xs, sizeof(double) * (size_t)Ms * D))) return rc;
     if ((rc = upload(h, h->ns, ns, sizeof(int32_t) * (size_t)Ms * D))) return rc;
     if (!var && !cov) {
@@ -865,46 +923,10 @@ int gpt_predict(gpt_handle* h, int Ms, const double* Xs, const int32_t* ns, doub
         a.diag_add = nullptr; a.diag_const = 0.0; a.pad_identity = 0;
         launch_assemble(a, s);
         h->launches++;
-        double* Ko = ptr<double>(h->Kst);
-        long ldk = Np;
-        if (h->hasT) {
-            GemmParams g;  // (K*^T) T^T
-            g.C = ptr<double>(h->Kso); g.ldc = Mp;
-            g.A = ptr<double>(h->Kst); g.lda = Np;
-            g.B = ptr<double>(h->T); g.ldb = Np;
-            g.tiles_m = rows_pad / NB; g.tiles_n = Mp / NB; g.K = Np;
-            g.alpha = 1.0; g.beta = 0.0; g.lower_only = 0; g.kbegin_row = 0;
-            launch_gemm_nt(g, s);
-            h->launches++;
-            Ko = ptr<double>(h->Kso);
-            ldk = Mp;
-        }
-        launch_rowdot(Ko, ldk, rows, M, ptr<double>(h->alpha), ptr<double>(h->mean) + s0, s);
-        h->launches++;
+        double* Ko = nullptr;
+        long ldk = 0;
+        if ((rc = predict_solve_chunk(h, s0, rows, rows_pad, var || cov, &Ko, &ldk))) return rc;
         if (var || cov) {
-            // V^T = K*^T L^{-T}: block forward substitution, every step a DMMA GEMM (gaussian_process.py:983)
-            for (int I = 0; I < nblk; I++) {
-                if (I > 0) {
-                    GemmParams g;
-                    g.C = Ko + (long)I * NB; g.ldc = ldk;
-                    g.A = Ko; g.lda = ldk;
-                    g.B = ptr<double>(h->A) + (long)I * NB * Mp; g.ldb = Mp;
-                    g.tiles_m = rows_pad / NB; g.tiles_n = 1; g.K = I * NB;
-                    g.alpha = -1.0; g.beta = 1.0; g.lower_only = 0; g.kbegin_row = 0;
-                    launch_gemm_nt(g, s);
-                    h->launches++;
-                }
-                // V_I = W_I Inv_I^T, out of place (two CTAs share the rows of W_I: in place would race), then back
-                GemmParams g2;
-                g2.C = ptr<double>(h->Vtmp); g2.ldc = NB;
-                g2.A = Ko + (long)I * NB; g2.lda = ldk;
-                g2.B = ptr<double>(h->Inv) + (size_t)I * NB * NB; g2.ldb = NB;
-                g2.tiles_m = rows_pad / NB; g2.tiles_n = 1; g2.K = NB;
-                g2.alpha = 1.0; g2.beta = 0.0; g2.lower_only = 0; g2.kbegin_row = 0;
-                launch_gemm_nt(g2, s);
-                launch_copy2d(Ko + (long)I * NB, ldk, ptr<double>(h->Vtmp), NB, rows_pad, NB, s);
-                h->launches += 2;
-            }
             launch_prior_diag(h->cp, ptr<double>(h->Xs) + (size_t)s0 * D, ptr<int32_t>(h->ns) + (size_t)s0 * D, rows,
                               ptr<double>(h->kss) + s0, s);
             launch_row_var(Ko, ldk, rows, M, ptr<double>(h->kss) + s0, ptr<double>(h->var) + s0, s);
@@ -932,6 +954,70 @@ int gpt_predict(gpt_handle* h, int Ms, const double* Xs, const int32_t* ns, doub
             }
         }
         if ((rc = check_launch(h))) return rc;
+    }
+    CUDA_OK(h, cudaMemcpyAsync(mean, h->mean.p, sizeof(double) * Ms, cudaMemcpyDeviceToHost, s));
+    if (var) CUDA_OK(h, cudaMemcpyAsync(var, h->var.p, sizeof(double) * Ms, cudaMemcpyDeviceToHost, s));
+    if (cov) {
+        const int Sp = round_up(Ms, NB);
+        CUDA_OK(h, cudaMemcpy2DAsync(cov, sizeof(double) * Ms, h->cov.p, sizeof(double) * Sp, sizeof(double) * Ms, Ms,
+                                     cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_OK(h, cudaStreamSynchronize(s));
+    return 0;
+}
+
+int gpt_predict_from_Kstar(gpt_handle* h, int Ms, const double* KstarT, const double* kss_diag, const double* Kss,
+                           double* mean, double* var, double* cov) {
+    if (h && Ms == 0) return 0;
+    if (!h || Ms < 1 || !KstarT || !mean || (var && !kss_diag && !Kss) || (cov && !Kss))
+        return fail(h, GPT_ERR_USAGE, "gpt_predict_from_Kstar: bad arguments");
+    if (!h->factor_valid) return fail(h, GPT_ERR_USAGE, "gpt_predict_from_Kstar: no valid factorisation (call gpt_ll / gpt_ll_from_K)");
+    CUDA_OK(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const int N = h->N, M = h->M, Np = h->Np, Mp = h->Mp;
+    int rc;
+    const int CH = predict_chunk_rows(h, Ms, cov != nullptr);
+    const int Msp = round_up(Ms, NB);
+    if (h->hasT && (rc = ensure(h, h->Kso, sizeof(double) * (size_t)CH * Mp))) return rc;
+    if ((rc = ensure(h, h->mean, sizeof(double) * (size_t)Msp))) return rc;
+    const bool second = var || cov;
+    if (second) {
+        if ((rc = ensure(h, h->Vtmp, sizeof(double) * (size_t)CH * NB))) return rc;
+        if ((rc = ensure(h, h->var, sizeof(double) * (size_t)Msp))) return rc;
+        if ((rc = ensure(h, h->kss, sizeof(double) * (size_t)Msp))) return rc;
+        if (kss_diag) {
+            CUDA_OK(h, cudaMemcpyAsync(h->kss.p, kss_diag, sizeof(double) * Ms, cudaMemcpyHostToDevice, s));
+        } else {  // diagonal of the full prior covariance
+            CUDA_OK(h, cudaMemcpy2DAsync(h->kss.p, sizeof(double), Kss, sizeof(double) * ((size_t)Ms + 1), sizeof(double),
+                                         Ms, cudaMemcpyHostToDevice, s));
+        }
+    }
+    for (int s0 = 0; s0 < Ms; s0 += CH) {
+        const int rows = (Ms - s0 < CH) ? (Ms - s0) : CH;
+        const int rows_pad = round_up(rows, NB);
+        // the caller's K*^T rows (test points as rows, N latent columns), zero padded into the chunk buffer
+        if ((rc = upload_padded(h, h->Kst, KstarT + (size_t)s0 * N, rows, N, rows_pad, Np))) return rc;
+        double* Ko = nullptr;
+        long ldk = 0;
+        if ((rc = predict_solve_chunk(h, s0, rows, rows_pad, second, &Ko, &ldk))) return rc;
+        if (second) {
+            launch_row_var(Ko, ldk, rows, M, ptr<double>(h->kss) + s0, ptr<double>(h->var) + s0, s);
+            h->launches++;
+            if (cov) {  // single chunk: cov = K** - V^T V
+                const int Sp = rows_pad;
+                if ((rc = upload_padded(h, h->cov, Kss, Ms, Ms, Sp, Sp))) return rc;
+                GemmParams g;
+                g.C = ptr<double>(h->cov); g.ldc = Sp;
+                g.A = Ko; g.lda = ldk;
+                g.B = Ko; g.ldb = ldk;
+                g.tiles_m = Sp / NB; g.tiles_n = Sp / NB; g.K = Mp;
+                g.alpha = -1.0; g.beta = 1.0; g.lower_only = 0; g.kbegin_row = 0;
+                launch_gemm_nt(g, s);
+                h->launches++;
+            }
+        }
+        if ((rc = check_launch(h))) return rc;
+        CUDA_OK(h, cudaStreamSynchronize(s));  // the next chunk overwrites the upload buffer
     }
     CUDA_OK(h, cudaMemcpyAsync(mean, h->mean.p, sizeof(double) * Ms, cudaMemcpyDeviceToHost, s));
     if (var) CUDA_OK(h, cudaMemcpyAsync(var, h->var.p, sizeof(double) * Ms, cudaMemcpyDeviceToHost, s));

@@ -686,10 +686,21 @@ class GaussianProcess(object):
         need_cov = need_second and (return_cov or full_output or full_MC or return_samples or
                                     output_transform is not None)
         if not self._device_mode():
-            raise NotImplementedError("predict with a user-defined (host) kernel is not available yet: the device "
-                                      "needs K* tiles; use an accelerated kernel")
-        self.k._check_orders(self.n, n)  # unsupported derivative orders raise before any device call
-        mean, var, covariance = self._dev().predict(Xstar, n, want_var=need_second and not need_cov, want_cov=need_cov)
+            # host-evaluated kernel (user-defined Python kernel, kernel sum): K* and the prior (co)variance of the
+            # test points are assembled exactly like the reference does (gaussian_process.py:966, 984), the solves
+            # run on the device against the resident factor
+            Kstar = self.compute_Kij(self.X, Xstar, self.n, n)
+            kss_diag = Kss = None
+            if need_cov:
+                Kss = self.compute_Kij(Xstar, None, n, None)
+            elif need_second:
+                kss_diag = np.asarray(self.k(Xstar, Xstar, n, n, symmetric=False), dtype=float).ravel()
+            mean, var, covariance = self._dev().predict_from_Kstar(
+                Kstar, kss_diag=kss_diag, Kss=Kss, want_var=need_second and not need_cov, want_cov=need_cov)
+        else:
+            self.k._check_orders(self.n, n)  # unsupported derivative orders raise before any device call
+            mean, var, covariance = self._dev().predict(Xstar, n, want_var=need_second and not need_cov,
+                                                        want_cov=need_cov)
         mean_func = None
         if self.mu is not None:
             mean_func = self.mu(Xstar, n)

@@ -108,6 +108,14 @@ int gpt_ll_batched_dev(gpt_handle* h, int B, const double* d_thetas, const doubl
  *   mean (Ms); var (Ms) or NULL: diag(K**) - |L^-1 K*|^2 ; cov (Ms x Ms) or NULL: K** - v'v */
 int gpt_predict(gpt_handle* h, int Ms, const double* Xs, const int32_t* ns, double* mean, double* var, double* cov);
 
+/* The same numeric core for kernels evaluated on the host (user-defined Python kernels, kernel sums): the caller
+ * supplies the cross-covariance exactly as gaussian_process.py:966 builds it, transposed --
+ * KstarT[s][i] = k(X_i, Xstar_s; n_i, nstar_s), Ms x N row-major over the LATENT points -- and the prior
+ * (co)variance of the test points: kss_diag (Ms) for var, Kss (Ms x Ms) for cov (gaussian_process.py:984).
+ * Uses the factorisation left by gpt_ll or gpt_ll_from_K; T is applied on the device. */
+int gpt_predict_from_Kstar(gpt_handle* h, int Ms, const double* KstarT, const double* kss_diag, const double* Kss,
+                           double* mean, double* var, double* cov);
+
 /* draw_sample, method='cholesky' with explicit rand_vars (gaussian_process.py:1295-1300, 1330):
  * out (Ms x S) = mean + chol(cov + jitter I) * rand_vars (Ms x S). */
 int gpt_draw_sample(gpt_handle* h, int Ms, int S, const double* mean, const double* cov, const double* rand_vars,

@@ -372,3 +372,34 @@ def test_c2_full_size_against_oracle(kernel):
     m2, s2 = gp.predict(Xs[sl])
     assert_close(m2, mean[sl], rtol=1e-12, atol=1e-13, what="chunking independence (mean)")
     assert_close(s2, std[sl], rtol=1e-9, atol=1e-12, what="chunking independence (std)")
+
+
+def test_host_kernel_sum_ll_and_predict_match_equivalent_device_kernel():
+    """Kernels evaluated on the host (here a SumKernel of two SE kernels with equal length scales) take the
+    gpt_ll_from_K / gpt_predict_from_Kstar path: K and K* assembled like the reference does, factorisation and
+    solves on the device.  SE(s1, l) + SE(s2, l) == SE(sqrt(s1^2 + s2^2), l), which runs fully on the device."""
+    rs = np.random.RandomState(3)
+    X = np.sort(rs.rand(150)) * 4
+    y = np.sin(2 * X) + 0.05 * rs.randn(150)
+    k1 = g.SquaredExponentialKernel(initial_params=[0.9, 0.7], param_bounds=[(0, 10)] * 2)
+    k2 = g.SquaredExponentialKernel(initial_params=[0.5, 0.7], param_bounds=[(0, 10)] * 2)
+    ks = k1 + k2
+    kd = g.SquaredExponentialKernel(initial_params=[np.sqrt(0.9 ** 2 + 0.5 ** 2), 0.7], param_bounds=[(0, 10)] * 2)
+    gp_s = g.GaussianProcess(ks, X=X, y=y, err_y=0.05)
+    gp_s.add_data(X[::10], 2 * np.cos(2 * X[::10]), err_y=0.1, n=1)
+    gp_d = g.GaussianProcess(kd, X=X, y=y, err_y=0.05)
+    gp_d.add_data(X[::10], 2 * np.cos(2 * X[::10]), err_y=0.1, n=1)
+    assert not gp_s._device_mode() and gp_d._device_mode()
+    gp_s.compute_K_L_alpha_ll()
+    gp_d.compute_K_L_alpha_ll()
+    assert_close(gp_s.ll - gp_s.hyperprior(gp_s.params), gp_d.ll - gp_d.hyperprior(gp_d.params), rtol=1e-9)
+    Xs = np.linspace(0, 4, 333)
+    ms, ss = gp_s.predict(Xs)
+    md, sd = gp_d.predict(Xs)
+    assert_close(ms, md, rtol=1e-9, atol=1e-9, what="mean")
+    assert np.all(np.abs(ss ** 2 - sd ** 2) <= 1e-9 * kd.params[0] ** 2)
+    ms1, cs = gp_s.predict(Xs[:50], n=1, return_cov=True)
+    md1, cd = gp_d.predict(Xs[:50], n=1, return_cov=True)
+    assert_close(ms1, md1, rtol=1e-9, atol=1e-9 * np.abs(md1).max(), what="derivative mean")
+    assert_close(cs, cd, rtol=0.0, atol=1e-9 * np.abs(cd).max(), what="full covariance")
+    assert_close(gp_s.predict(Xs, return_std=False), md, rtol=1e-9, atol=1e-9, what="mean only")
