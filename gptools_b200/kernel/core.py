@@ -17,7 +17,7 @@ import numpy as np
 from .._params import ParamHolder
 from ..error_handling import GPArgumentError
 
-__all__ = ["Kernel", "DeviceKernel", "SumKernel"]
+__all__ = ["Kernel", "DeviceKernel", "BinaryKernel", "SumKernel", "ProductKernel"]
 
 _default_device = None
 
@@ -54,6 +54,9 @@ class Kernel(ParamHolder):
 
     def __add__(self, other):
         return SumKernel(self, other)
+
+    def __mul__(self, other):
+        return ProductKernel(self, other)
 
     def _compute_r2l2(self, tau, return_l=False):
         """sum_d tau_d^2 / l_d^2 with 0/0 -> 0 (kernel/core.py:384-421); a host helper for user-defined
@@ -99,12 +102,9 @@ class DeviceKernel(Kernel):
         return default_device().cov_pairs(kid, params, Xi, Xj, ni, nj, hyper_deriv=hyper_deriv)
 
 
-class SumKernel(Kernel):
-    """k1 + k2 with concatenated hyperparameters (kernel/core.py:424-548 + 549-600, sum rule only).
-
-    Used by the GP when the noise kernel is neither ZeroKernel nor DiagonalNoiseKernel
-    (gaussian_process.py:1489-1490).  Host-side composition: each operand is evaluated through its own
-    ``__call__``."""
+class BinaryKernel(Kernel):
+    """Two kernels combined, with concatenated hyperparameters (kernel/core.py:424-548).  Host-side composition:
+    each operand is evaluated through its own ``__call__`` (device kernels through ``gpt_cov_pairs``)."""
 
     def __init__(self, k1, k2):
         if not isinstance(k1, Kernel) or not isinstance(k2, Kernel):
@@ -147,9 +147,50 @@ class SumKernel(Kernel):
         self.k1.set_hyperparams(new_params[:n1])
         self.k2.set_hyperparams(new_params[n1:])
 
+class SumKernel(BinaryKernel):
+    """k1 + k2 (kernel/core.py:549-600).  Used by the GP when the noise kernel is neither ZeroKernel nor
+    DiagonalNoiseKernel (gaussian_process.py:1489-1490)."""
+
     def __call__(self, Xi, Xj, ni, nj, hyper_deriv=None, symmetric=False):
         if hyper_deriv is None:
             return (self.k1(Xi, Xj, ni, nj, symmetric=symmetric) + self.k2(Xi, Xj, ni, nj, symmetric=symmetric))
         if hyper_deriv < self.k1.num_params:
             return self.k1(Xi, Xj, ni, nj, hyper_deriv=hyper_deriv, symmetric=symmetric)
         return self.k2(Xi, Xj, ni, nj, hyper_deriv=hyper_deriv - self.k1.num_params, symmetric=symmetric)
+
+
+class ProductKernel(BinaryKernel):
+    """k1 * k2 with the general Leibniz rule over the derivative orders (kernel/core.py:601-670).
+
+    For a pair with combined orders m = (ni, nj) (2 D slots) the reference sums k1^(s) k2^(m - s) over every subset
+    of the multiset of derivative slots; collecting equal terms gives
+    sum_{a <= m} prod_i C(m_i, a_i) k1^(a) k2^(m - a), which is what is evaluated here (one call of each operand per
+    distinct split instead of one per subset).  Like the reference, ``hyper_deriv`` raises NotImplementedError."""
+
+    def __call__(self, Xi, Xj, ni, nj, hyper_deriv=None, symmetric=False):
+        if hyper_deriv is not None:
+            raise NotImplementedError("hyper_deriv keyword not yet supported!")
+        from itertools import product as cartesian
+        from math import comb
+        Xi = np.atleast_2d(np.asarray(Xi, dtype=float))
+        Xj = np.atleast_2d(np.asarray(Xj, dtype=float))
+        ni = np.atleast_2d(np.asarray(ni, dtype=int))
+        nj = np.atleast_2d(np.asarray(nj, dtype=int))
+        D = self.num_dim
+        nij = np.hstack((ni, nj))
+        result = np.zeros(Xi.shape[0])
+        patterns, inverse = np.unique(nij, axis=0, return_inverse=True)
+        inverse = np.ravel(inverse)
+        for p_idx, m in enumerate(patterns):
+            sel = inverse == p_idx
+            xi, xj = Xi[sel], Xj[sel]
+            cnt = int(sel.sum())
+            for a in cartesian(*[range(int(mi) + 1) for mi in m]):
+                a = np.array(a, dtype=int)
+                weight = 1
+                for mi, ai in zip(m, a):
+                    weight *= comb(int(mi), int(ai))
+                n1 = np.tile(a, (cnt, 1))
+                n2 = np.tile(m - a, (cnt, 1))
+                result[sel] += weight * (self.k1(xi, xj, n1[:, :D], n1[:, D:]) * self.k2(xi, xj, n2[:, :D], n2[:, D:]))
+        return result

@@ -448,9 +448,25 @@ def case_hyperfd():
     _hyperfd("hyperfd_gibbs_T", gp, [0, 1, 2, 3, 4], 1e-3)
 
 
+# ---------------------------------------------------------------- kernel algebra: ProductKernel (kernel/core.py:601-670)
+def case_product():
+    rs = RandomState(11)
+    k1 = g.SquaredExponentialKernel(num_dim=2, initial_params=[1.3, 0.4, 0.9], param_bounds=[(0, 10)] * 3)
+    k2 = g.SquaredExponentialKernel(num_dim=2, initial_params=[0.8, 1.1, 0.5], param_bounds=[(0, 10)] * 3)
+    kp = k1 * k2
+    ks = k1 + k2
+    Mp = 60
+    Xi, Xj = rs.rand(Mp, 2), rs.rand(Mp, 2)
+    Xj[:5] = Xi[:5]
+    ni, nj = rs.randint(0, 3, size=(Mp, 2)), rs.randint(0, 2, size=(Mp, 2))
+    save("kernel_algebra_se2d", Xi=Xi, Xj=Xj, ni=ni, nj=nj, params1=k1.params.copy(), params2=k2.params.copy(),
+         prod=kp(Xi, Xj, ni, nj), sum=ks(Xi, Xj, ni, nj),
+         sum_hd1=ks(Xi, Xj, ni, nj, hyper_deriv=1), sum_hd4=ks(Xi, Xj, ni, nj, hyper_deriv=4))
+
+
 if __name__ == "__main__":
     cases = [case_se2d, case_se_pairs, case_matern52, case_matern_generic, case_gibbs, case_c5_full, case_demo,
-             case_c3, case_c2, case_noise, case_hyperfd]
+             case_c3, case_c2, case_noise, case_hyperfd, case_product]
     only = set(sys.argv[1:])          # e.g. `make_golden.py case_hyperfd` regenerates one family
     for c in cases:
         if not only or c.__name__ in only:

@@ -388,3 +388,34 @@ def test_sample_hyperparameter_posterior_uses_batched_calls():
     assert s.chain.shape == (8, 3, 3)
     assert gp._dev_obj.calls.count("ll_batched") == 1 + 2 * 3     # initial ensemble + two half-moves per step
     assert np.isfinite(s.lnprobability).any()
+
+
+class _OracleSE(g.Kernel):
+    """numpy stand-in for the device SE kernel (the pinned oracle's pair function), so that the host-side kernel
+    algebra can be checked without a GPU."""
+
+    def __init__(self, num_dim, params):
+        super(_OracleSE, self).__init__(num_dim=num_dim, num_params=num_dim + 1, initial_params=params,
+                                        param_bounds=[(0, 10)] * (num_dim + 1))
+
+    def __call__(self, Xi, Xj, ni, nj, hyper_deriv=None, symmetric=False):
+        from oracle import gp_oracle as orc
+        return orc.se_pairs(np.atleast_2d(Xi), np.atleast_2d(Xj), np.atleast_2d(ni), np.atleast_2d(nj),
+                            np.asarray(self.params, float), hyper_deriv=hyper_deriv)
+
+
+def test_sum_and_product_kernels_match_reference():
+    """k1 + k2 and k1 * k2 (general Leibniz rule over derivative orders up to (2, 1) per dimension) against the
+    reference's SumKernel / ProductKernel on seeded pair lists (kernel/core.py:549-670)."""
+    gd = load_golden("kernel_algebra_se2d")
+    k1, k2 = _OracleSE(2, gd["params1"]), _OracleSE(2, gd["params2"])
+    a = (gd["Xi"], gd["Xj"], gd["ni"], gd["nj"])
+    assert_close((k1 * k2)(*a), gd["prod"], rtol=1e-10, atol=1e-12 * np.abs(gd["prod"]).max(), what="product")
+    assert_close((k1 + k2)(*a), gd["sum"], rtol=1e-12, atol=1e-14 * np.abs(gd["sum"]).max(), what="sum")
+    ks = k1 + k2
+    assert_close(ks(*a, hyper_deriv=1), gd["sum_hd1"], rtol=1e-9, atol=1e-12 * np.abs(gd["sum_hd1"]).max())
+    assert_close(ks(*a, hyper_deriv=4), gd["sum_hd4"], rtol=1e-9, atol=1e-12 * np.abs(gd["sum_hd4"]).max())
+    kp = k1 * k2
+    assert kp.num_params == 6 and list(kp.params) == list(gd["params1"]) + list(gd["params2"])
+    with pytest.raises(NotImplementedError):
+        kp(*a, hyper_deriv=0)
