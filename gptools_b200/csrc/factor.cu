@@ -425,8 +425,10 @@ __global__ void __launch_bounds__(256, 1) panel_trsm_kernel(double* __restrict__
 }
 
 __global__ void transpose_kernel(double* __restrict__ out, long ldo, const double* __restrict__ in, long ldi,
-                                 int rows, int cols) {
+                                 int rows, int cols, long stride_out, long stride_in) {
     __shared__ double tile[32][33];
+    out += (long)blockIdx.z * stride_out;
+    in += (long)blockIdx.z * stride_in;
     const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
     for (int r = threadIdx.y; r < 32; r += 8) {
         const int ir = by + r, ic = bx + threadIdx.x;
@@ -682,7 +684,14 @@ void launch_backsolve_chain(const double* L, long ld, int nblk, const double* in
 
 void launch_transpose(double* out, long ldo, const double* in, long ldi, int rows, int cols, cudaStream_t s) {
     dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
-    transpose_kernel<<<grid, block, 0, s>>>(out, ldo, in, ldi, rows, cols);
+    transpose_kernel<<<grid, block, 0, s>>>(out, ldo, in, ldi, rows, cols, 0, 0);
+}
+
+void launch_transpose_batched(double* out, long ldo, long stride_out, const double* in, long ldi, long stride_in,
+                              int rows, int cols, int batch, cudaStream_t s) {
+    if (batch <= 0 || rows <= 0 || cols <= 0) return;
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32, batch), block(32, 8);
+    transpose_kernel<<<grid, block, 0, s>>>(out, ldo, in, ldi, rows, cols, stride_out, stride_in);
 }
 
 void launch_copy2d(double* out, long ldo, const double* in, long ldi, int rows, int cols, cudaStream_t s) {

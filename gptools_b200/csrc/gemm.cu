@@ -26,9 +26,12 @@ __global__ void __launch_bounds__(THREADS, 3) gemm_nt_kernel(GemmParams p) {
     const int bm = blockIdx.y, bn = blockIdx.x;
     if (p.lower_only && bn > 2 * bm + 1) return;  // bn counts 64-wide half tiles; diagonal 128-blocks are full
     const int kstart = p.kbegin_row ? bm * BM : 0;
-    const int nk = (p.K - kstart) / BK;
-    const double* __restrict__ Ag = p.A + (long)bm * BM * p.lda + kstart;
-    const double* __restrict__ Bg = p.B + (long)bn * BN * p.ldb + kstart;
+    const int kend = (p.kend_row && (bm + 1) * BM < p.K) ? (bm + 1) * BM : p.K;
+    const int nk = (kend - kstart) / BK;
+    const long zb = blockIdx.z;  // batch index
+    const double* __restrict__ Ag = p.A + zb * p.strideA + (long)bm * BM * p.lda + kstart;
+    const double* __restrict__ Bg = p.B + zb * p.strideB + (long)bn * BN * p.ldb + kstart;
+    double* __restrict__ Cg = p.C + zb * p.strideC;
     double* sA = smem;
     double* sB = smem + STAGES * BM * LDS_;
 
@@ -56,7 +59,7 @@ __global__ void __launch_bounds__(THREADS, 3) gemm_nt_kernel(GemmParams p) {
     // read-modify-write per tile into an HBM burst with the tensor pipe idle.  Pull the tile into L2 now so
     // the fetch overlaps the main loop (the operands are L2 resident panels).
     if (p.beta != 0.0) {
-        const char* cbase = reinterpret_cast<const char*>(p.C + (long)bm * BM * p.ldc + (long)bn * BN);
+        const char* cbase = reinterpret_cast<const char*>(Cg + (long)bm * BM * p.ldc + (long)bn * BN);
 #pragma unroll
         for (int i = tid; i < BM * 4; i += THREADS)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(cbase + (long)(i >> 2) * p.ldc * 8 + (i & 3) * 128));
@@ -109,7 +112,7 @@ __global__ void __launch_bounds__(THREADS, 3) gemm_nt_kernel(GemmParams p) {
             for (int ii = 0; ii < 2; ii++)
 #pragma unroll
                 for (int j = 0; j < 4; j++)
-                    old[ii][j] = __ldcg(reinterpret_cast<const double2*>(p.C + (row0 + (i0 + ii) * 8) * p.ldc + col0 + j * 8));
+                    old[ii][j] = __ldcg(reinterpret_cast<const double2*>(Cg + (row0 + (i0 + ii) * 8) * p.ldc + col0 + j * 8));
 #pragma unroll
             for (int ii = 0; ii < 2; ii++)
 #pragma unroll
@@ -117,7 +120,7 @@ __global__ void __launch_bounds__(THREADS, 3) gemm_nt_kernel(GemmParams p) {
                     double2 v;
                     v.x = p.alpha * acc[i0 + ii][j][0] + p.beta * old[ii][j].x;
                     v.y = p.alpha * acc[i0 + ii][j][1] + p.beta * old[ii][j].y;
-                    *reinterpret_cast<double2*>(p.C + (row0 + (i0 + ii) * 8) * p.ldc + col0 + j * 8) = v;
+                    *reinterpret_cast<double2*>(Cg + (row0 + (i0 + ii) * 8) * p.ldc + col0 + j * 8) = v;
                 }
         }
     } else {
@@ -128,7 +131,7 @@ __global__ void __launch_bounds__(THREADS, 3) gemm_nt_kernel(GemmParams p) {
                 double2 v;
                 v.x = p.alpha * acc[i][j][0];
                 v.y = p.alpha * acc[i][j][1];
-                *reinterpret_cast<double2*>(p.C + (row0 + i * 8) * p.ldc + col0 + j * 8) = v;
+                *reinterpret_cast<double2*>(Cg + (row0 + i * 8) * p.ldc + col0 + j * 8) = v;
             }
     }
 }
@@ -141,6 +144,6 @@ long gemm_rows_per_wave_n128(int num_sms) { return (long)num_sms * 3 /* CTAs per
 void launch_gemm_nt(const GemmParams& p, cudaStream_t s) {
     cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (p.tiles_m <= 0 || p.tiles_n <= 0) return;
-    dim3 grid(p.tiles_n * (128 / BN), p.tiles_m);
+    dim3 grid(p.tiles_n * (128 / BN), p.tiles_m, p.batch > 0 ? p.batch : 1);
     gemm_nt_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(p);
 }

@@ -22,6 +22,9 @@ struct GemmParams {
     double alpha, beta;
     int lower_only;  // only tiles with tile_n <= tile_m (symmetric rank-k updates, lauum)
     int kbegin_row;  // contraction starts at k = tile_m*128 (A upper block-triangular)
+    int kend_row = 0;   // contraction ends at k = (tile_m+1)*128 (A lower block-triangular)
+    int batch = 1;      // independent products in one launch: operand b lives at base + b * stride
+    long strideA = 0, strideB = 0, strideC = 0;
 };
 void launch_gemm_nt(const GemmParams& p, cudaStream_t s);
 long gemm_rows_per_wave_n128(int num_sms);
@@ -63,6 +66,9 @@ void launch_panel_trsm(double* A21, long lda, const double* L11, long ldl, const
 void launch_backsolve_chain(const double* L, long ld, int nblk, const double* inv, const double* z, double* alpha,
                             int* flags, cudaStream_t s);
 void launch_transpose(double* out, long ldo, const double* in, long ldi, int rows, int cols, cudaStream_t s);
+// `batch` independent transposes, operand b at base + b * stride
+void launch_transpose_batched(double* out, long ldo, long stride_out, const double* in, long ldi, long stride_in,
+                              int rows, int cols, int batch, cudaStream_t s);
 void launch_copy2d(double* out, long ldo, const double* in, long ldi, int rows, int cols, cudaStream_t s);
 void launch_add_diag(double* A, long lda, const double* d, int n, cudaStream_t s);
 void launch_fill(double* p, long n, double v, cudaStream_t s);
