@@ -593,14 +593,14 @@ void launch_panel_trsm(double* A21, long lda, const double* L11, long ldl, const
 }
 
 // ---- alpha = L^{-T} z in ONE launch: a chain of CTAs, one per 128-row block ----------------------------------------
-// CTA i owns block b = nblk-1-i of the solution (so it only ever waits for CTAs dispatched before it).  It folds
+// CTA i owns block b = bhi-i of the solution; launches cover at most one CTA per SM (see the launcher).  It folds
 // z_b -= L[k, b]^T alpha_k for k = nblk-1 .. b+1 as the alpha_k are published, then alpha_b = Inv_b^T z_b.  The two
 // operands on the critical path -- the tile L[b+1, b] needed last and Inv_b -- are fetched before the wait (into
 // registers and shared memory), so a link of the chain costs a flag poll + ~130 FMAs per thread, not a kernel
 // launch plus two cold 128 KB reads (the per-block launches took 29 us each: 15% of an M = 4000 factorisation).
 constexpr size_t BSC_SMEM = ((size_t)NB * NB + 6 * NB) * sizeof(double);
 
-__global__ void __launch_bounds__(256, 1) backsolve_chain_kernel(const double* __restrict__ L, long ld, int nblk,
+__global__ void __launch_bounds__(256, 1) backsolve_chain_kernel(const double* __restrict__ L, long ld, int nblk, int bhi,
                                                                  const double* __restrict__ inv,
                                                                  const double* __restrict__ z, double* alpha,
                                                                  int* flags) {
@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(256, 1) backsolve_chain_kernel(const double* _
     double* ak = zs + NB;              // alpha_k
     double* part = ak + NB;            // 4 x NB partial sums
     const int tid = threadIdx.x;
-    const int b = nblk - 1 - blockIdx.x;
+    const int b = bhi - blockIdx.x;  // this launch covers blocks bhi, bhi-1, ... (one per CTA)
     const int c = tid & (NB - 1), hh = tid >> 7;  // column, half of the rows
 
     const double* invb = inv + (size_t)b * NB * NB;
@@ -679,7 +679,20 @@ void launch_backsolve_chain(const double* L, long ld, int nblk, const double* in
         attr_set = true;
     }
     cudaMemsetAsync(flags, 0, sizeof(int) * nblk, s);
-    backsolve_chain_kernel<<<nblk, 256, BSC_SMEM, s>>>(L, ld, nblk, inv, z, alpha, flags);
+    // A CTA spins on flags published by CTAs of higher blocks.  One CTA fits per SM, so a launch never holds more CTAs
+    // than there are SMs: everything a CTA waits for is either co-resident or finished in an earlier launch, and the
+    // chain cannot deadlock whatever order the hardware dispatches blocks in.
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (num_sms < 1) num_sms = 1;
+    }
+    for (int bhi = nblk - 1; bhi >= 0; bhi -= num_sms) {
+        const int cnt = (bhi + 1 < num_sms) ? bhi + 1 : num_sms;
+        backsolve_chain_kernel<<<cnt, 256, BSC_SMEM, s>>>(L, ld, nblk, bhi, inv, z, alpha, flags);
+    }
 }
 
 void launch_transpose(double* out, long ldo, const double* in, long ldi, int rows, int cols, cudaStream_t s) {
