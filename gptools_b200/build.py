@@ -15,7 +15,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(CSRC, "libgptb200.so")
 HOSTCHECK = os.path.join(CSRC, "libgptb200_hostcheck.so")
 SOURCES = ["api.cu", "assemble.cu", "gemm.cu", "factor.cu", "predict.cu", "batched4.cu"]
-HEADERS = ["common.cuh", "covfn.cuh", "internal.h", "se_fast.cuh", os.path.join(INCLUDE, "gptb200.h")]
+HEADERS = ["common.cuh", "covfn.cuh", "covfn_hyper.cuh", "internal.h", "se_fast.cuh", os.path.join(INCLUDE, "gptb200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 
@@ -53,7 +53,7 @@ def build(force=False, verbose=False):
             print(" ".join(cmd))
         subprocess.check_call(cmd)
     hc_src = os.path.join(CSRC, "hostcheck.cpp")
-    if force or _stale(HOSTCHECK, [hc_src, os.path.join(CSRC, "covfn.cuh")]):
+    if force or _stale(HOSTCHECK, [hc_src, os.path.join(CSRC, "covfn.cuh"), os.path.join(CSRC, "covfn_hyper.cuh")]):
         subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-x", "c++", "-o", HOSTCHECK, hc_src, "-lm"])
     return LIB
 
