@@ -109,6 +109,7 @@ int supported_kernel(int kid, int D, int nparams) {
         case GPT_MATERN52: return nparams == D + 1;
         case GPT_MATERN: return nparams == D + 2;
         case GPT_GIBBS_TANH: return D == 1 && nparams == 5;
+        case GPT_GIBBS_AUX: return D == 3 && nparams == 1;
         default: return 0;
     }
 }
@@ -530,7 +531,7 @@ int gpt_set_y(gpt_handle* h, const double* y) {
 
 int gpt_set_kernel(gpt_handle* h, int kernel_id, int nparams, double diag_factor) {
     if (!h) return GPT_ERR_USAGE;
-    if (kernel_id < 0 || kernel_id > GPT_GIBBS_TANH || nparams < 1 || nparams > GPT_MAX_PARAMS)
+    if (kernel_id < 0 || kernel_id > GPT_GIBBS_AUX || nparams < 1 || nparams > GPT_MAX_PARAMS)
         return fail(h, GPT_ERR_UNSUPPORTED, "gpt_set_kernel: unsupported kernel / parameter count");
     CUDA_OK(h, cudaSetDevice(h->device));
     h->kid = kernel_id;
@@ -1123,6 +1124,8 @@ int gpt_draw_sample(gpt_handle* h, int Ms, int S, const double* mean, const doub
 static int batched_common(gpt_handle* h, int B, const double* d_thetas, const double* d_y, double* d_ll,
                           double* d_grad, const int32_t* grad_idx, int P, int* d_status, double* d_alpha) {
     if (h->hasT) return fail(h, GPT_ERR_UNSUPPORTED, "gpt_ll_batched: transformed observations (T) use gpt_ll");
+    if (h->kid == GPT_KERNEL_GIBBS_AUX)
+        return fail(h, GPT_ERR_UNSUPPORTED, "gpt_ll_batched: the per-point length scales of GPT_GIBBS_AUX depend on theta; use gpt_ll");
     if (!supported_kernel(h->kid, h->D, h->nparams)) return fail(h, GPT_ERR_UNSUPPORTED, "gpt_ll_batched: kernel unsupported");
     if (P < 0 || P > GPT_MAX_PARAMS) return fail(h, GPT_ERR_USAGE, "gpt_ll_batched: bad P");
     BatchedParams bp;

@@ -24,6 +24,7 @@
 #define GPT_KERNEL_MATERN52 1
 #define GPT_KERNEL_MATERN 2
 #define GPT_KERNEL_GIBBS_TANH 3
+#define GPT_KERNEL_GIBBS_AUX 4  // Gibbs kernel, length scale l(x) and l'(x) supplied per point in columns 1, 2
 
 #define GPT_MAX_DIM 6
 #define GPT_MAX_PARAMS 10
@@ -192,7 +193,7 @@ GPT_HD void cov_params_init(CovParams& cp, int kid, int D, int nparams, const do
     cp.sig2 = cp.p[0] * cp.p[0];
     const int loff = (kid == GPT_KERNEL_MATERN) ? 2 : 1;
     for (int d = 0; d < GPT_MAX_DIM; d++) cp.inv_l[d] = 0.0;
-    if (kid != GPT_KERNEL_GIBBS_TANH)
+    if (kid != GPT_KERNEL_GIBBS_TANH && kid != GPT_KERNEL_GIBBS_AUX)
         for (int d = 0; d < D; d++) cp.inv_l[d] = 1.0 / cp.p[loff + d];
     cp.matern_p = 0;
     cp.mat_c = 0.0;
@@ -527,11 +528,17 @@ GPT_HD double gibbs_cov(const CovParams& cp, const double* xi, const int32_t* ni
 // ------------------------------------------------------------------------------------------
 GPT_HD double cov_eval(const CovParams& cp, const double* xi, const int32_t* ni, const double* xj,
                        const int32_t* nj, int hyper_deriv) {
+    if (hyper_deriv >= 0 && cp.kid == GPT_KERNEL_GIBBS_AUX) {
+        // only sigma_f is a device-side parameter: dk/dsigma_f = 2 k / sigma_f
+        const double k = gibbs_cov_l(cp, xi[0], xi[1], xi[2], ni[0], xj[0], xj[1], xj[2], nj[0]);
+        return (hyper_deriv == 0 && cp.p[0] != 0.0) ? 2.0 * k / cp.p[0] : NAN;
+    }
     if (hyper_deriv >= 0 && cp.kid != GPT_KERNEL_SE) return cov_hyper_eval(cp, xi, ni, xj, nj, hyper_deriv);
     switch (cp.kid) {
         case GPT_KERNEL_SE: return se_cov(cp, xi, ni, xj, nj, hyper_deriv);
         case GPT_KERNEL_MATERN52: return matern52_cov(cp, xi, ni, xj, nj);
         case GPT_KERNEL_MATERN: return matern_cov(cp, xi, ni, xj, nj);
+        case GPT_KERNEL_GIBBS_AUX: return gibbs_cov_l(cp, xi[0], xi[1], xi[2], ni[0], xj[0], xj[1], xj[2], nj[0]);
         default: return gibbs_cov(cp, xi, ni, xj, nj);
     }
 }

@@ -358,10 +358,14 @@ class GaussianProcess(object):
     def _sync_device(self):
         dev = self._dev()
         y_alph = self._y_minus_mean()
-        if self._dev_data_version != self._data_version:
+        aux_key = self.k.device_points_key() if self.k.device_descriptor() is not None else None
+        if self._dev_data_version != self._data_version or getattr(self, "_dev_aux_key", None) != aux_key:
             if self.X is None or len(self.y) == 0:
                 raise GPArgumentError("No training data: call add_data first")
-            dev.set_data(self.X, self.n, y_alph, self.err_y, self.T)
+            Xd, nd = (self.k.device_points(self.X, self.n) if self.k.device_descriptor() is not None
+                      else (self.X, self.n))
+            dev.set_data(Xd, nd, y_alph, self.err_y, self.T)
+            self._dev_aux_key = aux_key
             self._dev_data_version = self._data_version
             self._dev_y_key = None if self.mu is None else tuple(self.mu.params)
             self._dev_kernel_key = None
@@ -392,10 +396,12 @@ class GaussianProcess(object):
             if hyper_deriv is not None:
                 k.check_hyper_deriv([int(hyper_deriv)])
             k._check_orders(ni, ni if nj is None else np.atleast_2d(np.asarray(nj, dtype=int)))
+            Xi_d, ni_d = k.device_points(Xi, ni)
             if Xj is None:
-                return self._dev().compute_Kij(desc[0], desc[1], Xi, ni, hyper_deriv=hyper_deriv)
-            return self._dev().compute_Kij(desc[0], desc[1], Xi, ni, np.atleast_2d(np.asarray(Xj, dtype=float)),
-                                           np.atleast_2d(np.asarray(nj, dtype=int)), hyper_deriv=hyper_deriv)
+                return self._dev().compute_Kij(desc[0], desc[1], Xi_d, ni_d, hyper_deriv=hyper_deriv)
+            Xj_d, nj_d = k.device_points(np.atleast_2d(np.asarray(Xj, dtype=float)),
+                                         np.atleast_2d(np.asarray(nj, dtype=int)))
+            return self._dev().compute_Kij(desc[0], desc[1], Xi_d, ni_d, Xj_d, nj_d, hyper_deriv=hyper_deriv)
         symmetric = Xj is None
         if symmetric:
             Xj, nj = Xi, ni
@@ -549,7 +555,8 @@ class GaussianProcess(object):
         B = thetas.shape[0]
         if with_deriv is None:
             with_deriv = bool(self.use_hyper_deriv)
-        if not self._device_mode() or self.T is not None:
+        if not self._device_mode() or self.T is not None or self.k.device_points_key() is not None:
+            # host kernels, transformed observations, and kernels whose per-point columns depend on theta
             return self._batch_by_loop(thetas, with_deriv)
         nk, nn = self.k.num_free_params, self.noise_k.num_free_params
         n_free = len(self.free_params)
@@ -699,7 +706,8 @@ class GaussianProcess(object):
                 Kstar, kss_diag=kss_diag, Kss=Kss, want_var=need_second and not need_cov, want_cov=need_cov)
         else:
             self.k._check_orders(self.n, n)  # unsupported derivative orders raise before any device call
-            mean, var, covariance = self._dev().predict(Xstar, n, want_var=need_second and not need_cov,
+            Xs_d, ns_d = self.k.device_points(Xstar, n)
+            mean, var, covariance = self._dev().predict(Xs_d, ns_d, want_var=need_second and not need_cov,
                                                         want_cov=need_cov)
         mean_func = None
         if self.mu is not None:

@@ -84,6 +84,15 @@ class DeviceKernel(Kernel):
     def _check_orders(self, ni, nj):
         pass
 
+    def device_points(self, X, n):
+        """The point / derivative-order arrays the device function consumes.  Identity for most kernels; kernels
+        whose closed form takes per-point auxiliary columns (GibbsKernel1d: l(x), l'(x)) append them here."""
+        return X, n
+
+    def device_points_key(self):
+        """Changes whenever ``device_points`` would return different auxiliary columns (None: never)."""
+        return None
+
     def check_hyper_deriv(self, idxs):
         """Raise NotImplementedError (the reference's exception, kernel/core.py:723) when the derivative with
         respect to any of the parameter indices ``idxs`` is not available on the device."""
@@ -99,6 +108,8 @@ class DeviceKernel(Kernel):
         nj = np.atleast_2d(np.asarray(nj, dtype=int))
         self._check_orders(ni, nj)
         kid, params = self.device_descriptor()
+        Xi, ni = self.device_points(Xi, ni)
+        Xj, nj = self.device_points(Xj, nj)
         return default_device().cov_pairs(kid, params, Xi, Xj, ni, nj, hyper_deriv=hyper_deriv)
 
 

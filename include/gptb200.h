@@ -33,6 +33,9 @@ typedef struct gpt_handle gpt_handle;
 #define GPT_MATERN52 1    /* Matern52Kernel            kernel/matern.py:468-555 + src/matern.c  params [sigma_f, l_1..l_D]   */
 #define GPT_MATERN 2      /* MaternKernel (nu = p+1/2) kernel/matern.py:251-465             params [sigma_f, nu, l_1..l_D]  */
 #define GPT_GIBBS_TANH 3  /* GibbsKernel1dTanh         kernel/gibbs.py:244-505              params [sigma_f, l1, l2, lw, x0] */
+#define GPT_GIBBS_AUX 4   /* GibbsKernel1d, any l_func kernel/gibbs.py:244-424, 508-1095      params [sigma_f]; the points carry
+                           * three columns (x, l(x), l'(x)) -- the length-scale profile is evaluated by the host l_func,
+                           * derivative orders apply to column 0 only */
 
 #define GPT_ERR_USAGE (-1)
 #define GPT_ERR_CUDA (-2)

@@ -464,9 +464,40 @@ def case_product():
          sum_hd1=ks(Xi, Xj, ni, nj, hyper_deriv=1), sum_hd4=ks(Xi, Xj, ni, nj, hyper_deriv=4))
 
 
+# ---------------------------------------------------------------- other Gibbs length-scale profiles (kernel/gibbs.py:508-902)
+def case_gibbs_profiles():
+    rs = RandomState(21)
+    X = np.sort(rs.rand(24)) * 1.1
+    y = 2.5 - 1.5 * np.tanh((X - 0.8) / 0.1) + 0.05 * rs.randn(24)
+    Xs = np.linspace(0.0, 1.1, 9)
+    kernels = {
+        "double_tanh": g.GibbsKernel1dDoubleTanh(
+            initial_params=[1.5, 0.6, 0.3, 0.08, 0.1, 0.05, 0.4, 0.9], param_bounds=[(0, 10)] * 8),
+        "cubic_bucket": g.GibbsKernel1dCubicBucket(
+            initial_params=[1.5, 0.5, 0.1, 0.3, 0.8, 0.2, 0.15, 0.1], param_bounds=[(0, 10)] * 8),
+        "quintic_bucket": g.GibbsKernel1dQuinticBucket(
+            initial_params=[1.5, 0.5, 0.1, 0.3, 0.8, 0.2, 0.15, 0.1], param_bounds=[(0, 10)] * 8),
+        # GibbsKernel1dExpGauss cannot be run here: exp_gauss_warp slices with len(msb) / 3 (kernel/gibbs.py:833),
+        # a float under Python 3, and the reference is loaded unmodified
+    }
+    for name, k in kernels.items():
+        gp = g.GaussianProcess(k)
+        gp.add_data(X, y, err_y=0.05)
+        gp.add_data(X[::5], -1.0 * np.ones(len(X[::5])), err_y=0.5, n=1)
+        gp.add_data(0, 0, n=1)
+        out = ll_and_grad(gp, False)
+        res = gp.predict(Xs, full_output=True)
+        out.update(Xs=Xs, mean=res["mean"], std=res["std"], cov=res["cov"])
+        res1 = gp.predict(Xs, n=1, full_output=True)
+        out.update(mean_d1=res1["mean"], std_d1=res1["std"])
+        lp = list(k.params[1:])
+        out.update(l=k.l_func(gp.X[:, 0], 0, *lp), l1=k.l_func(gp.X[:, 0], 1, *lp))
+        save("gibbs_profile_" + name, params=k.params.copy(), **gp_state(gp), **out)
+
+
 if __name__ == "__main__":
     cases = [case_se2d, case_se_pairs, case_matern52, case_matern_generic, case_gibbs, case_c5_full, case_demo,
-             case_c3, case_c2, case_noise, case_hyperfd, case_product]
+             case_c3, case_c2, case_noise, case_hyperfd, case_product, case_gibbs_profiles]
     only = set(sys.argv[1:])          # e.g. `make_golden.py case_hyperfd` regenerates one family
     for c in cases:
         if not only or c.__name__ in only:

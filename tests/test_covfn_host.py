@@ -163,3 +163,42 @@ def test_dual_value_component_is_the_value_path(lib, case):
         v, d = dual(lib, kid, gd["params"], X, n, int(p))
         assert_close(v, K, rtol=1e-14, atol=1e-300, what="%s dual value (seed %d)" % (case, p))
         assert np.array_equal(d, Kmat(lib, kid, gd["params"], X, n, hyper_deriv=int(p)))
+
+
+# ---- GibbsKernel1d with other length-scale profiles (kernel id 4: l(x), l'(x) as extra point columns) --------------
+GIBBS_PROFILES = {"double_tanh": "GibbsKernel1dDoubleTanh", "cubic_bucket": "GibbsKernel1dCubicBucket",
+                  "quintic_bucket": "GibbsKernel1dQuinticBucket"}
+
+
+@pytest.mark.parametrize("name", sorted(GIBBS_PROFILES))
+def test_gibbs_profiles_host_functions_and_device_closed_form(lib, name):
+    """(1) the host length-scale profile l(x), l'(x) against the reference's l_func (kernel/gibbs.py:508-760);
+    (2) the device closed form fed with (x, l, l') against the reference's K incl. derivative observations."""
+    import gptools_b200 as g
+    gd = load_golden("gibbs_profile_" + name)
+    k = getattr(g, GIBBS_PROFILES[name])(initial_params=gd["params"], param_bounds=[(0, 10)] * 8)
+    Xa, na = k.device_points(gd["X"], gd["n"])
+    assert_close(Xa[:, 1], gd["l"], rtol=1e-13, atol=1e-15, what="l(x)")
+    assert_close(Xa[:, 2], gd["l1"], rtol=1e-12, atol=1e-13, what="l'(x)")
+    K = Kmat(lib, 4, gd["params"][:1], Xa, na.astype(np.int32))
+    assert_close(K, gd["K"], rtol=1e-11, atol=1e-13 * np.abs(gd["K"]).max(), what="K")
+    dK = Kmat(lib, 4, gd["params"][:1], Xa, na.astype(np.int32), hyper_deriv=0)
+    assert_close(dK, 2.0 * gd["K"] / gd["params"][0], rtol=1e-11, atol=1e-12, what="dK/dsigma_f")
+
+
+def test_exp_gauss_profile_is_self_consistent():
+    """The reference's exp_gauss_warp cannot run under Python 3 (float slice index, kernel/gibbs.py:833), so there is
+    no golden: check the formula l = l0 exp(sum b exp(-(x-m)^2 / 2 s^2)) and that n = 1 is its derivative."""
+    import gptools_b200 as g
+    x = np.linspace(0, 1.2, 41)
+    p = [0.4, 0.3, 0.9, 0.1, 0.05, -0.8, -1.5]
+    l = g.exp_gauss_warp(x, 0, *p)
+    want = 0.4 * np.exp(-0.8 * np.exp(-(x - 0.3) ** 2 / (2 * 0.1 ** 2)) - 1.5 * np.exp(-(x - 0.9) ** 2 / (2 * 0.05 ** 2)))
+    assert_close(l, want, rtol=1e-14)
+    h = 1e-6
+    fd = (g.exp_gauss_warp(x + h, 0, *p) - g.exp_gauss_warp(x - h, 0, *p)) / (2 * h)
+    assert_close(g.exp_gauss_warp(x, 1, *p), fd, rtol=1e-6, atol=1e-8)
+    k = g.GibbsKernel1dExpGauss(2, initial_params=[1.5] + p, param_bounds=[(-10, 10)] * 8)
+    assert k.num_params == 8 and k.device_descriptor()[0] == 4
+    with pytest.raises(NotImplementedError):
+        g.exp_gauss_warp(x, 2, *p)

@@ -403,3 +403,41 @@ def test_host_kernel_sum_ll_and_predict_match_equivalent_device_kernel():
     assert_close(ms1, md1, rtol=1e-9, atol=1e-9 * np.abs(md1).max(), what="derivative mean")
     assert_close(cs, cd, rtol=0.0, atol=1e-9 * np.abs(cd).max(), what="full covariance")
     assert_close(gp_s.predict(Xs, return_std=False), md, rtol=1e-9, atol=1e-9, what="mean only")
+
+
+@pytest.mark.parametrize("name,cls", [("double_tanh", "GibbsKernel1dDoubleTanh"), ("cubic_bucket", "GibbsKernel1dCubicBucket"),
+                                      ("quintic_bucket", "GibbsKernel1dQuinticBucket")])
+def test_gibbs_other_profiles_end_to_end(name, cls):
+    """GibbsKernel1d with the reference's other length-scale functions.  l(x), l'(x) are evaluated on
+    the host per point and travel as extra point columns; assembly, factorisation, prediction run on the device."""
+    gd = load_golden("gibbs_profile_" + name)
+    k = getattr(g, cls)(initial_params=gd["params"], param_bounds=[(0, 10)] * 8)
+    gp = g.GaussianProcess(k)
+    nv = int((gd["n"][:, 0] == 0).sum())
+    gp.add_data(gd["X"][:nv, 0], gd["y"][:nv], err_y=gd["err_y"][:nv])
+    gp.add_data(gd["X"][nv:, 0], gd["y"][nv:], err_y=gd["err_y"][nv:], n=1)
+    gp.compute_K_L_alpha_ll()
+    assert_close(gp.ll, gd["ll"], rtol=1e-9, what="ll")
+    assert_close(gp.alpha.ravel(), gd["alpha"], rtol=1e-8, atol=1e-9 * np.abs(gd["alpha"]).max(), what="alpha")
+    assert_close(gp.K, gd["K"], rtol=1e-11, atol=1e-13 * np.abs(gd["K"]).max(), what="K")
+    res = gp.predict(gd["Xs"], full_output=True)
+    assert_close(res["mean"], gd["mean"], rtol=1e-9, atol=1e-9, what="mean")
+    assert_close(res["cov"], gd["cov"], rtol=0.0, atol=1e-9 * gd["params"][0] ** 2, what="cov")
+    m1, s1 = gp.predict(gd["Xs"], n=1)
+    assert_close(m1, gd["mean_d1"], rtol=1e-9, atol=1e-9 * np.abs(gd["mean_d1"]).max(), what="mean_d1")
+    assert np.all(np.abs(s1 ** 2 - gd["std_d1"] ** 2) <= 1e-8 * np.max(gd["std_d1"] ** 2))
+    assert_close(gp.predict(gd["Xs"], return_std=False), gd["mean"], rtol=1e-9, atol=1e-9, what="fused mean")
+    # changing a length-scale parameter re-evaluates l(x) on the host and refreshes the device copy
+    ll0 = gp.ll
+    new = np.array(gd["params"]); new[2] *= 1.3
+    f = gp.update_hyperparameters(new)
+    assert np.isfinite(f) and abs(-f - ll0) > 1e-6
+    gp.update_hyperparameters(np.array(gd["params"]))
+    assert_close(gp.ll, gd["ll"], rtol=1e-9, what="ll after round trip")
+    # theta batches fall back to one evaluation per theta (l(x) depends on theta), hyper-derivatives as the reference
+    fb = gp.update_hyperparameters_batch(np.stack([gd["params"], new]), with_deriv=False)
+    assert_close(-fb[0], gd["ll"], rtol=1e-9)
+    gp.use_hyper_deriv = True
+    gp.K_up_to_date = False
+    with pytest.raises(NotImplementedError):
+        gp.compute_K_L_alpha_ll()
