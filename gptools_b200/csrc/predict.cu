@@ -63,6 +63,8 @@ __global__ void __launch_bounds__(PM_THREADS) predict_mean_kernel(CovParams cp, 
     __shared__ double sx[PM_STAGE * GPT_MAX_DIM];
     __shared__ int32_t sn[PM_STAGE * GPT_MAX_DIM];
     __shared__ double su[PM_STAGE];
+    __shared__ double etab[64];  // 2^(j/64) for exp_nonpos_tab
+    if (threadIdx.x < 64) etab[threadIdx.x] = GPT_EXP2_64[threadIdx.x];  // published by the first barrier below
     const int D = cp.D;
     const int s = blockIdx.x * PM_THREADS + threadIdx.x;
     const bool live = s < Ms;
@@ -92,7 +94,8 @@ __global__ void __launch_bounds__(PM_THREADS) predict_mean_kernel(CovParams cp, 
             for (int r = 0; r < cnt; r++)
                 acc += cov_eval(cp, sx + r * GPT_MAX_DIM, sn + r * GPT_MAX_DIM, xs, ms, -1) * su[r];
         } else {
-            const SEHoist<FD> h = se_hoist<FD>(cp);
+            SEHoist<FD> h = se_hoist<FD>(cp);
+            h.etab = etab;
             PointReg<FD> pj;
 #pragma unroll
             for (int d = 0; d < FD; d++) {
@@ -109,7 +112,7 @@ __global__ void __launch_bounds__(PM_THREADS) predict_mean_kernel(CovParams cp, 
                         pi.x[d] = sx[r * GPT_MAX_DIM + d];
                         pi.n[d] = sn[r * GPT_MAX_DIM + d];
                     }
-                    acc = fma(se_value_low<FD>(h, pi, pj), su[r], acc);
+                    acc = fma(se_value_low<FD, true>(h, pi, pj), su[r], acc);
                 }
             } else {
 #pragma unroll 2
