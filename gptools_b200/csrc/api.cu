@@ -287,7 +287,7 @@ int transform_latent(gpt_handle* h) {
 }
 
 int assemble_train(gpt_handle* h, const CovParams& cp, double noise_sigma, int hyper_deriv, double* out, int pad,
-                   bool add_diag) {
+                   bool add_diag, bool lower_tiles_only = false) {
     AssembleParams a;
     a.cp = cp;
     a.Xr = ptr<double>(h->X); a.nr = ptr<int32_t>(h->n); a.Mr = h->N;
@@ -297,6 +297,8 @@ int assemble_train(gpt_handle* h, const CovParams& cp, double noise_sigma, int h
     a.diag_add = add_diag ? ptr<double>(h->diag) : nullptr;
     a.diag_const = noise_sigma * noise_sigma;
     a.pad_identity = add_diag ? 1 : 0;
+    a.lower_tiles_only = lower_tiles_only ? 1 : 0;
+    a.low_order = (h->max_order <= 1) ? 1 : 0;
     launch_assemble(a, h->stream);
     h->launches++;
     return check_launch(h);
@@ -643,7 +645,7 @@ int gpt_ll(gpt_handle* h, const double* params, double noise_sigma, double* ll, 
         if ((rc = transform_latent(h))) return rc;
     } else {
         if ((rc = ensure(h, h->A, (size_t)h->Mp * h->Mp * sizeof(double)))) return rc;
-        if ((rc = assemble_train(h, h->cp, noise_sigma, -1, ptr<double>(h->A), h->Mp, true))) return rc;
+        if ((rc = assemble_train(h, h->cp, noise_sigma, -1, ptr<double>(h->A), h->Mp, true, true))) return rc;
     }
     if ((rc = factor_and_solve(h, ll, status))) return rc;
     if (!(grad && P > 0)) return 0;

@@ -9,12 +9,60 @@
 // 128-byte row segments.  Bound: HBM write (8 B per entry) / FP64 ALU for exp + polynomial.
 #include "common.cuh"
 #include "internal.h"
+#include "se_fast.cuh"
 
 namespace {
 
 constexpr int TS = 64;
 
+// Squared-exponential value tiles, input dimension FD <= 3, derivative orders <= 1 on both sides: register-resident
+// branch-free closed forms with the table-based exp (se_fast.cuh) instead of the generic cov_eval -- the generic
+// path keeps per-dimension arrays in local memory and branches per entry.
+template <int FD>
+__device__ __forceinline__ void assemble_tile_se_low(const AssembleParams& p, const double* sxr, const int32_t* snr,
+                                                     const double* sxc, const int32_t* snc, const double* etab,
+                                                     int r0, int c0, int tid) {
+    using namespace sefast;
+    SEHoist<FD> h = se_hoist<FD>(p.cp);
+    h.etab = etab;
+    const int ty = tid >> 4, tx = tid & 15;
+    PointReg<FD> pc[4];
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+#pragma unroll
+        for (int d = 0; d < FD; d++) {
+            pc[b].x[d] = sxc[(tx + 16 * b) * GPT_MAX_DIM + d];
+            pc[b].n[d] = snc[(tx + 16 * b) * GPT_MAX_DIM + d];
+        }
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        const int lr = ty + 16 * a;
+        const int r = r0 + lr;
+        PointReg<FD> pr;
+#pragma unroll
+        for (int d = 0; d < FD; d++) {
+            pr.x[d] = sxr[lr * GPT_MAX_DIM + d];
+            pr.n[d] = snr[lr * GPT_MAX_DIM + d];
+        }
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int c = c0 + tx + 16 * b;
+            // out[r][c] = k(row_r, col_c), or k(col_c, row_r) with swapped roles (the sign depends on which side
+            // carries the odd derivative order)
+            double v = p.swap_roles ? se_value_low<FD, true>(h, pc[b], pr) : se_value_low<FD, true>(h, pr, pc[b]);
+            const bool inside = r < p.Mr && c < p.Mc;
+            v = inside ? v : 0.0;
+            if (p.symmetric && r == c) {
+                if (inside) v += p.diag_const + (p.diag_add ? p.diag_add[r] : 0.0);
+                else if (p.pad_identity) v = 1.0;
+            }
+            if (r < p.rows_pad && c < p.cols_pad) p.out[(long)r * p.ldo + c] = v;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) assemble_kernel(AssembleParams p) {
+    if (p.lower_tiles_only && blockIdx.x > blockIdx.y) return;  // the Cholesky never reads tiles above the diagonal
     __shared__ double sxr[TS * GPT_MAX_DIM];
     __shared__ double sxc[TS * GPT_MAX_DIM];
     __shared__ int32_t snr[TS * GPT_MAX_DIM];
@@ -30,7 +78,15 @@ __global__ void __launch_bounds__(256) assemble_kernel(AssembleParams p) {
         sxc[r * GPT_MAX_DIM + d] = okc ? p.Xc[(long)(c0 + r) * D + d] : 0.0;
         snc[r * GPT_MAX_DIM + d] = okc ? p.nc[(long)(c0 + r) * D + d] : 0;
     }
+    __shared__ double etab[64];
+    if (tid < 64) etab[tid] = GPT_EXP2_64[tid];
     __syncthreads();
+    if (p.cp.kid == GPT_KERNEL_SE && p.hyper_deriv < 0 && p.low_order && D <= 3) {
+        if (D == 1) assemble_tile_se_low<1>(p, sxr, snr, sxc, snc, etab, r0, c0, tid);
+        else if (D == 2) assemble_tile_se_low<2>(p, sxr, snr, sxc, snc, etab, r0, c0, tid);
+        else assemble_tile_se_low<3>(p, sxr, snr, sxc, snc, etab, r0, c0, tid);
+        return;
+    }
     const int ty = tid >> 4, tx = tid & 15;
 #pragma unroll 1
     for (int a = 0; a < 4; a++) {

@@ -47,6 +47,8 @@ struct AssembleParams {
     const double* diag_add;  // optional per-row additive diagonal (err_y^2 + jitter [+ noise]) or NULL
     double diag_const;       // added to every diagonal element r < Mr (sigma_n^2 for the latent K)
     int pad_identity;        // symmetric: out[r][r] = 1 for r >= Mr
+    int lower_tiles_only = 0;  // symmetric output consumed by the Cholesky only: skip tiles above the diagonal
+    int low_order = 0;         // every derivative order <= 1 (both point sets): branch-free SE closed forms
 };
 void launch_assemble(const AssembleParams& p, cudaStream_t s);
 void launch_cov_pairs(const CovParams& cp, int hyper_deriv, long npairs, const double* Xi, const double* Xj,
