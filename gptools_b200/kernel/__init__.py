@@ -5,3 +5,4 @@ from .noise import *  # noqa: F401,F403
 from .squared_exponential import *  # noqa: F401,F403
 from .matern import *  # noqa: F401,F403
 from .gibbs import *  # noqa: F401,F403
+from .warping import *  # noqa: F401,F403

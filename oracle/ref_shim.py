@@ -62,6 +62,13 @@ def _install_scipy_numpy_aliases():
         scipy.misc = misc
 
 
+def _install_py2_builtins():
+    """``long`` (kernel/warping.py:127) is a Python-2 builtin; under Python 3 it is ``int``."""
+    import builtins
+    if not hasattr(builtins, "long"):
+        builtins.long = int
+
+
 def _install_getargspec():
     if not hasattr(inspect, "getargspec"):
         def getargspec(func):
@@ -131,6 +138,7 @@ def load_reference():
         raise RuntimeError("reference tree not present at %s" % REF_ROOT)
     _install_scipy_numpy_aliases()
     _install_getargspec()
+    _install_py2_builtins()
     _install_matplotlib_stubs()
     matern_mod = _install_matern_module()
     sys.dont_write_bytecode = True

@@ -495,9 +495,31 @@ def case_gibbs_profiles():
         save("gibbs_profile_" + name, params=k.params.copy(), **gp_state(gp), **out)
 
 
+# ---------------------------------------------------------------- input warping (kernel/warping.py:464-720)
+def case_warped():
+    rs = RandomState(31)
+    X = np.sort(rs.rand(20)) * 3.0 + 1.0            # in [1, 4]
+    y = np.sin(2 * X) + 0.05 * rs.randn(20)
+    kse = g.SquaredExponentialKernel(initial_params=[1.2, 0.3], param_bounds=[(0, 10)] * 2)
+    kb = g.BetaWarpedKernel(kse, initial_params=[1.8, 0.7], param_bounds=[(0.01, 10)] * 2)
+    k = g.LinearWarpedKernel(kb, [0.5], [4.5])      # map [0.5, 4.5] -> [0, 1], then the beta CDF
+    gp = g.GaussianProcess(k)
+    gp.add_data(X, y, err_y=0.05)
+    gp.add_data(X[::4], 2 * np.cos(2 * X[::4]), err_y=0.1, n=1)
+    out = ll_and_grad(gp, False)
+    Xs = np.linspace(1.0, 4.0, 7)
+    res = gp.predict(Xs, full_output=True)
+    out.update(Xs=Xs, mean=res["mean"], std=res["std"], cov=res["cov"])
+    res1 = gp.predict(Xs, n=1, full_output=True)
+    out.update(mean_d1=res1["mean"], std_d1=res1["std"])
+    save("warped_beta_linear_se", params=np.array([float(v) for v in k.params[:]]),
+         fixed=np.array([bool(v) for v in k.fixed_params[:]]),
+         **gp_state(gp), **out)
+
+
 if __name__ == "__main__":
     cases = [case_se2d, case_se_pairs, case_matern52, case_matern_generic, case_gibbs, case_c5_full, case_demo,
-             case_c3, case_c2, case_noise, case_hyperfd, case_product, case_gibbs_profiles]
+             case_c3, case_c2, case_noise, case_hyperfd, case_product, case_gibbs_profiles, case_warped]
     only = set(sys.argv[1:])          # e.g. `make_golden.py case_hyperfd` regenerates one family
     for c in cases:
         if not only or c.__name__ in only:

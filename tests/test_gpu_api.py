@@ -441,3 +441,26 @@ def test_gibbs_other_profiles_end_to_end(name, cls):
     gp.K_up_to_date = False
     with pytest.raises(NotImplementedError):
         gp.compute_K_L_alpha_ll()
+
+
+def test_warped_kernel_end_to_end():
+    """Input warping (second half): LinearWarpedKernel(BetaWarpedKernel(SquaredExponentialKernel)).
+    The warped kernel is host-composed (its SE operand is evaluated by the device through gpt_cov_pairs), K / K* go
+    through gpt_ll_from_K / gpt_predict_from_Kstar."""
+    gd = load_golden("warped_beta_linear_se")
+    kse = g.SquaredExponentialKernel(initial_params=gd["params"][:2], param_bounds=[(0, 10)] * 2)
+    kb = g.BetaWarpedKernel(kse, initial_params=gd["params"][2:4], param_bounds=[(0.01, 10)] * 2)
+    k = g.LinearWarpedKernel(kb, [gd["params"][4]], [gd["params"][5]])
+    gp = g.GaussianProcess(k)
+    nv = int((gd["n"][:, 0] == 0).sum())
+    gp.add_data(gd["X"][:nv, 0], gd["y"][:nv], err_y=gd["err_y"][:nv])
+    gp.add_data(gd["X"][nv:, 0], gd["y"][nv:], err_y=gd["err_y"][nv:], n=1)
+    gp.compute_K_L_alpha_ll()
+    assert_close(gp.ll, gd["ll"], rtol=1e-9, what="ll")
+    assert_close(gp.alpha.ravel(), gd["alpha"], rtol=1e-8, atol=1e-9 * np.abs(gd["alpha"]).max(), what="alpha")
+    res = gp.predict(gd["Xs"], full_output=True)
+    assert_close(res["mean"], gd["mean"], rtol=1e-9, atol=1e-9, what="mean")
+    assert_close(res["cov"], gd["cov"], rtol=0.0, atol=1e-9 * gd["params"][0] ** 2, what="cov")
+    m1, s1 = gp.predict(gd["Xs"], n=1)
+    assert_close(m1, gd["mean_d1"], rtol=1e-9, atol=1e-9 * np.abs(gd["mean_d1"]).max(), what="mean_d1")
+    assert np.all(np.abs(s1 ** 2 - gd["std_d1"] ** 2) <= 1e-8 * np.max(gd["std_d1"] ** 2))

@@ -419,3 +419,22 @@ def test_sum_and_product_kernels_match_reference():
     assert kp.num_params == 6 and list(kp.params) == list(gd["params1"]) + list(gd["params2"])
     with pytest.raises(NotImplementedError):
         kp(*a, hyper_deriv=0)
+
+
+def test_warped_kernel_matches_reference():
+    """LinearWarpedKernel(BetaWarpedKernel(SE)) -- nested input warping with first-derivative observations -- against
+    the reference's K (kernel/warping.py:464-720).  The SE operand is the oracle stand-in, so this runs without a
+    GPU; the GPU suite runs the same golden end to end."""
+    gd = load_golden("warped_beta_linear_se")
+    kse = _OracleSE(1, gd["params"][:2])
+    kb = g.BetaWarpedKernel(kse, initial_params=gd["params"][2:4], param_bounds=[(0.01, 10)] * 2)
+    k = g.LinearWarpedKernel(kb, [gd["params"][4]], [gd["params"][5]])
+    assert_close(np.asarray(k.params, float), gd["params"], rtol=0, atol=0)
+    assert list(np.asarray(k.fixed_params, bool)) == list(gd["fixed"])
+    assert k.num_free_params == 4
+    X, n = gd["X"], gd["n"]
+    M = len(X)
+    K = k(np.repeat(X, M, axis=0), np.tile(X, (M, 1)), np.repeat(n, M, axis=0), np.tile(n, (M, 1))).reshape(M, M)
+    assert_close(K, gd["K"], rtol=1e-10, atol=1e-12 * np.abs(gd["K"]).max(), what="warped K")
+    with pytest.raises(ValueError):
+        k(X[:1], X[:1], np.array([[2]]), np.array([[0]]))
