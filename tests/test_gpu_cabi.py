@@ -356,3 +356,47 @@ def test_tiny_and_ragged_sizes_all_paths(dev, M):
     assert m0.shape == (0,) and v0.shape == (0,)
     l0, g0, s0 = dev.ll_batched(np.zeros((0, 3)), grad_idx=[0, 1])
     assert l0.shape == (0,) and g0.shape == (0, 2) and s0.shape == (0,)
+
+
+def test_T_path_gradient_multiblock_vs_oracle(dev):
+    """Transformed observations y = T f with N = 300 latent points (three 128-blocks) and M = 40 observations:
+    ll, analytic gradient (SE: the reference's own formula through the oracle; Gibbs-tanh: finite differences of the
+    oracle ll) and prediction with T, multi-block in both the latent and the observation dimension."""
+    from oracle import gp_oracle as orc
+    rs = np.random.RandomState(5)
+    N, Mo, W = 300, 40, 30
+    Xq = np.linspace(0, 1.1, N)[:, None]
+    T = np.zeros((Mo, N))
+    for i, s in enumerate(rs.randint(0, N - W, size=Mo)):
+        T[i, s:s + W] = 1.1 / N
+    y = rs.rand(Mo) * 0.3 + 0.1
+    err = np.full(Mo, 0.02)
+    n = np.zeros((N, 1), dtype=int)
+    dev.set_data(Xq, n, y, err, T)
+    # SE kernel: analytic gradient
+    th = np.array([1.3, 0.25])
+    ref = orc.compute_K_L_alpha_ll(orc.KERNEL_SE, th, Xq, n, y, err, T, 0.0, 1e2, grad_idx=[0, 1])
+    dev.set_kernel(KERNEL_SE, 2, 1e2)
+    ll, grad, st = dev.ll(th, 0.0, grad_idx=[0, 1])
+    assert st == 0
+    assert_close(ll, ref["ll"], rtol=1e-9, what="ll")
+    assert_close(grad, ref["ll_deriv"], rtol=1e-8, atol=1e-9 * np.abs(ref["ll_deriv"]).max(), what="gradient")
+    Xs = np.linspace(0, 1.1, 150)[:, None]
+    ns = np.zeros((150, 1), dtype=int)
+    mean, var, _ = dev.predict(Xs, ns, want_var=True)
+    pm, ps, pc = orc.predict(orc.KERNEL_SE, th, Xq, n, ref["L"], ref["alpha"], Xs, ns, T=T)
+    assert_close(mean, pm, rtol=1e-9, atol=1e-9, what="mean")
+    assert np.all(np.abs(var - np.diag(pc)) <= 1e-9 * th[0] ** 2)
+    # Gibbs-tanh: dual-number hyper-derivatives through T
+    from helpers import KERNEL_GIBBS_TANH
+    tg = np.array([1.5, 0.6, 0.1, 0.05, 0.9])
+    dev.set_kernel(KERNEL_GIBBS_TANH, 5, 1e2)
+    llg, gg, st = dev.ll(tg, 0.0, grad_idx=[0, 1, 2, 3, 4])
+    assert st == 0
+
+    def ll_of(t):
+        return orc.compute_K_L_alpha_ll(orc.KERNEL_GIBBS_TANH, t, Xq, n, y, err, T, 0.0, 1e2)["ll"]
+
+    assert_close(llg, ll_of(tg), rtol=1e-9, what="gibbs ll")
+    fd = np.array([richardson_fd(ll_of, tg, i, 1e-3 * tg[i]) for i in range(5)])
+    assert_close(gg, fd, rtol=0.0, atol=2e-6 * np.abs(fd).max(), what="gibbs gradient through T")
