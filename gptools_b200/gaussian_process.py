@@ -613,9 +613,16 @@ class GaussianProcess(object):
             finally:
                 self.mu.params[:] = saved
         free_idx = np.nonzero(free_mask)[0]
+        all_good = bool(good.all())
+        good_params = all_params if all_good else all_params[good]
         for i, pi in enumerate(free_idx):
-            g[good, i] += hp.dlogpdf_batch(all_params[good], int(pi))
-        g[~good] = 0.0
+            dlp = hp.dlogpdf_batch(good_params, int(pi))
+            if all_good:
+                g[:, i] += dlp
+            else:
+                g[good, i] += dlp
+        if not all_good:
+            g[~good] = 0.0
         return neg_ll, -g
 
     def _batch_by_loop(self, thetas, with_deriv):
