@@ -400,3 +400,42 @@ def test_T_path_gradient_multiblock_vs_oracle(dev):
     assert_close(llg, ll_of(tg), rtol=1e-9, what="gibbs ll")
     fd = np.array([richardson_fd(ll_of, tg, i, 1e-3 * tg[i]) for i in range(5)])
     assert_close(gg, fd, rtol=0.0, atol=2e-6 * np.abs(fd).max(), what="gibbs gradient through T")
+
+
+@pytest.mark.parametrize("trial", range(16))
+def test_randomised_paths_agree_with_oracle(dev, trial):
+    """Seeded sweep over input dimension (1..4: the SE fast paths and the generic one), derivative orders up to 2 (the
+    branch-free low-order forms and the general Hermite recurrence) and sizes around the tile edges: single-theta path,
+    batched path and prediction against the pinned oracle, all at the north-star tolerance."""
+    from oracle import gp_oracle as orc
+    rs = np.random.RandomState(1000 + trial)
+    D = [1, 2, 3, 4][trial % 4]
+    M = int(rs.choice([37, 64, 100, 129, 200, 260]))
+    maxord = [1, 2][(trial // 4) % 2]
+    X = rs.rand(M, D)
+    n = np.zeros((M, D), dtype=int)
+    for i in range(M // 3, M):
+        n[i, rs.randint(D)] = rs.randint(0, maxord + 1)
+    y = rs.randn(M)
+    err = np.full(M, 0.2)
+    th = np.concatenate([[1.0 + 0.5 * rs.rand()], 0.3 + 0.4 * rs.rand(D)])
+    idx = list(range(D + 1))
+    ref = orc.compute_K_L_alpha_ll(orc.KERNEL_SE, th, X, n, y, err, None, 0.0, 1e2, grad_idx=idx)
+    dev.set_data(X, n, y, err)
+    dev.set_kernel(KERNEL_SE, D + 1, 1e2)
+    ll, g, st = dev.ll(th, 0.0, grad_idx=idx)
+    llb, gb, stb = dev.ll_batched(np.array([list(th) + [0.0]] * 2), grad_idx=idx)
+    assert st == 0 and (stb == 0).all()
+    gs = np.abs(ref["ll_deriv"]).max()
+    assert_close(ll, ref["ll"], rtol=1e-9, what="ll")
+    assert_close(g, ref["ll_deriv"], rtol=0.0, atol=1e-9 * gs, what="gradient")
+    assert_close(llb[0], ref["ll"], rtol=1e-9, what="batched ll")
+    assert_close(gb[0], ref["ll_deriv"], rtol=0.0, atol=1e-9 * gs, what="batched gradient")
+    Xs = rs.rand(11, D)
+    ns = np.zeros((11, D), dtype=int)
+    ns[::3, 0] = 1
+    dev.ll(th, 0.0)
+    m, v, _ = dev.predict(Xs, ns, want_var=True)
+    pm, ps, pc = orc.predict(orc.KERNEL_SE, th, X, n, ref["L"], ref["alpha"], Xs, ns)
+    assert_close(m, pm, rtol=1e-9, atol=1e-9 * max(1.0, np.abs(pm).max()), what="mean")
+    assert np.all(np.abs(v - np.diag(pc)) <= 1e-9 * np.abs(np.diag(pc)).max())
