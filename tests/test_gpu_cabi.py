@@ -439,3 +439,53 @@ def test_randomised_paths_agree_with_oracle(dev, trial):
     pm, ps, pc = orc.predict(orc.KERNEL_SE, th, X, n, ref["L"], ref["alpha"], Xs, ns)
     assert_close(m, pm, rtol=1e-9, atol=1e-9 * max(1.0, np.abs(pm).max()), what="mean")
     assert np.all(np.abs(v - np.diag(pc)) <= 1e-9 * np.abs(np.diag(pc)).max())
+
+
+@pytest.mark.parametrize("trial", range(12))
+def test_randomised_matern_gibbs_paths_agree_with_oracle(dev, trial):
+    """The same sweep for the other kernels: Matern-5/2 (D = 1..3), generic Matern (nu = 1/2 .. 7/2, D = 1, 2) and
+    Gibbs-tanh, value and first-derivative observations, sizes around the tile edges."""
+    from oracle import gp_oracle as orc
+    from helpers import KERNEL_GIBBS_TANH
+    rs = np.random.RandomState(2000 + trial)
+    fam = trial % 3
+    M = int(rs.choice([37, 64, 100, 129, 200]))
+    if fam == 0:
+        D = 1 + (trial // 3) % 3
+        kid, okid = KERNEL_MATERN52, orc.KERNEL_MATERN52
+        th = np.concatenate([[1.0 + 0.5 * rs.rand()], 0.4 + 0.5 * rs.rand(D)])
+        tol = 1e-9
+    elif fam == 1:
+        D = 1 + (trial // 3) % 2
+        nu = [2.5, 3.5, 1.5, 0.5][(trial // 3) % 4]
+        kid, okid = KERNEL_MATERN, orc.KERNEL_MATERN
+        th = np.concatenate([[1.0 + 0.5 * rs.rand(), nu], 0.4 + 0.5 * rs.rand(D)])
+        tol = 2e-6       # the oracle mirrors the reference's kvp round-off (see test_ll_alpha_L)
+    else:
+        D = 1
+        kid, okid = KERNEL_GIBBS_TANH, orc.KERNEL_GIBBS_TANH
+        th = np.array([1.2 + 0.5 * rs.rand(), 0.5, 0.15, 0.08, 0.6])
+        tol = 1e-9
+    X = rs.rand(M, D)
+    n = np.zeros((M, D), dtype=int)
+    if not (fam == 1 and th[1] < 2):            # nu <= 3/2 has no usable derivative observations (SURVEY H1)
+        for i in range(2 * M // 3, M):
+            n[i, rs.randint(D)] = 1
+    y = rs.randn(M)
+    err = np.full(M, 0.2)
+    ref = orc.compute_K_L_alpha_ll(okid, th, X, n, y, err, None, 0.0, 1e2)
+    dev.set_data(X, n, y, err)
+    dev.set_kernel(kid, len(th), 1e2)
+    ll, _, st = dev.ll(th, 0.0)
+    llb, _, stb = dev.ll_batched(np.array([list(th) + [0.0]] * 2))
+    assert st == 0 and (stb == 0).all()
+    assert_close(ll, ref["ll"], rtol=max(tol, 1e-9), what="ll")
+    assert_close(llb[0], ref["ll"], rtol=max(tol, 1e-9), what="batched ll")
+    assert_close(dev.get_alpha(), np.ravel(ref["alpha"]), rtol=0.0, atol=max(tol, 1e-8) * np.abs(ref["alpha"]).max(),
+                 what="alpha")
+    Xs = rs.rand(9, D)
+    ns = np.zeros((9, D), dtype=int)
+    m, v, _ = dev.predict(Xs, ns, want_var=True)
+    pm, ps, pc = orc.predict(okid, th, X, n, ref["L"], ref["alpha"], Xs, ns)
+    assert_close(m, pm, rtol=0.0, atol=max(tol, 1e-9) * max(1.0, np.abs(pm).max()), what="mean")
+    assert np.all(np.abs(v - np.diag(pc)) <= max(tol, 1e-9) * th[0] ** 2)
