@@ -123,8 +123,13 @@ int supported_kernel(int kid, int D, int nparams) {
 // step-k update keeps the machine busy.  panel2 holds TWO panels (double buffered).  Writes the inverses of
 // the diagonal blocks to inv (nblk x 128 x 128), per-block log-det shares, info, and (optionally) overwrites rhs
 // with L^{-1} rhs.  All heavy work is DMMA GEMM (gemm.cu).
-int blocked_potrf(gpt_handle* h, double* A, long ld, int nblk, double* inv, double* panel2, double* rhs, double* logdet,
-                  int* info) {
+// doubles of panel scratch blocked_potrf needs for an nblk-block matrix: two pair buffers + one 128 x 128 block
+size_t potrf_panel_doubles(int nblk) { return (size_t)4 * nblk * NB * NB + (size_t)NB * NB; }
+
+// Unpaired variant (rank-128 updates): for small matrices the per-step critical chain decides, and the pairing below
+// doubles the in-kernel diagonal update of every other step (M = 4000: 3.1 ms against 3.6 ms).
+int blocked_potrf_k128(gpt_handle* h, double* A, long ld, int nblk, double* inv, double* panel2, double* rhs, double* logdet,
+                       int* info) {
     cudaStream_t sm = h->stream;
     if (!h->side_stream) {
         // highest priority: its few CTAs are placed as soon as an SM frees up, ahead of the queued update tiles
@@ -152,15 +157,15 @@ int blocked_potrf(gpt_handle* h, double* A, long ld, int nblk, double* inv, doub
         if (k == 0) CUDA_OK(h, cudaStreamWaitEvent(ss, h->ev_col, 0));
         if (k >= 2) CUDA_OK(h, cudaStreamWaitEvent(ss, h->ev_rest[k & 1], 0));
         launch_potrf_diag(Akk, ld, inv_k, rhs ? rhs + (long)k * NB : nullptr, logdet + k, info, k * NB,
-                          k > 0 ? panel_prev : nullptr, ss);
+                          k > 0 ? panel_prev : nullptr, NB, NB, ss);
         h->launches++;
         if (rest > 0) {
             double* A21 = A + (long)(k + 1) * NB * ld + (long)k * NB;
             if (k > 0) CUDA_OK(h, cudaStreamWaitEvent(ss, h->ev_col, 0));
             // panel P = A21 L11^{-T}: one-pass blocked substitution (factor.cu: panel_trsm_kernel), in place, plus the
             // contiguous copy the rank-128 update reads and the right-hand-side update
-            launch_panel_trsm(A21, ld, Akk, ld, inv_k, panel, rest * NB, rhs ? rhs + (long)k * NB : nullptr,
-                              rhs ? rhs + (long)(k + 1) * NB : nullptr, ss);
+            launch_panel_trsm(A21, ld, Akk, ld, inv_k, panel, NB, 0, panel, NB, rest * NB,
+                              rhs ? rhs + (long)k * NB : nullptr, rhs ? rhs + (long)(k + 1) * NB : nullptr, ss);
             h->launches++;
         }
         CUDA_OK(h, cudaEventRecord(h->ev_panel, ss));
@@ -189,6 +194,125 @@ int blocked_potrf(gpt_handle* h, double* A, long ld, int nblk, double* inv, doub
                 h->launches++;
             }
             CUDA_OK(h, cudaEventRecord(h->ev_rest[k & 1], sm));
+        }
+    }
+    // join: nothing is left running on the side stream that the main stream has not waited for (ev_panel of the
+    // last step), so work queued on the main stream after this call sees the complete factor
+    return check_launch(h);
+}
+
+constexpr int PAIR_MIN_BLOCKS = 48;  // M >= 6144: the trailing update dominates and rank-256 pays
+
+int blocked_potrf(gpt_handle* h, double* A, long ld, int nblk, double* inv, double* pbuf, double* rhs, double* logdet,
+                  int* info) {
+    int pair_min = PAIR_MIN_BLOCKS;
+    if (const char* e = getenv("GPT_POTRF_PAIR_MIN")) pair_min = atoi(e);  // tests: force either variant
+    if (nblk < pair_min) return blocked_potrf_k128(h, A, ld, nblk, inv, pbuf, rhs, logdet, info);
+    cudaStream_t sm = h->stream;
+    if (!h->side_stream) {
+        // highest priority: its few CTAs are placed as soon as an SM frees up, ahead of the queued update tiles
+        int prio_lo = 0, prio_hi = 0;
+        CUDA_OK(h, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CUDA_OK(h, cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, prio_hi));
+        CUDA_OK(h, cudaEventCreateWithFlags(&h->ev_col, cudaEventDisableTiming));
+        CUDA_OK(h, cudaEventCreateWithFlags(&h->ev_panel, cudaEventDisableTiming));
+        CUDA_OK(h, cudaEventCreateWithFlags(&h->ev_rest[0], cudaEventDisableTiming));
+        CUDA_OK(h, cudaEventCreateWithFlags(&h->ev_rest[1], cudaEventDisableTiming));
+    }
+    cudaStream_t ss = h->side_stream;
+    CUDA_OK(h, cudaMemsetAsync(info, 0, sizeof(int), sm));
+    // Panels are taken in PAIRS (2p, 2p+1) so that the big trailing update runs with a contraction of 256 (33.0 vs
+    // 31.2 TFLOP/s for the GEMM).  Pair buffer: row 0 = block row 2p+2, columns 0..127 = panel 2p (without its first
+    // block, which goes to pfirst), columns 128..255 = panel 2p+1.  Per pair, on the main stream:
+    //   strip(2p)    : column 2p+1, rows >= 2p+2,  -= P_2p P_2p[first]^T                         (K = 128)
+    //   strip2(2p+1) : columns 2p+2, 2p+3, rows >= 2p+3 (incl. the diagonal block of 2p+3)         (K = 256)
+    //   rest(2p+1)   : block columns >= 2p+4, lower tiles                                         (K = 256)
+    // and on the side stream potrf(k) / trsm(k); potrf applies the update its diagonal block still lacks itself
+    // (even k: K = 256 from the previous pair buffer, odd k: K = 128 from pfirst).  Dependencies: trsm(k) waits for
+    // the latest strip (ev_col), the strips wait for trsm (ev_panel), potrf of pair p waits for rest of pair p-2
+    // (ev_rest, alternating) -- never for the rest that is running, which is what the lookahead hides it behind.
+    const long LP = 2 * NB;
+    double* pair[2] = {pbuf, pbuf + (size_t)nblk * NB * LP};
+    double* pfirst = pbuf + (size_t)2 * nblk * NB * LP;
+    CUDA_OK(h, cudaEventRecord(h->ev_col, sm));  // everything queued so far (assembly, rhs set-up)
+    for (int k = 0; k < nblk; k++) {
+        const bool even = (k & 1) == 0;
+        const int p = k >> 1;
+        double* pb = pair[p & 1];
+        double* Akk = A + (long)k * NB * ld + (long)k * NB;
+        double* inv_k = inv + (size_t)k * NB * NB;
+        const int rest = nblk - k - 1;
+        // ---- side stream: diagonal block + panel of step k ----
+        if (k == 0) CUDA_OK(h, cudaStreamWaitEvent(ss, h->ev_col, 0));
+        if (even && p >= 2) CUDA_OK(h, cudaStreamWaitEvent(ss, h->ev_rest[p & 1], 0));
+        const double* pprev = nullptr;
+        long ldp = NB;
+        int pcols = NB;
+        if (even && k > 0) {
+            pprev = pair[(p - 1) & 1];
+            ldp = LP;
+            pcols = 2 * NB;
+        } else if (!even) {
+            pprev = pfirst;
+        }
+        launch_potrf_diag(Akk, ld, inv_k, rhs ? rhs + (long)k * NB : nullptr, logdet + k, info, k * NB, pprev, ldp, pcols,
+                          ss);
+        h->launches++;
+        if (rest > 0) {
+            double* A21 = A + (long)(k + 1) * NB * ld + (long)k * NB;
+            // column k is final after strip2 of the previous pair (main stream: ev_col); for odd k also after strip(k-1),
+            // which runs on this stream
+            if (even && k > 0) CUDA_OK(h, cudaStreamWaitEvent(ss, h->ev_col, 0));
+            // panel P = A21 L11^{-T}: one-pass blocked substitution (factor.cu: panel_trsm_kernel), in place, plus the
+            // copy the rank updates read and the right-hand-side update
+            if (even)
+                launch_panel_trsm(A21, ld, Akk, ld, inv_k, pfirst, NB, NB, pb, LP, rest * NB,
+                                  rhs ? rhs + (long)k * NB : nullptr, rhs ? rhs + (long)(k + 1) * NB : nullptr, ss);
+            else
+                launch_panel_trsm(A21, ld, Akk, ld, inv_k, pb + NB, LP, 0, pb + NB, LP, rest * NB,
+                                  rhs ? rhs + (long)k * NB : nullptr, rhs ? rhs + (long)(k + 1) * NB : nullptr, ss);
+            h->launches++;
+            if (even && rest > 1) {
+                // strip: block column k+1, rows >= k+2, panel k only.  On the side stream: it touches nothing the
+                // running rank-256 update touches, and trsm(k+1) needs it.
+                GemmParams c;
+                c.C = A + (long)(k + 2) * NB * ld + (long)(k + 1) * NB; c.ldc = ld;
+                c.A = pb; c.lda = LP;
+                c.B = pfirst; c.ldb = NB;
+                c.tiles_m = rest - 1; c.tiles_n = 1; c.K = NB;
+                c.alpha = -1.0; c.beta = 1.0; c.lower_only = 0; c.kbegin_row = 0;
+                launch_gemm_nt(c, ss);
+                h->launches++;
+            }
+        }
+        CUDA_OK(h, cudaEventRecord(h->ev_panel, ss));
+        // ---- main stream ----
+        CUDA_OK(h, cudaStreamWaitEvent(sm, h->ev_panel, 0));
+        if (!even) {
+            const int tm = nblk - (k + 2);  // block rows >= k+2
+            if (tm >= 1) {
+                GemmParams c;  // strip2: block columns k+1 and k+2, rows >= k+2, both panels of the pair
+                c.C = A + (long)(k + 2) * NB * ld + (long)(k + 1) * NB; c.ldc = ld;
+                c.A = pb + (size_t)NB * LP; c.lda = LP;
+                c.B = pb; c.ldb = LP;
+                c.tiles_m = tm; c.tiles_n = 2; c.K = 2 * NB;
+                c.alpha = -1.0; c.beta = 1.0; c.lower_only = 0; c.kbegin_row = 0;
+                launch_gemm_nt(c, sm);
+                h->launches++;
+            }
+            CUDA_OK(h, cudaEventRecord(h->ev_col, sm));
+            const int tr = nblk - (k + 3);  // block rows / columns >= k+3
+            if (tr >= 1) {
+                GemmParams u;  // rest: lower tiles of the trailing matrix, rank-256 update
+                u.C = A + (long)(k + 3) * NB * ld + (long)(k + 3) * NB; u.ldc = ld;
+                u.A = pb + (size_t)2 * NB * LP; u.lda = LP;
+                u.B = pb + (size_t)2 * NB * LP; u.ldb = LP;
+                u.tiles_m = tr; u.tiles_n = tr; u.K = 2 * NB;
+                u.alpha = -1.0; u.beta = 1.0; u.lower_only = 1; u.kbegin_row = 0;
+                launch_gemm_nt(u, sm);
+                h->launches++;
+            }
+            CUDA_OK(h, cudaEventRecord(h->ev_rest[p & 1], sm));
         }
     }
     // join: nothing is left running on the side stream that the main stream has not waited for (ev_panel of the
@@ -229,7 +353,7 @@ int factor_and_solve(gpt_handle* h, double* ll, int* status) {
     const int Mp = h->Mp, M = h->M, nblk = Mp / NB;
     int rc;
     if ((rc = ensure(h, h->Inv, (size_t)nblk * NB * NB * sizeof(double)))) return rc;
-    if ((rc = ensure(h, h->P, (size_t)2 * Mp * NB * sizeof(double)))) return rc;
+    if ((rc = ensure(h, h->P, potrf_panel_doubles(nblk) * sizeof(double)))) return rc;
     if ((rc = ensure(h, h->z, (size_t)Mp * sizeof(double)))) return rc;
     if ((rc = ensure(h, h->alpha, (size_t)Mp * sizeof(double)))) return rc;
     if ((rc = ensure(h, h->logdet, (size_t)nblk * sizeof(double)))) return rc;
@@ -1076,7 +1200,7 @@ int gpt_draw_sample(gpt_handle* h, int Ms, int S, const double* mean, const doub
     std::vector<double> hj(Ms, jitter);
     if ((rc = upload_padded(h, C, cov, Ms, Ms, Sp, Sp)) || (rc = upload(h, jit, hj.data(), sizeof(double) * Ms)) ||
         (rc = ensure(h, inv, sizeof(double) * (size_t)nblk * NB * NB)) ||
-        (rc = ensure(h, panel, sizeof(double) * (size_t)2 * Sp * NB)) ||
+        (rc = ensure(h, panel, sizeof(double) * potrf_panel_doubles(nblk))) ||
         (rc = ensure(h, logdet, sizeof(double) * nblk)) ||
         (rc = ensure(h, info, sizeof(int))) || (rc = upload_padded(h, R, rand_vars, Ms, S, Sp, Rp)) ||
         (rc = ensure(h, Rt, sizeof(double) * (size_t)Rp * Sp)) || (rc = ensure(h, O, sizeof(double) * (size_t)Sp * Rp)) ||

@@ -135,13 +135,13 @@ __device__ __forceinline__ void pivot8(double* P, double* G, long ldg, double* d
     __syncwarp();
 }
 
-// Pprev != null: the block still lacks the rank-128 update of the previous step, A -= Pprev Pprev^T (Pprev = the
-// 128 x 128 block of the previous panel that sits beside this diagonal block); applying it here takes the strip
-// GEMM of the blocked Cholesky off the critical path.
+// Pprev != null: the block still lacks the rank-128 / rank-256 update of the previous step(s), A -= Pprev Pprev^T
+// (Pprev = the 128 x (16 pchunks) block of the previous panel(s) that sits beside this diagonal block, leading
+// dimension ldp); applying it here takes that update off the critical path of the blocked Cholesky.
 __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__ A, long lda, double* __restrict__ inv,
                                                             double* __restrict__ yk, double* __restrict__ logdet_part,
                                                             int* __restrict__ info, int row0,
-                                                            const double* __restrict__ Pprev) {
+                                                            const double* __restrict__ Pprev, long ldp, int pchunks) {
     extern __shared__ __align__(16) double sm[];
     double* V = sm;                  // NB x LDB
     double* yv = sm + NB * LDB;      // right-hand side block
@@ -177,13 +177,13 @@ __global__ void __launch_bounds__(256, 1) potrf_diag_kernel(double* __restrict__
         auto load_chunk = [&](int st, int kc) {
             for (int idx = tid; idx < NB * 8; idx += 256) {
                 const int r = idx >> 3, c2 = (idx & 7) * 2;
-                cp_async16(Pc + st * PCH + r * 20 + c2, Pprev + (long)r * NB + kc * 16 + c2);
+                cp_async16(Pc + st * PCH + r * 20 + c2, Pprev + (long)r * ldp + kc * 16 + c2);
             }
         };
         load_chunk(0, 0);
         cp_async_commit();
-        for (int kc = 0; kc < 8; kc++) {
-            if (kc + 1 < 8) load_chunk((kc + 1) & 1, kc + 1);
+        for (int kc = 0; kc < pchunks; kc++) {
+            if (kc + 1 < pchunks) load_chunk((kc + 1) & 1, kc + 1);
             cp_async_commit();
             cp_async_wait<1>();
             __syncthreads();
@@ -345,7 +345,9 @@ constexpr size_t TRSM_SMEM = ((size_t)NB * LDB + (size_t)TR_ROWS * LDB + NBLK * 
 
 __global__ void __launch_bounds__(256, 1) panel_trsm_kernel(double* __restrict__ A21, long lda,
                                                             const double* __restrict__ L11, long ldl,
-                                                            const double* __restrict__ inv_k, double* __restrict__ panel,
+                                                            const double* __restrict__ inv_k,
+                                                            double* __restrict__ out0, long ld0, int split,
+                                                            double* __restrict__ out1, long ld1,
                                                             int rows, const double* __restrict__ zk,
                                                             double* __restrict__ y) {
     extern __shared__ __align__(16) double sm[];
@@ -415,8 +417,10 @@ __global__ void __launch_bounds__(256, 1) panel_trsm_kernel(double* __restrict__
         double sdot = (va.x * za.x + va.y * za.y) + (vb.x * zb.x + vb.y * zb.y);
         sdot = warp_sum(sdot);
         if (row < rows) {
-            *reinterpret_cast<double2*>(panel + (long)row * NB + lane * 4) = va;
-            *reinterpret_cast<double2*>(panel + (long)row * NB + lane * 4 + 2) = vb;
+            // panel copy for the rank updates: rows < split go to out0, the others (re-based) to out1
+            double* pout = (row < split) ? out0 + (long)row * ld0 : out1 + (long)(row - split) * ld1;
+            *reinterpret_cast<double2*>(pout + lane * 4) = va;
+            *reinterpret_cast<double2*>(pout + lane * 4 + 2) = vb;
             *reinterpret_cast<double2*>(A21 + (long)row * lda + lane * 4) = va;
             *reinterpret_cast<double2*>(A21 + (long)row * lda + lane * 4 + 2) = vb;
             if (lane == 0 && y != nullptr) y[row] -= sdot;
@@ -572,24 +576,25 @@ __global__ void trace_sumsq_kernel(const double* __restrict__ A, long lda, const
 }  // namespace
 
 void launch_potrf_diag(double* Ablk, long lda, double* inv, double* yk, double* logdet_part, int* info, int row0,
-                       const double* Pprev, cudaStream_t s) {
+                       const double* Pprev, long ldp, int pcols, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM);
         attr_set = true;
     }
-    potrf_diag_kernel<<<1, 256, POTRF_SMEM, s>>>(Ablk, lda, inv, yk, logdet_part, info, row0, Pprev);
+    potrf_diag_kernel<<<1, 256, POTRF_SMEM, s>>>(Ablk, lda, inv, yk, logdet_part, info, row0, Pprev, ldp, pcols / 16);
 }
 
-void launch_panel_trsm(double* A21, long lda, const double* L11, long ldl, const double* inv_k, double* panel, int rows,
-                       const double* zk, double* y, cudaStream_t s) {
+void launch_panel_trsm(double* A21, long lda, const double* L11, long ldl, const double* inv_k, double* out0, long ld0,
+                       int split, double* out1, long ld1, int rows, const double* zk, double* y, cudaStream_t s) {
     if (rows <= 0) return;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(panel_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRSM_SMEM);
         attr_set = true;
     }
-    panel_trsm_kernel<<<(rows + TR_ROWS - 1) / TR_ROWS, 256, TRSM_SMEM, s>>>(A21, lda, L11, ldl, inv_k, panel, rows, zk, y);
+    panel_trsm_kernel<<<(rows + TR_ROWS - 1) / TR_ROWS, 256, TRSM_SMEM, s>>>(A21, lda, L11, ldl, inv_k, out0, ld0, split, out1,
+                                                                             ld1, rows, zk, y);
 }
 
 // ---- alpha = L^{-T} z in ONE launch: a chain of CTAs, one per 128-row block ----------------------------------------

@@ -57,13 +57,15 @@ void launch_cov_pairs(const CovParams& cp, int hyper_deriv, long npairs, const d
 // ---- factor.cu : blocked Cholesky pieces, solves, reductions -----------------------------------
 // Factor one 128x128 diagonal block in place (lower), write its inverse (lower, zero above) to
 // inv, optionally z_k = inv * y_k (in place on y), accumulate sum(log diag) and the LAPACK-style info.
-// Pprev (128 x 128, ld 128) or NULL: first apply the pending update Ablk -= Pprev Pprev^T.
+// Pprev (128 x pcols, leading dimension ldp, pcols = 128 or 256) or NULL: first apply the pending update
+// Ablk -= Pprev Pprev^T.
 void launch_potrf_diag(double* Ablk, long lda, double* inv, double* yk, double* logdet_part, int* info,
-                       int row0, const double* Pprev, cudaStream_t s);
-// panel solve in place: A21 (rows x 128, ld lda) <- A21 L11^{-T}; copy to panel (ld 128); y -= P zk when y != NULL.
+                       int row0, const double* Pprev, long ldp, int pcols, cudaStream_t s);
+// panel solve in place: A21 (rows x 128, ld lda) <- A21 L11^{-T}; y -= P zk when y != NULL.  The copy the rank updates
+// read goes to out0 (rows < split, leading dimension ld0) and out1 (rows >= split, re-based to row 0, ld1).
 // inv_k supplies the 8x8 diagonal-block inverses of L11 (its own diagonal blocks).
-void launch_panel_trsm(double* A21, long lda, const double* L11, long ldl, const double* inv_k, double* panel, int rows,
-                       const double* zk, double* y, cudaStream_t s);
+void launch_panel_trsm(double* A21, long lda, const double* L11, long ldl, const double* inv_k, double* out0, long ld0,
+                       int split, double* out1, long ld1, int rows, const double* zk, double* y, cudaStream_t s);
 // alpha = L^{-T} z in one launch (chain of CTAs, flags: nblk ints of scratch)
 void launch_backsolve_chain(const double* L, long ld, int nblk, const double* inv, const double* z, double* alpha,
                             int* flags, cudaStream_t s);

@@ -489,3 +489,36 @@ def test_randomised_matern_gibbs_paths_agree_with_oracle(dev, trial):
     pm, ps, pc = orc.predict(okid, th, X, n, ref["L"], ref["alpha"], Xs, ns)
     assert_close(m, pm, rtol=0.0, atol=max(tol, 1e-9) * max(1.0, np.abs(pm).max()), what="mean")
     assert np.all(np.abs(v - np.diag(pc)) <= max(tol, 1e-9) * th[0] ** 2)
+
+
+@pytest.mark.parametrize("pair_min", ["1", "100000"])
+@pytest.mark.parametrize("M", [130, 300, 700, 800, 1100])
+def test_blocked_cholesky_variants_vs_oracle(dev, M, pair_min, monkeypatch):
+    """Both variants of the blocked Cholesky -- paired rank-256 trailing updates (default from 48 blocks) and the
+    unpaired one -- forced onto the same small problems (2 .. 9 blocks, odd and even counts): ll, gradient, alpha,
+    L and the predictive variance against the pinned oracle."""
+    from oracle import gp_oracle as orc
+    monkeypatch.setenv("GPT_POTRF_PAIR_MIN", pair_min)
+    rs = np.random.RandomState(M)
+    X = rs.rand(M, 2)
+    n = np.zeros((M, 2), dtype=int)
+    n[M // 2:, 0] = 1
+    y = rs.randn(M)
+    err = np.full(M, 0.3)
+    th = np.array([1.1, 0.35, 0.5])
+    ref = orc.compute_K_L_alpha_ll(orc.KERNEL_SE, th, X, n, y, err, None, 0.0, 1e2, grad_idx=[0, 1, 2])
+    dev.set_data(X, n, y, err)
+    dev.set_kernel(KERNEL_SE, 3, 1e2)
+    ll, g, st = dev.ll(th, 0.0, grad_idx=[0, 1, 2])
+    assert st == 0
+    assert_close(ll, ref["ll"], rtol=1e-9, what="ll")
+    assert_close(g, ref["ll_deriv"], rtol=0.0, atol=1e-9 * np.abs(ref["ll_deriv"]).max(), what="gradient")
+    assert_close(dev.get_alpha(), np.ravel(ref["alpha"]), rtol=0.0, atol=1e-9 * np.abs(ref["alpha"]).max(), what="alpha")
+    assert_close(dev.get_L(), ref["L"], rtol=0.0, atol=1e-10 * np.abs(ref["L"]).max(), what="L")
+    Xs = rs.rand(20, 2)
+    ns = np.zeros((20, 2), dtype=int)
+    dev.ll(th, 0.0)
+    m, v, _ = dev.predict(Xs, ns, want_var=True)
+    pm, ps, pc = orc.predict(orc.KERNEL_SE, th, X, n, ref["L"], ref["alpha"], Xs, ns)
+    assert_close(m, pm, rtol=1e-9, atol=1e-9, what="mean")
+    assert np.all(np.abs(v - np.diag(pc)) <= 1e-9 * th[0] ** 2)
