@@ -201,7 +201,7 @@ int blocked_potrf_k128(gpt_handle* h, double* A, long ld, int nblk, double* inv,
     return check_launch(h);
 }
 
-constexpr int PAIR_MIN_BLOCKS = 48;  // M >= 6144: the trailing update dominates and rank-256 pays
+constexpr int PAIR_MIN_BLOCKS = 80;  // M >= ~10k: the trailing update dominates and rank-256 pays (tools/pair_tune.py)
 
 int blocked_potrf(gpt_handle* h, double* A, long ld, int nblk, double* inv, double* pbuf, double* rhs, double* logdet,
                   int* info) {

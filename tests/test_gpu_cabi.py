@@ -494,7 +494,7 @@ def test_randomised_matern_gibbs_paths_agree_with_oracle(dev, trial):
 @pytest.mark.parametrize("pair_min", ["1", "100000"])
 @pytest.mark.parametrize("M", [130, 300, 700, 800, 1100])
 def test_blocked_cholesky_variants_vs_oracle(dev, M, pair_min, monkeypatch):
-    """Both variants of the blocked Cholesky -- paired rank-256 trailing updates (default from 48 blocks) and the
+    """Both variants of the blocked Cholesky -- paired rank-256 trailing updates (default from 80 blocks) and the
     unpaired one -- forced onto the same small problems (2 .. 9 blocks, odd and even counts): ll, gradient, alpha,
     L and the predictive variance against the pinned oracle."""
     from oracle import gp_oracle as orc
