@@ -1279,6 +1279,15 @@ static int batched_common(gpt_handle* h, int B, const double* d_thetas, const do
     if (ctas > B) ctas = B;
     bp.ws_per_cta = batched_ws_doubles_per_cta(bp.nT);
     int rc;
+    // SE in one or two dimensions with derivative orders <= 1: short closed forms; phase 1 leaves sigma^2 exp(-r^2/2)
+    // of every lower tile behind in the CTA workspace for the gradient pass
+    if (h->kid == GPT_KERNEL_SE && h->D <= 2 && bp.low_order && !getenv("GPT_B4_LONG_FORMS")) {
+        bp.short_forms = 1;
+        if (bp.nidx > 0) {
+            bp.eb_off = bp.ws_per_cta;
+            bp.ws_per_cta += batched_lower_tiles(bp.nT) * 4096;
+        }
+    }
     if ((rc = ensure(h, h->b_ws, sizeof(double) * bp.ws_per_cta * (size_t)ctas))) return rc;
     if ((rc = ensure(h, h->b_counter, sizeof(int)))) return rc;
     bp.workspace = ptr<double>(h->b_ws);

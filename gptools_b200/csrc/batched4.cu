@@ -8,7 +8,13 @@
 // CTAs (= two thetas) fit on an SM.  Here a CTA is 4 warps / 128 threads with a ~39 KB footprint, so four CTAs
 // (four thetas) share an SM and the chance that nobody feeds the tensor pipe drops from ~29% to ~8%:
 //   * one 64x64 output tile per job, 32x32 warp tiles (16 DMMA.8x8x4 per k-step, 64 accumulator registers);
-//   * operands stream through a double-buffered cp.async ring of 64x16 chunks (A, B) with an XOR swizzle;
+//   * operands stream through a ring of 64xBK chunks (A, B) filled by BULK ASYNC COPIES (cp.async.bulk, the TMA engine)
+//     that complete on mbarriers: the workspace tiles are stored chunk-major and pre-swizzled (tix()), so a chunk is
+//     one contiguous copy issued by a single lane; warps wait on the chunk's mbarrier, never on each other (the
+//     warp that releases a slot last refills it), so the four warps of a CTA -- which sit on four different SM
+//     sub-partitions -- drift by up to a ring's depth instead of meeting at a CTA barrier after every chunk;
+//   * diagonal output tiles: the two warps on the 32x32 diagonal blocks issue only the 10 lower 8x8 products of
+//     their 16, the other two warps split the contraction of the off-diagonal block between them;
 //   * no dedicated diagonal-tile buffer: the Gauss-Jordan sweep runs in registers (32 entries per thread) and
 //     its result goes straight to the workspace; panel products take their B fragments directly from L2.
 // Algorithmic work: M^3 flop per theta; roofline = FP64 tensor pipe.
@@ -22,10 +28,15 @@ namespace {
 using namespace sefast;
 
 constexpr int TB = 64;
-constexpr int BK = 16;
-#ifndef GPT_B4_STAGES
-#define GPT_B4_STAGES 2  // 2 stages = 39 KB per CTA: the smaller carve-out leaves ~90 KB of L1 per SM (measured +3% over 3)
+#ifndef GPT_B4_BK
+#define GPT_B4_BK 16
 #endif
+#ifndef GPT_B4_STAGES
+#define GPT_B4_STAGES 2  // BK x STAGES = 32 columns in flight = 32 KB per CTA (the staging tile aliases the ring)
+#endif
+constexpr int BK = GPT_B4_BK;
+constexpr int CPT = TB / BK;           // chunks per 64-deep tile step
+static_assert(BK == 8 || BK == 16, "chunk depth");
 #ifndef GPT_B4_MINB
 #define GPT_B4_MINB 4
 #endif
@@ -45,6 +56,8 @@ constexpr int PTS_ORD = 192;
 
 struct Smem {
     double R[R_D];
+    unsigned long long full[STAGES];  // mbarriers: chunk landed (transaction count)
+    unsigned int cnt[STAGES];         // warps done with the slot (mod 4); the last one refills it
     double piv[8];  // product of the 8 pivots of each 8x8 pivot block of the tile being factored
     double exptab[64];  // 2^(j/64), for exp_nonpos_tab
     double rk[TB], zk[TB];
@@ -52,11 +65,11 @@ struct Smem {
     const double* a[MAXT];
     const double* b[MAXT];
     unsigned char flag[MAXT];  // bit0: A operand upper triangular, bit2: B operand upper triangular
-    int skip_upper;            // output is a diagonal tile: its upper-right 32x32 block is not needed
     CovParams cp;
     double noise2;
     int theta;
     int info;
+    int use_tab;  // this theta takes the short closed forms (SE, D <= 2, orders <= 1, every 1/l finite)
 };
 
 __device__ __forceinline__ double* slot(double* ws, int I, int J) { return ws + (size_t)(I * (I + 1) / 2 + J) * TILE; }
@@ -68,59 +81,115 @@ struct Lane {
     int tid, warp, lane, g, t, wr, wc;
 };
 
-__device__ __forceinline__ void issue_chunk(Smem& sm, const Lane& L, int q) {
-    const int s = q >> 2, kc = q & 3;
-    double* base = sm.R + (q % STAGES) * STAGE_D;
-    const double* srcs[2] = {sm.a[s], sm.b[s]};
+// ---- workspace tile layout: chunk-major, pre-swizzled -------------------------------------------------------------
+// A 64x64 tile is stored as CPT chunks of 64 rows x BK columns; inside a chunk row r holds its BK columns with the
+// XOR swizzle that makes the DMMA fragment reads conflict-free.  A chunk is therefore ONE contiguous block of
+// CHUNK doubles in global memory and lands in the ring exactly as the fragment loader wants it.
+__device__ __forceinline__ int swz(int r) { return (BK == 16) ? ((r & 3) << 2) : (((r >> 1) & 1) << 2); }
+__device__ __forceinline__ int tix(int r, int c) { return (c / BK) * CHUNK + r * BK + ((c % BK) ^ swz(r)); }
+
+// ---- mbarrier / bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP) -------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// generic-proxy accesses to shared memory (the staging tile) ordered before the async-proxy writes of the ring
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// one lane: chunk q of the current job -> ring slot q % STAGES
+__device__ __forceinline__ void issue_chunk(Smem& sm, int q) {
+    const int s = q / CPT, kc = q % CPT, slt = q % STAGES;
+    double* base = sm.R + slt * STAGE_D;
+    mbar_expect_tx(&sm.full[slt], 2 * CHUNK * sizeof(double));
+    bulk_g2s(base, sm.a[s] + kc * CHUNK, CHUNK * sizeof(double), &sm.full[slt]);
+    bulk_g2s(base + CHUNK, sm.b[s] + kc * CHUNK, CHUNK * sizeof(double), &sm.full[slt]);
+}
+
+// acc += A[arow.., :] * B[brow.., :]^T over one chunk; LOWER: only the 8x8 products on and below the block diagonal
+template <bool LOWER>
+__device__ __forceinline__ void chunk_mma(const double* stage, int arow, int brow, const Lane& L, double (&acc)[4][4][2]) {
+    const double* aS = stage + (arow + L.g) * BK;
+    const double* bS = stage + CHUNK + (brow + L.g) * BK;
+    const int sw = swz(L.g);
 #pragma unroll
-    for (int op = 0; op < 2; op++) {
-        const double* src = srcs[op];
+    for (int kk = 0; kk < BK / 4; kk++) {
+        const int col = ((kk << 2) ^ sw) + L.t;
+        double a[4], b[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int idx = L.tid + u * THREADS;
-            const int r = idx >> 3, c2 = (idx & 7) * 2;
-            cp_async16(base + op * CHUNK + r * BK + (c2 ^ ((r & 3) << 2)), src + r * TB + kc * BK + c2);
-        }
+        for (int i = 0; i < 4; i++) a[i] = aS[i * 8 * BK + col];
+#pragma unroll
+        for (int j = 0; j < 4; j++) b[j] = bS[j * 8 * BK + col];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (!LOWER || j <= i) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
 }
 
-// acc += A[s] * B[s]^T over the steps of the job table
-__device__ __forceinline__ void run_job(Smem& sm, const Lane& L, int nsteps, double (&acc)[4][4][2]) {
-    const int total = nsteps * 4;
-    __syncthreads();  // table visible, ring free
-#pragma unroll
-    for (int q = 0; q < STAGES - 1; q++) {
-        if (q < total) issue_chunk(sm, L, q);
-        cp_async_commit();
+// acc += A[s] * B[s]^T over the steps of the job table.  DIAG (the output is a diagonal tile, only its lower
+// triangle is consumed): warps 0 and 3 own the diagonal 32x32 blocks (lower 8x8 products only), warps 1 and 2 share
+// block (1,0), taking alternate chunks -- warp 1's partial sums end up in the (unused) upper-right block of the
+// staging tile and are folded in by st_lower().
+__device__ __forceinline__ void run_job(Smem& sm, const Lane& L, int nsteps, const bool DIAG, double (&acc)[4][4][2],
+                                        uint32_t& phase) {
+    const int total = nsteps * CPT;
+    fence_proxy_async();
+    __syncthreads();  // table visible, ring free (its last use as staging tile is over)
+    if (L.tid == 0) {
+        const int pre = total < STAGES ? total : STAGES;
+        for (int q = 0; q < pre; q++) issue_chunk(sm, q);
     }
-    const bool dead = sm.skip_upper && L.wr == 0 && L.wc == 1;
+    const bool offd = DIAG && (L.warp == 1 || L.warp == 2);
+    const int arow = (DIAG ? (L.warp != 0) : L.wr) * 32;  // block row of the A operand / of the output
+    const int brow = (DIAG ? (L.warp == 3) : L.wc) * 32;
     for (int q = 0; q < total; q++) {
-        cp_async_wait<STAGES - 2>();
-        __syncthreads();
-        if (q + STAGES - 1 < total) issue_chunk(sm, L, q + STAGES - 1);
-        cp_async_commit();
-        const int fl = sm.flag[q >> 2];
-        const bool half_zero = ((fl & 1) && L.wr == 1) || ((fl & 4) && L.wc == 1);
-        if (!dead && !(half_zero && (q & 3) < 2)) {
-            const double* aS = sm.R + (q % STAGES) * STAGE_D + (L.wr * 32 + L.g) * BK;
-            const double* bS = sm.R + (q % STAGES) * STAGE_D + CHUNK + (L.wc * 32 + L.g) * BK;
-#pragma unroll
-            for (int kk = 0; kk < 4; kk++) {
-                const int col = ((kk ^ (L.g & 3)) << 2) + L.t;
-                double a[4], b[4];
-#pragma unroll
-                for (int i = 0; i < 4; i++) a[i] = aS[i * 8 * BK + col];
-#pragma unroll
-                for (int j = 0; j < 4; j++) b[j] = bS[j * 8 * BK + col];
-#pragma unroll
-                for (int i = 0; i < 4; i++)
-#pragma unroll
-                    for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-            }
+        const int slt = q % STAGES;
+        mbar_wait(&sm.full[slt], (phase >> slt) & 1u);
+        phase ^= 1u << slt;
+        const int fl = sm.flag[q / CPT];
+        // structural zeros: operand upper triangular (bit0: A, bit2: B) => rows >= 32 vanish for k < 32
+        const bool zero = ((q % CPT) < CPT / 2) && (((fl & 1) && arow) || ((fl & 4) && brow));
+        const bool mine = !offd || ((q & 1) == (L.warp & 1));
+        if (!zero && mine) {
+            const double* stage = sm.R + slt * STAGE_D;
+            if (DIAG && !offd) chunk_mma<true>(stage, arow, brow, L, acc);
+            else chunk_mma<false>(stage, arow, brow, L, acc);
+        }
+        __syncwarp();
+        if (L.lane == 0) {
+            const unsigned old = atomicAdd(&sm.cnt[slt], 1u);
+            if ((old & 3u) == 3u && q + STAGES < total) issue_chunk(sm, q + STAGES);  // last warp out refills the slot
         }
     }
-    cp_async_wait<0>();
     __syncthreads();  // ring may now be reused as staging
+}
+
+// Entry (r, c), c <= r, of the lower triangle that a DIAG job left in the staging tile.
+__device__ __forceinline__ double st_lower(const double* St, int r, int c) {
+    double s = St[r * LDT + c];
+    if (r >= 32 && c < 32) s += St[(r - 32) * LDT + c + 32];
+    return s;
 }
 
 __device__ __forceinline__ void zero_acc(double (&acc)[4][4][2]) {
@@ -146,25 +215,27 @@ __device__ __forceinline__ void acc_to_global(double* tile, const Lane& L, const
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             double2 v = make_double2(scale * acc[i][j][0], scale * acc[i][j][1]);
-            *reinterpret_cast<double2*>(tile + (L.wr * 32 + i * 8 + L.g) * TB + L.wc * 32 + j * 8 + 2 * L.t) = v;
+            *reinterpret_cast<double2*>(tile + tix(L.wr * 32 + i * 8 + L.g, L.wc * 32 + j * 8 + 2 * L.t)) = v;
         }
 }
 
-// out = St * Binv^T, St in shared (stride LDT), Binv a lower-triangular 64x64 tile in GLOBAL memory (row-major):
+// out = St * Binv^T, St in shared (stride LDT), Binv a lower-triangular 64x64 tile in GLOBAL memory (tix layout):
 // the B fragments are fetched straight from L2, four k-steps per batch, so no shared buffer is needed for them.
 __device__ __forceinline__ void mult_lower_global(const double* St, const double* Binv, const Lane& L,
                                                   double (&out)[4][4][2]) {
     zero_acc(out);
     const int kmax = (L.wc + 1) * 32;  // Binv[n][c] = 0 for c > n
     const double* aS = St + (L.wr * 32 + L.g) * LDT + L.t;
-    const double* bG = Binv + (size_t)(L.wc * 32 + L.g) * TB + L.t;
+    const double* bG = Binv + (L.wc * 32 + L.g) * BK + L.t;
+    const int sw = swz(L.g);
 #pragma unroll 1
     for (int kb = 0; kb < kmax; kb += 16) {
         double b[4][4];
 #pragma unroll
         for (int kk = 0; kk < 4; kk++)
 #pragma unroll
-            for (int j = 0; j < 4; j++) b[kk][j] = bG[(size_t)j * 8 * TB + kb + kk * 4];
+            for (int j = 0; j < 4; j++)
+                b[kk][j] = bG[((kb + kk * 4) / BK) * CHUNK + j * 8 * BK + (((kb + kk * 4) % BK) ^ sw)];
 #pragma unroll
         for (int kk = 0; kk < 4; kk++) {
             double a[4];
@@ -176,6 +247,19 @@ __device__ __forceinline__ void mult_lower_global(const double* St, const double
                 for (int j = 0; j < 4; j++) dmma884(out[i][j][0], out[i][j][1], a[i], b[kk][j]);
         }
     }
+}
+
+// sum_{c < 32} tile(r, c0 + c) * v[c] for a workspace tile (tix layout), c0 a multiple of 32; 16-byte loads
+__device__ __forceinline__ double row_dot32(const double* tile, int r, int c0, const double* v) {
+    const int sw = swz(r);
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < 32; c += 2) {
+        const double2 t2 = *reinterpret_cast<const double2*>(tile + ((c0 + c) / BK) * CHUNK + r * BK + (((c0 + c) % BK) ^ sw));
+        s += t2.x * v[c];
+        s += t2.y * v[c + 1];
+    }
+    return s;
 }
 
 // ---- diagonal tile: X = chol(tile)^{-1} by a BLOCKED in-place Gauss-Jordan sweep (8x8 blocks) -------------------
@@ -372,6 +456,148 @@ __device__ __forceinline__ PointReg<FD> staged_point(const double* pts, int r) {
     return q;
 }
 
+// ---- short closed forms (SE, D <= 2, derivative orders <= 1, every l finite and non-zero) ---------------------------
+// Scalar FP64 instructions are arbitrated one-for-one against the DMMAs of the co-resident CTAs, so each of them costs
+// the issuing warp ~20 cycles: the closed forms are cut to the minimum.  The (-1)^{sum nj} sign and sigma^2 are hoisted
+// per column, the common factor 1/l of the length-scale derivative is applied once per thread, and the gradient pass
+// re-reads sigma^2 exp(-r^2/2) (eb, written by phase 1, prefetched into L2 while the tile's products run) instead of
+// recomputing the exponential.  (A theta-independent table of the coordinate differences was measured and lost: its
+// L2 reads stall the loops for longer than the two subtractions they replace, profiles/r02d_*.)
+//   m = 0: f = 1,               g = il u            (u = tau^2 / l^2, il = 1 / l, f: value factor, g: d f / d l
+//   m = 1: f = -tau il^2,       g = il f (u - 2)     up to the common exponential whose own l-derivative il u f is
+//   m = 2: f = il^2 (u - 1),    g = il il^2 (2 + u (u - 5))          included in g)
+// staging-tile entry (r, c) of a job's result: DIAG jobs leave part of block (1,0) in the upper-right block
+__device__ __forceinline__ double st_get(const double* St, int r, int c, bool diag) {
+    const double s = St[r * LDT + c];
+    const bool fold = diag && (r >= 32) && (c < 32);
+    const double e = St[fold ? (r - 32) * LDT + c + 32 : r * LDT + c];  // always a valid address: select, no branch
+    return fold ? s + e : s;
+}
+
+template <int FD>
+__device__ __forceinline__ void gen_ktot_tab(const Smem& sm, const BatchedParams& p, double* St, int tid, int I, int Jc,
+                                             double* __restrict__ eb) {
+    const bool DIAG = (I == Jc), EB = (eb != nullptr);
+    const int c = tid & (TB - 1);
+    const int gj = Jc * TB + c;
+    const bool col_ok = gj < p.M;
+    int nj[FD], sj = 0;
+    double il2[FD], nil2[FD], nh[FD], xj[FD];
+#pragma unroll
+    for (int d = 0; d < FD; d++) {
+        nj[d] = col_ok ? __ldg(p.n + (size_t)gj * FD + d) : 0;
+        sj += nj[d];
+        il2[d] = sm.cp.inv_l[d] * sm.cp.inv_l[d];
+        nil2[d] = -il2[d];
+        nh[d] = -0.5 * il2[d];
+        xj[d] = col_ok ? __ldg(p.X + (size_t)gj * FD + d) : 0.0;
+    }
+    const double ssig2 = (sj & 1) ? -sm.cp.sig2 : sm.cp.sig2;
+    const double dj = col_ok ? sm.noise2 + __ldg(p.diag + gj) : 0.0;
+    const double* pts = sm.R + PTS_OFF;
+    const int* ord = reinterpret_cast<const int*>(pts + PTS_ORD);
+#pragma unroll 4
+    for (int u = 0; u < 32; u++) {
+        const int r = (tid >> 6) + 2 * u;
+        const int gi = I * TB + r;
+        double tau[FD], q[FD];
+#pragma unroll
+        for (int d = 0; d < FD; d++) {
+            tau[d] = pts[r * FD + d] - xj[d];
+            q[d] = tau[d] * tau[d];
+        }
+        double arg = q[0] * nh[0];
+#pragma unroll
+        for (int d = 1; d < FD; d++) arg = fma(q[d], nh[d], arg);
+        const double base = ssig2 * exp_nonpos_tab(arg, sm.exptab);
+        if (EB) eb[tid + u * THREADS] = base;
+        const int pk = ord[r];
+        double v = base;
+#pragma unroll
+        for (int d = 0; d < FD; d++) {
+            const int m = ((pk >> (8 * d)) & 255) + nj[d];
+            const double f1 = tau[d] * nil2[d];
+            const double f2 = il2[d] * fma(q[d], il2[d], -1.0);
+            double f = (m == 1) ? f1 : 1.0;
+            f = (m == 2) ? f2 : f;
+            v *= f;
+        }
+        const double vd = v + dj;
+        v = (gi == gj) ? vd : v;
+        const double pad = (gi == gj) ? 1.0 : 0.0;
+        v = (col_ok && gi < p.M) ? v : pad;
+        const double out = v - st_get(St, r, c, DIAG);
+        if (!DIAG || c <= r) St[r * LDT + c] = out;
+    }
+}
+
+template <int FD>
+__device__ __forceinline__ void grad_tab(const Smem& sm, const BatchedParams& p, const double* St, int tid, int I, int J,
+                                         const double* __restrict__ avec, const double* __restrict__ eb,
+                                         double (&gall)[1 + GPT_MAX_DIM], double& tr_kinv) {
+    const bool DIAG = (I == J);
+    const int c = tid & (TB - 1);
+    const int gj = J * TB + c;
+    if (gj >= p.M) return;
+    const double aj = avec[gj];
+    int nj[FD];
+    double il2[FD], nil2[FD], xj[FD];
+#pragma unroll
+    for (int d = 0; d < FD; d++) {
+        nj[d] = __ldg(p.n + (size_t)gj * FD + d);
+        il2[d] = sm.cp.inv_l[d] * sm.cp.inv_l[d];
+        nil2[d] = -il2[d];
+        xj[d] = __ldg(p.X + (size_t)gj * FD + d);
+    }
+    const double* pts = sm.R + PTS_OFF;
+    const int* ord = reinterpret_cast<const int*>(pts + PTS_ORD);
+    double wk = 0.0, trl = 0.0, gl[FD];
+#pragma unroll
+    for (int d = 0; d < FD; d++) gl[d] = 0.0;
+#pragma unroll 4
+    for (int u = 0; u < 32; u++) {
+        const int r = (tid >> 6) + 2 * u;
+        const int gi = I * TB + r;
+        const bool use = (gi < p.M) && (!DIAG || c <= r);
+        const bool on_diag = DIAG && (c == r);
+        const double kinv = st_get(St, r, (DIAG && c > r) ? r : c, DIAG);
+        double w = pts[PTS_ALPHA + r] * aj - kinv;
+        const double hw = 0.5 * w;
+        w = on_diag ? hw : w;
+        w = use ? w : 0.0;
+        trl += (use && on_diag) ? kinv : 0.0;
+        const double wb = w * eb[tid + u * THREADS];
+        const int pk = ord[r];
+        double f[FD], g[FD];  // g without its common factor il (applied once at the end)
+#pragma unroll
+        for (int d = 0; d < FD; d++) {
+            const double tau = pts[r * FD + d] - xj[d];
+            const double uu = tau * tau * il2[d];
+            const int m = ((pk >> (8 * d)) & 255) + nj[d];
+            const double f1 = tau * nil2[d];
+            const double g1 = f1 * (uu - 2.0);
+            const double f2 = il2[d] * (uu - 1.0);
+            const double g2 = il2[d] * fma(uu, uu - 5.0, 2.0);
+            double ff = (m == 1) ? f1 : 1.0, gg = (m == 1) ? g1 : uu;
+            f[d] = (m == 2) ? f2 : ff;
+            g[d] = (m == 2) ? g2 : gg;
+        }
+        if constexpr (FD == 1) {
+            wk = fma(wb, f[0], wk);
+            gl[0] = fma(wb, g[0], gl[0]);
+        } else {
+            const double t0 = wb * f[0];
+            wk = fma(t0, f[1], wk);
+            gl[1] = fma(t0, g[1], gl[1]);
+            gl[0] = fma(wb * g[0], f[1], gl[0]);
+        }
+    }
+    tr_kinv += trl;
+#pragma unroll
+    for (int d = 0; d < FD; d++) gall[1 + d] += gl[d] * sm.cp.inv_l[d];
+    gall[0] += (sm.cp.p[0] != 0.0) ? 2.0 * wk / sm.cp.p[0] : 0.0;
+}
+
 // C = K_tot - S in place on the staging tile.  Thread tid owns column c = tid & 63 and rows (tid >> 6) + 2u.
 template <int FD>
 __device__ __forceinline__ void gen_ktot_tile(const Smem& sm, const BatchedParams& p, double* St, int tid, int I, int Jc) {
@@ -386,7 +612,7 @@ __device__ __forceinline__ void gen_ktot_tile(const Smem& sm, const BatchedParam
         for (int u = 0; u < 32; u++) {
             const int r = (tid >> 6) + 2 * u;
             if (diag_tile && c > r) continue;
-            St[r * LDT + c] = ktot_entry(sm, p, I * TB + r, gj) - St[r * LDT + c];
+            St[r * LDT + c] = ktot_entry(sm, p, I * TB + r, gj) - (diag_tile ? st_lower(St, r, c) : St[r * LDT + c]);
         }
     } else {
         SEHoist<FD> h = se_hoist<FD>(sm.cp);
@@ -396,7 +622,7 @@ __device__ __forceinline__ void gen_ktot_tile(const Smem& sm, const BatchedParam
         const double dj = col_ok ? sm.noise2 + __ldg(p.diag + gj) : 0.0;
         const double* pts = sm.R + PTS_OFF;
         if (FD <= 2 && p.low_order) {
-#pragma unroll 8
+#pragma unroll 2
             for (int u = 0; u < 32; u++) {
                 const int r = (tid >> 6) + 2 * u;
                 const int gi = I * TB + r;
@@ -405,7 +631,7 @@ __device__ __forceinline__ void gen_ktot_tile(const Smem& sm, const BatchedParam
                 v = (gi == gj) ? v + dj : v;
                 const double pad = (gi == gj) ? 1.0 : 0.0;
                 v = (col_ok && gi < p.M) ? v : pad;
-                if (!(diag_tile && c > r)) St[r * LDT + c] = v - St[r * LDT + c];
+                if (!(diag_tile && c > r)) St[r * LDT + c] = v - (diag_tile ? st_lower(St, r, c) : St[r * LDT + c]);
             }
         } else {
 #pragma unroll 2
@@ -423,7 +649,7 @@ __device__ __forceinline__ void gen_ktot_tile(const Smem& sm, const BatchedParam
                 } else {
                     v = (gi == gj) ? 1.0 : 0.0;
                 }
-                St[r * LDT + c] = v - St[r * LDT + c];
+                St[r * LDT + c] = v - (diag_tile ? st_lower(St, r, c) : St[r * LDT + c]);
             }
         }
     }
@@ -447,7 +673,7 @@ __device__ __forceinline__ void grad_tile(const Smem& sm, const BatchedParams& p
             const int r = (tid >> 6) + 2 * u;
             const int gi = I * TB + r;
             if (gi >= p.M || (diag_tile && c > r)) continue;
-            const double kinv = St[r * LDT + c];
+            const double kinv = diag_tile ? st_lower(St, r, c) : St[r * LDT + c];
             double w = avec[gi] * aj - kinv;
             if (diag_tile && c == r) {
                 tr_kinv += kinv;
@@ -477,13 +703,13 @@ __device__ __forceinline__ void grad_tile(const Smem& sm, const BatchedParams& p
         double wk = 0.0;
         if (FD <= 2 && p.low_order) {
             double trl = 0.0;
-#pragma unroll 8
+#pragma unroll 2
             for (int u = 0; u < 32; u++) {
                 const int r = (tid >> 6) + 2 * u;
                 const int gi = I * TB + r;
                 const bool use = (gi < p.M) && !(diag_tile && c > r);
                 const bool on_diag = diag_tile && (c == r);
-                const double kinv = St[r * LDT + c];
+                const double kinv = (diag_tile && c <= r) ? st_lower(St, r, c) : St[r * LDT + c];
                 const PointReg<FD> pi = staged_point<FD>(pts, r);
                 const double ai = pts[PTS_ALPHA + r];
                 double w = ai * aj - kinv;
@@ -503,7 +729,7 @@ __device__ __forceinline__ void grad_tile(const Smem& sm, const BatchedParams& p
                 const int r = (tid >> 6) + 2 * u;
                 const int gi = I * TB + r;
                 if (gi >= p.M || (diag_tile && c > r)) continue;
-                const double kinv = St[r * LDT + c];
+                const double kinv = diag_tile ? st_lower(St, r, c) : St[r * LDT + c];
                 PointReg<FD> pi;
                 double ai;
                 if constexpr (FD <= 2) {
@@ -550,6 +776,14 @@ __global__ void __launch_bounds__(THREADS, GPT_B4_MINB) ll_batched4_kernel(Batch
     double* St = sm.R;
     double acc[4][4][2];
     if (L.tid < 64) sm.exptab[L.tid] = GPT_EXP2_64[L.tid];  // published by the first barrier of the theta loop
+    if (L.tid == 0) {
+        for (int q = 0; q < STAGES; q++) {
+            mbar_init(&sm.full[q], 1);
+            sm.cnt[q] = 0u;
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    uint32_t ring_phase = 0u;  // parity of the next completion of every ring slot (same in all threads)
 
     for (;;) {
         __syncthreads();
@@ -564,185 +798,183 @@ __global__ void __launch_bounds__(THREADS, GPT_B4_MINB) ll_batched4_kernel(Batch
             const double* th = p.thetas + (size_t)b * np1;
             cov_params_init(sm.cp, p.kid, p.D, p.nparams, th);
             sm.noise2 = th[p.nparams] * th[p.nparams];
+            int tab = (p.short_forms != 0) ? 1 : 0;
+            for (int d = 0; d < p.D; d++)
+                if (!(sm.cp.inv_l[d] <= 1.79769313486231570e+308)) tab = 0;  // l = 0 (or NaN): the guarded closed forms
+            sm.use_tab = tab;
         }
         __syncthreads();
         const double* yb = p.y + (size_t)b * p.y_stride;
         double logdet = 0.0, zz = 0.0;  // thread 0
         PT_DECL;
 
-        // =========================== phase 1: Cholesky ===========================
-        for (int k = 0; k < nT; k++) {
-            for (int I = k; I < nT; I++) {
-                if (L.tid < k) {
-                    sm.a[L.tid] = slot(ws, I, L.tid);
-                    sm.b[L.tid] = slot(ws, k, L.tid);
-                    sm.flag[L.tid] = 0;
-                }
-                if (L.tid == 0) sm.skip_upper = (I == k) ? 1 : 0;
-                zero_acc(acc);
-                PT_MARK(7);
-                run_job(sm, L, k, acc);
-                PT_MARK(0);
-                // S -> staging, then C = K_tot - S in place (K_tot generated from the closed forms, never stored)
-                acc_to_tile(St, L, acc);
-                stage_rows<FD>(sm, p, L, I, nullptr);
-                __syncthreads();
-                gen_ktot_tile<FD>(sm, p, St, L.tid, I, k);
-                PT_MARK(1);
-                if (I == k) {
-                    // residual r_k = y_k - sum_j L(k,j) z_j : 2 threads per row, 32 columns each
-                    {
-                        const int r = L.tid >> 1, h2 = L.tid & 1;
-                        double s = 0.0;
-                        for (int j = 0; j < k; j++) {
-                            const double* row = slot(ws, k, j) + r * TB + h2 * 32;
-                            const double* zj = zvec + j * TB + h2 * 32;
-#pragma unroll
-                            for (int c = 0; c < 32; c++) s += row[c] * zj[c];
-                        }
-                        s += __shfl_xor_sync(0xffffffffu, s, 1);
-                        if (h2 == 0) {
-                            const int gi = k * TB + r;
-                            sm.rk[r] = ((gi < p.M) ? yb[gi] : 0.0) - s;
-                        }
-                    }
-                    __syncthreads();
-                    PT_MARK(4);
-                    potrf_inv_tile(sm, L, St, k * TB);
-                    PT_MARK(2);
-                    if (L.tid == 0) logdet += sm.red[0][0];
-                    {
-                        // Inv_k, Inv_k^T to the workspace; z_k = Inv_k r_k
-                        double* Dk = slot(ws, k, k);
-                        double* DTk = slotDT(ws, nT, k);
-                        for (int idx = L.tid; idx < TILE; idx += THREADS) {
-                            const int r = idx >> 6, c = idx & (TB - 1);
-                            Dk[idx] = St[r * LDT + c];
-                            DTk[idx] = St[c * LDT + r];
-                        }
-                        if (L.tid < TB) {
-                            double s = 0.0;
-                            for (int c = 0; c <= L.tid; c++) s += St[L.tid * LDT + c] * sm.rk[c];
-                            zvec[k * TB + L.tid] = s;
-                            sm.zk[L.tid] = s;
-                        }
-                    }
-                    __syncthreads();
-                    if (L.tid == 0) {
-                        double s = 0.0;
-                        for (int c = 0; c < TB; c++) s += sm.zk[c] * sm.zk[c];
-                        zz += s;
-                    }
-                } else {
-                    __syncthreads();
-                    double out[4][4][2];
-                    mult_lower_global(St, slot(ws, k, k), L, out);
-                    acc_to_global(slot(ws, I, k), L, out, 1.0);
-                }
-                __syncthreads();
-                PT_MARK(3);
-            }
-        }
-        __threadfence_block();
-
-        const bool need_alpha = (p.nidx > 0) || (p.alpha_out != nullptr);
-        if (need_alpha) {
-            PT_MARK(7);
-            // ======================= alpha = L^{-T} z (block back substitution) =======================
-            for (int i = L.tid; i < nT * TB; i += THREADS) rvec[i] = zvec[i];
-            __syncthreads();
-            for (int J = nT - 1; J >= 0; J--) {
-                {
-                    const int a = L.tid >> 1, h2 = L.tid & 1;
-                    const double* row = slotDT(ws, nT, J) + a * TB + h2 * 32;
-                    const double* rj = rvec + J * TB + h2 * 32;
-                    double s = 0.0;
-#pragma unroll
-                    for (int c = 0; c < 32; c++) s += row[c] * rj[c];
-                    s += __shfl_xor_sync(0xffffffffu, s, 1);
-                    if (h2 == 0) {
-                        sm.zk[a] = s;
-                        avec[J * TB + a] = s;
-                    }
-                }
-                __syncthreads();
-                for (int I = 0; I < J; I++) {
-                    const int c = L.tid >> 1, h2 = L.tid & 1;
-                    const double* tile = slot(ws, J, I) + (h2 * 32) * TB + c;
-                    double s = 0.0;
-#pragma unroll
-                    for (int r = 0; r < 32; r++) s += tile[r * TB] * sm.zk[h2 * 32 + r];
-                    s += __shfl_xor_sync(0xffffffffu, s, 1);
-                    if (h2 == 0) rvec[I * TB + c] -= s;
-                }
-                __syncthreads();
-            }
-            if (p.alpha_out != nullptr)
-                for (int i = L.tid; i < p.M; i += THREADS) p.alpha_out[(size_t)b * p.M + i] = avec[i];
-            PT_MARK(5);
-        }
-
         double gall[1 + GPT_MAX_DIM];
 #pragma unroll
         for (int q = 0; q < 1 + GPT_MAX_DIM; q++) gall[q] = 0.0;
         double tr_kinv = 0.0;
+        const bool need_alpha = (p.nidx > 0) || (p.alpha_out != nullptr);
 
-        if (p.nidx > 0 && sm.info == 0) {
-            // =========================== phase 2: XT = L^{-T} in place ===========================
-            for (int I = 1; I < nT; I++) {
-                for (int J = 0; J < I; J++) {
-                    const int nsteps = I - J;
-                    if (L.tid < nsteps) {
-                        const int m = J + L.tid;
-                        sm.a[L.tid] = (m == J) ? slotDT(ws, nT, J) : slot(ws, m, J);
-                        sm.b[L.tid] = slot(ws, I, m);
-                        sm.flag[L.tid] = (m == J) ? 1 : 0;
-                    }
-                    if (L.tid == 0) sm.skip_upper = 0;
-                    zero_acc(acc);
+        // One job loop for the three tile sweeps, so that the operand ring, the panel product and the tile epilogues are
+        // each instantiated ONCE: the four CTAs of an SM sit in different phases, and the instruction cache has to
+        // hold all of them at the same time (a third of the kernel's code size was worth 8% of its run time).
+        //   sweep 1: left-looking Cholesky, tile (I, J = k): outer k, inner I >= k
+        //   sweep 2: XT = L^{-T} in place,  tile (I, J):      outer I, inner J < I
+        //   sweep 3: K^{-1} tiles + gradient contraction:     outer J, inner I >= J
+#pragma unroll 1
+        for (int ph = 1; ph <= 3; ph++) {
+            if (ph == 2) {
+                __threadfence_block();
+                if (need_alpha) {
                     PT_MARK(7);
-                    run_job(sm, L, nsteps, acc);
-                    PT_MARK(0);
-                    acc_to_tile(St, L, acc);
+                    // ======================= alpha = L^{-T} z (block back substitution) =======================
+                    for (int i = L.tid; i < nT * TB; i += THREADS) rvec[i] = zvec[i];
                     __syncthreads();
-                    double out[4][4][2];
-                    mult_lower_global(St, slot(ws, I, I), L, out);
-                    acc_to_global(slot(ws, I, J), L, out, -1.0);
-                    __syncthreads();
-                    PT_MARK(3);
+                    for (int J = nT - 1; J >= 0; J--) {
+                        {
+                            const int a = L.tid >> 1, h2 = L.tid & 1;
+                            double s = row_dot32(slotDT(ws, nT, J), a, h2 * 32, rvec + J * TB + h2 * 32);
+                            s += __shfl_xor_sync(0xffffffffu, s, 1);
+                            if (h2 == 0) {
+                                sm.zk[a] = s;
+                                avec[J * TB + a] = s;
+                            }
+                        }
+                        __syncthreads();
+                        for (int I = 0; I < J; I++) {
+                            const int c = L.tid >> 1, h2 = L.tid & 1;
+                            const double* tile = slot(ws, J, I);
+                            double s = 0.0;
+#pragma unroll
+                            for (int r = 0; r < 32; r++) s += tile[tix(h2 * 32 + r, c)] * sm.zk[h2 * 32 + r];
+                            s += __shfl_xor_sync(0xffffffffu, s, 1);
+                            if (h2 == 0) rvec[I * TB + c] -= s;
+                        }
+                        __syncthreads();
+                    }
+                    if (p.alpha_out != nullptr)
+                        for (int i = L.tid; i < p.M; i += THREADS) p.alpha_out[(size_t)b * p.M + i] = avec[i];
+                    PT_MARK(5);
                 }
+                if (!(p.nidx > 0 && sm.info == 0)) break;
             }
-            __threadfence_block();
-            // ================== phase 3: K^{-1} tiles + gradient contraction ==================
-            for (int J = 0; J < nT; J++) {
-                for (int I = J; I < nT; I++) {
-                    const int nsteps = nT - I;
+            if (ph == 3) __threadfence_block();
+#pragma unroll 1
+            for (int o = (ph == 2) ? 1 : 0; o < nT; o++) {
+                const int i0 = (ph == 2) ? 0 : o, i1 = (ph == 2) ? o : nT;
+#pragma unroll 1
+                for (int i = i0; i < i1; i++) {
+                    const int I = (ph == 2) ? o : i, J = (ph == 2) ? i : o;
+                    const bool diag = (I == J);  // never in sweep 2
+                    const int nsteps = (ph == 1) ? J : ((ph == 2) ? I - J : nT - I);
                     if (L.tid < nsteps) {
-                        const int m = I + L.tid;
-                        int fl = 0;
                         const double *aa, *bb;
-                        if (m == I) {
-                            aa = slotDT(ws, nT, I);
-                            bb = (I == J) ? slotDT(ws, nT, J) : slot(ws, I, J);
-                            fl = 1 | ((I == J) ? 4 : 0);
-                        } else {
-                            aa = slot(ws, m, I);
-                            bb = slot(ws, m, J);
+                        int fl = 0;
+                        if (ph == 1) {  // S(I,k) = sum_{j<k} L(I,j) L(k,j)^T
+                            aa = slot(ws, I, L.tid);
+                            bb = slot(ws, J, L.tid);
+                        } else if (ph == 2) {  // sum_{m=J}^{I-1} XT(J,m)-as-stored * L(I,m)^T
+                            const int m = J + L.tid;
+                            aa = (m == J) ? slotDT(ws, nT, J) : slot(ws, m, J);
+                            bb = slot(ws, I, m);
+                            fl = (m == J) ? 1 : 0;
+                        } else {  // K^{-1}(I,J) = sum_{m>=I} XT(I,m) XT(J,m)^T
+                            const int m = I + L.tid;
+                            if (m == I) {
+                                aa = slotDT(ws, nT, I);
+                                bb = diag ? slotDT(ws, nT, J) : slot(ws, I, J);
+                                fl = 1 | (diag ? 4 : 0);
+                            } else {
+                                aa = slot(ws, m, I);
+                                bb = slot(ws, m, J);
+                            }
                         }
                         sm.a[L.tid] = aa;
                         sm.b[L.tid] = bb;
                         sm.flag[L.tid] = (unsigned char)fl;
                     }
-                    if (L.tid == 0) sm.skip_upper = (I == J) ? 1 : 0;
                     zero_acc(acc);
+                    const double* ebt = ws + p.eb_off + (size_t)(I * (I + 1) / 2 + J) * TILE;
+                    if (ph == 3 && sm.use_tab) {  // the cached exponentials of this tile: on their way to L2 while the products run
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(ebt + L.tid * 16));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(ebt + 2048 + L.tid * 16));
+                    }
                     PT_MARK(7);
-                    run_job(sm, L, nsteps, acc);
+                    run_job(sm, L, nsteps, diag, acc, ring_phase);
                     PT_MARK(0);
                     acc_to_tile(St, L, acc);
-                    stage_rows<FD>(sm, p, L, I, avec);
+                    if (ph != 2) stage_rows<FD>(sm, p, L, I, (ph == 3) ? avec : nullptr);
                     __syncthreads();
-                    grad_tile<FD>(sm, p, St, L.tid, I, J, avec, gall, tr_kinv);
-                    PT_MARK(6);
+                    if (ph == 1) {
+                        // C = K_tot - S in place (K_tot generated from the closed forms, never stored)
+                        if constexpr (FD == 1 || FD == 2) {
+                            if (sm.use_tab) gen_ktot_tab<FD>(sm, p, St, L.tid, I, J, p.eb_off ? const_cast<double*>(ebt) : nullptr);
+                            else gen_ktot_tile<FD>(sm, p, St, L.tid, I, J);
+                        } else {
+                            gen_ktot_tile<FD>(sm, p, St, L.tid, I, J);
+                        }
+                        PT_MARK(1);
+                        if (diag) {
+                            const int k = J;
+                            // residual r_k = y_k - sum_j L(k,j) z_j : 2 threads per row, 32 columns each
+                            {
+                                const int r = L.tid >> 1, h2 = L.tid & 1;
+                                double s = 0.0;
+                                for (int j = 0; j < k; j++) s += row_dot32(slot(ws, k, j), r, h2 * 32, zvec + j * TB + h2 * 32);
+                                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                                if (h2 == 0) {
+                                    const int gi = k * TB + r;
+                                    sm.rk[r] = ((gi < p.M) ? yb[gi] : 0.0) - s;
+                                }
+                            }
+                            __syncthreads();
+                            PT_MARK(4);
+                            potrf_inv_tile(sm, L, St, k * TB);
+                            PT_MARK(2);
+                            if (L.tid == 0) logdet += sm.red[0][0];
+                            {
+                                // Inv_k, Inv_k^T to the workspace; z_k = Inv_k r_k
+                                double* Dk = slot(ws, k, k);
+                                double* DTk = slotDT(ws, nT, k);
+                                for (int idx = L.tid; idx < TILE; idx += THREADS) {
+                                    const int r = idx >> 6, c = idx & (TB - 1);
+                                    Dk[tix(r, c)] = St[r * LDT + c];
+                                    DTk[tix(r, c)] = St[c * LDT + r];
+                                }
+                                if (L.tid < TB) {
+                                    double s = 0.0;
+                                    for (int c = 0; c <= L.tid; c++) s += St[L.tid * LDT + c] * sm.rk[c];
+                                    zvec[k * TB + L.tid] = s;
+                                    sm.zk[L.tid] = s;
+                                }
+                            }
+                            __syncthreads();
+                            if (L.tid == 0) {
+                                double s = 0.0;
+                                for (int c = 0; c < TB; c++) s += sm.zk[c] * sm.zk[c];
+                                zz += s;
+                            }
+                        } else {
+                            __syncthreads();
+                        }
+                    }
+                    if (ph == 2 || (ph == 1 && !diag)) {
+                        // panel: L(I,k) = C(I,k) Inv_k^T   /   XT tile: -(sum) Inv_I^T
+                        double out[4][4][2];
+                        mult_lower_global(St, (ph == 1) ? slot(ws, J, J) : slot(ws, I, I), L, out);
+                        acc_to_global(slot(ws, I, J), L, out, (ph == 1) ? 1.0 : -1.0);
+                    }
+                    if (ph != 3) {
+                        __syncthreads();
+                        PT_MARK(3);
+                    } else {
+                        if constexpr (FD == 1 || FD == 2) {
+                            if (sm.use_tab) grad_tab<FD>(sm, p, St, L.tid, I, J, avec, ebt, gall, tr_kinv);
+                            else grad_tile<FD>(sm, p, St, L.tid, I, J, avec, gall, tr_kinv);
+                        } else {
+                            grad_tile<FD>(sm, p, St, L.tid, I, J, avec, gall, tr_kinv);
+                        }
+                        PT_MARK(6);
+                    }
                 }
             }
         }
@@ -823,6 +1055,8 @@ void launch_t(const BatchedParams& p, int num_ctas, cudaStream_t s) {
 }
 
 }  // namespace
+
+size_t batched_lower_tiles(int nT) { return (size_t)nT * (nT + 1) / 2; }
 
 size_t batched_ws_doubles_per_cta(int nT) {
     return (size_t)(nT * (nT + 1) / 2 + nT) * TILE + (size_t)3 * nT * TB;

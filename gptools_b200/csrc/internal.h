@@ -133,8 +133,11 @@ struct BatchedParams {
     double* workspace;     // per-CTA tile storage
     size_t ws_per_cta;     // in doubles
     int* counter;          // dynamic theta scheduler
+    int short_forms = 0;     // SE, D <= 2, orders <= 1: short closed forms + cached exponentials (batched4.cu)
+    size_t eb_off = 0;       // offset (doubles) inside the CTA workspace of the cached sigma^2 exp(-r^2/2) tiles
     long long* phase_cycles;  // optional (8): per-phase cycle sums, only with -DGPT_PHASE_TIMING
 };
 size_t batched_ws_doubles_per_cta(int nT);
+size_t batched_lower_tiles(int nT);
 int batched4_ctas_per_sm();
 void launch_ll_batched4(const BatchedParams& p, int num_ctas, cudaStream_t s);
