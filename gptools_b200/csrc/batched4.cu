@@ -40,7 +40,11 @@ static_assert(BK == 8 || BK == 16, "chunk depth");
 #ifndef GPT_B4_MINB
 #define GPT_B4_MINB 4
 #endif
+#ifndef GPT_B4_UNROLL
+#define GPT_B4_UNROLL 4  // entries in flight per thread in the short closed-form loops (8: +40% code, measured slower)
+#endif
 constexpr int STAGES = GPT_B4_STAGES;
+constexpr int UNROLL = GPT_B4_UNROLL;
 constexpr int THREADS = 128;
 constexpr int CHUNK = TB * BK;         // doubles per operand chunk
 constexpr int STAGE_D = 2 * CHUNK;     // A, B
@@ -107,11 +111,26 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
             : "memory");
     } while (!ok);
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
+// L2 eviction policies for the operand stream: the 592 per-theta workspaces (1.4 MB each) cannot live in the 126 MB
+// L2 together, but the B operand of a job (a tile row / column shared by all jobs of one sweep column) is re-read by
+// the next job of the same CTA: B chunks are kept (evict_last), A chunks -- read once per column -- go first.
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar,
+                                         unsigned long long policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
 }
 // generic-proxy accesses to shared memory (the staging tile) ordered before the async-proxy writes of the ring
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -121,8 +140,13 @@ __device__ __forceinline__ void issue_chunk(Smem& sm, int q) {
     const int s = q / CPT, kc = q % CPT, slt = q % STAGES;
     double* base = sm.R + slt * STAGE_D;
     mbar_expect_tx(&sm.full[slt], 2 * CHUNK * sizeof(double));
-    bulk_g2s(base, sm.a[s] + kc * CHUNK, CHUNK * sizeof(double), &sm.full[slt]);
-    bulk_g2s(base + CHUNK, sm.b[s] + kc * CHUNK, CHUNK * sizeof(double), &sm.full[slt]);
+#ifdef GPT_B4_NO_L2_HINTS
+    const unsigned long long pa = l2_policy_evict_first(), pb = pa;
+#else
+    const unsigned long long pa = l2_policy_evict_first(), pb = l2_policy_evict_last();
+#endif
+    bulk_g2s(base, sm.a[s] + kc * CHUNK, CHUNK * sizeof(double), &sm.full[slt], pa);
+    bulk_g2s(base + CHUNK, sm.b[s] + kc * CHUNK, CHUNK * sizeof(double), &sm.full[slt], pb);
 }
 
 // acc += A[arow.., :] * B[brow.., :]^T over one chunk; LOWER: only the 8x8 products on and below the block diagonal
@@ -496,7 +520,7 @@ __device__ __forceinline__ void gen_ktot_tab(const Smem& sm, const BatchedParams
     const double dj = col_ok ? sm.noise2 + __ldg(p.diag + gj) : 0.0;
     const double* pts = sm.R + PTS_OFF;
     const int* ord = reinterpret_cast<const int*>(pts + PTS_ORD);
-#pragma unroll 4
+#pragma unroll UNROLL
     for (int u = 0; u < 32; u++) {
         const int r = (tid >> 6) + 2 * u;
         const int gi = I * TB + r;
@@ -554,7 +578,7 @@ __device__ __forceinline__ void grad_tab(const Smem& sm, const BatchedParams& p,
     double wk = 0.0, trl = 0.0, gl[FD];
 #pragma unroll
     for (int d = 0; d < FD; d++) gl[d] = 0.0;
-#pragma unroll 4
+#pragma unroll UNROLL
     for (int u = 0; u < 32; u++) {
         const int r = (tid >> 6) + 2 * u;
         const int gi = I * TB + r;
