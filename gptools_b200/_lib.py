@@ -49,6 +49,7 @@ SIGNATURES = {
     "gpt_ll_batched_dev": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp, _vp, _c_int32_p, ctypes.c_int, _vp, _vp]),
     "gpt_predict": (ctypes.c_int, [_vp, ctypes.c_int, _c_double_p, _c_int32_p, _c_double_p, _c_double_p,
                                    _c_double_p]),
+    "gpt_predict_dev": (ctypes.c_int, [_vp, ctypes.c_int, _c_double_p, _c_int32_p, _vp, _vp]),
     "gpt_predict_from_Kstar": (ctypes.c_int, [_vp, ctypes.c_int, _c_double_p, _c_double_p, _c_double_p, _c_double_p,
                                               _c_double_p, _c_double_p]),
     "gpt_draw_sample": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _c_double_p, _c_double_p, _c_double_p,
@@ -295,6 +296,14 @@ class Device(object):
         cov = np.empty((Ms, Ms), dtype=np.float64) if want_cov else None
         self._check(self._lib.gpt_predict(self._h, Ms, _dp(Xs), _ip(ns), _dp(mean), _dp(var), _dp(cov)), "gpt_predict")
         return mean, var, cov
+
+    def predict_dev(self, Xs, ns, d_mean, d_var=0):
+        """Host test points, raw DEVICE output pointers (ints); asynchronous on the handle's stream."""
+        Xs = _f64(np.atleast_2d(Xs))
+        Ms, D = Xs.shape
+        ns = _i32(np.atleast_2d(ns), (Ms, D))
+        self._check(self._lib.gpt_predict_dev(self._h, Ms, _dp(Xs), _ip(ns), _vp(d_mean), _vp(d_var) if d_var else None),
+                    "gpt_predict_dev")
 
     def predict_from_Kstar(self, Kstar, kss_diag=None, Kss=None, want_var=True, want_cov=False):
         """Host-evaluated kernels: ``Kstar`` is the (N latent x Ms) cross-covariance of gaussian_process.py:966,

@@ -1022,15 +1022,14 @@ static int predict_chunk_rows(gpt_handle* h, int Ms, bool full_cov) {
     return CH;
 }
 
-int gpt_predict(gpt_handle* h, int Ms, const double* Xs, const int32_t* ns, double* mean, double* var, double* cov) {
-    if (h && Ms == 0) return 0;  // empty test set: nothing to write
-    if (!h || Ms < 1 || !Xs || !ns || !mean) return fail(h, GPT_ERR_USAGE, "gpt_predict: bad arguments");
+// Results stay in h->mean / h->var / h->cov (device); the entry points below copy them out.
+static int predict_core(gpt_handle* h, int Ms, const double* Xs, const int32_t* ns, bool var, bool cov) {
     if (!h->factor_valid || h->cp.kid < 0) return fail(h, GPT_ERR_USAGE, "gpt_predict: no valid factorisation (call gpt_ll)");
     CUDA_OK(h, cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
-    const int D = h->D, N = h->N, M = h->M, Np = h->Np, Mp = h->Mp, nblk = Mp / NB;
+    const int D = h->D, N = h->N, M = h->M, Np = h->Np, Mp = h->Mp;
     int rc;
-    const int CH = predict_chunk_rows(h, Ms, cov != nullptr);
+    const int CH = predict_chunk_rows(h, Ms, cov);
     if ((rc = upload(h, h->Xs, Xs, sizeof(double) * (size_t)Ms * D))) return rc;
     if ((rc = upload(h, h->ns, ns, sizeof(int32_t) * (size_t)Ms * D))) return rc;
     if (!var && !cov) {
@@ -1051,10 +1050,7 @@ int gpt_predict(gpt_handle* h, int Ms, const double* Xs, const int32_t* ns, doub
                                   ptr<int32_t>(h->ns), Ms, (h->max_order <= 1 && max_ns <= 1) ? 1 : 0,
                                   ptr<double>(h->Kst), ptr<double>(h->mean), s);
         h->launches += 2;
-        if ((rc = check_launch(h))) return rc;
-        CUDA_OK(h, cudaMemcpyAsync(mean, h->mean.p, sizeof(double) * Ms, cudaMemcpyDeviceToHost, s));
-        CUDA_OK(h, cudaStreamSynchronize(s));
-        return 0;
+        return check_launch(h);
     }
     if ((rc = ensure(h, h->Kst, sizeof(double) * (size_t)CH * Np))) return rc;
     if (h->hasT && (rc = ensure(h, h->Kso, sizeof(double) * (size_t)CH * Mp))) return rc;
@@ -1109,6 +1105,15 @@ int gpt_predict(gpt_handle* h, int Ms, const double* Xs, const int32_t* ns, doub
         }
         if ((rc = check_launch(h))) return rc;
     }
+    return 0;
+}
+
+int gpt_predict(gpt_handle* h, int Ms, const double* Xs, const int32_t* ns, double* mean, double* var, double* cov) {
+    if (h && Ms == 0) return 0;  // empty test set: nothing to write
+    if (!h || Ms < 1 || !Xs || !ns || !mean) return fail(h, GPT_ERR_USAGE, "gpt_predict: bad arguments");
+    int rc = predict_core(h, Ms, Xs, ns, var != nullptr, cov != nullptr);
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
     CUDA_OK(h, cudaMemcpyAsync(mean, h->mean.p, sizeof(double) * Ms, cudaMemcpyDeviceToHost, s));
     if (var) CUDA_OK(h, cudaMemcpyAsync(var, h->var.p, sizeof(double) * Ms, cudaMemcpyDeviceToHost, s));
     if (cov) {
@@ -1117,6 +1122,17 @@ int gpt_predict(gpt_handle* h, int Ms, const double* Xs, const int32_t* ns, doub
                                      cudaMemcpyDeviceToHost, s));
     }
     CUDA_OK(h, cudaStreamSynchronize(s));
+    return 0;
+}
+
+int gpt_predict_dev(gpt_handle* h, int Ms, const double* Xs, const int32_t* ns, double* d_mean, double* d_var) {
+    if (h && Ms == 0) return 0;
+    if (!h || Ms < 1 || !Xs || !ns || !d_mean) return fail(h, GPT_ERR_USAGE, "gpt_predict_dev: bad arguments");
+    int rc = predict_core(h, Ms, Xs, ns, d_var != nullptr, false);
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    CUDA_OK(h, cudaMemcpyAsync(d_mean, h->mean.p, sizeof(double) * Ms, cudaMemcpyDeviceToDevice, s));
+    if (d_var) CUDA_OK(h, cudaMemcpyAsync(d_var, h->var.p, sizeof(double) * Ms, cudaMemcpyDeviceToDevice, s));
     return 0;
 }
 

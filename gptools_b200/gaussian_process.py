@@ -552,12 +552,35 @@ class GaussianProcess(object):
         The GP's own hyperparameters are left unchanged.
         """
         thetas = np.atleast_2d(np.asarray(thetas, dtype=float))
-        B = thetas.shape[0]
         if with_deriv is None:
             with_deriv = bool(self.use_hyper_deriv)
-        if not self._device_mode() or self.T is not None or self.k.device_points_key() is not None:
-            # host kernels, transformed observations, and kernels whose per-point columns depend on theta
+        if not self._batchable(with_deriv):
+            # host kernels, transformed observations, kernels whose per-point columns depend on theta, M > 2048
             return self._batch_by_loop(thetas, with_deriv)
+        plan = self._batch_prepare(thetas, with_deriv)
+        res = plan["dev"].ll_batched(plan["full_eval"], grad_idx=plan["grad_idx"], y_batch=plan["y_batch"],
+                                     return_alpha=plan["need_alpha"])
+        return self._batch_finish(plan, res[0], res[1], res[2], res[3] if plan["need_alpha"] else None)
+
+    #: largest number of observations the batched device entry takes (32 tiles of 64 rows, gptb200.h gpt_ll_batched)
+    BATCHED_MAX_M = 2048
+
+    def _batchable(self, with_deriv):
+        """True when ``gpt_ll_batched`` can evaluate this GP: an accelerated kernel with theta-independent point
+        columns, no transformation matrix, at most BATCHED_MAX_M observations, and -- with gradients -- free
+        kernel parameters inside the batched gradient slots.  Everything else takes the per-theta loop."""
+        if not self._device_mode() or self.T is not None or self.k.device_points_key() is not None:
+            return False
+        if len(self.y) > self.BATCHED_MAX_M:
+            return False
+        if not self.k.batchable(with_deriv):
+            return False
+        return True
+
+    def _batch_prepare(self, thetas, with_deriv):
+        """Host side of a batched evaluation that does not depend on the device results: full parameter rows,
+        per-theta hyperprior, parameter validity, per-theta mean-function residuals."""
+        B = thetas.shape[0]
         nk, nn = self.k.num_free_params, self.noise_k.num_free_params
         n_free = len(self.free_params)
         if thetas.shape[1] != n_free:
@@ -565,7 +588,8 @@ class GaussianProcess(object):
         dev, y_alph = self._sync_device()
         kid, kparams = self.k.device_descriptor()
         nparams = len(kparams)
-        full = np.tile(np.concatenate([kparams, [self._noise_sigma()]]), (B, 1))
+        base_row = np.concatenate([kparams, [self._noise_sigma()]])
+        full = np.tile(base_row, (B, 1))
         kfree = self.k.free_param_idxs
         full[:, kfree] = thetas[:, :nk]
         if nn > 0:
@@ -577,6 +601,9 @@ class GaussianProcess(object):
         hp = self.hyperprior
         logp = np.asarray(hp.logpdf_batch(all_params), dtype=float)
         ok = np.isfinite(logp)
+        # rows the device closed forms do not cover (e.g. a Matern nu that is not a half-integer): same result as the
+        # per-theta path, which raises before the device call and returns inf
+        ok &= self.k.batch_rows_supported(full[:, :nparams])
         y_batch = None
         if self.mu is not None and self.mu.num_free_params > 0:
             y_batch = np.empty((B, len(self.y)))
@@ -591,19 +618,24 @@ class GaussianProcess(object):
         if with_deriv:
             self.k.check_hyper_deriv(list(kfree))
             grad_idx = list(kfree) + ([nparams] if nn > 0 else [])
-        need_alpha = with_deriv and self.mu is not None and self.mu.num_free_params > 0
-        full_eval = np.where(ok[:, None], full, np.tile(np.concatenate([kparams, [self._noise_sigma()]]), (B, 1)))
-        res = dev.ll_batched(full_eval, grad_idx=grad_idx, y_batch=y_batch, return_alpha=need_alpha)
-        ll, grad, status = res[0], res[1], res[2]
-        good = ok & (status == 0)
-        neg_ll = np.where(good, -(ll + logp), np.inf)
-        if not with_deriv:
+        need_alpha = bool(with_deriv and self.mu is not None and self.mu.num_free_params > 0)
+        full_eval = np.where(ok[:, None], full, np.tile(base_row, (B, 1)))
+        return dict(dev=dev, thetas=thetas, B=B, nk=nk, nn=nn, n_free=n_free, with_deriv=with_deriv, logp=logp, ok=ok,
+                    y_batch=y_batch, grad_idx=grad_idx, need_alpha=need_alpha, full_eval=full_eval,
+                    all_params=all_params, free_mask=free_mask)
+
+    def _batch_finish(self, plan, ll, grad, status, alpha=None):
+        """-ll / -grad from the device results of ``_batch_prepare``'s rows (prior terms, inf / zero masks)."""
+        B, nk, nn, n_free = plan["B"], plan["nk"], plan["nn"], plan["n_free"]
+        thetas, logp, all_params, free_mask = plan["thetas"], plan["logp"], plan["all_params"], plan["free_mask"]
+        good = plan["ok"] & (np.asarray(status) == 0)
+        neg_ll = np.where(good, -(np.asarray(ll) + logp), np.inf)
+        if not plan["with_deriv"]:
             return neg_ll
         g = np.zeros((B, n_free))
         if grad is not None and grad.shape[1] > 0:
             g[:, :grad.shape[1]] = grad
-        if need_alpha:
-            alpha = res[3]
+        if plan["need_alpha"]:
             saved = np.array(self.mu.params, dtype=float)
             try:
                 for b in np.nonzero(good)[0]:
@@ -612,6 +644,7 @@ class GaussianProcess(object):
                         g[b, nk + nn + i] = self.mu(self.X, self.n, hyper_deriv=int(pi)).dot(alpha[b])
             finally:
                 self.mu.params[:] = saved
+        hp = self.hyperprior
         free_idx = np.nonzero(free_mask)[0]
         all_good = bool(good.all())
         good_params = all_params if all_good else all_params[good]
@@ -624,6 +657,17 @@ class GaussianProcess(object):
         if not all_good:
             g[~good] = 0.0
         return neg_ll, -g
+
+    def _set_free_params(self, values):
+        """Write the free parameters of kernel, noise kernel and mean function (the split update_hyperparameters
+        uses, gaussian_process.py:1369-1375)."""
+        values = np.asarray(values, dtype=float)
+        nk, nn = self.k.num_free_params, self.noise_k.num_free_params
+        self.k.set_hyperparams(values[:nk])
+        self.noise_k.set_hyperparams(values[nk:nk + nn])
+        if self.mu is not None:
+            self.mu.set_hyperparams(values[nk + nn:])
+        self.K_up_to_date = False
 
     def _batch_by_loop(self, thetas, with_deriv):
         saved = np.array(self.free_params[:], dtype=float)
@@ -640,7 +684,7 @@ class GaussianProcess(object):
                     out.append(r)
         finally:
             self.use_hyper_deriv = saved_flag
-            self.free_params = saved
+            self._set_free_params(saved)
         if with_deriv:
             return np.asarray(out), np.asarray(grads)
         return np.asarray(out)

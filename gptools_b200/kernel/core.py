@@ -16,6 +16,7 @@ import numpy as np
 
 from .._params import ParamHolder
 from ..error_handling import GPArgumentError
+from ..utils import CombinedBounds
 
 __all__ = ["Kernel", "DeviceKernel", "BinaryKernel", "SumKernel", "ProductKernel"]
 
@@ -93,6 +94,21 @@ class DeviceKernel(Kernel):
         """Changes whenever ``device_points`` would return different auxiliary columns (None: never)."""
         return None
 
+    #: gradient slots of the batched device kernel for kernels other than SE (csrc/batched4.cu: 1 + GPT_MAX_DIM)
+    BATCHED_GRAD_SLOTS = 7
+
+    def batchable(self, with_deriv):
+        """False when ``gpt_ll_batched`` cannot serve this kernel's free parameters (the caller then evaluates one
+        theta at a time through ``gpt_ll``)."""
+        if with_deriv and self.kernel_id != 0:
+            return not np.any(np.asarray(self.free_param_idxs) >= self.BATCHED_GRAD_SLOTS)
+        return True
+
+    def batch_rows_supported(self, param_rows):
+        """Per-row validity of a (B, num_params) array of FULL parameter vectors for the device closed forms: rows
+        flagged False evaluate to ``inf`` like the per-theta path, which raises before its device call."""
+        return np.ones(np.atleast_2d(param_rows).shape[0], dtype=bool)
+
     def check_hyper_deriv(self, idxs):
         """Raise NotImplementedError (the reference's exception, kernel/core.py:723) when the derivative with
         respect to any of the parameter indices ``idxs`` is not available on the device."""
@@ -130,17 +146,94 @@ class BinaryKernel(Kernel):
     def num_params(self):
         return self.k1.num_params + self.k2.num_params
 
+    # Write-through views of the operands' arrays, with setters that split and forward (kernel/core.py:466-548):
+    # ``gp.params[i] = v``, ``gp.free_params = ...`` and friends must reach k1 / k2.
+    def _split_set(self, attr, value, n1):
+        value = list(value) if not isinstance(value, np.ndarray) else value
+        if len(value) != n1 + len(getattr(self.k2, attr)):
+            raise ValueError("Length of %s must be %d!" % (attr, n1 + len(getattr(self.k2, attr))))
+        setattr(self.k1, attr, value[:n1])
+        setattr(self.k2, attr, value[n1:])
+
     @property
     def params(self):
-        return np.concatenate((self.k1.params, self.k2.params))
+        return CombinedBounds(self.k1.params, self.k2.params)
+
+    @params.setter
+    def params(self, value):
+        value = np.asarray(value, dtype=float)
+        n1 = self.k1.num_params
+        if len(value) != self.num_params:
+            raise ValueError("Length of params must be %d!" % self.num_params)
+        self.k1.params[:] = value[:n1]
+        self.k2.params[:] = value[n1:]
 
     @property
     def fixed_params(self):
-        return np.concatenate((self.k1.fixed_params, self.k2.fixed_params))
+        return CombinedBounds(self.k1.fixed_params, self.k2.fixed_params)
+
+    @fixed_params.setter
+    def fixed_params(self, value):
+        value = np.asarray(value, dtype=bool)
+        n1 = self.k1.num_params
+        if len(value) != self.num_params:
+            raise ValueError("Length of fixed_params must be %d!" % self.num_params)
+        self.k1.fixed_params = value[:n1]
+        self.k2.fixed_params = value[n1:]
 
     @property
     def param_names(self):
-        return np.concatenate((self.k1.param_names, self.k2.param_names))
+        return CombinedBounds(self.k1.param_names, self.k2.param_names)
+
+    @param_names.setter
+    def param_names(self, value):
+        n1 = self.k1.num_params
+        if len(value) != self.num_params:
+            raise ValueError("Length of param_names must be %d!" % self.num_params)
+        self.k1.param_names = np.asarray(value[:n1], dtype=str)
+        self.k2.param_names = np.asarray(value[n1:], dtype=str)
+
+    @property
+    def num_free_params(self):
+        return self.k1.num_free_params + self.k2.num_free_params
+
+    @property
+    def free_param_idxs(self):
+        return np.concatenate((np.asarray(self.k1.free_param_idxs, dtype=int),
+                               np.asarray(self.k2.free_param_idxs, dtype=int) + self.k1.num_params))
+
+    @property
+    def free_params(self):
+        return CombinedBounds(self.k1.free_params, self.k2.free_params)
+
+    @free_params.setter
+    def free_params(self, value):
+        value = np.asarray(value, dtype=float)
+        n1 = self.k1.num_free_params
+        if len(value) != self.num_free_params:
+            raise ValueError("Length of free_params must be %d!" % self.num_free_params)
+        self.k1.free_params = value[:n1]
+        self.k2.free_params = value[n1:]
+
+    @property
+    def free_param_bounds(self):
+        return CombinedBounds(self.k1.free_param_bounds, self.k2.free_param_bounds)
+
+    @free_param_bounds.setter
+    def free_param_bounds(self, value):
+        n1 = self.k1.num_free_params
+        self.k1.free_param_bounds = value[:n1]
+        self.k2.free_param_bounds = value[n1:]
+
+    @property
+    def free_param_names(self):
+        return CombinedBounds(self.k1.free_param_names, self.k2.free_param_names)
+
+    @free_param_names.setter
+    def free_param_names(self, value):
+        n1 = self.k1.num_free_params
+        self.k1.free_param_names = value[:n1]
+        self.k2.free_param_names = value[n1:]
 
     @property
     def hyperprior(self):

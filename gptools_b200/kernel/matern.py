@@ -57,6 +57,12 @@ class MaternKernel(DeviceKernel):
             raise NotImplementedError("MaternKernel on the device supports half-integer nu (1/2, 3/2, 5/2, ...); "
                                       "got nu = %r" % nu)
 
+    def batch_rows_supported(self, param_rows):
+        nu = np.atleast_2d(param_rows)[:, 1]
+        twice = 2.0 * nu
+        with np.errstate(invalid="ignore"):
+            return (nu > 0) & (np.abs(twice - np.round(twice)) <= 1e-12) & (np.round(twice) % 2 == 1)
+
     def _check_orders(self, ni, nj):
         ti, tj = np.sum(ni, axis=1), np.sum(nj, axis=1)
         too_high = np.any(ti + tj > 2) if len(ti) == len(tj) else (ti.max() + tj.max() > 2)

@@ -1,14 +1,20 @@
 """Multi-GPU use of the hot path: one process per GPU (torchrun), units sharded by rank.
 
 Only the two axes the path shards on naturally are split:
-  * batched hyperparameter vectors theta (emcee walkers, optimizer restarts, ll grids): independent units,
-    contiguous slice per rank, no data-path collective; ONE all-gather of the (1 + P) scalars per theta
-    over NCCL/NVLink at the end so every rank sees the whole batch;
-  * test points of predict: contiguous slice per rank, the (small) factorisation is recomputed on every
-    rank from the replicated training set, one all-gather of mean / std.
+  * batched hyperparameter vectors theta (emcee walkers, optimizer restarts, ll grids, MCMC-posterior prediction):
+    independent units, contiguous slice per rank, no data-path collective; ONE all-gather of the (1 + P) scalars
+    and the status word per theta over NCCL/NVLink at the end so every rank sees the whole batch.  On the NCCL
+    backend the batched kernel writes ll / gradient / status straight into the all-gather SEND buffer (device
+    memory owned by torch), the gathered buffer comes back to the host in one copy: no host round trip between
+    the kernel and the collective;
+  * test points of predict: contiguous slice per rank, mean / variance written by the library into device buffers
+    that are gathered the same way.  The factorisation is replicated: every rank factors the (replicated) training
+    set itself -- bit-identical across ranks, and all ranks finish at the time one would (broadcasting the factor
+    from rank 0 instead leaves the other ranks idle for exactly that time and then moves 19 GB at config 4).
 Everything else (single large Cholesky, T K T^T, draw_sample) runs as independent replicas.
 
-torch.distributed is plumbing only; on CPU (tests) the same code runs over gloo.
+torch.distributed is plumbing only (process group, NCCL communicator, device buffers); on CPU (tests) the same
+code runs over gloo with host buffers.
 """
 import numpy as np
 
@@ -20,6 +26,10 @@ def shard_bounds(count, rank, world_size):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def shard_counts(count, world_size):
+    return [shard_bounds(count, r, world_size)[1] - shard_bounds(count, r, world_size)[0] for r in range(world_size)]
+
+
 def _dist():
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()):
@@ -27,58 +37,135 @@ def _dist():
     return dist
 
 
-def _all_gather_rows(local, counts, device=None):
-    """All-gather row blocks of unequal length (padded to the largest block). ``local``: (n_local, C) float64."""
+def world():
+    """(rank, world_size) of the default process group, (0, 1) without one."""
+    dist = _dist()
+    if dist is None:
+        return 0, 1
+    return dist.get_rank(), dist.get_world_size()
+
+
+def _on_nccl(dist):
+    return dist.get_backend() == "nccl"
+
+
+def _all_gather_rows(local, counts):
+    """All-gather row blocks of unequal length (padded to the largest block). ``local``: (n_local, C) float64 on the
+    host.  Used by the gloo path and by callers whose per-rank results only exist on the host."""
     import torch
     dist = _dist()
     if dist is None or dist.get_world_size() == 1:
         return local
-    world = dist.get_world_size()
+    world_size = dist.get_world_size()
     nmax = max(counts)
     C = local.shape[1]
-    use_cuda = dist.get_backend() == "nccl"
-    dev = torch.device("cuda", torch.cuda.current_device()) if use_cuda else torch.device("cpu")
+    dev = torch.device("cuda", torch.cuda.current_device()) if _on_nccl(dist) else torch.device("cpu")
     buf = torch.zeros((nmax, C), dtype=torch.float64, device=dev)
     if local.shape[0] > 0:
         buf[:local.shape[0]] = torch.from_numpy(np.ascontiguousarray(local)).to(dev)
-    out = torch.empty((world * nmax, C), dtype=torch.float64, device=dev)
+    out = torch.empty((world_size * nmax, C), dtype=torch.float64, device=dev)
     dist.all_gather_into_tensor(out, buf)
-    out = out.cpu().numpy().reshape(world, nmax, C)
-    return np.concatenate([out[r, :counts[r]] for r in range(world)], axis=0)
+    out = out.cpu().numpy().reshape(world_size, nmax, C)
+    return np.concatenate([out[r, :counts[r]] for r in range(world_size)], axis=0)
+
+
+def _device_handles(gp):
+    """(Device, torch.device, current torch stream) with the library pointed at torch's current stream, so that kernel
+    launches, torch copies and NCCL collectives are ordered on ONE stream."""
+    import torch
+    dev = gp._dev()
+    tdev = torch.device("cuda", dev.device)
+    torch.cuda.set_device(tdev)
+    stream = torch.cuda.current_stream(tdev)
+    dev.set_stream(stream.cuda_stream)
+    return dev, tdev, stream
+
+
+def _theta_batch_device(gp, plan, lo, hi, counts):
+    """Local slice [lo, hi) of a prepared theta batch on this rank's GPU, results gathered device to device.
+
+    Send-buffer layout per rank (bytes): ll  nmax x f64 | grad  nmax x P x f64 | status  nmax x i32 (padded to 8):
+    the kernel's output pointers are views of it."""
+    import torch
+    dist = _dist()
+    world_size = dist.get_world_size()
+    dev, tdev, stream = _device_handles(gp)
+    grad_idx = plan["grad_idx"]
+    P = len(grad_idx) if grad_idx else 0
+    nmax = max(counts)
+    off_grad = 8 * nmax
+    off_status = off_grad + 8 * nmax * P
+    nbytes = off_status + 8 * ((4 * nmax + 7) // 8)
+    send = torch.zeros(nbytes, dtype=torch.uint8, device=tdev)
+    nloc = hi - lo
+    if nloc > 0:
+        th = torch.from_numpy(np.ascontiguousarray(plan["full_eval"][lo:hi])).to(tdev, non_blocking=True)
+        base = send.data_ptr()
+        dev.ll_batched_dev(nloc, th.data_ptr(), base, base + off_status, d_grad=(base + off_grad) if P else 0,
+                           grad_idx=grad_idx)
+    recv = torch.empty(world_size * nbytes, dtype=torch.uint8, device=tdev)
+    dist.all_gather_into_tensor(recv, send)
+    host = recv.cpu().numpy().reshape(world_size, nbytes)
+    ll = np.concatenate([host[r, :8 * counts[r]].view(np.float64) for r in range(world_size)])
+    status = np.concatenate([host[r, off_status:off_status + 4 * counts[r]].view(np.int32) for r in range(world_size)])
+    grad = None
+    if P:
+        grad = np.concatenate([host[r, off_grad:off_grad + 8 * counts[r] * P].view(np.float64).reshape(counts[r], P)
+                               for r in range(world_size)], axis=0)
+    return ll, grad, status
 
 
 def update_hyperparameters_batch_sharded(gp, thetas, with_deriv=None):
     """``gp.update_hyperparameters_batch`` with the theta rows split contiguously over the ranks of the default
     process group and a single all-gather of the results.  Every rank passes the SAME ``thetas`` and gets the
-    full (B,) / (B, P) result back."""
+    full (B,) / (B, P) result back (bit-identical on every rank)."""
     thetas = np.atleast_2d(np.asarray(thetas, dtype=float))
     dist = _dist()
     if with_deriv is None:
         with_deriv = bool(gp.use_hyper_deriv)
     if dist is None or dist.get_world_size() == 1:
         return gp.update_hyperparameters_batch(thetas, with_deriv=with_deriv)
-    rank, world = dist.get_rank(), dist.get_world_size()
+    rank, world_size = dist.get_rank(), dist.get_world_size()
     B = thetas.shape[0]
-    counts = [shard_bounds(B, r, world)[1] - shard_bounds(B, r, world)[0] for r in range(world)]
-    lo, hi = shard_bounds(B, rank, world)
-    P = thetas.shape[1]
+    counts = shard_counts(B, world_size)
+    lo, hi = shard_bounds(B, rank, world_size)
+    if gp._batchable(with_deriv):
+        plan = gp._batch_prepare(thetas, with_deriv)  # host arithmetic over the whole batch, identical on all ranks
+        if _on_nccl(dist) and plan["y_batch"] is None and not plan["need_alpha"]:
+            ll, grad, status = _theta_batch_device(gp, plan, lo, hi, counts)
+            return gp._batch_finish(plan, ll, grad, status)
+        # per-theta mean-function residuals / alpha (host arrays in the C-ABI), or the gloo backend
+        P = len(plan["grad_idx"]) if plan["grad_idx"] else 0
+        M = len(gp.y)
+        na = M if plan["need_alpha"] else 0
+        local = np.zeros((hi - lo, 2 + P + na))
+        if hi > lo:
+            res = plan["dev"].ll_batched(plan["full_eval"][lo:hi], grad_idx=plan["grad_idx"],
+                                         y_batch=None if plan["y_batch"] is None else plan["y_batch"][lo:hi],
+                                         return_alpha=plan["need_alpha"])
+            local[:, 0] = res[0]
+            local[:, 1] = res[2]
+            if P:
+                local[:, 2:2 + P] = res[1]
+            if na:
+                local[:, 2 + P:] = res[3]
+        full = _all_gather_rows(local, counts)
+        return gp._batch_finish(plan, full[:, 0], full[:, 2:2 + P] if P else None, full[:, 1].astype(np.int32),
+                                full[:, 2 + P:] if na else None)
+    # kernels the batched device entry does not take: one theta at a time on the owning rank
+    nfree = thetas.shape[1]
     if hi > lo:
         res = gp.update_hyperparameters_batch(thetas[lo:hi], with_deriv=with_deriv)
-        if with_deriv:
-            local = np.hstack([res[0][:, None], res[1]])
-        else:
-            local = np.asarray(res)[:, None]
+        local = np.hstack([res[0][:, None], res[1]]) if with_deriv else np.asarray(res)[:, None]
     else:
-        local = np.zeros((0, 1 + (P if with_deriv else 0)))
+        local = np.zeros((0, 1 + (nfree if with_deriv else 0)))
     full = _all_gather_rows(local, counts)
     if with_deriv:
         return full[:, 0], full[:, 1:]
     return full[:, 0]
 
 
-def predict_sharded(gp, Xstar, n=0, return_std=True):
-    """Predictive mean (and std) with the test points split over the ranks; each rank factors the replicated
-    training set itself (identical bits on every rank) and one all-gather assembles the result."""
+def _canonical_test_points(gp, Xstar, n):
     Xstar = np.atleast_2d(np.asarray(Xstar, dtype=float))
     if gp.num_dim == 1 and Xstar.shape[0] == 1:
         Xstar = Xstar.T
@@ -90,13 +177,40 @@ def predict_sharded(gp, Xstar, n=0, return_std=True):
         n = np.atleast_2d(np.asarray(n, dtype=int))
         if gp.num_dim == 1 and n.shape[0] == 1:
             n = n.T
+    return Xstar, n
+
+
+def predict_sharded(gp, Xstar, n=0, return_std=True):
+    """Predictive mean (and std) with the test points split over the ranks; each rank factors the replicated
+    training set itself (identical bits on every rank) and one all-gather assembles the result."""
+    Xstar, n = _canonical_test_points(gp, Xstar, n)
     dist = _dist()
     if dist is None or dist.get_world_size() == 1:
         return gp.predict(Xstar, n=n, return_std=return_std)
-    rank, world = dist.get_rank(), dist.get_world_size()
+    rank, world_size = dist.get_rank(), dist.get_world_size()
     Ms = Xstar.shape[0]
-    counts = [shard_bounds(Ms, r, world)[1] - shard_bounds(Ms, r, world)[0] for r in range(world)]
-    lo, hi = shard_bounds(Ms, rank, world)
+    counts = shard_counts(Ms, world_size)
+    lo, hi = shard_bounds(Ms, rank, world_size)
+    if _on_nccl(dist) and gp._device_mode() and gp.mu is None:
+        import torch
+        gp.compute_K_L_alpha_ll()
+        dev, tdev, stream = _device_handles(gp)
+        nmax = max(counts)
+        C = 2 if return_std else 1
+        send = torch.zeros((C, nmax), dtype=torch.float64, device=tdev)
+        if hi > lo:
+            gp.k._check_orders(gp.n, n[lo:hi])
+            Xs_d, ns_d = gp.k.device_points(Xstar[lo:hi], n[lo:hi])
+            dev.predict_dev(Xs_d, ns_d, send[0].data_ptr(), send[1].data_ptr() if return_std else 0)
+        recv = torch.empty((world_size, C, nmax), dtype=torch.float64, device=tdev)
+        dist.all_gather_into_tensor(recv, send)
+        host = recv.cpu().numpy()
+        mean = np.concatenate([host[r, 0, :counts[r]] for r in range(world_size)])
+        if not return_std:
+            return mean
+        with np.errstate(invalid="ignore"):
+            std = np.sqrt(np.concatenate([host[r, 1, :counts[r]] for r in range(world_size)]))
+        return mean, std
     if hi > lo:
         res = gp.predict(Xstar[lo:hi], n=n[lo:hi], return_std=return_std)
         local = np.column_stack(res) if return_std else np.asarray(res)[:, None]

@@ -111,6 +111,11 @@ int gpt_ll_batched_dev(gpt_handle* h, int B, const double* d_thetas, const doubl
  *   mean (Ms); var (Ms) or NULL: diag(K**) - |L^-1 K*|^2 ; cov (Ms x Ms) or NULL: K** - v'v */
 int gpt_predict(gpt_handle* h, int Ms, const double* Xs, const int32_t* ns, double* mean, double* var, double* cov);
 
+/* gpt_predict with DEVICE output buffers (mean, and variance when d_var != NULL; Xs / ns are host arrays): the results
+ * are copied device to device on the handle's stream and the call does not synchronise -- the multi-GPU host layer
+ * points them at the send buffer of its all-gather (gptools_b200/parallel.py: predict_sharded). */
+int gpt_predict_dev(gpt_handle* h, int Ms, const double* Xs, const int32_t* ns, double* d_mean, double* d_var);
+
 /* The same numeric core for kernels evaluated on the host (user-defined Python kernels, kernel sums): the caller
  * supplies the cross-covariance exactly as gaussian_process.py:966 builds it, transposed --
  * KstarT[s][i] = k(X_i, Xstar_s; n_i, nstar_s), Ms x N row-major over the LATENT points -- and the prior
