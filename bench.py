@@ -42,7 +42,9 @@ M_OBS = 512
 B_GLOBAL = 4096      # config 3: the theta batch, split over the ranks (strong scaling)
 B_PER_GPU = 4096     # secondary weak-scaling leg: thetas per rank
 C4_LOCATIONS = 16384  # config 4: value + both gradient components at every location -> M = 49152
-C4_PREDICT_POINTS = 65536  # bounded sample of the 10^6 test points of config 4 (whole job, split by rank)
+C4_PREDICT_POINTS = 8 * 28416  # bounded sample of the 10^6 test points of config 4 (whole job, split by rank):
+                               # 8 whole waves of the variance-solve GEMMs (148 SMs x 3 CTAs x 64 rows), so that
+                               # every rank count 1/2/4/8 works on whole waves
 METRIC = "log-ML+grad evals/sec (batched theta, N=512)"
 UNIT = "evals/s"
 FLOP_PER_EVAL = float(M_OBS) ** 3  # potrf M^3/3 + explicit inverse 2M^3/3

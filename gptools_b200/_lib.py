@@ -41,6 +41,7 @@ SIGNATURES = {
                               _c_int_p]),
     "gpt_ll_from_K": (ctypes.c_int, [_vp, _c_double_p, _c_double_p, _c_int_p]),
     "gpt_grad_from_dK": (ctypes.c_int, [_vp, _c_double_p, _c_double_p]),
+    "gpt_noise_grad": (ctypes.c_int, [_vp, ctypes.c_double, _c_double_p]),
     "gpt_get_alpha": (ctypes.c_int, [_vp, _c_double_p]),
     "gpt_get_L": (ctypes.c_int, [_vp, _c_double_p]),
     "gpt_get_K": (ctypes.c_int, [_vp, _c_double_p]),
@@ -239,6 +240,11 @@ class Device(object):
         dK_latent = _f64(dK_latent, (self.N, self.N))
         g = ctypes.c_double(0.0)
         self._check(self._lib.gpt_grad_from_dK(self._h, _dp(dK_latent), ctypes.byref(g)), "gpt_grad_from_dK")
+        return g.value
+
+    def noise_grad(self, noise_sigma):
+        g = ctypes.c_double(0.0)
+        self._check(self._lib.gpt_noise_grad(self._h, float(noise_sigma), ctypes.byref(g)), "gpt_noise_grad")
         return g.value
 
     def get_alpha(self):

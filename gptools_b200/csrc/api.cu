@@ -48,7 +48,7 @@ struct gpt_handle {
     bool factor_valid = false;
     CovParams cp;
     double noise_sigma = 0.0;
-    DevBuf A, Klat, W, Inv, P, z, alpha, logdet, info, scal;
+    DevBuf A, Klat, W, Inv, P, z, alpha, logdet, info, scal, llred;
     // gradient workspaces
     DevBuf XT, Kinv, S, partials, gout, u, Sg, Yt;
     // predict workspaces
@@ -368,18 +368,18 @@ int factor_and_solve(gpt_handle* h, double* ll, int* status) {
                            ptr<int>(h->flags), s);
     h->launches++;
     if ((rc = check_launch(h))) return rc;
-    std::vector<double> hz(M), hl(nblk);
+    // fused reduction on the device: -1/2 z^T z - sum log diag(L) - M/2 log 2 pi; one scalar and the info word come back
+    if ((rc = ensure(h, h->llred, sizeof(double)))) return rc;
+    launch_ll_reduce(ptr<double>(h->z), M, ptr<double>(h->logdet), nblk, ptr<double>(h->llred), s);
+    h->launches++;
+    double hll = 0.0;
     int hinfo = 0;
-    CUDA_OK(h, cudaMemcpyAsync(hz.data(), h->z.p, sizeof(double) * M, cudaMemcpyDeviceToHost, s));
-    CUDA_OK(h, cudaMemcpyAsync(hl.data(), h->logdet.p, sizeof(double) * nblk, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(h, cudaMemcpyAsync(&hll, h->llred.p, sizeof(double), cudaMemcpyDeviceToHost, s));
     CUDA_OK(h, cudaMemcpyAsync(&hinfo, h->info.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     CUDA_OK(h, cudaStreamSynchronize(s));
-    double zz = 0.0, ld = 0.0;
-    for (int i = 0; i < M; i++) zz += hz[i] * hz[i];
-    for (int k = 0; k < nblk; k++) ld += hl[k];
     if (hinfo > M) hinfo = 0;  // only padding rows (identity) could report beyond M; cannot happen, be safe
     *status = hinfo;
-    *ll = -0.5 * zz - ld - 0.5 * M * log(2.0 * M_PI);
+    *ll = hll;
     h->factor_valid = (hinfo == 0);
     return 0;
 }
@@ -570,7 +570,7 @@ void gpt_destroy(gpt_handle* h) {
                      &h->alpha, &h->logdet, &h->info, &h->scal, &h->XT, &h->Kinv, &h->S, &h->partials,
                      &h->gout, &h->u, &h->Sg, &h->Yt, &h->Xs, &h->ns, &h->Kst, &h->Kso, &h->kss, &h->mean, &h->var,
                      &h->cov, &h->Rt, &h->smp, &h->b_thetas, &h->b_y, &h->b_ll, &h->b_grad, &h->b_status,
-                     &h->b_alpha, &h->b_ws, &h->b_counter, &h->Vtmp, &h->flags, &h->ds_C, &h->ds_inv, &h->ds_panel, &h->ds_logdet,
+                     &h->llred, &h->b_alpha, &h->b_ws, &h->b_counter, &h->Vtmp, &h->flags, &h->ds_C, &h->ds_inv, &h->ds_panel, &h->ds_logdet,
                      &h->ds_info, &h->ds_R, &h->ds_Rt, &h->ds_O, &h->ds_mu, &h->ds_jit};
     for (DevBuf* b : all) release(*b);
     if (h->side_stream) {
@@ -906,6 +906,24 @@ int gpt_grad_from_dK(gpt_handle* h, const double* dK_latent, double* g) {
     double sum = 0.0;
     for (int i = 0; i < n; i++) sum += part[i];
     *g = 0.5 * sum;
+    return 0;
+}
+
+int gpt_noise_grad(gpt_handle* h, double noise_sigma, double* g) {
+    if (!h || !g) return fail(h, GPT_ERR_USAGE, "gpt_noise_grad: bad arguments");
+    if (!h->factor_valid) return fail(h, GPT_ERR_USAGE, "gpt_noise_grad: no valid factorisation");
+    CUDA_OK(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    int rc;
+    if ((rc = compute_Kinv(h))) return rc;
+    if ((rc = ensure(h, h->gout, sizeof(double) * (GPT_MAX_PARAMS + 2)))) return rc;
+    launch_trace_and_sumsq(ptr<double>(h->Kinv), h->Mp, ptr<double>(h->alpha), h->M, ptr<double>(h->gout) + GPT_MAX_PARAMS, s);
+    h->launches++;
+    if ((rc = check_launch(h))) return rc;
+    double hg[2];
+    CUDA_OK(h, cudaMemcpyAsync(hg, ptr<double>(h->gout) + GPT_MAX_PARAMS, sizeof(hg), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(h, cudaStreamSynchronize(s));
+    *g = noise_sigma * (hg[1] - hg[0]);  // 1/2 tr((alpha alpha^T - K_tot^{-1}) 2 sigma_n I_M)
     return 0;
 }
 

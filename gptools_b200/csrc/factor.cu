@@ -573,7 +573,31 @@ __global__ void trace_sumsq_kernel(const double* __restrict__ A, long lda, const
     }
 }
 
+// out[0] = -1/2 z^T z - sum_k logdet_k - M/2 log(2 pi)   (gaussian_process.py:1463-1468), one CTA, fixed summation order
+__global__ void ll_reduce_kernel(const double* __restrict__ z, int M, const double* __restrict__ logdet, int nblk,
+                                 double* __restrict__ out) {
+    __shared__ double sh[2][256];
+    double zz = 0.0, ld = 0.0;
+    for (int i = threadIdx.x; i < M; i += 256) zz += z[i] * z[i];
+    for (int i = threadIdx.x; i < nblk; i += 256) ld += logdet[i];
+    sh[0][threadIdx.x] = zz;
+    sh[1][threadIdx.x] = ld;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            sh[0][threadIdx.x] += sh[0][threadIdx.x + o];
+            sh[1][threadIdx.x] += sh[1][threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = -0.5 * sh[0][0] - sh[1][0] - 0.5 * M * 1.8378770664093453;  // log(2 pi)
+}
+
 }  // namespace
+
+void launch_ll_reduce(const double* z, int M, const double* logdet, int nblk, double* out, cudaStream_t s) {
+    ll_reduce_kernel<<<1, 256, 0, s>>>(z, M, logdet, nblk, out);
+}
 
 void launch_potrf_diag(double* Ablk, long lda, double* inv, double* yk, double* logdet_part, int* info, int row0,
                        const double* Pprev, long ldp, int pcols, cudaStream_t s) {

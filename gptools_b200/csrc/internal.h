@@ -95,6 +95,8 @@ struct GradReduceParams {
     double* out;         // nidx
 };
 void launch_grad_reduce(const GradReduceParams& p, cudaStream_t s);
+// out[0] = -1/2 z^T z - sum_k logdet[k] - M/2 log(2 pi): the fused log-likelihood reduction (one CTA, fixed order)
+void launch_ll_reduce(const double* z, int M, const double* logdet, int nblk, double* out, cudaStream_t s);
 // out[0] = sum_{i<n} A[i][i], out[1] = sum_{i<n} v[i]^2
 void launch_trace_and_sumsq(const double* A, long lda, const double* v, int n, double* out, cudaStream_t s);
 

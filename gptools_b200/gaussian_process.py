@@ -294,7 +294,8 @@ class GaussianProcess(object):
         self.K_up_to_date = False
 
     def condense_duplicates(self):
-        """Merge duplicate (X, n) rows through the transformation matrix (gaussian_process.py:505-533)."""
+        """Merge duplicate (X, n) rows through the transformation matrix and, when a transformation matrix is present,
+        drop the quadrature points whose weights are all zero (gaussian_process.py:505-541)."""
         from .utils import unique_rows
         unique, inv = unique_rows(np.hstack((self.X, self.n)), return_inverse=True)
         if len(unique) != len(self.X):
@@ -308,22 +309,55 @@ class GaussianProcess(object):
             self.X = unique[:, :self.X.shape[1]]
             self._data_version += 1
             self.K_up_to_date = False
+        if self.T is not None:
+            # columns of T (= quadrature points) that actually enter (gaussian_process.py:535-541)
+            good_cols = (self.T != 0.0).any(axis=0)
+            if not good_cols.all():
+                self.T = self.T[:, good_cols]
+                self.X = self.X[good_cols, :]
+                self.n = self.n[good_cols, :]
+                self._data_version += 1
+                self.K_up_to_date = False
 
     def remove_outliers(self, thresh=3, **predict_kwargs):
-        """Drop points more than ``thresh`` standard errors from the GP mean (gaussian_process.py:535-621).
-        Not supported with transformed observations (same restriction as the reference)."""
-        if self.T is not None:
-            raise NotImplementedError("remove_outliers is not supported with transformed observations")
-        mean = self.predict(self.X, n=self.n, noise=False, return_std=False, output_transform=None, **predict_kwargs)
-        deltas = np.abs(self.y - mean) / np.where(self.err_y > 0, self.err_y, 1.0)
+        """Drop observations more than ``thresh`` * ``err_y`` from the GP mean (gaussian_process.py:543-621).
+
+        Returns ``(X_bad, y_bad, err_y_bad, n_bad, bad_idxs)`` and, when the GP has a transformation matrix, a sixth
+        element ``T_bad``.  With T the reference keeps a quadrature point only if EVERY remaining row weights it
+        (``(T != 0).all(axis=0)``, :603-604 and :613-614); that rule is reproduced as it stands."""
+        mean = self.predict(self.X, n=self.n, noise=False, return_std=False, output_transform=self.T, **predict_kwargs)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            deltas = np.absolute(mean - self.y) / self.err_y
         deltas[self.err_y == 0] = 0
-        bad = deltas >= thresh
-        good = ~bad
-        X_bad, y_bad, err_bad, n_bad = self.X[bad], self.y[bad], self.err_y[bad], self.n[bad]
-        self.X, self.y, self.err_y, self.n = self.X[good], self.y[good], self.err_y[good], self.n[good]
+        bad_idxs = (deltas >= thresh)
+        good_idxs = ~bad_idxs
+        y_bad = self.y[bad_idxs]
+        err_y_bad = self.err_y[bad_idxs]
+        if self.T is not None:
+            T_bad = self.T[bad_idxs, :]
+            non_zero_cols = (T_bad != 0).all(axis=0)
+            T_bad = T_bad[:, non_zero_cols]
+            X_bad = self.X[non_zero_cols, :]
+            n_bad = self.n[non_zero_cols, :]
+        else:
+            X_bad = self.X[bad_idxs, :]
+            n_bad = self.n[bad_idxs, :]
+        if self.T is None:
+            self.X = self.X[good_idxs, :]
+            self.n = self.n[good_idxs, :]
+        else:
+            self.T = self.T[good_idxs, :]
+            non_zero_cols = (self.T != 0).all(axis=0)
+            self.T = self.T[:, non_zero_cols]
+            self.X = self.X[non_zero_cols, :]
+            self.n = self.n[non_zero_cols, :]
+        self.y = self.y[good_idxs]
+        self.err_y = self.err_y[good_idxs]
         self._data_version += 1
         self.K_up_to_date = False
-        return (X_bad, y_bad, err_bad, n_bad, bad)
+        if self.T is None:
+            return (X_bad, y_bad, err_y_bad, n_bad, bad_idxs)
+        return (X_bad, y_bad, err_y_bad, n_bad, bad_idxs, T_bad)
 
     # ------------------------------------------------------------------------------------------
     # device plumbing
@@ -362,8 +396,13 @@ class GaussianProcess(object):
         if self._dev_data_version != self._data_version or getattr(self, "_dev_aux_key", None) != aux_key:
             if self.X is None or len(self.y) == 0:
                 raise GPArgumentError("No training data: call add_data first")
-            Xd, nd = (self.k.device_points(self.X, self.n) if self.k.device_descriptor() is not None
-                      else (self.X, self.n))
+            if self.k.device_descriptor() is not None:
+                Xd, nd = self.k.device_points(self.X, self.n)
+            else:
+                # host-evaluated kernel: the device never reads the points (K, dK, K* arrive assembled), so the input
+                # dimension is not limited by GPT_MAX_DIM
+                Xd = np.zeros((self.X.shape[0], 1))
+                nd = np.zeros((self.X.shape[0], 1), dtype=int)
             dev.set_data(Xd, nd, y_alph, self.err_y, self.T)
             self._dev_aux_key = aux_key
             self._dev_data_version = self._data_version
@@ -464,9 +503,8 @@ class GaussianProcess(object):
                 if isinstance(self.noise_k, DiagonalNoiseKernel):
                     knk = self.k
                     if nn_free > 0:
-                        ll_deriv[nk_free] = dev.grad_from_dK(
-                            2.0 * self.noise_k.params[0] * np.eye(self.X.shape[0])) if self.T is None else \
-                            self._noise_grad_with_T(dev)
+                        # gaussian_process.py:1484-1488: dK = 2 sigma_n I_M over the observations, also with T
+                        ll_deriv[nk_free] = dev.noise_grad(self.noise_k.params[0])
                 else:
                     knk = self.k + self.noise_k
                 idxs = np.arange(0, len(knk.params), dtype=int)[~np.asarray(knk.fixed_params, dtype=bool)]
@@ -489,13 +527,6 @@ class GaussianProcess(object):
                 ll_deriv[i] += hp(params, hyper_deriv=int(pi))
             self.ll_deriv = ll_deriv
         self._up_to_date = True
-
-    def _noise_grad_with_T(self, dev):
-        # gaussian_process.py:1484-1488 uses 2 sigma_n I_M over the observations, also when T is present
-        alpha = dev.get_alpha()
-        L = dev.get_L()
-        Kinv = scipy.linalg.cho_solve((L, True), np.eye(len(alpha)))
-        return self.noise_k.params[0] * (alpha.dot(alpha) - np.trace(Kinv))
 
     def update_hyperparameters(self, new_params, hyper_deriv_handling='default', exit_on_bounds=True,
                                inf_on_error=True):
@@ -771,7 +802,16 @@ class GaussianProcess(object):
         if not need_second:
             return mean
         if noise and not isinstance(self.noise_k, ZeroKernel):
-            if need_cov:
+            if isinstance(self.noise_k, DiagonalNoiseKernel) and type(self.noise_k).__call__ is DiagonalNoiseKernel.__call__:
+                # sigma_n^2 [n* == n_noise] on the diagonal (kernel/noise.py:103-110) without forming the M*^2 pair lists
+                nvar = self.noise_k.params[0] ** 2.0 * np.all(n == np.asarray(self.noise_k.n), axis=1)
+                if not need_cov:
+                    var = var + nvar
+                elif len(np.unique(Xstar, axis=0)) == len(Xstar):
+                    covariance = covariance + np.diag(nvar)
+                else:  # repeated test points share their noise in the reference (Xi == Xj off the diagonal too)
+                    covariance = covariance + self.compute_Kij(Xstar, None, n, None, noise=True)
+            elif need_cov:
                 covariance = covariance + self.compute_Kij(Xstar, None, n, None, noise=True)
             else:
                 var = var + np.diagonal(self.compute_Kij(Xstar, None, n, None, noise=True))

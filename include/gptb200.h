@@ -91,6 +91,12 @@ int gpt_ll_from_K(gpt_handle* h, const double* K_latent, double* ll, int* status
 /* 1/2 (alpha' T dK T' alpha - tr(K_tot^-1 T dK T')) for a host-supplied dK (N x N); after gpt_ll / gpt_ll_from_K. */
 int gpt_grad_from_dK(gpt_handle* h, const double* dK_latent, double* g);
 
+/* d ll / d sigma_n of a DiagonalNoiseKernel for host-evaluated kernels: 1/2 tr((alpha alpha^T - K_tot^{-1}) 2 sigma_n I_M)
+ * = sigma_n (alpha^T alpha - tr K_tot^{-1}), the identity taken over the M observations also when T is present
+ * (gaussian_process.py:1484-1488).  K_tot^{-1} comes from the resident factor (DMMA GEMMs), trace and alpha^T alpha are
+ * reduced on the device. */
+int gpt_noise_grad(gpt_handle* h, double noise_sigma, double* g);
+
 int gpt_get_alpha(gpt_handle* h, double* alpha /* M */);
 int gpt_get_L(gpt_handle* h, double* L /* M x M, lower, zeros above */);
 int gpt_get_K(gpt_handle* h, double* K /* N x N latent covariance of the last gpt_ll, without noise */);

@@ -438,3 +438,113 @@ def test_warped_kernel_matches_reference():
     assert_close(K, gd["K"], rtol=1e-10, atol=1e-12 * np.abs(gd["K"]).max(), what="warped K")
     with pytest.raises(ValueError):
         k(X[:1], X[:1], np.array([[2]]), np.array([[0]]))
+
+
+# ------------------------------------------------------------------ round-2 host fixes
+def test_binary_kernel_parameters_are_write_through():
+    """kernel/core.py:466-548: the combined kernel exposes write-through views with setters (gp.params = ...,
+    gp.free_params[i] = v, restoring parameters after a per-theta loop)."""
+    k1 = g.SquaredExponentialKernel(initial_params=[0.9, 0.7], param_bounds=[(0, 10)] * 2)
+    k2 = g.SquaredExponentialKernel(initial_params=[0.5, 0.3], fixed_params=[False, True], param_bounds=[(0, 10)] * 2)
+    ks = k1 + k2
+    assert list(ks.params) == [0.9, 0.7, 0.5, 0.3] and ks.num_free_params == 3
+    assert list(ks.free_param_idxs) == [0, 1, 2]
+    ks.params = [1.0, 2.0, 3.0, 4.0]
+    assert list(k1.params) == [1.0, 2.0] and list(k2.params) == [3.0, 4.0]
+    ks.free_params = [1.5, 2.5, 3.5]
+    assert list(k1.params) == [1.5, 2.5] and list(k2.params) == [3.5, 4.0]
+    ks.free_params[2] = 0.25
+    assert k2.params[0] == 0.25
+    ks.params[1] = 7.0
+    assert k1.params[1] == 7.0
+    gp = g.GaussianProcess(ks, X=[0.0, 1.0, 2.0], y=[0.0, 1.0, 0.5], err_y=0.1)
+    gp.params = [1.0, 1.0, 1.0, 4.0, 0.0]          # kernel (4) + ZeroKernel (1)
+    assert list(ks.params) == [1.0, 1.0, 1.0, 4.0]
+    gp.free_params = [0.2, 0.3, 0.4]
+    assert list(k1.params) == [0.2, 0.3] and k2.params[0] == 0.4
+    gp.free_params[0] = 0.9
+    assert k1.params[0] == 0.9
+    saved = np.array(gp.free_params[:], dtype=float)
+    gp._set_free_params([5.0, 6.0, 7.0])
+    gp._set_free_params(saved)
+    assert list(gp.free_params[:]) == list(saved)
+
+
+def test_batched_entry_falls_back_where_the_device_kernel_cannot_go():
+    """M > 2048 (32 tiles) and free Matern parameters beyond the batched gradient slots take the per-theta loop
+    instead of raising; Matern rows whose nu the device closed forms do not cover evaluate to inf."""
+    rs = np.random.RandomState(0)
+    X = np.sort(rs.rand(40)) * 3
+    k = g.MaternKernel(num_dim=1, initial_params=[1.0, 2.5, 0.8], param_bounds=[(0, 10)] * 3)
+    gp = with_fake(g.GaussianProcess(k, X=X, y=np.sin(X), err_y=0.05))
+    assert gp._batchable(False)
+    th = np.array([[1.0, 2.5, 0.8], [1.1, 2.2, 0.7], [0.9, 1.5, 0.9]])
+    f = gp.update_hyperparameters_batch(th, with_deriv=False)
+    assert np.isfinite(f[0]) and np.isinf(f[1]) and np.isfinite(f[2])
+    assert "ll_batched" in gp._dev_obj.calls
+    gp.BATCHED_MAX_M = 16                                  # pretend the data is beyond the batched kernel's size
+    gp._dev_obj.calls = []
+    f2 = gp.update_hyperparameters_batch(th[[0, 2]], with_deriv=False)
+    assert "ll_batched" not in gp._dev_obj.calls and gp._dev_obj.calls.count("ll") == 2
+    assert_close(f2, f[[0, 2]], rtol=1e-12)
+    k6 = g.MaternKernel(num_dim=6, initial_params=[1.0, 2.5] + [1.0] * 6, fixed_params=[False, True] + [False] * 6,
+                        param_bounds=[(0, 10)] * 8)
+    assert k6.batchable(False) and not k6.batchable(True)    # l_6 is parameter 7: outside the gradient slots
+
+
+def test_condense_duplicates_prunes_unused_quadrature_points_and_remove_outliers_with_T():
+    """gaussian_process.py:535-541 (all-zero T columns are dropped) and :583-621 (remove_outliers with T returns T_bad);
+    compared with the reference itself where it is available."""
+    rs = np.random.RandomState(5)
+    Xq = np.linspace(0, 1, 9)
+    T = np.zeros((3, 9))
+    T[0, :4] = 0.25
+    T[1, 2:6] = 0.25
+    T[2, 3:7] = 0.25                                       # columns 7, 8 never enter
+    y = np.array([1.0, 1.2, 5.0])
+    k = g.SquaredExponentialKernel(initial_params=[1.0, 0.5], param_bounds=[(0, 10)] * 2)
+    gp = with_fake(g.GaussianProcess(k))
+    gp.add_data(Xq, y, err_y=0.1, T=T)
+    gp.condense_duplicates()
+    assert gp.T.shape == (3, 7) and gp.X.shape == (7, 1) and gp.n.shape == (7, 1)
+    assert np.array_equal(gp.X.ravel(), Xq[:7])
+    from oracle.ref_shim import load_reference, reference_available
+    if reference_available():
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            r = load_reference()
+            kr = r.SquaredExponentialKernel(initial_params=[1.0, 0.5], param_bounds=[(0, 10)] * 2)
+            gr = r.GaussianProcess(kr)
+            gr.add_data(Xq, y, err_y=0.1, T=T)
+            gr.condense_duplicates()
+            assert np.array_equal(gr.T, gp.T) and np.array_equal(gr.X, gp.X) and np.array_equal(gr.n, gp.n)
+            out_r = gr.remove_outliers(thresh=3)
+            with_fake(gp)
+            out_g = gp.remove_outliers(thresh=3)
+            assert len(out_r) == len(out_g) == 6
+            for a, b in zip(out_r, out_g):
+                assert np.array_equal(np.asarray(a), np.asarray(b))
+            for a, b in ((gr.X, gp.X), (gr.n, gp.n), (gr.y, gp.y), (gr.err_y, gp.err_y), (gr.T, gp.T)):
+                assert np.array_equal(a, b)
+    else:
+        out = gp.remove_outliers(thresh=3)
+        assert len(out) == 6 and out[4].shape == (3,)
+
+
+def test_predict_noise_diagonal_without_pair_lists():
+    """predict(noise=True, return_std=True) adds sigma_n^2 [n* == n_noise] per test point (kernel/noise.py:103-110)."""
+    rs = np.random.RandomState(1)
+    X = np.sort(rs.rand(12)) * 2
+    k = g.SquaredExponentialKernel(initial_params=[1.0, 0.5], param_bounds=[(0, 10)] * 2)
+    nk = g.DiagonalNoiseKernel(1, initial_noise=0.3, noise_bound=(0, 5))
+    gp = with_fake(g.GaussianProcess(k, noise_k=nk, X=X, y=np.sin(X), err_y=0.05))
+    Xs = np.linspace(0, 2, 7)
+    m0, s0 = gp.predict(Xs, noise=False)
+    m1, s1 = gp.predict(Xs, noise=True)
+    assert_close(s1 ** 2, s0 ** 2 + 0.09, rtol=1e-12)
+    _, s1d = gp.predict(Xs, n=1, noise=True)               # the noise sits on order 0 only
+    _, s0d = gp.predict(Xs, n=1, noise=False)
+    assert_close(s1d, s0d, rtol=1e-12)
+    _, c1 = gp.predict(Xs, noise=True, return_cov=True)
+    _, c0 = gp.predict(Xs, noise=False, return_cov=True)
+    assert_close(c1, c0 + 0.09 * np.eye(7), rtol=1e-12, atol=1e-15)
