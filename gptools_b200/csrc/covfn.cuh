@@ -38,11 +38,13 @@ struct CovParams {
     // derived
     double sig2;               // sigma_f^2
     double inv_l[GPT_MAX_DIM]; // 1 / l_d
-    // generic Matern (half-integer nu): derivative-series constants, utils.py:1496-1516
-    int matern_p;              // nu = matern_p + 1/2
+    // generic Matern: derivative-series constants, utils.py:1496-1516
+    int matern_p;              // floor(nu)
+    int mat_kind;              // 0: nu = p + 1/2 (closed form K_nu), 1: any other non-integer nu, 2: integer nu
     double mat_c;              // 2^{1-nu} / Gamma(nu)
-    double mat_A[3];           // value of f^{(n)}(0), n = 1,2 (index n)
-    double mat_B[3];           // c * Gamma(-nu) (1+nu-n)_n / 2^{1+nu}
+    double mat_nu[2];          // the order(s) the series zone is evaluated at: {nu, nu}; integer nu: {nu - 0.001, nu + 0.001}
+    double mat_A[2][4];        // [side][n]: c * Gamma(nu') / (2^{1-nu'+2n} (1-nu')_n)       (x 1/2 for integer nu)
+    double mat_B[2][4];        // [side][n]: c * Gamma(-nu') (1+nu'-n)_n / 2^{1+nu'}         (x 1/2 for integer nu)
 };
 
 // exp(x) for x <= 0 (the squared-exponential / Gibbs exponents): Cody-Waite reduction x = k ln2 + r,
@@ -196,21 +198,36 @@ GPT_HD void cov_params_init(CovParams& cp, int kid, int D, int nparams, const do
     if (kid != GPT_KERNEL_GIBBS_TANH && kid != GPT_KERNEL_GIBBS_AUX)
         for (int d = 0; d < D; d++) cp.inv_l[d] = 1.0 / cp.p[loff + d];
     cp.matern_p = 0;
+    cp.mat_kind = 0;
     cp.mat_c = 0.0;
-    for (int i = 0; i < 3; i++) { cp.mat_A[i] = 0.0; cp.mat_B[i] = 0.0; }
+    for (int sd = 0; sd < 2; sd++) {
+        cp.mat_nu[sd] = 0.0;
+        for (int i = 0; i < 4; i++) { cp.mat_A[sd][i] = 0.0; cp.mat_B[sd][i] = 0.0; }
+    }
     if (kid == GPT_KERNEL_MATERN) {
         const double nu = cp.p[1];
         cp.matern_p = (int)floor(nu);
-        const double g_nu = tgamma(nu);
-        const double g_mnu = tgamma(-nu);
-        cp.mat_c = pow(2.0, 1.0 - nu) / g_nu;
-        for (int n = 1; n <= 2; n++) {
-            double poch1 = 1.0, poch2 = 1.0;  // (1-nu)_n and (1+nu-n)_n
-            for (int k = 0; k < n; k++) { poch1 *= (1.0 - nu + k); poch2 *= (1.0 + nu - n + k); }
-            // Gamma(nu) n! / (2^{1-nu+2n} (1-nu)_n n!)   (utils.py:1503-1507 with k = n, nterms = 1)
-            cp.mat_A[n] = cp.mat_c * g_nu / (pow(2.0, 1.0 - nu + 2.0 * n) * poch1);
-            // Gamma(-nu) (1+nu-n)_n y^{nu-n} / 2^{1+nu}   (utils.py:1508-1515 with k = 0)
-            cp.mat_B[n] = cp.mat_c * g_mnu * poch2 / pow(2.0, 1.0 + nu);
+        const double twice = 2.0 * nu;
+        if (floor(nu) == nu) cp.mat_kind = 2;
+        else if (floor(twice) == twice) cp.mat_kind = 0;
+        else cp.mat_kind = 1;
+        cp.mat_c = pow(2.0, 1.0 - nu) / tgamma(nu);
+        // integer nu: the reference averages the series at nu -+ 0.001 (utils.py:1480-1484, 1498-1502) and keeps the
+        // normalisation 2^{1-nu} / Gamma(nu) of the integer order (matern.py:377)
+        const double half = (cp.mat_kind == 2) ? 0.5 : 1.0;
+        cp.mat_nu[0] = (cp.mat_kind == 2) ? nu - 0.001 : nu;
+        cp.mat_nu[1] = (cp.mat_kind == 2) ? nu + 0.001 : nu;
+        for (int sd = 0; sd < 2; sd++) {
+            const double v = cp.mat_nu[sd];
+            const double g_nu = tgamma(v), g_mnu = tgamma(-v);
+            for (int n = 1; n <= 3; n++) {
+                double poch1 = 1.0, poch2 = 1.0;  // (1-nu)_n and (1+nu-n)_n
+                for (int k = 0; k < n; k++) { poch1 *= (1.0 - v + k); poch2 *= (1.0 + v - n + k); }
+                // Gamma(nu) n! / (2^{1-nu+2n} (1-nu)_n n!)   (utils.py:1503-1507 with k = n, nterms = 1)
+                cp.mat_A[sd][n] = half * cp.mat_c * g_nu / (pow(2.0, 1.0 - v + 2.0 * n) * poch1);
+                // Gamma(-nu) (1+nu-n)_n y^{nu-n} / 2^{1+nu}   (utils.py:1508-1515 with k = 0)
+                cp.mat_B[sd][n] = half * cp.mat_c * g_mnu * poch2 / pow(2.0, 1.0 + v);
+            }
         }
     }
 }
@@ -382,7 +399,7 @@ GPT_HD double matern52_cov(const CovParams& cp, const double* xi, const int32_t*
 }
 
 // ------------------------------------------------------------------------------------------
-// Generic Matern, nu = p + 1/2, total derivative order <= 2.
+// Generic Matern, any nu > 0, total derivative order <= 2.
 //   f(y) = c y^{nu/2} K_nu(sqrt y),  c = 2^{1-nu}/Gamma(nu),  y = 2 nu r2l2
 //   g_mu(y) := y^{mu/2} K_|mu|(sqrt y);  d/dy g_mu = -1/2 g_{mu-1}   =>   f^{(n)} = c (-1/2)^n g_{nu-n}
 //   K_{q+1/2}(r) = sqrt(pi/(2r)) e^{-r} sum_{k<=q} (q+k)!/(k!(q-k)!) (2r)^{-k}
@@ -397,31 +414,136 @@ GPT_HD double bessel_k_half(int q, double r) {
     return sqrt(1.5707963267948966 / r) * exp(-r) * sum;
 }
 
+// ---- K_nu(x) for real order (generic Matern with nu not a half-integer, kernel/matern.py:296-312 calls scipy's kv) ----
+// Temme's method (N. M. Temme, J. Comput. Phys. 19 (1975) 324): for |mu| <= 1/2, K_mu and K_{mu+1} from the series
+// in x/2 when x <= 2 and from Steed's continued fraction CF2 when x > 2; upward recurrence in the order (stable for
+// K) reaches |nu|.  The two Gamma-function combinations of the series,
+//   gam1 = (1/Gamma(1-mu) - 1/Gamma(1+mu)) / (2 mu),   gam2 = (1/Gamma(1-mu) + 1/Gamma(1+mu)) / 2,
+// come from the Taylor series 1/Gamma(1+z) = sum c_k z^k (odd / even parts: no cancellation at small mu).
+GPT_HD void temme_gammas(double mu, double& gam1, double& gam2, double& gampl, double& gammi) {
+    const double C[27] = {
+        1.0, 0.57721566490153286061, -0.65587807152025388108, -0.042002635034095235529, 0.1665386113822914895,
+        -0.042197734555544336748, -0.0096219715278769735621, 0.0072189432466630995424, -0.0011651675918590651121,
+        -0.00021524167411495097282, 0.00012805028238811618615, -0.000020134854780788238656,
+        -1.2504934821426706573e-6, 1.1330272319816958824e-6, -2.0563384169776071035e-7, 6.1160951044814158179e-9,
+        5.0020076444692229301e-9, -1.1812745704870201446e-9, 1.0434267116911005105e-10, 7.782263439905071254e-12,
+        -3.6968056186422057082e-12, 5.100370287454475979e-13, -2.0583260535665067832e-14, -5.3481225394230179824e-15,
+        1.2267786282382607902e-15, -1.1812593016974587695e-16, 1.1866922547516003326e-18};
+    const double m2 = mu * mu;
+    double odd = 0.0, even = 0.0;
+    for (int k = 25; k >= 1; k -= 2) odd = odd * m2 + C[k];
+    for (int k = 26; k >= 0; k -= 2) even = even * m2 + C[k];
+    gam1 = -odd;
+    gam2 = even;
+    gampl = gam2 - mu * gam1;  // 1 / Gamma(1 + mu)
+    gammi = gam2 + mu * gam1;  // 1 / Gamma(1 - mu)
+}
+
+GPT_HD void bessel_k_pair(double mu, double x, double& kmu, double& kmu1) {
+    const double PI = 3.14159265358979323846;
+    if (x <= 2.0) {
+        const double b = 0.5 * x, d0 = -log(b);
+        double e = mu * d0;
+        const double fact2 = (fabs(e) < 1e-8) ? 1.0 : sinh(e) / e;
+        const double pimu = PI * mu;
+        const double fact = (fabs(pimu) < 1e-8) ? 1.0 : pimu / sin(pimu);
+        double gam1, gam2, gampl, gammi;
+        temme_gammas(mu, gam1, gam2, gampl, gammi);
+        double ff = fact * (gam1 * cosh(e) + gam2 * fact2 * d0);
+        double sum = ff;
+        e = exp(e);
+        double p = 0.5 * e / gampl, q = 0.5 / (e * gammi), c = 1.0, sum1 = p;
+        const double d = b * b, mu2 = mu * mu;
+        for (int i = 1; i <= 500; i++) {
+            ff = (i * ff + p + q) / (i * (double)i - mu2);
+            c *= d / i;
+            p /= (i - mu);
+            q /= (i + mu);
+            const double del = c * ff;
+            sum += del;
+            sum1 += c * (p - i * ff);
+            if (fabs(del) < fabs(sum) * 1e-17) break;
+        }
+        kmu = sum;
+        kmu1 = sum1 * (2.0 / x);
+    } else {
+        double b = 2.0 * (1.0 + x), d = 1.0 / b, h = d, delh = d;
+        double q1 = 0.0, q2 = 1.0;
+        const double a1 = 0.25 - mu * mu;
+        double q = a1, c = a1, a = -a1;
+        double s = 1.0 + q * delh;
+        for (int i = 2; i <= 10000; i++) {
+            a -= 2 * (i - 1);
+            c = -a * c / i;
+            const double qnew = (q1 - b * q2) / a;
+            q1 = q2;
+            q2 = qnew;
+            q += c * qnew;
+            b += 2.0;
+            d = 1.0 / (b + a * d);
+            delh = (b * d - 1.0) * delh;
+            h += delh;
+            const double dels = q * delh;
+            s += dels;
+            if (fabs(dels / s) < 1e-17) break;
+        }
+        h = a1 * h;
+        kmu = sqrt(PI / (2.0 * x)) * exp(-x) / s;
+        kmu1 = kmu * (mu + x + 0.5 - h) / x;
+    }
+}
+
+GPT_HD double bessel_k_real(double order, double x) {
+    const double a = fabs(order);  // K_{-a} = K_a
+    const int nl = (int)(a + 0.5);
+    const double mu = a - nl;      // |mu| <= 1/2
+    double k0, k1;
+    bessel_k_pair(mu, x, k0, k1);
+    const double xi2 = 2.0 / x;
+    for (int i = 1; i <= nl; i++) {
+        const double kt = (mu + i) * xi2 * k1 + k0;
+        k0 = k1;
+        k1 = kt;
+    }
+    return k0;
+}
+
 GPT_HD double matern_fn(const CovParams& cp, double y, int n) {
-    // exact f^{(n)}(y) for y > 0 and half-integer nu
+    // exact f^{(n)}(y) = c (-1/2)^n y^{(nu-n)/2} K_{|nu-n|}(sqrt y) for y > 0
     const double nu = cp.p[1];
     const double r = sqrt(y);
-    const double mu = nu - n;  // half-integer, may be negative
+    const double mu = nu - n;  // may be negative
     const double amu = fabs(mu);
-    const int q = (int)floor(amu);
     double s = (n & 1) ? -1.0 : 1.0;
     for (int k = 0; k < n; k++) s *= 0.5;
-    return cp.mat_c * s * pow(r, mu) * bessel_k_half(q, r);
+    const double kv = (cp.mat_kind == 0) ? bessel_k_half((int)floor(amu), r) : bessel_k_real(amu, r);
+    return cp.mat_c * s * pow(r, mu) * kv;
+}
+
+// one side of utils.py:1477-1492 at y == 0 (without the normalisation c): +-inf when n > nu', the series constant else
+GPT_HD double matern_origin_side(double v, int n) {
+    if ((double)n > v) {
+        double poch = 1.0;
+        for (int k = 0; k < n; k++) poch *= (1.0 + v - n + k);
+        return (tgamma(-v) * poch) * INFINITY;
+    }
+    double poch1 = 1.0;
+    for (int k = 0; k < n; k++) poch1 *= (1.0 - v + k);
+    return tgamma(v) / (pow(2.0, 1.0 - v + 2.0 * n) * poch1);
 }
 
 GPT_HD double matern_dk_dy(const CovParams& cp, double y, int n) {
     // utils.py:1429-1518 for n >= 1 (value n == 0 is handled by the caller)
-    const double nu = cp.p[1];
     if (y == 0.0) {
-        if ((double)n > nu) {
-            // Gamma(-nu) (1+nu-n)_n * inf (utils.py:1487-1488)
-            double poch = 1.0;
-            for (int k = 0; k < n; k++) poch *= (1.0 + nu - n + k);
-            return cp.mat_c * (tgamma(-nu) * poch) * INFINITY;
-        }
-        return cp.mat_A[n];
+        if (cp.mat_kind == 2)
+            return cp.mat_c * 0.5 * (matern_origin_side(cp.mat_nu[0], n) + matern_origin_side(cp.mat_nu[1], n));
+        return cp.mat_c * matern_origin_side(cp.p[1], n);
     }
-    if (y <= 5e-4) return cp.mat_A[n] + cp.mat_B[n] * pow(y, nu - n);
+    if (y <= 5e-4) {
+        double v = cp.mat_A[0][n] + cp.mat_B[0][n] * pow(y, cp.mat_nu[0] - n);
+        if (cp.mat_kind == 2) v += cp.mat_A[1][n] + cp.mat_B[1][n] * pow(y, cp.mat_nu[1] - n);
+        return v;
+    }
     return matern_fn(cp, y, n);
 }
 

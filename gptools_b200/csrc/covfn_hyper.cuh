@@ -118,7 +118,7 @@ GPT_HD GptDual matern52_cov_dual(const CovParams& cp, const double* xi, const in
     return sf * sf * v;
 }
 
-// ---- generic Matern, nu = p + 1/2 fixed, total derivative order <= 2 (value path: matern_cov) ----------------------
+// ---- generic Matern, nu fixed (any nu > 0), total derivative order <= 2 (value path: matern_cov) --------------------
 GPT_HD GptDual bessel_k_half_dual(int q, GptDual r) {
     GptDual sum = dmk(1.0), term = dmk(1.0);
     for (int k = 1; k <= q; k++) {
@@ -130,6 +130,10 @@ GPT_HD GptDual bessel_k_half_dual(int q, GptDual r) {
 
 GPT_HD GptDual matern_fn_dual(const CovParams& cp, GptDual y, int n) {
     const double nu = cp.p[1];
+    if (cp.mat_kind != 0) {
+        // any other order: d f^{(n)} / dy = f^{(n+1)}, both from the real-order Bessel routine
+        return dmk(matern_fn(cp, y.v, n), matern_fn(cp, y.v, n + 1) * y.d);
+    }
     const GptDual r = dsqrt(y);
     const double mu = nu - n;
     const int q = (int)floor(fabs(mu));
@@ -139,9 +143,12 @@ GPT_HD GptDual matern_fn_dual(const CovParams& cp, GptDual y, int n) {
 }
 
 GPT_HD GptDual matern_dk_dy_dual(const CovParams& cp, GptDual y, int n) {
-    const double nu = cp.p[1];
     if (y.v == 0.0) return dmk(matern_dk_dy(cp, 0.0, n));  // y == 0 has dy/dl == 0 as well
-    if (y.v <= 5e-4) return cp.mat_A[n] + cp.mat_B[n] * dpow(y, nu - n);
+    if (y.v <= 5e-4) {
+        GptDual v = cp.mat_A[0][n] + cp.mat_B[0][n] * dpow(y, cp.mat_nu[0] - n);
+        if (cp.mat_kind == 2) v = v + (cp.mat_A[1][n] + cp.mat_B[1][n] * dpow(y, cp.mat_nu[1] - n));
+        return v;
+    }
     return matern_fn_dual(cp, y, n);
 }
 

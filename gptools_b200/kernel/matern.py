@@ -30,10 +30,12 @@ class MaternKernel(DeviceKernel):
     r"""Generic Matern; params = [sigma_f, nu, l_1, ..., l_D] (kernel/matern.py:251-465).
 
     The device function ``matern_cov`` reproduces the reference's behaviour -- including its one-term
-    power series for derivative orders >= 1 when 0 < 2 nu r^2 <= 5e-4 (utils.py:1493-1516) and the origin
-    limits (kernel/matern.py:444-457) -- for half-integer nu and total derivative order <= 2 per pair,
-    which covers value + first-derivative observations and predictions.  ``hyper_deriv`` is supported for
-    sigma_f and the length scales (dual numbers, csrc/covfn_hyper.cuh); nu must be a fixed parameter then."""
+    power series for derivative orders >= 1 when 0 < 2 nu r^2 <= 5e-4 (utils.py:1493-1516), its averaging over
+    nu -+ 0.001 there for integer nu (utils.py:1480-1484, 1498-1502) and the origin limits
+    (kernel/matern.py:444-457) -- for any nu > 0 (K_nu of real order by Temme's method; the closed form for
+    half-integer nu) and total derivative order <= 2 per pair, which covers value + first-derivative observations
+    and predictions.  ``hyper_deriv`` is supported for sigma_f and the length scales (dual numbers,
+    csrc/covfn_hyper.cuh); nu must be a fixed parameter then (the reference has no hyper-derivatives at all here)."""
 
     kernel_id = 2
     supports_hyper_deriv = True
@@ -53,15 +55,12 @@ class MaternKernel(DeviceKernel):
 
     def _check_params_for_device(self):
         nu = float(self.params[1])
-        if abs(2.0 * nu - round(2.0 * nu)) > 1e-12 or int(round(2.0 * nu)) % 2 == 0 or nu <= 0:
-            raise NotImplementedError("MaternKernel on the device supports half-integer nu (1/2, 3/2, 5/2, ...); "
-                                      "got nu = %r" % nu)
+        if not nu > 0:
+            raise ValueError("MaternKernel needs nu > 0; got nu = %r" % nu)
 
     def batch_rows_supported(self, param_rows):
-        nu = np.atleast_2d(param_rows)[:, 1]
-        twice = 2.0 * nu
         with np.errstate(invalid="ignore"):
-            return (nu > 0) & (np.abs(twice - np.round(twice)) <= 1e-12) & (np.round(twice) % 2 == 1)
+            return np.atleast_2d(param_rows)[:, 1] > 0
 
     def _check_orders(self, ni, nj):
         ti, tj = np.sum(ni, axis=1), np.sum(nj, axis=1)

@@ -172,6 +172,48 @@ def case_matern_generic():
     save("matern_generic_2d", params=k.params.copy(), **gp_state(gp), **out)
 
 
+def case_matern_real_nu():
+    """Round 2: orders that are not half-integers (K_nu of real order on the device) and an integer order (the
+    reference averages its power series over nu -+ 0.001 there, utils.py:1480-1484, 1498-1502)."""
+    rs = RandomState(3)
+    X = np.sort(rs.rand(30)) * 3.0
+    X[5] = X[4] + 1e-3       # y = 2 nu r^2 inside (0, 5e-4]
+    X[11] = X[10] + 4e-3
+    X[20] = X[19]            # exact duplicate -> origin limits
+    for nu in (2.2, 3.0):
+        k = g.MaternKernel(num_dim=1, initial_params=[1.4, nu, 0.6], param_bounds=[(0, 10)] * 3)
+        gp = g.GaussianProcess(k)
+        gp.add_data(X, np.sin(2 * X), err_y=0.05)
+        gp.add_data(X[::3], 2 * np.cos(2 * X[::3]), n=1, err_y=0.05)
+        out = ll_and_grad(gp, False)
+        Xs = np.linspace(0.05, 2.95, 7)
+        res = gp.predict(Xs, full_output=True)
+        out.update(Xs=Xs, mean=res["mean"], std=res["std"], cov=res["cov"])
+        resd = gp.predict(Xs, n=1, full_output=True)
+        out.update(dmean=resd["mean"], dstd=resd["std"])
+        save("matern_generic_nu%s" % str(nu).replace(".", "p"), params=k.params.copy(), **gp_state(gp), **out)
+    rs = RandomState(4)
+    X2 = rs.rand(12, 2)
+    X2[3] = X2[2] + [2e-3, 0.0]
+    X2[7] = X2[6]
+    k = g.MaternKernel(num_dim=2, initial_params=[0.9, 2.2, 0.5, 0.8], param_bounds=[(0, 10)] * 4)
+    gp = g.GaussianProcess(k)
+    gp.add_data(X2, np.sin(X2).sum(1), err_y=0.05)
+    gp.add_data(X2, np.cos(X2[:, 0]), n=np.tile([1, 0], (12, 1)), err_y=0.05)
+    gp.add_data(X2, np.cos(X2[:, 1]), n=np.tile([0, 1], (12, 1)), err_y=0.05)
+    out = ll_and_grad(gp, False)
+    save("matern_generic_2d_nu2p2", params=k.params.copy(), **gp_state(gp), **out)
+    # hyper-derivative oracle (Richardson differences of the reference's ll and K), smooth inputs
+    rs = RandomState(3)
+    X = np.sort(rs.rand(14)) * 3.0
+    for nu in (2.2, 3.0):
+        k = g.MaternKernel(num_dim=1, initial_params=[1.4, nu, 0.6], param_bounds=[(0, 10)] * 3)
+        gp = g.GaussianProcess(k)
+        gp.add_data(X, np.sin(2 * X), err_y=0.05)
+        gp.add_data(X[::3], 2 * np.cos(2 * X[::3]), n=1, err_y=0.05)
+        _hyperfd("hyperfd_matern_generic_nu%s" % str(nu).replace(".", "p"), gp, [0, 2], 4e-3)
+
+
 # ---------------------------------------------------------------- KAT-3: Gibbs-tanh + T + draw_sample
 def case_gibbs():
     k = g.GibbsKernel1dTanh(initial_params=[1.5, 0.6, 0.1, 0.05, 0.9],
@@ -519,7 +561,8 @@ def case_warped():
 
 if __name__ == "__main__":
     cases = [case_se2d, case_se_pairs, case_matern52, case_matern_generic, case_gibbs, case_c5_full, case_demo,
-             case_c3, case_c2, case_noise, case_hyperfd, case_product, case_gibbs_profiles, case_warped]
+             case_c3, case_c2, case_noise, case_hyperfd, case_product, case_gibbs_profiles, case_warped,
+             case_matern_real_nu]
     only = set(sys.argv[1:])          # e.g. `make_golden.py case_hyperfd` regenerates one family
     for c in cases:
         if not only or c.__name__ in only:

@@ -16,6 +16,9 @@ CASE_KERNEL = {
     "matern_generic_nu3p5": KERNEL_MATERN,
     "matern_generic_nu1p5": KERNEL_MATERN,
     "matern_generic_2d": KERNEL_MATERN,
+    "matern_generic_nu2p2": KERNEL_MATERN,       # real order: K_nu by Temme's method on the device
+    "matern_generic_nu3p0": KERNEL_MATERN,       # integer order: series zone averaged over nu -+ 0.001
+    "matern_generic_2d_nu2p2": KERNEL_MATERN,
     "gibbs_kat3": KERNEL_GIBBS_TANH,
     "gibbs_c5_small": KERNEL_GIBBS_TANH,
     "demo_c1_kat4": KERNEL_SE,
@@ -59,6 +62,7 @@ def var_tol(cov_diag_prior, rtol=1e-9):
 HYPERFD_KERNEL = {"hyperfd_matern52_1d": KERNEL_MATERN52, "hyperfd_matern52_2d": KERNEL_MATERN52,
                   "hyperfd_matern_generic_nu2p5": KERNEL_MATERN, "hyperfd_matern_generic_nu3p5": KERNEL_MATERN,
                   "hyperfd_matern_generic_nu1p5": KERNEL_MATERN, "hyperfd_matern_generic_2d": KERNEL_MATERN,
+                  "hyperfd_matern_generic_nu2p2": KERNEL_MATERN, "hyperfd_matern_generic_nu3p0": KERNEL_MATERN,
                   "hyperfd_gibbs_direct": KERNEL_GIBBS_TANH, "hyperfd_gibbs_T": KERNEL_GIBBS_TANH}
 
 

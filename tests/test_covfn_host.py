@@ -4,6 +4,7 @@ tile generators inline, so a formula error is caught before any GPU time is spen
 import ctypes
 import os
 import subprocess
+import warnings
 
 import numpy as np
 import pytest
@@ -123,6 +124,7 @@ def test_matern_generic_series_zone_is_emulated(lib):
 # ---- hyper-parameter derivatives of the Matern / Gibbs kernels (csrc/covfn_hyper.cuh) ----------
 HYPERFD = {"hyperfd_matern52_1d": 1, "hyperfd_matern52_2d": 1, "hyperfd_matern_generic_nu2p5": 2,
            "hyperfd_matern_generic_nu3p5": 2, "hyperfd_matern_generic_nu1p5": 2, "hyperfd_matern_generic_2d": 2,
+           "hyperfd_matern_generic_nu2p2": 2, "hyperfd_matern_generic_nu3p0": 2,
            "hyperfd_gibbs_direct": 3, "hyperfd_gibbs_T": 3}
 
 
@@ -202,3 +204,39 @@ def test_exp_gauss_profile_is_self_consistent():
     assert k.num_params == 8 and k.device_descriptor()[0] == 4
     with pytest.raises(NotImplementedError):
         g.exp_gauss_warp(x, 2, *p)
+
+
+def test_bessel_k_real_order_value_path_against_scipy(lib):
+    """Round 2: K_nu of real order on the device (Temme series / Steed CF2 + recurrence).  The n = 0 value path is
+    2^{1-nu}/Gamma(nu) y^{nu/2} K_nu(sqrt y) (kernel/matern.py:309-312): compare with scipy.special.kv over the
+    orders and arguments the closed form sees, including integer orders and both branches (x <= 2, x > 2)."""
+    import scipy.special
+    r = np.concatenate([np.logspace(-6, np.log10(2.0), 40), np.linspace(2.0001, 40.0, 40)])
+    for nu in (0.3, 0.7, 1.0, 1.2, 2.0, 2.2, 3.0, 4.3, 7.9):
+        params = np.array([1.0, nu, 1.0])
+        Xi = (r / np.sqrt(2.0 * nu))[:, None]           # y = 2 nu tau^2 / l^2 = r^2
+        Xj = np.zeros_like(Xi)
+        z = np.zeros(Xi.shape, dtype=int)
+        got = pairs(lib, KERNEL_MATERN, params, Xi, Xj, z, z)
+        want = 2.0 ** (1.0 - nu) / scipy.special.gamma(nu) * r ** nu * scipy.special.kv(nu, r)
+        assert_close(got, want, rtol=2e-13, atol=1e-300, what="Matern value, nu = %g" % nu)
+
+
+def test_matern_real_and_integer_order_match_the_oracle(lib):
+    """Series zone, origin limits (+-inf / NaN included) and the regular branch for orders that are not
+    half-integers, against the pinned restatement of utils.py:1429-1518."""
+    from oracle import gp_oracle as orc
+    tau = np.array([0.0, 1e-4, 3e-3, 6e-3, 9e-3, 0.05, 0.3, 0.5, 1.0, 2.0, 5.0, 15.0])
+    Xi = np.repeat(tau, 4)[:, None] + 0.25
+    Xj = np.full_like(Xi, 0.25)
+    ni = np.tile([0, 1, 0, 1], len(tau))[:, None]
+    nj = np.tile([0, 0, 1, 1], len(tau))[:, None]
+    for nu in (0.7, 1.0, 2.0, 2.2, 3.0, 4.3):
+        params = np.array([1.3, nu, 0.7])
+        with np.errstate(all="ignore"), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want = orc.matern_pairs(Xi, Xj, ni, nj, params)
+        got = pairs(lib, KERNEL_MATERN, params, Xi, Xj, ni, nj)
+        fin = np.isfinite(want)
+        assert np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(got[~fin & ~np.isnan(want)], want[~fin & ~np.isnan(want)])
+        assert_close(got[fin], want[fin], rtol=1e-9, atol=1e-9, what="generic Matern nu=%g" % nu)

@@ -94,7 +94,8 @@ def test_ll_gradient(dev, case):
 
 
 @pytest.mark.parametrize("case", ["se2d_kat1", "matern52_kat2", "gibbs_kat3", "gibbs_c5_small", "se_diagnoise",
-                                  "matern_generic_nu2p5", "matern_generic_nu3p5"])
+                                  "matern_generic_nu2p5", "matern_generic_nu3p5", "matern_generic_nu2p2",
+                                  "matern_generic_nu3p0"])
 def test_predict_full(dev, case):
     gd = load_golden(case)
     _setup(dev, case, gd)

@@ -294,8 +294,10 @@ def test_unsupported_orders_raise_before_any_device_call():
     with pytest.raises(NotImplementedError):
         gk._check_orders(np.array([[2]]), np.array([[0]]))
     mk = g.MaternKernel(num_dim=1, initial_params=[1.0, 2.0, 0.5], param_bounds=[(0, 10)] * 3)
-    with pytest.raises(NotImplementedError):
-        mk.device_descriptor()            # integer nu is not available on the device
+    assert mk.device_descriptor()[0] == 2    # any nu > 0 runs on the device (round 2: K_nu of real order)
+    mk = g.MaternKernel(num_dim=1, initial_params=[1.0, 0.0, 0.5], param_bounds=[(0, 10)] * 3)
+    with pytest.raises(ValueError):
+        mk.device_descriptor()
     mk = g.MaternKernel(num_dim=1, initial_params=[1.0, 2.5, 0.5], param_bounds=[(0, 10)] * 3)
     with pytest.raises(NotImplementedError):          # d/dnu is the one derivative the device does not have
         mk(np.zeros((1, 1)), np.zeros((1, 1)), np.zeros((1, 1), int), np.zeros((1, 1), int), hyper_deriv=1)
@@ -472,13 +474,13 @@ def test_binary_kernel_parameters_are_write_through():
 
 def test_batched_entry_falls_back_where_the_device_kernel_cannot_go():
     """M > 2048 (32 tiles) and free Matern parameters beyond the batched gradient slots take the per-theta loop
-    instead of raising; Matern rows whose nu the device closed forms do not cover evaluate to inf."""
+    instead of raising; Matern rows with an invalid order (nu <= 0) evaluate to inf."""
     rs = np.random.RandomState(0)
     X = np.sort(rs.rand(40)) * 3
-    k = g.MaternKernel(num_dim=1, initial_params=[1.0, 2.5, 0.8], param_bounds=[(0, 10)] * 3)
+    k = g.MaternKernel(num_dim=1, initial_params=[1.0, 2.5, 0.8], param_bounds=[(0, 10), (-5, 10), (0, 10)])
     gp = with_fake(g.GaussianProcess(k, X=X, y=np.sin(X), err_y=0.05))
     assert gp._batchable(False)
-    th = np.array([[1.0, 2.5, 0.8], [1.1, 2.2, 0.7], [0.9, 1.5, 0.9]])
+    th = np.array([[1.0, 2.5, 0.8], [1.1, -1.0, 0.7], [0.9, 1.5, 0.9]])
     f = gp.update_hyperparameters_batch(th, with_deriv=False)
     assert np.isfinite(f[0]) and np.isinf(f[1]) and np.isfinite(f[2])
     assert "ll_batched" in gp._dev_obj.calls

@@ -75,7 +75,8 @@ def test_kat1_values_from_survey():
 
 
 @pytest.mark.parametrize("case", ["se2d_kat1", "matern52_kat2", "gibbs_kat3", "gibbs_c5_small", "se_diagnoise",
-                                  "matern_generic_nu2p5", "matern_generic_nu3p5"])
+                                  "matern_generic_nu2p5", "matern_generic_nu3p5", "matern_generic_nu2p2",
+                                  "matern_generic_nu3p0"])
 def test_predict_full(case):
     gd = load_golden(case)
     kid = CASE_KERNEL[case]
