@@ -689,6 +689,16 @@ class GaussianProcess(object):
             g[~good] = 0.0
         return neg_ll, -g
 
+    def _eval_batch(self, thetas, with_deriv):
+        """The unit of work of the L4 drivers (multi-start optimisation, ensemble sampler, ll grids): one batched
+        device evaluation, split over the ranks of the default torch.distributed process group when there is one
+        (the reference farms the same units to worker processes, gaussian_process.py:723-735, 1757-1763)."""
+        if "torch" in sys.modules:
+            from . import parallel
+            if parallel.world()[1] > 1:
+                return parallel.update_hyperparameters_batch_sharded(self, thetas, with_deriv=with_deriv)
+        return self.update_hyperparameters_batch(thetas, with_deriv=with_deriv)
+
     def _set_free_params(self, values):
         """Write the free parameters of kernel, noise kernel and mean function (the split update_hyperparameters
         uses, gaussian_process.py:1369-1375)."""
@@ -909,10 +919,17 @@ class GaussianProcess(object):
     # MAP estimation (gaussian_process.py:623-783)
     # ------------------------------------------------------------------------------------------
     def optimize_hyperparameters(self, method='SLSQP', opt_kwargs={}, verbose=False, random_starts=None,
-                                 num_proc=None, max_tries=1):
+                                 num_proc=None, max_tries=1, batched_starts=True):
         """Maximise the log-posterior with scipy.optimize.minimize from ``random_starts`` starting points drawn
-        from the hyperprior.  ``num_proc`` is accepted for compatibility: every likelihood evaluation already
-        runs on the GPU, so the starts are run one after the other in this process instead of in a pool."""
+        from the hyperprior (gaussian_process.py:623-783).
+
+        The reference maps the starts over a pool of ``num_proc`` worker processes (:723-735).  Here the starts advance
+        in LOCK-STEP: every start runs the same scipy minimiser (same method, bounds, jac) in its own thread, the
+        objective calls of all starts that are waiting are collected into one batch, and the batch is evaluated by a
+        single device launch (``update_hyperparameters_batch``; split over the GPUs of an active process group).  The
+        result of every start is what its own sequential ``minimize`` run returns -- the optimiser never sees the
+        batching.  ``num_proc`` only sets the default number of starts (like the reference when ``random_starts`` is
+        None); ``batched_starts=False`` runs the starts one after the other through ``gpt_ll``."""
         opt_kwargs = {} if opt_kwargs is None else dict(opt_kwargs)
         if 'method' in opt_kwargs:
             method = opt_kwargs['method']
@@ -948,16 +965,19 @@ class GaussianProcess(object):
                               RuntimeWarning)
             starts = draw_starts()
             trial += 1
-            res = []
-            for samp in starts:
-                try:
-                    r = scipy.optimize.minimize(self.update_hyperparameters, samp, **opt_kwargs)
-                except Exception:
-                    if self.verbose:
-                        warnings.warn("Minimizer failed, skipping sample. Error is:\n{:s}\nState of params is: "
-                                      "{:s}".format(traceback.format_exc(), str(self.free_params[:])), RuntimeWarning)
-                    continue
-                res.append(r)
+            if len(starts) > 1 and batched_starts:
+                res = self._minimize_starts_lockstep(starts, opt_kwargs)
+            else:
+                res = []
+                for samp in starts:
+                    try:
+                        r = scipy.optimize.minimize(self.update_hyperparameters, samp, **opt_kwargs)
+                    except Exception:
+                        if self.verbose:
+                            warnings.warn("Minimizer failed, skipping sample. Error is:\n{:s}\nState of params is: "
+                                          "{:s}".format(traceback.format_exc(), str(self.free_params[:])), RuntimeWarning)
+                        continue
+                    res.append(r)
             finite = [r for r in res if not (np.isnan(r.fun) or np.isinf(r.fun))]
             res_min = min(finite, key=lambda r: r.fun) if finite else None
         if res_min is None:
@@ -981,6 +1001,76 @@ class GaussianProcess(object):
                           "used.".format(str(bounds), str(res_min.x)))
         return (res_min, len(res))
 
+    def _minimize_starts_lockstep(self, starts, opt_kwargs):
+        """Run scipy.optimize.minimize from every start with the objective evaluations batched across the starts.
+
+        Each start owns a thread that blocks inside its objective call; once EVERY unfinished start is blocked, the
+        pending parameter vectors (ordered by start index, so the batch is deterministic and identical on every rank
+        of a process group) go to the device as one batch and the threads are released with their own row."""
+        import threading
+        nstart = len(starts)
+        want_grad = bool(opt_kwargs.get('jac', False))
+        cond = threading.Condition()
+        pending, results, active = {}, {}, set(range(nstart))
+        out = [None] * nstart
+        failure = []
+
+        def objective(idx):
+            def f(theta):
+                with cond:
+                    pending[idx] = np.array(theta, dtype=float)
+                    cond.notify_all()
+                    while idx not in results and not failure:
+                        cond.wait()
+                    if failure:
+                        raise RuntimeError("batched evaluation failed")
+                    return results.pop(idx)
+            return f
+
+        def worker(idx):
+            try:
+                out[idx] = scipy.optimize.minimize(objective(idx), starts[idx], **opt_kwargs)
+            except Exception:
+                if self.verbose:
+                    warnings.warn("Minimizer failed, skipping sample. Error is:\n{:s}".format(traceback.format_exc()),
+                                  RuntimeWarning)
+            finally:
+                with cond:
+                    active.discard(idx)
+                    pending.pop(idx, None)
+                    cond.notify_all()
+
+        threads = [threading.Thread(target=worker, args=(i,), daemon=True) for i in range(nstart)]
+        for t in threads:
+            t.start()
+        saved = np.array(self.free_params[:], dtype=float)
+        try:
+            while True:
+                with cond:
+                    while active and set(pending) != active:
+                        cond.wait()
+                    if not active:
+                        break
+                    order = sorted(pending)
+                    thetas = np.array([pending[i] for i in order])
+                    pending.clear()
+                try:
+                    r = self._eval_batch(thetas, want_grad)
+                except Exception:
+                    with cond:
+                        failure.append(traceback.format_exc())
+                        cond.notify_all()
+                    raise
+                with cond:
+                    for row, i in enumerate(order):
+                        results[i] = (float(r[0][row]), np.array(r[1][row])) if want_grad else float(r[row])
+                    cond.notify_all()
+        finally:
+            for t in threads:
+                t.join()
+            self._set_free_params(saved)
+        return [r for r in out if r is not None]
+
     # ------------------------------------------------------------------------------------------
     # ll over a grid of hyperparameters (gaussian_process.py:1607-1692): one batched device launch
     # ------------------------------------------------------------------------------------------
@@ -1001,7 +1091,7 @@ class GaussianProcess(object):
                 raise ValueError("Length of num_pts must match the number of free parameters!")
         param_vals = [np.linspace(b[0], b[1], int(npt)) for b, npt in zip(bounds, num_pts)]
         grid = np.stack(np.meshgrid(*param_vals, indexing='ij'), axis=-1).reshape(-1, len(param_vals))
-        neg_ll = self.update_hyperparameters_batch(grid, with_deriv=False)
+        neg_ll = self._eval_batch(grid, False)
         ll_vals = -np.asarray(neg_ll).reshape([len(v) for v in param_vals])
         return (ll_vals, param_vals)
 
@@ -1022,14 +1112,23 @@ class GaussianProcess(object):
         if plot_posterior or plot_chains:
             warnings.warn("plotting is out of scope of gptools_b200; ignoring plot_* keywords")
         ndim = len(self.free_params)
+        nranks = 1
+        if "torch" in sys.modules:
+            from . import parallel
+            nranks = parallel.world()[1]
         if sampler is None:
-            sampler = EnsembleSampler(nwalkers, ndim, lambda th: -self.update_hyperparameters_batch(th, with_deriv=False),
-                                      a=sampler_a)
+            # with several ranks every rank runs the same chain (proposals from identical random streams) and
+            # evaluates its slice of each half-ensemble: the walkers are the sharded units (gaussian_process.py:1757-1763)
+            rstate = np.random.RandomState(parallel.shared_seed()) if nranks > 1 else None
+            sampler = EnsembleSampler(nwalkers, ndim, lambda th: -self._eval_batch(th, False), a=sampler_a,
+                                      random_state=rstate)
         else:
-            sampler.lnprob_batch = lambda th: -self.update_hyperparameters_batch(th, with_deriv=False)
+            sampler.lnprob_batch = lambda th: -self._eval_batch(th, False)
         if sampler.chain.shape[1] == 0:
             theta0 = self.hyperprior.random_draw(size=nwalkers).T
             theta0 = theta0[:, ~np.asarray(self.fixed_params[:], dtype=bool)]
+            if nranks > 1:
+                theta0 = parallel.broadcast_array(theta0)
         else:
             theta0 = sampler.chain[:, -1, :]
         sampler.run_mcmc(theta0, nsamp)
@@ -1049,6 +1148,16 @@ class GaussianProcess(object):
             flat_trace = np.asarray(flat_trace, dtype=float)
         saved = np.array(self.free_params[:], dtype=float)
         out = {k_: [] for k_ in ('mean', 'std', 'cov', 'samp', 'mean_func')}
+        # the hyperparameter samples are independent units (the reference maps them over a process pool,
+        # gaussian_process.py:1944-1969): with a process group every rank takes a contiguous slice
+        rank, nranks = 0, 1
+        if "torch" in sys.modules:
+            from . import parallel
+            rank, nranks = parallel.world()
+        full_trace = flat_trace
+        if nranks > 1:
+            lo, hi = parallel.shard_bounds(len(flat_trace), rank, nranks)
+            flat_trace = flat_trace[lo:hi]
         try:
             for th in flat_trace:
                 val = self.update_hyperparameters(th)
@@ -1067,6 +1176,8 @@ class GaussianProcess(object):
                     out['mean_func'].append(res['mean_func'])
         finally:
             self.update_hyperparameters(saved)
+        if nranks > 1:
+            out = parallel.gather_result_lists(out, len(full_trace))
         return {k_: v for k_, v in out.items() if len(v) > 0}
 
     def predict_MCMC(self, X, ddof=1, full_MC=False, rejection_func=None, **kwargs):

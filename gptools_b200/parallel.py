@@ -69,6 +69,52 @@ def _all_gather_rows(local, counts):
     return np.concatenate([out[r, :counts[r]] for r in range(world_size)], axis=0)
 
 
+def broadcast_array(arr, src=0):
+    """``arr`` of rank ``src`` on every rank (same shape and dtype float64 everywhere)."""
+    import torch
+    dist = _dist()
+    if dist is None or dist.get_world_size() == 1:
+        return arr
+    dev = torch.device("cuda", torch.cuda.current_device()) if _on_nccl(dist) else torch.device("cpu")
+    t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64)).to(dev)
+    dist.broadcast(t, src=src)
+    return t.cpu().numpy().reshape(np.shape(arr))
+
+
+def shared_seed():
+    """A random 31-bit seed drawn on rank 0 and broadcast: identical random streams on every rank."""
+    seed = np.array([float(np.random.randint(0, 2 ** 31 - 1))])
+    return int(broadcast_array(seed)[0])
+
+
+def gather_result_lists(out, total):
+    """compute_from_MCMC: every rank holds lists of equally shaped arrays for its slice of the ``total`` hyperparameter
+    samples (entries of failed samples are missing); returns the concatenation over ranks in rank order."""
+    dist = _dist()
+    world_size = dist.get_world_size()
+    merged = {}
+    for key in sorted(out):
+        vals = out[key]
+        shape = np.array([len(vals)] + (list(np.shape(vals[0])) if len(vals) else []), dtype=float)
+        # how many entries / which shape each rank holds (ranks with nothing report the shape of the others)
+        meta = np.zeros(8)
+        meta[:len(shape)] = shape
+        meta[7] = len(shape)
+        metas = _all_gather_rows(meta[None, :], [1] * world_size)
+        ref = metas[np.argmax(metas[:, 0])]
+        nd = int(ref[7])
+        if nd == 0 or ref[0] == 0:
+            merged[key] = []
+            continue
+        item_shape = tuple(int(v) for v in ref[1:nd])
+        width = int(np.prod(item_shape)) if item_shape else 1
+        counts = [int(m[0]) for m in metas]
+        local = np.asarray(vals, dtype=float).reshape(len(vals), width) if len(vals) else np.zeros((0, width))
+        full = _all_gather_rows(local, counts)
+        merged[key] = [full[i].reshape(item_shape) for i in range(full.shape[0])]
+    return merged
+
+
 def _device_handles(gp):
     """(Device, torch.device, current torch stream) with the library pointed at torch's current stream, so that kernel
     launches, torch copies and NCCL collectives are ordered on ONE stream."""

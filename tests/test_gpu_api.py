@@ -464,3 +464,42 @@ def test_warped_kernel_end_to_end():
     m1, s1 = gp.predict(gd["Xs"], n=1)
     assert_close(m1, gd["mean_d1"], rtol=1e-9, atol=1e-9 * np.abs(gd["mean_d1"]).max(), what="mean_d1")
     assert np.all(np.abs(s1 ** 2 - gd["std_d1"] ** 2) <= 1e-8 * np.max(gd["std_d1"] ** 2))
+
+
+@pytest.mark.parametrize("case", ["matern_generic_nu2p2", "matern_generic_nu3p0"])
+def test_matern_real_order_through_the_class(case):
+    """Round 2: MaternKernel with an order that is not a half-integer (and an integer one) drops in: ll, alpha, K,
+    prediction of values and derivatives against the reference's own output; nu as a FREE parameter of a batch."""
+    gd = load_golden(case)
+    nu = float(gd["params"][1])
+    k = g.MaternKernel(num_dim=1, initial_params=gd["params"], param_bounds=[(0, 10)] * 3)
+    gp = g.GaussianProcess(k)
+    nval = int((gd["n"][:, 0] == 0).sum())
+    gp.add_data(gd["X"][:nval], gd["y"][:nval], err_y=gd["err_y"][:nval])
+    gp.add_data(gd["X"][nval:], gd["y"][nval:], err_y=gd["err_y"][nval:], n=1)
+    gp.compute_K_L_alpha_ll()
+    assert_close(gp.ll, float(gd["ll"]), rtol=1e-9, what="ll")
+    assert_close(gp.K, gd["K"], rtol=1e-9, atol=1e-9 * np.abs(gd["K"]).max(), what="K")
+    assert_close(gp.alpha.ravel(), gd["alpha"], rtol=0.0, atol=2e-6 * np.abs(gd["alpha"]).max(), what="alpha")
+    mean, std = gp.predict(gd["Xs"])
+    assert_close(mean, gd["mean"], rtol=1e-8, atol=1e-8 * np.abs(gd["mean"]).max(), what="mean")
+    assert np.all(np.abs(std ** 2 - gd["std"] ** 2) <= 1e-8 * k.params[0] ** 2)
+    dmean, dstd = gp.predict(gd["Xs"], n=1)
+    assert_close(dmean, gd["dmean"], rtol=1e-8, atol=1e-8 * np.abs(gd["dmean"]).max(), what="derivative mean")
+    assert np.all(np.abs(dstd ** 2 - gd["dstd"] ** 2) <= 1e-8 * np.abs(gd["dstd"] ** 2).max())
+    # nu free: every row of a batch may carry its own order; batched == one at a time
+    th = np.array([[1.4, nu, 0.6], [1.3, 2.7, 0.55], [1.5, 1.9, 0.7], [1.2, 3.0, 0.5], [1.4, 2.5, 0.6]])
+    f = gp.update_hyperparameters_batch(th, with_deriv=False)
+    for b in range(len(th)):
+        assert_close(f[b], gp.update_hyperparameters(th[b]), rtol=1e-10, what="batched row %d" % b)
+    # gradient with nu fixed (sigma_f, l): against the Richardson differences of the reference's ll
+    gh = load_golden("hyperfd_" + case)
+    k2 = g.MaternKernel(num_dim=1, initial_params=gh["params"], fixed_params=[False, True, False], param_bounds=[(0, 10)] * 3)
+    gp2 = g.GaussianProcess(k2, use_hyper_deriv=True)
+    nv = int((gh["n"][:, 0] == 0).sum())
+    gp2.add_data(gh["X"][:nv], gh["y"][:nv], err_y=gh["err_y"][:nv])
+    gp2.add_data(gh["X"][nv:], gh["y"][nv:], err_y=gh["err_y"][nv:], n=1)
+    gp2.compute_K_L_alpha_ll()
+    assert_close(gp2.ll_deriv, gh["ll_grad_fd"], rtol=2e-5, atol=2e-6 * np.abs(gh["ll_grad_fd"]).max(), what="ll gradient")
+    fb, gb = gp2.update_hyperparameters_batch(np.array([gh["params"][[0, 2]], gh["params"][[0, 2]] * 1.05]))
+    assert_close(-gb[0], gp2.ll_deriv, rtol=1e-8, atol=1e-9 * np.abs(gp2.ll_deriv).max(), what="batched gradient")

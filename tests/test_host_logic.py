@@ -550,3 +550,28 @@ def test_predict_noise_diagonal_without_pair_lists():
     _, c1 = gp.predict(Xs, noise=True, return_cov=True)
     _, c0 = gp.predict(Xs, noise=False, return_cov=True)
     assert_close(c1, c0 + 0.09 * np.eye(7), rtol=1e-12, atol=1e-15)
+
+
+def test_lockstep_multistart_equals_sequential_starts():
+    """optimize_hyperparameters runs its random starts in lock-step on the batched entry; every start must end where
+    its own sequential scipy.optimize.minimize run ends (the optimiser cannot see the batching)."""
+    rs = np.random.RandomState(2)
+    X = np.sort(rs.rand(25)) * 3
+    y = np.sin(2 * X) + 0.05 * rs.randn(25)
+    outs = []
+    for batched in (True, False):
+        k = g.SquaredExponentialKernel(initial_params=[1.0, 0.5], param_bounds=[(0.1, 5), (0.05, 3)])
+        gp = with_fake(g.GaussianProcess(k, X=X, y=y, err_y=0.05, use_hyper_deriv=True))
+        np.random.seed(11)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            res, n = gp.optimize_hyperparameters(random_starts=5, batched_starts=batched,
+                                                 opt_kwargs={"options": {"maxiter": 30}})
+        outs.append((res, n, list(gp._dev_obj.calls), np.array(gp.free_params[:], dtype=float)))
+    (rb, nb, calls_b, pb), (rq, nq, calls_q, pq) = outs
+    assert nb == nq == 5
+    assert_close(rb.x, rq.x, rtol=1e-10)
+    assert_close(rb.fun, rq.fun, rtol=1e-12)
+    assert_close(pb, pq, rtol=1e-10)                        # the GP is left at the optimum in both modes
+    assert calls_b.count("ll_batched") > 0 and calls_q.count("ll_batched") == 0
+    assert calls_b.count("ll_batched") < calls_q.count("ll") / 2   # one launch serves all waiting starts
