@@ -61,15 +61,10 @@ __device__ __forceinline__ void assemble_tile_se_low(const AssembleParams& p, co
     }
 }
 
-__global__ void __launch_bounds__(256) assemble_kernel(AssembleParams p) {
-    if (p.lower_tiles_only && blockIdx.x > blockIdx.y) return;  // the Cholesky never reads tiles above the diagonal
-    __shared__ double sxr[TS * GPT_MAX_DIM];
-    __shared__ double sxc[TS * GPT_MAX_DIM];
-    __shared__ int32_t snr[TS * GPT_MAX_DIM];
-    __shared__ int32_t snc[TS * GPT_MAX_DIM];
+// Stage the 64 row points and 64 column points of the tile (coordinates + derivative orders) and the exp table.
+__device__ __forceinline__ void stage_tile_points(const AssembleParams& p, double* sxr, double* sxc, int32_t* snr,
+                                                  int32_t* snc, double* etab, int r0, int c0, int tid) {
     const int D = p.cp.D;
-    const int r0 = blockIdx.y * TS, c0 = blockIdx.x * TS;
-    const int tid = threadIdx.x;
     for (int i = tid; i < TS * D; i += 256) {
         const int r = i / D, d = i - r * D;
         const bool okr = (r0 + r) < p.Mr, okc = (c0 + r) < p.Mc;
@@ -78,15 +73,37 @@ __global__ void __launch_bounds__(256) assemble_kernel(AssembleParams p) {
         sxc[r * GPT_MAX_DIM + d] = okc ? p.Xc[(long)(c0 + r) * D + d] : 0.0;
         snc[r * GPT_MAX_DIM + d] = okc ? p.nc[(long)(c0 + r) * D + d] : 0;
     }
-    __shared__ double etab[64];
     if (tid < 64) etab[tid] = GPT_EXP2_64[tid];
+}
+
+// The SE / orders <= 1 value tiles have their OWN kernel: inside the generic kernel they inherited its 255 registers
+// (cov_eval covers Matern with K_nu of real order, Gibbs, Hermite recurrences ...) and ran at one CTA per SM --
+// 12% occupancy, 14% of the FP64 pipe, 250 GB/s of output (profiles/r02j_*).  Three CTAs per SM here.
+template <int FD>
+__global__ void __launch_bounds__(256, 3) assemble_se_low_kernel(AssembleParams p) {
+    if (p.lower_tiles_only && blockIdx.x > blockIdx.y) return;  // the Cholesky never reads tiles above the diagonal
+    __shared__ double sxr[TS * GPT_MAX_DIM];
+    __shared__ double sxc[TS * GPT_MAX_DIM];
+    __shared__ int32_t snr[TS * GPT_MAX_DIM];
+    __shared__ int32_t snc[TS * GPT_MAX_DIM];
+    __shared__ double etab[64];
+    const int r0 = blockIdx.y * TS, c0 = blockIdx.x * TS;
+    stage_tile_points(p, sxr, sxc, snr, snc, etab, r0, c0, threadIdx.x);
     __syncthreads();
-    if (p.cp.kid == GPT_KERNEL_SE && p.hyper_deriv < 0 && p.low_order && D <= 3) {
-        if (D == 1) assemble_tile_se_low<1>(p, sxr, snr, sxc, snc, etab, r0, c0, tid);
-        else if (D == 2) assemble_tile_se_low<2>(p, sxr, snr, sxc, snc, etab, r0, c0, tid);
-        else assemble_tile_se_low<3>(p, sxr, snr, sxc, snc, etab, r0, c0, tid);
-        return;
-    }
+    assemble_tile_se_low<FD>(p, sxr, snr, sxc, snc, etab, r0, c0, threadIdx.x);
+}
+
+__global__ void __launch_bounds__(256) assemble_kernel(AssembleParams p) {
+    if (p.lower_tiles_only && blockIdx.x > blockIdx.y) return;  // the Cholesky never reads tiles above the diagonal
+    __shared__ double sxr[TS * GPT_MAX_DIM];
+    __shared__ double sxc[TS * GPT_MAX_DIM];
+    __shared__ int32_t snr[TS * GPT_MAX_DIM];
+    __shared__ int32_t snc[TS * GPT_MAX_DIM];
+    __shared__ double etab[64];
+    const int r0 = blockIdx.y * TS, c0 = blockIdx.x * TS;
+    const int tid = threadIdx.x;
+    stage_tile_points(p, sxr, sxc, snr, snc, etab, r0, c0, tid);
+    __syncthreads();
     const int ty = tid >> 4, tx = tid & 15;
 #pragma unroll 1
     for (int a = 0; a < 4; a++) {
@@ -139,6 +156,12 @@ __global__ void cov_pairs_kernel(CovParams cp, int hyper_deriv, long npairs, con
 
 void launch_assemble(const AssembleParams& p, cudaStream_t s) {
     dim3 grid((p.cols_pad + TS - 1) / TS, (p.rows_pad + TS - 1) / TS);
+    if (p.cp.kid == GPT_KERNEL_SE && p.hyper_deriv < 0 && p.low_order && p.cp.D <= 3) {
+        if (p.cp.D == 1) assemble_se_low_kernel<1><<<grid, 256, 0, s>>>(p);
+        else if (p.cp.D == 2) assemble_se_low_kernel<2><<<grid, 256, 0, s>>>(p);
+        else assemble_se_low_kernel<3><<<grid, 256, 0, s>>>(p);
+        return;
+    }
     assemble_kernel<<<grid, 256, 0, s>>>(p);
 }
 
