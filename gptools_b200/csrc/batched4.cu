@@ -92,49 +92,6 @@ struct Lane {
 __device__ __forceinline__ int swz(int r) { return (BK == 16) ? ((r & 3) << 2) : (((r >> 1) & 1) << 2); }
 __device__ __forceinline__ int tix(int r, int c) { return (c / BK) * CHUNK + r * BK + ((c % BK) ^ swz(r)); }
 
-// ---- mbarrier / bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP) -------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
-    const uint32_t a = smem_u32(bar);
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(a), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-// L2 eviction policies for the operand stream: the 592 per-theta workspaces (1.4 MB each) cannot live in the 126 MB
-// L2 together, but the B operand of a job (a tile row / column shared by all jobs of one sweep column) is re-read by
-// the next job of the same CTA: B chunks are kept (evict_last), A chunks -- read once per column -- go first.
-__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
-    unsigned long long pol;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
-    unsigned long long pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar,
-                                         unsigned long long policy) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-            smem_u32(dst)),
-        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
-        : "memory");
-}
-// generic-proxy accesses to shared memory (the staging tile) ordered before the async-proxy writes of the ring
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 // one lane: chunk q of the current job -> ring slot q % STAGES
 __device__ __forceinline__ void issue_chunk(Smem& sm, int q) {
     const int s = q / CPT, kc = q % CPT, slt = q % STAGES;

@@ -358,21 +358,30 @@ __global__ void __launch_bounds__(256, 1) panel_trsm_kernel(double* __restrict__
     const int g = lane >> 2, t = lane & 3;
     const int r0 = blockIdx.x * TR_ROWS;
 
-    for (int idx = tid; idx < NB * 64; idx += 256) {
-        const int r = idx >> 6, c2 = (idx & 63) * 2;
-        cp_async16(Ls + r * LDB + c2, L11 + (long)r * ldl + c2);
+    // TMA-staged panel: every 1 KB row of L11 (128 rows) and of the A21 slab (64 rows) is ONE bulk async copy
+    // (cp.async.bulk -> UBLKCP) issued by one thread and completing on an mbarrier with a transaction count; no
+    // per-thread 16-byte copies, no wait_group.  The 8x8 diagonal blocks of Inv (64 B pieces) stay on cp.async.
+    __shared__ unsigned long long bar;
+    const int nrows_here = (rows - r0 < TR_ROWS) ? (rows - r0) : TR_ROWS;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int idx = tid; idx < TR_ROWS * 64; idx += 256) {
-        const int r = idx >> 6, c2 = (idx & 63) * 2;
-        if (r0 + r < rows) cp_async16(As + r * LDB + c2, A21 + (long)(r0 + r) * lda + c2);
-        else As[r * LDB + c2] = As[r * LDB + c2 + 1] = 0.0;
-    }
+    for (int idx = tid; idx < (TR_ROWS - nrows_here) * NB; idx += 256)   // rows beyond the matrix: zeros
+        As[(nrows_here + idx / NB) * LDB + (idx % NB)] = 0.0;
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) mbar_expect_tx(&bar, (uint32_t)((NB + nrows_here) * NB * sizeof(double)));
+    __syncthreads();  // the expected byte count is posted before any copy can complete
+    if (tid < NB) bulk_g2s(Ls + tid * LDB, L11 + (long)tid * ldl, NB * sizeof(double), &bar);
+    else if (tid - NB < nrows_here) bulk_g2s(As + (tid - NB) * LDB, A21 + (long)(r0 + tid - NB) * lda, NB * sizeof(double), &bar);
     for (int idx = tid; idx < NBLK * 32; idx += 256) {
         const int J = idx >> 5, rr = (idx >> 2) & 7, cc = (idx & 3) * 2;
         cp_async16(Xs + J * 64 + rr * 8 + cc, inv_k + (long)(8 * J + rr) * NB + 8 * J + cc);
     }
     cp_async_commit();
     cp_async_wait<0>();
+    mbar_wait(&bar, 0);
     __syncthreads();
 
     double* Aw = As + (warp * 8 + g) * LDB;  // this lane's row of the warp's 8-row slab
