@@ -214,6 +214,62 @@ def case_matern_real_nu():
         _hyperfd("hyperfd_matern_generic_nu%s" % str(nu).replace(".", "p"), gp, [0, 2], 4e-3)
 
 
+def case_hyper_mp():
+    """Hyper-parameter derivatives of the covariance pinned BEYOND finite-difference accuracy: the reference's own
+    mpmath covariance functions (kernel/matern.py:44-100 matern_function, kernel/gibbs.py:41-160 GibbsFunction1dArb with
+    tanh_warp_arb -- the functions its ArbitraryKernel differentiates with mpmath.diff, kernel/core.py:946-953) are
+    differentiated with mpmath.diff at 40 digits with respect to the inputs (observation derivative orders) AND one
+    hyperparameter.  Pairs are kept outside the generic Matern kernel's series zone (y > 5e-4), where the closed
+    form is the exact function."""
+    import mpmath
+    from gptools.kernel.matern import matern_function
+    from gptools.kernel.gibbs import GibbsFunction1dArb, tanh_warp_arb
+    mpmath.mp.dps = 40
+    rs = RandomState(11)
+
+    def run(name, fun, D, params, hyper_idx, npairs):
+        Xi = rs.rand(npairs, D) * 2.0
+        Xj = Xi + (0.05 + 0.6 * rs.rand(npairs, D)) * rs.choice([-1.0, 1.0], size=(npairs, D))
+        orders = []
+        for q in range(npairs):
+            oi = np.zeros(D, dtype=int)
+            oj = np.zeros(D, dtype=int)
+            c = q % 4
+            if c in (1, 3):
+                oi[rs.randint(D)] = 1
+            if c in (2, 3):
+                oj[rs.randint(D)] = 1
+            orders.append((oi, oj))
+        ni = np.array([o[0] for o in orders])
+        nj = np.array([o[1] for o in orders])
+        val = np.zeros(npairs)
+        dval = np.zeros((len(hyper_idx), npairs))
+
+        def f(*a):
+            xi, xj, th = a[:D], a[D:2 * D], a[2 * D:]
+            if D == 1:
+                return fun(xi[0], xj[0], *th)
+            return fun(tuple(xi), tuple(xj), *th)
+        for q in range(npairs):
+            point = [mpmath.mpf(float(v)) for v in Xi[q]] + [mpmath.mpf(float(v)) for v in Xj[q]] + \
+                    [mpmath.mpf(float(v)) for v in params]
+            base = tuple(int(v) for v in ni[q]) + tuple(int(v) for v in nj[q])
+            zero = (0,) * len(params)
+            val[q] = float(mpmath.diff(f, tuple(point), base + zero)) if sum(base) else float(f(*point))
+            for k_, pidx in enumerate(hyper_idx):
+                hd = [0] * len(params)
+                hd[pidx] = 1
+                dval[k_, q] = float(mpmath.diff(f, tuple(point), base + tuple(hd)))
+        save(name, params=np.array(params, dtype=float), Xi=Xi, Xj=Xj, ni=ni, nj=nj, val=val, idx=np.array(hyper_idx),
+             dval=dval)
+
+    run("hypermp_matern_nu2p5_1d", matern_function, 1, [1.4, 2.5, 0.6], [0, 2], 24)
+    run("hypermp_matern_nu2p2_1d", matern_function, 1, [1.4, 2.2, 0.6], [0, 2], 24)
+    run("hypermp_matern_nu2p5_2d", matern_function, 2, [0.9, 2.5, 0.5, 0.8], [0, 2, 3], 24)
+    gibbs = GibbsFunction1dArb(tanh_warp_arb)
+    run("hypermp_gibbs_tanh", gibbs, 1, [1.5, 0.6, 0.1, 0.05, 0.9], [0, 1, 2, 3, 4], 24)
+
+
 # ---------------------------------------------------------------- KAT-3: Gibbs-tanh + T + draw_sample
 def case_gibbs():
     k = g.GibbsKernel1dTanh(initial_params=[1.5, 0.6, 0.1, 0.05, 0.9],
@@ -562,7 +618,7 @@ def case_warped():
 if __name__ == "__main__":
     cases = [case_se2d, case_se_pairs, case_matern52, case_matern_generic, case_gibbs, case_c5_full, case_demo,
              case_c3, case_c2, case_noise, case_hyperfd, case_product, case_gibbs_profiles, case_warped,
-             case_matern_real_nu]
+             case_matern_real_nu, case_hyper_mp]
     only = set(sys.argv[1:])          # e.g. `make_golden.py case_hyperfd` regenerates one family
     for c in cases:
         if not only or c.__name__ in only:

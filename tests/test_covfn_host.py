@@ -240,3 +240,33 @@ def test_matern_real_and_integer_order_match_the_oracle(lib):
         fin = np.isfinite(want)
         assert np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(got[~fin & ~np.isnan(want)], want[~fin & ~np.isnan(want)])
         assert_close(got[fin], want[fin], rtol=1e-9, atol=1e-9, what="generic Matern nu=%g" % nu)
+
+
+# ---- hyper-derivatives pinned beyond finite-difference accuracy (round 2) --------------------------------------------
+HYPERMP = {"hypermp_matern_nu2p5_1d": [KERNEL_MATERN, 1], "hypermp_matern_nu2p2_1d": [KERNEL_MATERN],
+           "hypermp_matern_nu2p5_2d": [KERNEL_MATERN, 1], "hypermp_gibbs_tanh": [3]}
+
+
+def hypermp_check(evaluate, case, rtol=1e-12):
+    """``evaluate(kid, params, Xi, Xj, ni, nj, hyper_deriv)`` against the 40-digit mpmath derivatives of the reference's
+    own covariance functions (tests/golden/make_golden.py: case_hyper_mp).  Matern 5/2 is checked twice: through the
+    generic kernel and through Matern52Kernel (parameter vector without nu)."""
+    gd = load_golden(case)
+    for kid in HYPERMP[case]:
+        params, idx = gd["params"], [int(i) for i in gd["idx"]]
+        if kid == 1:                                      # Matern52: [sigma, l...]
+            params = np.delete(params, 1)
+            idx = [i if i == 0 else i - 1 for i in idx]
+        scale = np.abs(gd["val"]).max()
+        got = evaluate(kid, params, gd["Xi"], gd["Xj"], gd["ni"], gd["nj"], None)
+        assert_close(got, gd["val"], rtol=rtol, atol=rtol * scale, what="%s value (kernel %d)" % (case, kid))
+        for q, p in enumerate(idx):
+            got = evaluate(kid, params, gd["Xi"], gd["Xj"], gd["ni"], gd["nj"], p)
+            ref = gd["dval"][q]
+            assert_close(got, ref, rtol=rtol, atol=rtol * np.abs(ref).max(), what="%s d/dtheta_%d (kernel %d)" % (case, p, kid))
+
+
+@pytest.mark.parametrize("case", sorted(HYPERMP))
+def test_hyper_derivatives_against_mpmath_derivatives_of_the_reference_functions(lib, case):
+    hypermp_check(lambda kid, params, Xi, Xj, ni, nj, hd: pairs(lib, kid, params, Xi, Xj, ni, nj,
+                                                               hyper_deriv=-1 if hd is None else hd), case)

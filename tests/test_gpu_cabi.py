@@ -523,3 +523,12 @@ def test_blocked_cholesky_variants_vs_oracle(dev, M, pair_min, monkeypatch):
     pm, ps, pc = orc.predict(orc.KERNEL_SE, th, X, n, ref["L"], ref["alpha"], Xs, ns)
     assert_close(m, pm, rtol=1e-9, atol=1e-9, what="mean")
     assert np.all(np.abs(v - np.diag(pc)) <= 1e-9 * th[0] ** 2)
+
+
+@pytest.mark.parametrize("case", ["hypermp_matern_nu2p5_1d", "hypermp_matern_nu2p2_1d", "hypermp_matern_nu2p5_2d",
+                                  "hypermp_gibbs_tanh"])
+def test_hyper_derivatives_against_mpmath_derivatives_of_the_reference_functions(dev, case):
+    """gpt_cov_pairs with hyper_deriv on the device against 40-digit mpmath derivatives of the reference's own
+    covariance functions (the north-star tolerance 1e-9 with three orders of margin)."""
+    from test_covfn_host import hypermp_check
+    hypermp_check(lambda kid, params, Xi, Xj, ni, nj, hd: dev.cov_pairs(kid, params, Xi, Xj, ni, nj, hyper_deriv=hd), case)
