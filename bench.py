@@ -303,6 +303,7 @@ def run_ours(args, rank, world, local_rank):
     dev_t = torch.device("cuda", local_rank)
     distributed = world > 1
     if distributed:
+        os.environ["NCCL_DEBUG"] = os.environ.get("GPT_NCCL_DEBUG", "WARN")   # keep stdout to the ONE JSON line
         dist.init_process_group("nccl", device_id=dev_t)
 
     X, n, y, err = c3_problem()

@@ -22,6 +22,10 @@ struct DevBuf {
     size_t bytes = 0;
 };
 
+struct GradSlots {
+    int s[GPT_MAX_PARAMS];
+};
+
 }  // namespace
 
 struct gpt_handle {
@@ -347,8 +351,28 @@ int refresh_diag(gpt_handle* h) {
     return 0;
 }
 
-// Factor the matrix currently in h->A (Mp x Mp, K_tot with identity padding), then alpha and ll.
+// Factor the matrix currently in h->A (Mp x Mp, K_tot with identity padding), then alpha; ll is left in h->llred and
+// the LAPACK-style info word in h->info (device).  No synchronisation.
+int factor_and_solve_device(gpt_handle* h);
+
+// ... and bring ll / info back to the host.
 int factor_and_solve(gpt_handle* h, double* ll, int* status) {
+    int rc = factor_and_solve_device(h);
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    double hll = 0.0;
+    int hinfo = 0;
+    CUDA_OK(h, cudaMemcpyAsync(&hll, h->llred.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(h, cudaMemcpyAsync(&hinfo, h->info.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(h, cudaStreamSynchronize(s));
+    if (hinfo > h->M) hinfo = 0;  // only padding rows (identity) could report beyond M; cannot happen, be safe
+    *status = hinfo;
+    *ll = hll;
+    h->factor_valid = (hinfo == 0);
+    return 0;
+}
+
+int factor_and_solve_device(gpt_handle* h) {
     cudaStream_t s = h->stream;
     const int Mp = h->Mp, M = h->M, nblk = Mp / NB;
     int rc;
@@ -372,16 +396,7 @@ int factor_and_solve(gpt_handle* h, double* ll, int* status) {
     if ((rc = ensure(h, h->llred, sizeof(double)))) return rc;
     launch_ll_reduce(ptr<double>(h->z), M, ptr<double>(h->logdet), nblk, ptr<double>(h->llred), s);
     h->launches++;
-    double hll = 0.0;
-    int hinfo = 0;
-    CUDA_OK(h, cudaMemcpyAsync(&hll, h->llred.p, sizeof(double), cudaMemcpyDeviceToHost, s));
-    CUDA_OK(h, cudaMemcpyAsync(&hinfo, h->info.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-    CUDA_OK(h, cudaStreamSynchronize(s));
-    if (hinfo > M) hinfo = 0;  // only padding rows (identity) could report beyond M; cannot happen, be safe
-    *status = hinfo;
-    *ll = hll;
-    h->factor_valid = (hinfo == 0);
-    return 0;
+    return check_launch(h);
 }
 
 // K_tot from a latent covariance already in h->Klat (Np x Np, symmetric, noise included): T K T' + diag
@@ -744,45 +759,16 @@ int gpt_compute_Kij(gpt_handle* h, int kernel_id, int D, int nparams, const doub
     return 0;
 }
 
-int gpt_ll(gpt_handle* h, const double* params, double noise_sigma, double* ll, double* grad,
-           const int32_t* grad_idx, int P, int* status) {
-    if (!h || !params || !ll || !status) return fail(h, GPT_ERR_USAGE, "gpt_ll: bad arguments");
-    if (h->M < 1 || h->kid < 0) return fail(h, GPT_ERR_USAGE, "gpt_ll: set_data / set_kernel first");
-    if (!supported_kernel(h->kid, h->D, h->nparams)) return fail(h, GPT_ERR_UNSUPPORTED, "gpt_ll: kernel/dimension unsupported");
-    if (grad && P > 0) {
-        if (P > GPT_MAX_PARAMS || !grad_idx) return fail(h, GPT_ERR_USAGE, "gpt_ll: bad gradient request");
-        for (int q = 0; q < P; q++) {
-            if (grad_idx[q] < 0 || grad_idx[q] > h->nparams) return fail(h, GPT_ERR_USAGE, "gpt_ll: bad grad_idx");
-            if (grad_idx[q] == 1 && h->kid == GPT_KERNEL_MATERN)
-                return fail(h, GPT_ERR_UNSUPPORTED, "hyper-parameter derivatives: d/dnu of the Matern kernel is not available");
-        }
-    }
-    CUDA_OK(h, cudaSetDevice(h->device));
+// Gradient of the resident factorisation, device part: h->gout[0 .. nkern) = the kernel-parameter entries (slot[i] is the
+// position of entry i in the caller's grad_idx), h->gout[GPT_MAX_PARAMS] = tr K_tot^{-1}, [GPT_MAX_PARAMS + 1] = alpha^T alpha.
+static int gradient_device(gpt_handle* h, const int32_t* grad_idx, int P, int* slot, int* nkern, int* noise_slot_out) {
     cudaStream_t s = h->stream;
-    h->factor_valid = false;
-    cov_params_init(h->cp, h->kid, h->D, h->nparams, params);
-    h->noise_sigma = noise_sigma;
     int rc;
-    if (h->hasT) {
-        if ((rc = ensure(h, h->Klat, (size_t)h->Np * h->Np * sizeof(double)))) return rc;
-        if ((rc = assemble_train(h, h->cp, noise_sigma, -1, ptr<double>(h->Klat), h->Np, false))) return rc;
-        if ((rc = transform_latent(h))) return rc;
-    } else {
-        if ((rc = ensure(h, h->A, (size_t)h->Mp * h->Mp * sizeof(double)))) return rc;
-        if ((rc = assemble_train(h, h->cp, noise_sigma, -1, ptr<double>(h->A), h->Mp, true, true))) return rc;
-    }
-    if ((rc = factor_and_solve(h, ll, status))) return rc;
-    if (!(grad && P > 0)) return 0;
-    for (int q = 0; q < P; q++) grad[q] = 0.0;
-    if (*status != 0) return 0;
-
-    // ---- gradient: 1/2 tr((alpha alpha^T - K^-1) dK_p), dK tiles regenerated on the fly ----
     if ((rc = compute_Kinv(h))) return rc;
     GradReduceParams gp;
     gp.cp = h->cp;
     gp.X = ptr<double>(h->X); gp.n = ptr<int32_t>(h->n); gp.N = h->N;
     gp.nidx = 0;
-    int slot[GPT_MAX_PARAMS];
     int noise_slot = -1;
     for (int q = 0; q < P; q++) {
         if (grad_idx[q] == h->nparams) noise_slot = q;
@@ -826,11 +812,50 @@ int gpt_ll(gpt_handle* h, const double* params, double noise_sigma, double* ll, 
     }
     launch_trace_and_sumsq(ptr<double>(h->Kinv), h->Mp, ptr<double>(h->alpha), h->M, ptr<double>(h->gout) + GPT_MAX_PARAMS, s);
     h->launches++;
-    if ((rc = check_launch(h))) return rc;
+    *nkern = gp.nidx;
+    *noise_slot_out = noise_slot;
+    return check_launch(h);
+}
+
+int gpt_ll(gpt_handle* h, const double* params, double noise_sigma, double* ll, double* grad,
+           const int32_t* grad_idx, int P, int* status) {
+    if (!h || !params || !ll || !status) return fail(h, GPT_ERR_USAGE, "gpt_ll: bad arguments");
+    if (h->M < 1 || h->kid < 0) return fail(h, GPT_ERR_USAGE, "gpt_ll: set_data / set_kernel first");
+    if (!supported_kernel(h->kid, h->D, h->nparams)) return fail(h, GPT_ERR_UNSUPPORTED, "gpt_ll: kernel/dimension unsupported");
+    if (grad && P > 0) {
+        if (P > GPT_MAX_PARAMS || !grad_idx) return fail(h, GPT_ERR_USAGE, "gpt_ll: bad gradient request");
+        for (int q = 0; q < P; q++) {
+            if (grad_idx[q] < 0 || grad_idx[q] > h->nparams) return fail(h, GPT_ERR_USAGE, "gpt_ll: bad grad_idx");
+            if (grad_idx[q] == 1 && h->kid == GPT_KERNEL_MATERN)
+                return fail(h, GPT_ERR_UNSUPPORTED, "hyper-parameter derivatives: d/dnu of the Matern kernel is not available");
+        }
+    }
+    CUDA_OK(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    h->factor_valid = false;
+    cov_params_init(h->cp, h->kid, h->D, h->nparams, params);
+    h->noise_sigma = noise_sigma;
+    int rc;
+    if (h->hasT) {
+        if ((rc = ensure(h, h->Klat, (size_t)h->Np * h->Np * sizeof(double)))) return rc;
+        if ((rc = assemble_train(h, h->cp, noise_sigma, -1, ptr<double>(h->Klat), h->Np, false))) return rc;
+        if ((rc = transform_latent(h))) return rc;
+    } else {
+        if ((rc = ensure(h, h->A, (size_t)h->Mp * h->Mp * sizeof(double)))) return rc;
+        if ((rc = assemble_train(h, h->cp, noise_sigma, -1, ptr<double>(h->A), h->Mp, true, true))) return rc;
+    }
+    if ((rc = factor_and_solve(h, ll, status))) return rc;
+    if (!(grad && P > 0)) return 0;
+    for (int q = 0; q < P; q++) grad[q] = 0.0;
+    if (*status != 0) return 0;
+
+    // ---- gradient: 1/2 tr((alpha alpha^T - K^-1) dK_p), dK tiles regenerated on the fly ----
+    int slot[GPT_MAX_PARAMS], nkern = 0, noise_slot = -1;
+    if ((rc = gradient_device(h, grad_idx, P, slot, &nkern, &noise_slot))) return rc;
     double hg[GPT_MAX_PARAMS + 2];
     CUDA_OK(h, cudaMemcpyAsync(hg, h->gout.p, sizeof(hg), cudaMemcpyDeviceToHost, s));
     CUDA_OK(h, cudaStreamSynchronize(s));
-    for (int i = 0; i < gp.nidx; i++) grad[slot[i]] = hg[i];
+    for (int i = 0; i < nkern; i++) grad[slot[i]] = hg[i];
     if (noise_slot >= 0) {
         // gaussian_process.py:1484-1488: dK = 2 sigma_n I_M  (identity over the observations, also with T)
         grad[noise_slot] = noise_sigma * (hg[GPT_MAX_PARAMS + 1] - hg[GPT_MAX_PARAMS]);
@@ -1281,9 +1306,96 @@ int gpt_draw_sample(gpt_handle* h, int Ms, int S, const double* mean, const doub
 // ------------------------------------------------------------------------------------------------
 // batched many-theta path
 // ------------------------------------------------------------------------------------------------
+// ll / gradient scalars of one theta from the handle's scratch into row b of the batch outputs
+__global__ void batch_row_scatter_kernel(const double* __restrict__ llred, const int* __restrict__ info, int M,
+                                         const double* __restrict__ gout, int P, int nkern, int noise_slot,
+                                         double noise_sigma, double* __restrict__ ll, int* __restrict__ status,
+                                         double* __restrict__ grad, int b, GradSlots slots) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int inf = info[0];
+    if (inf > M) inf = 0;
+    ll[b] = llred[0];
+    status[b] = inf;
+    if (grad != nullptr) {
+        for (int q = 0; q < P; q++) grad[(size_t)b * P + q] = 0.0;
+        if (inf == 0) {
+            for (int i = 0; i < nkern; i++) grad[(size_t)b * P + slots.s[i]] = gout[i];
+            if (noise_slot >= 0) grad[(size_t)b * P + noise_slot] = noise_sigma * (gout[GPT_MAX_PARAMS + 1] - gout[GPT_MAX_PARAMS]);
+        }
+    }
+}
+
+// Batches the persistent kernel does not take -- a transformation matrix T (the T K T^T products are GEMMs that fill the
+// device on their own) or more than 2048 observations: the thetas run one after the other through the single-matrix
+// path (assembly, [T K T^T,] blocked Cholesky, solves, inverse + trace reduction) on the handle's stream, every scalar
+// stays on the device and lands in row b of the outputs, and nothing synchronises between thetas.
+static int batched_serial(gpt_handle* h, int B, const double* d_thetas, const double* d_y, double* d_ll, double* d_grad,
+                          const int32_t* grad_idx, int P, int* d_status, double* d_alpha) {
+    cudaStream_t s = h->stream;
+    const int np1 = h->nparams + 1, M = h->M;
+    const bool want_grad = (d_grad && P > 0);
+    if (want_grad) {
+        if (P > GPT_MAX_PARAMS || !grad_idx) return fail(h, GPT_ERR_USAGE, "gpt_ll_batched: bad gradient request");
+        for (int q = 0; q < P; q++) {
+            if (grad_idx[q] < 0 || grad_idx[q] > h->nparams) return fail(h, GPT_ERR_USAGE, "gpt_ll_batched: bad grad_idx");
+            if (grad_idx[q] == 1 && h->kid == GPT_KERNEL_MATERN)
+                return fail(h, GPT_ERR_UNSUPPORTED, "hyper-parameter derivatives: d/dnu of the Matern kernel is not available");
+        }
+    }
+    std::vector<double> th((size_t)B * np1);   // CovParams travel by value in the launches
+    CUDA_OK(h, cudaMemcpyAsync(th.data(), d_thetas, sizeof(double) * th.size(), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(h, cudaStreamSynchronize(s));
+    int rc;
+    DevBuf ykeep;
+    if (d_y) {  // per-theta right-hand sides: h->y is restored afterwards
+        if ((rc = ensure(h, ykeep, sizeof(double) * M))) return rc;
+        CUDA_OK(h, cudaMemcpyAsync(ykeep.p, h->y.p, sizeof(double) * M, cudaMemcpyDeviceToDevice, s));
+    }
+    h->factor_valid = false;
+    for (int b = 0; b < B && !rc; b++) {
+        const double* tb = th.data() + (size_t)b * np1;
+        cov_params_init(h->cp, h->kid, h->D, h->nparams, tb);
+        h->noise_sigma = tb[h->nparams];
+        if (d_y) CUDA_OK(h, cudaMemcpyAsync(h->y.p, d_y + (size_t)b * M, sizeof(double) * M, cudaMemcpyDeviceToDevice, s));
+        if (h->hasT) {
+            if ((rc = ensure(h, h->Klat, (size_t)h->Np * h->Np * sizeof(double)))) break;
+            if ((rc = assemble_train(h, h->cp, h->noise_sigma, -1, ptr<double>(h->Klat), h->Np, false))) break;
+            if ((rc = transform_latent(h))) break;
+        } else {
+            if ((rc = ensure(h, h->A, (size_t)h->Mp * h->Mp * sizeof(double)))) break;
+            if ((rc = assemble_train(h, h->cp, h->noise_sigma, -1, ptr<double>(h->A), h->Mp, true, true))) break;
+        }
+        if ((rc = factor_and_solve_device(h))) break;
+        if (d_alpha) CUDA_OK(h, cudaMemcpyAsync(d_alpha + (size_t)b * M, h->alpha.p, sizeof(double) * M, cudaMemcpyDeviceToDevice, s));
+        GradSlots slots;
+        int nkern = 0, noise_slot = -1;
+        if (want_grad) {
+            if ((rc = gradient_device(h, grad_idx, P, slots.s, &nkern, &noise_slot))) break;
+        } else if ((rc = ensure(h, h->gout, sizeof(double) * (GPT_MAX_PARAMS + 2)))) {
+            break;
+        }
+        batch_row_scatter_kernel<<<1, 32, 0, s>>>(ptr<double>(h->llred), ptr<int>(h->info), M, ptr<double>(h->gout),
+                                                  want_grad ? P : 0, nkern, noise_slot, h->noise_sigma, d_ll, d_status,
+                                                  want_grad ? d_grad : nullptr, b, slots);
+        h->launches++;
+    }
+    if (d_y) {
+        cudaMemcpyAsync(h->y.p, ykeep.p, sizeof(double) * M, cudaMemcpyDeviceToDevice, s);
+        cudaStreamSynchronize(s);
+        release(ykeep);
+    }
+    if (rc) return rc;
+    return check_launch(h);
+}
+
 static int batched_common(gpt_handle* h, int B, const double* d_thetas, const double* d_y, double* d_ll,
                           double* d_grad, const int32_t* grad_idx, int P, int* d_status, double* d_alpha) {
-    if (h->hasT) return fail(h, GPT_ERR_UNSUPPORTED, "gpt_ll_batched: transformed observations (T) use gpt_ll");
+    if (h->hasT || (h->M + 63) / 64 > 32) {
+        if (h->kid == GPT_KERNEL_GIBBS_AUX)
+            return fail(h, GPT_ERR_UNSUPPORTED, "gpt_ll_batched: the per-point length scales of GPT_GIBBS_AUX depend on theta; use gpt_ll");
+        if (!supported_kernel(h->kid, h->D, h->nparams)) return fail(h, GPT_ERR_UNSUPPORTED, "gpt_ll_batched: kernel unsupported");
+        return batched_serial(h, B, d_thetas, d_y, d_ll, d_grad, grad_idx, P, d_status, d_alpha);
+    }
     if (h->kid == GPT_KERNEL_GIBBS_AUX)
         return fail(h, GPT_ERR_UNSUPPORTED, "gpt_ll_batched: the per-point length scales of GPT_GIBBS_AUX depend on theta; use gpt_ll");
     if (!supported_kernel(h->kid, h->D, h->nparams)) return fail(h, GPT_ERR_UNSUPPORTED, "gpt_ll_batched: kernel unsupported");
@@ -1291,7 +1403,6 @@ static int batched_common(gpt_handle* h, int B, const double* d_thetas, const do
     BatchedParams bp;
     bp.kid = h->kid; bp.D = h->D; bp.nparams = h->nparams;
     bp.M = h->M; bp.nT = (h->M + 63) / 64;
-    if (bp.nT > 32) return fail(h, GPT_ERR_UNSUPPORTED, "gpt_ll_batched: M > 2048 uses gpt_ll");
     bp.X = ptr<double>(h->X); bp.n = ptr<int32_t>(h->n);
     bp.low_order = (h->max_order <= 1) ? 1 : 0;
     bp.y = d_y ? d_y : ptr<double>(h->y); bp.y_stride = d_y ? h->M : 0;

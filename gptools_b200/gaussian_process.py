@@ -586,25 +586,25 @@ class GaussianProcess(object):
         if with_deriv is None:
             with_deriv = bool(self.use_hyper_deriv)
         if not self._batchable(with_deriv):
-            # host kernels, transformed observations, kernels whose per-point columns depend on theta, M > 2048
+            # host kernels and kernels whose per-point columns depend on theta
             return self._batch_by_loop(thetas, with_deriv)
         plan = self._batch_prepare(thetas, with_deriv)
         res = plan["dev"].ll_batched(plan["full_eval"], grad_idx=plan["grad_idx"], y_batch=plan["y_batch"],
                                      return_alpha=plan["need_alpha"])
         return self._batch_finish(plan, res[0], res[1], res[2], res[3] if plan["need_alpha"] else None)
 
-    #: largest number of observations the batched device entry takes (32 tiles of 64 rows, gptb200.h gpt_ll_batched)
-    BATCHED_MAX_M = 2048
+    #: observations up to which ``gpt_ll_batched`` runs its persistent many-theta kernel (32 tiles of 64 rows); beyond
+    #: that, and with a transformation matrix, the same call runs the thetas back to back through the single-matrix path
+    BATCHED_KERNEL_MAX_M = 2048
 
     def _batchable(self, with_deriv):
         """True when ``gpt_ll_batched`` can evaluate this GP: an accelerated kernel with theta-independent point
-        columns, no transformation matrix, at most BATCHED_MAX_M observations, and -- with gradients -- free
-        kernel parameters inside the batched gradient slots.  Everything else takes the per-theta loop."""
-        if not self._device_mode() or self.T is not None or self.k.device_points_key() is not None:
+        columns and -- for the persistent kernel with gradients -- free kernel parameters inside its gradient slots.
+        Everything else (host kernels, GibbsKernel1d with a user length-scale function) takes the per-theta loop."""
+        if not self._device_mode() or self.k.device_points_key() is not None:
             return False
-        if len(self.y) > self.BATCHED_MAX_M:
-            return False
-        if not self.k.batchable(with_deriv):
+        persistent = self.T is None and len(self.y) <= self.BATCHED_KERNEL_MAX_M
+        if persistent and not self.k.batchable(with_deriv):
             return False
         return True
 

@@ -106,7 +106,12 @@ int gpt_get_K(gpt_handle* h, double* K /* N x N latent covariance of the last gp
  *   thetas   B x (nparams + 1): kernel params then sigma_n
  *   y_batch  B x M or NULL (per-theta mean-subtracted targets)
  *   ll (B), grad (B x P) or NULL, status (B), alpha_out (B x M) or NULL
- * Requires T == NULL. One persistent CTA per theta; see DESIGN.md. */
+ * Up to 2048 observations without a transformation matrix: ONE launch of the persistent many-theta kernel (one CTA
+ * per theta, four per SM); gradients of kernels other than SE are limited to parameter
+ * indices < 7 there.  With a transformation matrix T, or beyond 2048 observations, the same call runs the thetas back
+ * to back through the single-matrix path (assembly, T K T^T, blocked Cholesky, solves, inverse + trace reduction) on
+ * the handle's stream: every scalar stays on the device, nothing synchronises between thetas, one copy at the end.
+ * GPT_GIBBS_AUX (per-point columns that depend on theta) is not batched. */
 int gpt_ll_batched(gpt_handle* h, int B, const double* thetas, const double* y_batch, double* ll, double* grad,
                    const int32_t* grad_idx, int P, int* status, double* alpha_out);
 /* Same, with thetas / outputs already resident in device memory (raw device pointers). */

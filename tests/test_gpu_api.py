@@ -503,3 +503,42 @@ def test_matern_real_order_through_the_class(case):
     assert_close(gp2.ll_deriv, gh["ll_grad_fd"], rtol=2e-5, atol=2e-6 * np.abs(gh["ll_grad_fd"]).max(), what="ll gradient")
     fb, gb = gp2.update_hyperparameters_batch(np.array([gh["params"][[0, 2]], gh["params"][[0, 2]] * 1.05]))
     assert_close(-gb[0], gp2.ll_deriv, rtol=1e-8, atol=1e-9 * np.abs(gp2.ll_deriv).max(), what="batched gradient")
+
+
+def test_batched_entry_with_T_and_beyond_2048_observations():
+    """Round 2: gpt_ll_batched also serves GPs with a transformation matrix (config-5 walkers) and M > 2048 -- the thetas
+    run back to back on the device inside ONE C call -- and returns what the per-theta path returns."""
+    rs = np.random.RandomState(0)
+    Nq, Mo, W = 600, 60, 80
+    Xq = np.linspace(0, 1.1, Nq)
+    T = np.zeros((Mo, Nq))
+    for i, s in enumerate(rs.randint(0, Nq - W, size=Mo)):
+        T[i, s:s + W] = 1.1 / Nq
+    k = g.GibbsKernel1dTanh(initial_params=[1.5, 0.6, 0.1, 0.05, 0.9],
+                            param_bounds=[(0, 10), (0, 5), (0, 5), (0, 1), (0, 2)])
+    gp = g.GaussianProcess(k, use_hyper_deriv=True)
+    gp.add_data(Xq, rs.rand(Mo) * 0.3 + 0.1, err_y=0.02, T=T)
+    gp.add_data(0, 0, n=1)
+    assert gp._batchable(True)
+    th = np.array([1.5, 0.6, 0.1, 0.05, 0.9]) * np.exp(0.05 * rs.randn(6, 5))
+    n0 = gp._dev().launch_count()
+    f, df = gp.update_hyperparameters_batch(th)
+    assert gp._dev().launch_count() > n0
+    for b in (0, 3, 5):
+        fs, dfs = gp.update_hyperparameters(th[b])
+        assert_close(f[b], fs, rtol=1e-11, what="ll with T, row %d" % b)
+        assert_close(df[b], dfs, rtol=1e-8, atol=1e-9 * np.abs(dfs).max(), what="gradient with T, row %d" % b)
+    # M = 2304 > 2048 without T: same call, single-matrix path per theta
+    X = np.sort(rs.rand(2304)) * 20
+    k2 = g.SquaredExponentialKernel(initial_params=[1.0, 0.7], param_bounds=[(0, 10)] * 2)
+    gp2 = g.GaussianProcess(k2, X=X, y=np.sin(X) + 0.05 * rs.randn(2304), err_y=0.05, use_hyper_deriv=True)
+    th2 = np.array([[1.0, 0.7], [1.2, 0.5], [0.8, 1.0]])
+    f2, df2 = gp2.update_hyperparameters_batch(th2)
+    for b in range(3):
+        fs, dfs = gp2.update_hyperparameters(th2[b])
+        assert_close(f2[b], fs, rtol=1e-11, what="ll at M = 2304, row %d" % b)
+        assert_close(df2[b], dfs, rtol=1e-8, atol=1e-9 * np.abs(dfs).max(), what="gradient at M = 2304, row %d" % b)
+    # a theta that is not positive definite is flagged, the others are unaffected
+    bad = np.array([[1.0, 0.7], [1.0, 1e3], [1.1, 0.6]])
+    fb = gp2.update_hyperparameters_batch(bad, with_deriv=False)
+    assert np.isfinite(fb[0]) and np.isfinite(fb[2])

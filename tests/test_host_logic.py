@@ -473,8 +473,8 @@ def test_binary_kernel_parameters_are_write_through():
 
 
 def test_batched_entry_falls_back_where_the_device_kernel_cannot_go():
-    """M > 2048 (32 tiles) and free Matern parameters beyond the batched gradient slots take the per-theta loop
-    instead of raising; Matern rows with an invalid order (nu <= 0) evaluate to inf."""
+    """Free Matern parameters beyond the persistent kernel's gradient slots take the per-theta loop instead of raising;
+    Matern rows with an invalid order (nu <= 0) evaluate to inf; T and M > 2048 stay on the batched C entry."""
     rs = np.random.RandomState(0)
     X = np.sort(rs.rand(40)) * 3
     k = g.MaternKernel(num_dim=1, initial_params=[1.0, 2.5, 0.8], param_bounds=[(0, 10), (-5, 10), (0, 10)])
@@ -484,14 +484,23 @@ def test_batched_entry_falls_back_where_the_device_kernel_cannot_go():
     f = gp.update_hyperparameters_batch(th, with_deriv=False)
     assert np.isfinite(f[0]) and np.isinf(f[1]) and np.isfinite(f[2])
     assert "ll_batched" in gp._dev_obj.calls
-    gp.BATCHED_MAX_M = 16                                  # pretend the data is beyond the batched kernel's size
-    gp._dev_obj.calls = []
-    f2 = gp.update_hyperparameters_batch(th[[0, 2]], with_deriv=False)
-    assert "ll_batched" not in gp._dev_obj.calls and gp._dev_obj.calls.count("ll") == 2
-    assert_close(f2, f[[0, 2]], rtol=1e-12)
     k6 = g.MaternKernel(num_dim=6, initial_params=[1.0, 2.5] + [1.0] * 6, fixed_params=[False, True] + [False] * 6,
                         param_bounds=[(0, 10)] * 8)
     assert k6.batchable(False) and not k6.batchable(True)    # l_6 is parameter 7: outside the gradient slots
+    X6 = rs.rand(12, 6)
+    gp6 = with_fake(g.GaussianProcess(k6, X=X6, y=np.sin(X6).sum(1), err_y=0.05, use_hyper_deriv=True))
+    assert not gp6._batchable(True) and gp6._batchable(False)
+    gp6.BATCHED_KERNEL_MAX_M = 4                           # beyond the persistent kernel: the call runs the thetas serially
+    assert gp6._batchable(True)
+    # transformed observations stay on the batched entry (gpt_ll_batched runs them back to back on the device)
+    kt = g.SquaredExponentialKernel(initial_params=[1.0, 0.5], param_bounds=[(0, 10)] * 2)
+    gpt_ = with_fake(g.GaussianProcess(kt))
+    gpt_.add_data(np.linspace(0, 1, 6), [0.5, 0.7], err_y=0.1, T=np.array([[0.5, 0.5, 0, 0, 0, 0], [0, 0, 0, 0.25, 0.25, 0.5]]))
+    gpt_._dev_obj.calls = []
+    thT = np.array([[1.0, 0.5], [1.2, 0.4]])
+    fT = gpt_.update_hyperparameters_batch(thT, with_deriv=False)
+    assert gpt_._dev_obj.calls.count("ll_batched") == 1 and "ll" not in gpt_._dev_obj.calls
+    assert_close(fT[1], gpt_.update_hyperparameters(thT[1]), rtol=1e-12)
 
 
 def test_condense_duplicates_prunes_unused_quadrature_points_and_remove_outliers_with_T():

@@ -94,6 +94,16 @@ def c5():
     td, (samp, sst) = timed(lambda: d.draw_sample(mean, cov, rv, 1e3 * 2.220446049250313e-16), 3)
     print("C5 Gibbs+T N=4001 M=501: ll %.4f s (status %d ll %.6f); predict full cov 400 pts %.4f s; draw 1000 samples %.4f s (status %d)" % (
         t, st, ll, tp, td, sst))
+    # 64 walkers: one gpt_ll_batched call (thetas back to back on the device) against 64 gpt_ll calls
+    B = 64
+    ths = np.hstack([th * np.exp(0.03 * rs.randn(B, 5)), np.zeros((B, 1))])
+    gi = [0, 1, 2, 3, 4]
+    tb, (llb, gb, stb) = timed(lambda: d.ll_batched(ths, grad_idx=gi), 1)
+    tl, _ = timed(lambda: [d.ll(ths[b, :5], 0.0, grad_idx=gi) for b in range(B)], 1)
+    tbv, _ = timed(lambda: d.ll_batched(ths), 1)
+    tlv, _ = timed(lambda: [d.ll(ths[b, :5], 0.0) for b in range(B)], 1)
+    print("C5 64 thetas, ll+grad: gpt_ll_batched %.4f s (%.2f ms / theta), 64 x gpt_ll %.4f s; ll only: %.4f s against %.4f s; all ok %s" % (
+        tb, 1e3 * tb / B, tl, tbv, tlv, (stb == 0).all()))
 
 
 if __name__ == "__main__":
