@@ -12,6 +12,38 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GPTB200_LIB", os.path.join(_HERE, "csrc", "libgptb200.so"))  # override: development builds
 
 GPT_SE, GPT_MATERN52, GPT_MATERN, GPT_GIBBS_TANH = 0, 1, 2, 3
+GPT_COMPOSITE = 5
+MAX_LEAVES, MAX_TERMS, MAX_PARAMS = 4, 8, 10
+
+
+class CompositeId(int):
+    """Kernel id GPT_COMPOSITE together with the structure ``gpt_define_composite`` takes: the operand kernels in
+    parameter order and the product terms (bit masks over the operands) whose sum is the kernel."""
+
+    def __new__(cls, leaf_kids, leaf_nparams, term_masks):
+        obj = int.__new__(cls, GPT_COMPOSITE)
+        obj.leaf_kids = tuple(int(k) for k in leaf_kids)
+        obj.leaf_nparams = tuple(int(k) for k in leaf_nparams)
+        obj.term_masks = tuple(int(k) for k in term_masks)
+        return obj
+
+    @property
+    def structure(self):
+        return (self.leaf_kids, self.leaf_nparams, self.term_masks)
+
+    def __eq__(self, other):
+        if isinstance(other, CompositeId):
+            return self.structure == other.structure
+        return int(self) == other
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+    def __hash__(self):
+        return hash((GPT_COMPOSITE,) + self.structure)
+
+    def __repr__(self):
+        return "CompositeId(%r, %r, %r)" % self.structure
 
 _c_double_p = ctypes.POINTER(ctypes.c_double)
 _c_int32_p = ctypes.POINTER(ctypes.c_int32)
@@ -32,6 +64,7 @@ SIGNATURES = {
                                     _c_double_p, _c_double_p, _c_double_p]),
     "gpt_set_y": (ctypes.c_int, [_vp, _c_double_p]),
     "gpt_set_kernel": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_double]),
+    "gpt_define_composite": (ctypes.c_int, [_vp, ctypes.c_int, _c_int32_p, _c_int32_p, ctypes.c_int, _c_int32_p]),
     "gpt_cov_pairs": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_double_p, ctypes.c_int,
                                      ctypes.c_int64, _c_double_p, _c_double_p, _c_int32_p, _c_int32_p, _c_double_p]),
     "gpt_compute_Kij": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_double_p, ctypes.c_int,
@@ -176,7 +209,30 @@ class Device(object):
         y = _f64(y, (self.M,))
         self._check(self._lib.gpt_set_y(self._h, _dp(y)), "gpt_set_y")
 
+    def define_composite(self, cid):
+        """Make ``cid`` (a CompositeId) the structure behind kernel id GPT_COMPOSITE on this handle (no-op when it
+        already is)."""
+        if getattr(self, "_composite", None) is not None and self._composite == cid:
+            return
+        kids, nps, masks = _i32(cid.leaf_kids), _i32(cid.leaf_nparams), _i32(cid.term_masks)
+        self._check(self._lib.gpt_define_composite(self._h, len(kids), _ip(kids), _ip(nps), len(masks), _ip(masks)),
+                    "gpt_define_composite")
+        self._composite = cid
+
+    def _own_structure(self):
+        """Re-establish the structure of the kernel given to ``set_kernel`` (another composite may have been evaluated
+        through ``cov_pairs`` / ``compute_Kij`` on this handle since)."""
+        if getattr(self, "_kernel_cid", None) is not None:
+            self.define_composite(self._kernel_cid)
+
+    def _prepare_kernel_id(self, kernel_id):
+        if isinstance(kernel_id, CompositeId):
+            self.define_composite(kernel_id)
+        return int(kernel_id)
+
     def set_kernel(self, kernel_id, nparams, diag_factor):
+        self._prepare_kernel_id(kernel_id)
+        self._kernel_cid = kernel_id if isinstance(kernel_id, CompositeId) else None
         self._check(self._lib.gpt_set_kernel(self._h, int(kernel_id), int(nparams), float(diag_factor)), "gpt_set_kernel")
         self.kernel_id, self.nparams = int(kernel_id), int(nparams)
 
@@ -190,7 +246,7 @@ class Device(object):
         params = _f64(params)
         out = np.empty(npairs, dtype=np.float64)
         hd = -1 if hyper_deriv is None else int(hyper_deriv)
-        self._check(self._lib.gpt_cov_pairs(self._h, int(kernel_id), D, len(params), _dp(params), hd, npairs, _dp(Xi),
+        self._check(self._lib.gpt_cov_pairs(self._h, self._prepare_kernel_id(kernel_id), D, len(params), _dp(params), hd, npairs, _dp(Xi),
                                             _dp(Xj), _ip(ni), _ip(nj), _dp(out)), "gpt_cov_pairs")
         return out
 
@@ -207,13 +263,14 @@ class Device(object):
         params = _f64(params)
         out = np.empty((Mi, Mj), dtype=np.float64)
         hd = -1 if hyper_deriv is None else int(hyper_deriv)
-        self._check(self._lib.gpt_compute_Kij(self._h, int(kernel_id), D, len(params), _dp(params), hd, Mi, _dp(Xi),
+        self._check(self._lib.gpt_compute_Kij(self._h, self._prepare_kernel_id(kernel_id), D, len(params), _dp(params), hd, Mi, _dp(Xi),
                                               _ip(ni), Mj, _dp(Xj), _ip(nj), _dp(out)), "gpt_compute_Kij")
         return out
 
     # -- likelihood -----------------------------------------------------------------------------
     def ll(self, params, noise_sigma=0.0, grad_idx=None):
         """Returns (ll, grad or None, status)."""
+        self._own_structure()
         params = _f64(params, (self.nparams,))
         ll = ctypes.c_double(0.0)
         status = ctypes.c_int(0)
@@ -264,6 +321,7 @@ class Device(object):
 
     def ll_batched(self, thetas, grad_idx=None, y_batch=None, return_alpha=False):
         """thetas: (B, nparams + 1) = kernel params then sigma_n.  Returns (ll, grad or None, status[, alpha])."""
+        self._own_structure()
         thetas = _f64(np.atleast_2d(thetas))
         B = thetas.shape[0]
         if thetas.shape[1] != self.nparams + 1:
@@ -286,6 +344,7 @@ class Device(object):
 
     def ll_batched_dev(self, B, d_thetas, d_ll, d_status, d_grad=0, grad_idx=None, d_y_batch=0, d_alpha=0):
         """Raw device pointers (ints); nothing is copied."""
+        self._own_structure()
         gi = _i32(grad_idx) if grad_idx is not None and len(grad_idx) else None
         P = 0 if gi is None else len(gi)
         self._check(self._lib.gpt_ll_batched_dev(self._h, int(B), _vp(d_thetas), _vp(d_y_batch) if d_y_batch else None,

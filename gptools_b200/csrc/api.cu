@@ -47,6 +47,11 @@ struct gpt_handle {
     // kernel
     int kid = -1, nparams = 0;
     double diag_factor = 1e2;
+    // kernel algebra (gpt_define_composite): structure, and the per-theta leaf parameters on the device
+    int comp_nleaf = 0, comp_nterms = 0, comp_nparams = 0;
+    int32_t comp_kids[GPT_MAX_LEAVES] = {0}, comp_nps[GPT_MAX_LEAVES] = {0}, comp_masks[GPT_MAX_TERMS] = {0};
+    std::vector<CovComposite> comp_host;  // staging (kept alive: the uploads are asynchronous)
+    DevBuf comp_dev;
 
     // single-theta factor state
     bool factor_valid = false;
@@ -104,6 +109,34 @@ int check_launch(gpt_handle* h) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(h, GPT_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
     return 0;
+}
+
+int supported_kernel(int kid, int D, int nparams);
+
+// Composite (sum of products of device kernels): every leaf must be supported in dimension D on its own.
+int supported_composite(const gpt_handle* h, int D, int nparams) {
+    if (!h || h->comp_nleaf < 1 || nparams != h->comp_nparams) return 0;
+    for (int q = 0; q < h->comp_nleaf; q++)
+        if (h->comp_kids[q] == GPT_GIBBS_AUX || !supported_kernel(h->comp_kids[q], D, h->comp_nps[q])) return 0;
+    return 1;
+}
+
+int supported_kernel_h(const gpt_handle* h, int kid, int D, int nparams) {
+    if (kid == GPT_COMPOSITE) return (D >= 1 && D <= GPT_MAX_DIM) ? supported_composite(h, D, nparams) : 0;
+    return supported_kernel(kid, D, nparams);
+}
+
+// d/dnu of the generic Matern kernel is the one hyper-derivative the device does not have
+bool hyper_deriv_unavailable(const gpt_handle* h, int kid, int idx) {
+    if (kid == GPT_KERNEL_MATERN) return idx == 1;
+    if (kid == GPT_COMPOSITE) {
+        int off = 0;
+        for (int q = 0; q < h->comp_nleaf; q++) {
+            if (h->comp_kids[q] == GPT_KERNEL_MATERN && idx == off + 1) return true;
+            off += h->comp_nps[q];
+        }
+    }
+    return false;
 }
 
 int supported_kernel(int kid, int D, int nparams) {
@@ -328,6 +361,23 @@ int upload(gpt_handle* h, DevBuf& b, const void* src, size_t bytes) {
     int rc = ensure(h, b, bytes);
     if (rc) return rc;
     CUDA_OK(h, cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+
+// CovParams for (kid, params); a composite's leaves go to slot `slot` of the device array `dev` (`nslots` long) through
+// the handle's staging vector, and cp.comp points at that slot.
+int make_cov_params(gpt_handle* h, int kid, int D, int nparams, const double* params, CovParams& cp, DevBuf& dev,
+                    int slot = 0, int nslots = 1) {
+    cov_params_init(cp, kid, D, nparams, params);
+    if (kid != GPT_COMPOSITE) return 0;
+    if ((int)h->comp_host.size() < nslots) h->comp_host.resize(nslots);
+    if (comp_init(h->comp_host[slot], D, h->comp_nleaf, h->comp_kids, h->comp_nps, h->comp_nterms, h->comp_masks, params) < 0)
+        return fail(h, GPT_ERR_USAGE, "composite kernel: invalid description");
+    int rc = ensure(h, dev, sizeof(CovComposite) * (size_t)nslots);
+    if (rc) return rc;
+    CovComposite* d = reinterpret_cast<CovComposite*>(dev.p) + slot;
+    CUDA_OK(h, cudaMemcpyAsync(d, &h->comp_host[slot], sizeof(CovComposite), cudaMemcpyHostToDevice, h->stream));
+    cp.comp = d;
     return 0;
 }
 
@@ -586,7 +636,7 @@ void gpt_destroy(gpt_handle* h) {
                      &h->gout, &h->u, &h->Sg, &h->Yt, &h->Xs, &h->ns, &h->Kst, &h->Kso, &h->kss, &h->mean, &h->var,
                      &h->cov, &h->Rt, &h->smp, &h->b_thetas, &h->b_y, &h->b_ll, &h->b_grad, &h->b_status,
                      &h->llred, &h->b_alpha, &h->b_ws, &h->b_counter, &h->Vtmp, &h->flags, &h->ds_C, &h->ds_inv, &h->ds_panel, &h->ds_logdet,
-                     &h->ds_info, &h->ds_R, &h->ds_Rt, &h->ds_O, &h->ds_mu, &h->ds_jit};
+                     &h->ds_info, &h->ds_R, &h->ds_Rt, &h->ds_O, &h->ds_mu, &h->ds_jit, &h->comp_dev};
     for (DevBuf* b : all) release(*b);
     if (h->side_stream) {
         cudaStreamSynchronize(h->side_stream);
@@ -672,8 +722,10 @@ int gpt_set_y(gpt_handle* h, const double* y) {
 
 int gpt_set_kernel(gpt_handle* h, int kernel_id, int nparams, double diag_factor) {
     if (!h) return GPT_ERR_USAGE;
-    if (kernel_id < 0 || kernel_id > GPT_GIBBS_AUX || nparams < 1 || nparams > GPT_MAX_PARAMS)
+    if (kernel_id < 0 || kernel_id > GPT_COMPOSITE || nparams < 1 || nparams > GPT_MAX_PARAMS)
         return fail(h, GPT_ERR_UNSUPPORTED, "gpt_set_kernel: unsupported kernel / parameter count");
+    if (kernel_id == GPT_COMPOSITE && (h->comp_nleaf < 1 || nparams != h->comp_nparams))
+        return fail(h, GPT_ERR_USAGE, "gpt_set_kernel: GPT_COMPOSITE needs gpt_define_composite first (parameter counts must agree)");
     CUDA_OK(h, cudaSetDevice(h->device));
     h->kid = kernel_id;
     h->nparams = nparams;
@@ -688,23 +740,56 @@ int gpt_set_kernel(gpt_handle* h, int kernel_id, int nparams, double diag_factor
     return 0;
 }
 
+int gpt_define_composite(gpt_handle* h, int nleaf, const int32_t* leaf_kernel_ids, const int32_t* leaf_nparams,
+                         int nterms, const int32_t* term_masks) {
+    if (!h || !leaf_kernel_ids || !leaf_nparams || !term_masks) return fail(h, GPT_ERR_USAGE, "gpt_define_composite: bad arguments");
+    if (nleaf < 1 || nleaf > GPT_MAX_LEAVES || nterms < 1 || nterms > GPT_MAX_TERMS)
+        return fail(h, GPT_ERR_UNSUPPORTED, "gpt_define_composite: at most 4 operand kernels and 8 product terms");
+    int total = 0;
+    for (int q = 0; q < nleaf; q++) {
+        if (leaf_kernel_ids[q] < 0 || leaf_kernel_ids[q] >= GPT_GIBBS_AUX || leaf_nparams[q] < 1)
+            return fail(h, GPT_ERR_UNSUPPORTED, "gpt_define_composite: operand kernels are SE, Matern-5/2, Matern, Gibbs-tanh");
+        total += leaf_nparams[q];
+    }
+    if (total > GPT_MAX_PARAMS) return fail(h, GPT_ERR_UNSUPPORTED, "gpt_define_composite: more than 10 parameters in total");
+    for (int t = 0; t < nterms; t++)
+        if (term_masks[t] <= 0 || term_masks[t] >= (1 << nleaf)) return fail(h, GPT_ERR_USAGE, "gpt_define_composite: bad term mask");
+    bool same = (h->comp_nleaf == nleaf && h->comp_nterms == nterms);
+    for (int q = 0; same && q < nleaf; q++) same = (h->comp_kids[q] == leaf_kernel_ids[q] && h->comp_nps[q] == leaf_nparams[q]);
+    for (int t = 0; same && t < nterms; t++) same = (h->comp_masks[t] == term_masks[t]);
+    if (same) return 0;
+    h->comp_nleaf = nleaf;
+    h->comp_nterms = nterms;
+    h->comp_nparams = total;
+    for (int q = 0; q < nleaf; q++) { h->comp_kids[q] = leaf_kernel_ids[q]; h->comp_nps[q] = leaf_nparams[q]; }
+    for (int t = 0; t < nterms; t++) h->comp_masks[t] = term_masks[t];
+    if (h->kid == GPT_COMPOSITE) {  // the kernel set by gpt_set_kernel changed under the handle
+        h->factor_valid = false;
+        h->nparams = total;
+    }
+    return 0;
+}
+
 int gpt_cov_pairs(gpt_handle* h, int kernel_id, int D, int nparams, const double* params, int hyper_deriv,
                   int64_t npairs, const double* Xi, const double* Xj, const int32_t* ni, const int32_t* nj,
                   double* out) {
     if (!h || !params || npairs < 0) return fail(h, GPT_ERR_USAGE, "gpt_cov_pairs: bad arguments");
-    if (!supported_kernel(kernel_id, D, nparams)) return fail(h, GPT_ERR_UNSUPPORTED, "gpt_cov_pairs: unsupported kernel");
-    if (hyper_deriv >= nparams || (hyper_deriv == 1 && kernel_id == GPT_KERNEL_MATERN))
+    if (!supported_kernel_h(h, kernel_id, D, nparams)) return fail(h, GPT_ERR_UNSUPPORTED, "gpt_cov_pairs: unsupported kernel");
+    if (hyper_deriv >= nparams || hyper_deriv_unavailable(h, kernel_id, hyper_deriv))
         return fail(h, GPT_ERR_UNSUPPORTED, "hyper_deriv: index out of range, or d/dnu of the Matern kernel");
     if (npairs == 0) return 0;
     CUDA_OK(h, cudaSetDevice(h->device));
     CovParams cp;
-    cov_params_init(cp, kernel_id, D, nparams, params);
     const size_t xb = sizeof(double) * npairs * D, nb_ = sizeof(int32_t) * npairs * D;
-    DevBuf dXi, dXj, dni, dnj, dout;
+    DevBuf dXi, dXj, dni, dnj, dout, dcomp;
     int rc = 0;
+    if ((rc = make_cov_params(h, kernel_id, D, nparams, params, cp, dcomp))) {
+        release(dcomp);
+        return rc;
+    }
     if ((rc = upload(h, dXi, Xi, xb)) || (rc = upload(h, dXj, Xj, xb)) || (rc = upload(h, dni, ni, nb_)) ||
         (rc = upload(h, dnj, nj, nb_)) || (rc = ensure(h, dout, sizeof(double) * npairs))) {
-        release(dXi); release(dXj); release(dni); release(dnj); release(dout);
+        release(dXi); release(dXj); release(dni); release(dnj); release(dout); release(dcomp);
         return rc;
     }
     launch_cov_pairs(cp, hyper_deriv, npairs, ptr<double>(dXi), ptr<double>(dXj), ptr<int32_t>(dni), ptr<int32_t>(dnj),
@@ -712,7 +797,7 @@ int gpt_cov_pairs(gpt_handle* h, int kernel_id, int D, int nparams, const double
     h->launches++;
     cudaError_t e = cudaMemcpyAsync(out, dout.p, sizeof(double) * npairs, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    release(dXi); release(dXj); release(dni); release(dnj); release(dout);
+    release(dXi); release(dXj); release(dni); release(dnj); release(dout); release(dcomp);
     if (e != cudaSuccess) return fail(h, GPT_ERR_CUDA, "gpt_cov_pairs: %s", cudaGetErrorString(e));
     return 0;
 }
@@ -721,17 +806,20 @@ int gpt_compute_Kij(gpt_handle* h, int kernel_id, int D, int nparams, const doub
                     int Mi, const double* Xi, const int32_t* ni, int Mj, const double* Xj, const int32_t* nj,
                     double* K_out) {
     if (!h || !params || Mi < 1 || !Xi || !ni || !K_out) return fail(h, GPT_ERR_USAGE, "gpt_compute_Kij: bad arguments");
-    if (!supported_kernel(kernel_id, D, nparams)) return fail(h, GPT_ERR_UNSUPPORTED, "gpt_compute_Kij: unsupported kernel");
-    if (hyper_deriv >= nparams || (hyper_deriv == 1 && kernel_id == GPT_KERNEL_MATERN))
+    if (!supported_kernel_h(h, kernel_id, D, nparams)) return fail(h, GPT_ERR_UNSUPPORTED, "gpt_compute_Kij: unsupported kernel");
+    if (hyper_deriv >= nparams || hyper_deriv_unavailable(h, kernel_id, hyper_deriv))
         return fail(h, GPT_ERR_UNSUPPORTED, "hyper_deriv: index out of range, or d/dnu of the Matern kernel");
     CUDA_OK(h, cudaSetDevice(h->device));
     const bool sym = (Xj == nullptr);
     if (sym) Mj = Mi;
     CovParams cp;
-    cov_params_init(cp, kernel_id, D, nparams, params);
-    DevBuf dXi, dXj, dni, dnj, dout;
+    DevBuf dXi, dXj, dni, dnj, dout, dcomp;
     int rc = 0;
-    auto cleanup = [&]() { release(dXi); release(dXj); release(dni); release(dnj); release(dout); };
+    auto cleanup = [&]() { release(dXi); release(dXj); release(dni); release(dnj); release(dout); release(dcomp); };
+    if ((rc = make_cov_params(h, kernel_id, D, nparams, params, cp, dcomp))) {
+        cleanup();
+        return rc;
+    }
     if ((rc = upload(h, dXi, Xi, sizeof(double) * Mi * D)) || (rc = upload(h, dni, ni, sizeof(int32_t) * Mi * D)) ||
         (rc = ensure(h, dout, sizeof(double) * (size_t)Mi * Mj))) {
         cleanup();
@@ -821,19 +909,22 @@ int gpt_ll(gpt_handle* h, const double* params, double noise_sigma, double* ll, 
            const int32_t* grad_idx, int P, int* status) {
     if (!h || !params || !ll || !status) return fail(h, GPT_ERR_USAGE, "gpt_ll: bad arguments");
     if (h->M < 1 || h->kid < 0) return fail(h, GPT_ERR_USAGE, "gpt_ll: set_data / set_kernel first");
-    if (!supported_kernel(h->kid, h->D, h->nparams)) return fail(h, GPT_ERR_UNSUPPORTED, "gpt_ll: kernel/dimension unsupported");
+    if (!supported_kernel_h(h, h->kid, h->D, h->nparams)) return fail(h, GPT_ERR_UNSUPPORTED, "gpt_ll: kernel/dimension unsupported");
     if (grad && P > 0) {
         if (P > GPT_MAX_PARAMS || !grad_idx) return fail(h, GPT_ERR_USAGE, "gpt_ll: bad gradient request");
         for (int q = 0; q < P; q++) {
             if (grad_idx[q] < 0 || grad_idx[q] > h->nparams) return fail(h, GPT_ERR_USAGE, "gpt_ll: bad grad_idx");
-            if (grad_idx[q] == 1 && h->kid == GPT_KERNEL_MATERN)
+            if (hyper_deriv_unavailable(h, h->kid, grad_idx[q]))
                 return fail(h, GPT_ERR_UNSUPPORTED, "hyper-parameter derivatives: d/dnu of the Matern kernel is not available");
         }
     }
     CUDA_OK(h, cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
     h->factor_valid = false;
-    cov_params_init(h->cp, h->kid, h->D, h->nparams, params);
+    {
+        int rcp = make_cov_params(h, h->kid, h->D, h->nparams, params, h->cp, h->comp_dev);
+        if (rcp) return rcp;
+    }
     h->noise_sigma = noise_sigma;
     int rc;
     if (h->hasT) {
@@ -1338,7 +1429,7 @@ static int batched_serial(gpt_handle* h, int B, const double* d_thetas, const do
         if (P > GPT_MAX_PARAMS || !grad_idx) return fail(h, GPT_ERR_USAGE, "gpt_ll_batched: bad gradient request");
         for (int q = 0; q < P; q++) {
             if (grad_idx[q] < 0 || grad_idx[q] > h->nparams) return fail(h, GPT_ERR_USAGE, "gpt_ll_batched: bad grad_idx");
-            if (grad_idx[q] == 1 && h->kid == GPT_KERNEL_MATERN)
+            if (hyper_deriv_unavailable(h, h->kid, grad_idx[q]))
                 return fail(h, GPT_ERR_UNSUPPORTED, "hyper-parameter derivatives: d/dnu of the Matern kernel is not available");
         }
     }
@@ -1354,7 +1445,7 @@ static int batched_serial(gpt_handle* h, int B, const double* d_thetas, const do
     h->factor_valid = false;
     for (int b = 0; b < B && !rc; b++) {
         const double* tb = th.data() + (size_t)b * np1;
-        cov_params_init(h->cp, h->kid, h->D, h->nparams, tb);
+        if ((rc = make_cov_params(h, h->kid, h->D, h->nparams, tb, h->cp, h->comp_dev, b, B))) break;  // one slot per theta
         h->noise_sigma = tb[h->nparams];
         if (d_y) CUDA_OK(h, cudaMemcpyAsync(h->y.p, d_y + (size_t)b * M, sizeof(double) * M, cudaMemcpyDeviceToDevice, s));
         if (h->hasT) {
@@ -1390,10 +1481,10 @@ static int batched_serial(gpt_handle* h, int B, const double* d_thetas, const do
 
 static int batched_common(gpt_handle* h, int B, const double* d_thetas, const double* d_y, double* d_ll,
                           double* d_grad, const int32_t* grad_idx, int P, int* d_status, double* d_alpha) {
-    if (h->hasT || (h->M + 63) / 64 > 32) {
+    if (h->hasT || (h->M + 63) / 64 > 32 || h->kid == GPT_COMPOSITE) {
         if (h->kid == GPT_KERNEL_GIBBS_AUX)
             return fail(h, GPT_ERR_UNSUPPORTED, "gpt_ll_batched: the per-point length scales of GPT_GIBBS_AUX depend on theta; use gpt_ll");
-        if (!supported_kernel(h->kid, h->D, h->nparams)) return fail(h, GPT_ERR_UNSUPPORTED, "gpt_ll_batched: kernel unsupported");
+        if (!supported_kernel_h(h, h->kid, h->D, h->nparams)) return fail(h, GPT_ERR_UNSUPPORTED, "gpt_ll_batched: kernel unsupported");
         return batched_serial(h, B, d_thetas, d_y, d_ll, d_grad, grad_idx, P, d_status, d_alpha);
     }
     if (h->kid == GPT_KERNEL_GIBBS_AUX)

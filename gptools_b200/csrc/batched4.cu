@@ -121,10 +121,11 @@ __device__ __forceinline__ void chunk_mma(const double* stage, int arow, int bro
 #pragma unroll
         for (int j = 0; j < 4; j++) b[j] = bS[j * 8 * BK + col];
 #pragma unroll
-        for (int i = 0; i < 4; i++)
+        for (int i = 0; i < 4; i++) {
 #pragma unroll
             for (int j = 0; j < 4; j++)
                 if (!LOWER || j <= i) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
     }
 }
 
@@ -223,9 +224,10 @@ __device__ __forceinline__ void mult_lower_global(const double* St, const double
 #pragma unroll
             for (int i = 0; i < 4; i++) a[i] = aS[i * 8 * LDT + kb + kk * 4];
 #pragma unroll
-            for (int i = 0; i < 4; i++)
+            for (int j = 0; j < 4; j++) {
 #pragma unroll
-                for (int j = 0; j < 4; j++) dmma884(out[i][j][0], out[i][j][1], a[i], b[kk][j]);
+                for (int i = 0; i < 4; i++) dmma884(out[i][j][0], out[i][j][1], a[i], b[kk][j]);
+            }
         }
     }
 }
@@ -512,6 +514,16 @@ __device__ __forceinline__ void gen_ktot_tab(const Smem& sm, const BatchedParams
     }
 }
 
+
+// grad_tab with fewer FP64 instructions per entry (each one waits for a slot between the DMMAs of the co-resident
+// CTAs, so the contraction's time is its FP64 instruction count).  With u = tau^2 the per-dimension factors are
+//   f = s (c0 + c2 u),  g = s (g0 + g2 u + g4 u^2),  s = tau for m = 1 and 1 otherwise,
+//   m = 0: (1, 0 | 0, il2, 0)   m = 1: (-il2, 0 | 2 il2, -il2^2, 0)   m = 2: (-il2, il2^2 | 2 il2, -5 il2^2, il2^3)
+// (g without its common factor 1 / l).  A thread's column fixes nj, the row order is 0 or 1, so the coefficients are two
+// register-resident sets per dimension picked by selects (ALU pipe), the polynomials are 1 + 2 fused multiply-adds, and
+// s_0 s_1 multiplies the weight once.  Diagonal tiles: the loop takes the lower triangle with the diagonal at full
+// weight; the half weight of the diagonal entries and tr K^-1 are a per-thread correction after the loop (each thread
+// owns at most one diagonal entry).
 template <int FD>
 __device__ __forceinline__ void grad_tab(const Smem& sm, const BatchedParams& p, const double* St, int tid, int I, int J,
                                          const double* __restrict__ avec, const double* __restrict__ eb,
@@ -521,59 +533,82 @@ __device__ __forceinline__ void grad_tab(const Smem& sm, const BatchedParams& p,
     const int gj = J * TB + c;
     if (gj >= p.M) return;
     const double aj = avec[gj];
+    double xj[FD], c0[FD][2], c2B[FD], g0[FD][2], g2[FD][2], g4B[FD];
     int nj[FD];
-    double il2[FD], nil2[FD], xj[FD];
 #pragma unroll
     for (int d = 0; d < FD; d++) {
         nj[d] = __ldg(p.n + (size_t)gj * FD + d);
-        il2[d] = sm.cp.inv_l[d] * sm.cp.inv_l[d];
-        nil2[d] = -il2[d];
         xj[d] = __ldg(p.X + (size_t)gj * FD + d);
+        const double il2 = sm.cp.inv_l[d] * sm.cp.inv_l[d];
+        const double il4 = il2 * il2;
+        const bool j1 = (nj[d] != 0);
+        // row order 0: m = nj (0 or 1); row order 1: m = nj + 1 (1 or 2)
+        c0[d][0] = j1 ? -il2 : 1.0;
+        g0[d][0] = j1 ? 2.0 * il2 : 0.0;
+        g2[d][0] = j1 ? -il4 : il2;
+        c0[d][1] = -il2;
+        c2B[d] = j1 ? il4 : 0.0;
+        g0[d][1] = 2.0 * il2;
+        g2[d][1] = j1 ? -5.0 * il4 : -il4;
+        g4B[d] = j1 ? il4 * il2 : 0.0;
     }
     const double* pts = sm.R + PTS_OFF;
     const int* ord = reinterpret_cast<const int*>(pts + PTS_ORD);
-    double wk = 0.0, trl = 0.0, gl[FD];
+    double wk = 0.0, gl[FD];
 #pragma unroll
     for (int d = 0; d < FD; d++) gl[d] = 0.0;
+    // contribution of entry (r, c) with weight w (already multiplied by the cached exponential)
+    auto entry = [&](int r, double wb, double& awk, double (&agl)[FD]) {
+        const int pk = ord[r];
+        double F[FD], G[FD], tau[FD];
+        bool odd[FD];
+#pragma unroll
+        for (int d = 0; d < FD; d++) {
+            tau[d] = pts[r * FD + d] - xj[d];
+            const double q = tau[d] * tau[d];
+            const bool b = ((pk >> (8 * d)) & 255) != 0;
+            odd[d] = (b != (nj[d] != 0));
+            const double cc0 = b ? c0[d][1] : c0[d][0];
+            const double cc2 = b ? c2B[d] : 0.0;
+            const double gg0 = b ? g0[d][1] : g0[d][0];
+            const double gg2 = b ? g2[d][1] : g2[d][0];
+            const double gg4 = b ? g4B[d] : 0.0;
+            F[d] = fma(cc2, q, cc0);
+            G[d] = fma(fma(gg4, q, gg2), q, gg0);
+        }
+        if constexpr (FD == 1) {
+            const double ws = odd[0] ? wb * tau[0] : wb;
+            awk = fma(ws, F[0], awk);
+            agl[0] = fma(ws, G[0], agl[0]);
+        } else {
+            const double pp = tau[0] * tau[1];
+            double sel = odd[0] ? tau[0] : 1.0;
+            sel = odd[1] ? (odd[0] ? pp : tau[1]) : sel;
+            const double ws = wb * sel;
+            const double t0 = ws * F[0];
+            awk = fma(t0, F[1], awk);
+            agl[1] = fma(t0, G[1], agl[1]);
+            agl[0] = fma(ws * G[0], F[1], agl[0]);
+        }
+    };
+    const int u0 = (DIAG && c >= 32) ? 16 : 0;  // warp-uniform: columns >= 32 of a diagonal tile start at row 32
 #pragma unroll UNROLL
-    for (int u = 0; u < 32; u++) {
+    for (int u = u0; u < 32; u++) {
         const int r = (tid >> 6) + 2 * u;
         const int gi = I * TB + r;
         const bool use = (gi < p.M) && (!DIAG || c <= r);
-        const bool on_diag = DIAG && (c == r);
         const double kinv = st_get(St, r, (DIAG && c > r) ? r : c, DIAG);
-        double w = pts[PTS_ALPHA + r] * aj - kinv;
-        const double hw = 0.5 * w;
-        w = on_diag ? hw : w;
+        double w = fma(pts[PTS_ALPHA + r], aj, -kinv);
         w = use ? w : 0.0;
-        trl += (use && on_diag) ? kinv : 0.0;
-        const double wb = w * eb[tid + u * THREADS];
-        const int pk = ord[r];
-        double f[FD], g[FD];  // g without its common factor il (applied once at the end)
-#pragma unroll
-        for (int d = 0; d < FD; d++) {
-            const double tau = pts[r * FD + d] - xj[d];
-            const double uu = tau * tau * il2[d];
-            const int m = ((pk >> (8 * d)) & 255) + nj[d];
-            const double f1 = tau * nil2[d];
-            const double g1 = f1 * (uu - 2.0);
-            const double f2 = il2[d] * (uu - 1.0);
-            const double g2 = il2[d] * fma(uu, uu - 5.0, 2.0);
-            double ff = (m == 1) ? f1 : 1.0, gg = (m == 1) ? g1 : uu;
-            f[d] = (m == 2) ? f2 : ff;
-            g[d] = (m == 2) ? g2 : gg;
-        }
-        if constexpr (FD == 1) {
-            wk = fma(wb, f[0], wk);
-            gl[0] = fma(wb, g[0], gl[0]);
-        } else {
-            const double t0 = wb * f[0];
-            wk = fma(t0, f[1], wk);
-            gl[1] = fma(t0, g[1], gl[1]);
-            gl[0] = fma(wb * g[0], f[1], gl[0]);
-        }
+        entry(r, w * eb[tid + u * THREADS], wk, gl);
     }
-    tr_kinv += trl;
+    if (DIAG && ((c & 1) == (tid >> 6))) {  // this thread's diagonal entry (r = c): half weight, trace
+        const int r = c;
+        const double kinv = st_get(St, r, c, true);
+        tr_kinv += kinv;
+        const double w = -0.5 * fma(pts[PTS_ALPHA + r], aj, -kinv);
+        entry(r, w * eb[tid + ((c - (tid >> 6)) >> 1) * THREADS], wk, gl);
+    }
 #pragma unroll
     for (int d = 0; d < FD; d++) gall[1 + d] += gl[d] * sm.cp.inv_l[d];
     gall[0] += (sm.cp.p[0] != 0.0) ? 2.0 * wk / sm.cp.p[0] : 0.0;
@@ -736,6 +771,33 @@ __device__ __forceinline__ void grad_tile(const Smem& sm, const BatchedParams& p
     }
 }
 
+// Operands of contraction step `st` of the job that produces tile (I, J) in sweep ph; returns the structure flags
+// (bit0: A upper triangular, bit2: B upper triangular).
+__device__ __forceinline__ int job_step(double* ws, int nT, int ph, int I, int J, int st, const double*& aa,
+                                        const double*& bb) {
+    int fl = 0;
+    if (ph == 1) {  // S(I,k) = sum_{j<k} L(I,j) L(k,j)^T
+        aa = slot(ws, I, st);
+        bb = slot(ws, J, st);
+    } else if (ph == 2) {  // sum_{m=J}^{I-1} XT(J,m)-as-stored * L(I,m)^T
+        const int m = J + st;
+        aa = (m == J) ? slotDT(ws, nT, J) : slot(ws, m, J);
+        bb = slot(ws, I, m);
+        fl = (m == J) ? 1 : 0;
+    } else {  // K^{-1}(I,J) = sum_{m>=I} XT(I,m) XT(J,m)^T
+        const int m = I + st;
+        if (m == I) {
+            aa = slotDT(ws, nT, I);
+            bb = (I == J) ? slotDT(ws, nT, J) : slot(ws, I, J);
+            fl = 1 | ((I == J) ? 4 : 0);
+        } else {
+            aa = slot(ws, m, I);
+            bb = slot(ws, m, J);
+        }
+    }
+    return fl;
+}
+
 template <int FD>
 __global__ void __launch_bounds__(THREADS, GPT_B4_MINB) ll_batched4_kernel(BatchedParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -849,26 +911,7 @@ __global__ void __launch_bounds__(THREADS, GPT_B4_MINB) ll_batched4_kernel(Batch
                     const int nsteps = (ph == 1) ? J : ((ph == 2) ? I - J : nT - I);
                     if (L.tid < nsteps) {
                         const double *aa, *bb;
-                        int fl = 0;
-                        if (ph == 1) {  // S(I,k) = sum_{j<k} L(I,j) L(k,j)^T
-                            aa = slot(ws, I, L.tid);
-                            bb = slot(ws, J, L.tid);
-                        } else if (ph == 2) {  // sum_{m=J}^{I-1} XT(J,m)-as-stored * L(I,m)^T
-                            const int m = J + L.tid;
-                            aa = (m == J) ? slotDT(ws, nT, J) : slot(ws, m, J);
-                            bb = slot(ws, I, m);
-                            fl = (m == J) ? 1 : 0;
-                        } else {  // K^{-1}(I,J) = sum_{m>=I} XT(I,m) XT(J,m)^T
-                            const int m = I + L.tid;
-                            if (m == I) {
-                                aa = slotDT(ws, nT, I);
-                                bb = diag ? slotDT(ws, nT, J) : slot(ws, I, J);
-                                fl = 1 | (diag ? 4 : 0);
-                            } else {
-                                aa = slot(ws, m, I);
-                                bb = slot(ws, m, J);
-                            }
-                        }
+                        const int fl = job_step(ws, nT, ph, I, J, L.tid, aa, bb);
                         sm.a[L.tid] = aa;
                         sm.b[L.tid] = bb;
                         sm.flag[L.tid] = (unsigned char)fl;

@@ -26,8 +26,14 @@
 #define GPT_KERNEL_GIBBS_TANH 3
 #define GPT_KERNEL_GIBBS_AUX 4  // Gibbs kernel, length scale l(x) and l'(x) supplied per point in columns 1, 2
 
+#define GPT_KERNEL_COMPOSITE 5  // sum of products of up to GPT_MAX_LEAVES of the kernels above (kernel/core.py:424-670)
+
 #define GPT_MAX_DIM 6
 #define GPT_MAX_PARAMS 10
+#define GPT_MAX_LEAVES 4
+#define GPT_MAX_TERMS 8
+
+struct CovComposite;
 
 // Kernel hyperparameters in the reference's order plus quantities derived once per theta.
 struct CovParams {
@@ -45,6 +51,19 @@ struct CovParams {
     double mat_nu[2];          // the order(s) the series zone is evaluated at: {nu, nu}; integer nu: {nu - 0.001, nu + 0.001}
     double mat_A[2][4];        // [side][n]: c * Gamma(nu') / (2^{1-nu'+2n} (1-nu')_n)       (x 1/2 for integer nu)
     double mat_B[2][4];        // [side][n]: c * Gamma(-nu') (1+nu'-n)_n / 2^{1+nu'}         (x 1/2 for integer nu)
+    // kid == GPT_KERNEL_COMPOSITE: the operand kernels with their parameters (device memory inside the CUDA kernels,
+    // host memory in the host build); p[] then holds the concatenated vector for reference only
+    const CovComposite* comp;
+};
+
+// SumKernel / ProductKernel trees of the reference (kernel/core.py:549-670), flattened by the host into a sum of
+// products: k = sum_t prod_{q in mask[t]} leaf_q.  The parameter vector is the reference's concatenation
+// [leaf_0 params, leaf_1 params, ...] (BinaryKernel, kernel/core.py:452-459); off[q] is leaf q's first index in it.
+struct CovComposite {
+    int nleaf, nterms;
+    int off[GPT_MAX_LEAVES];
+    int mask[GPT_MAX_TERMS];
+    CovParams leaf[GPT_MAX_LEAVES];
 };
 
 // exp(x) for x <= 0 (the squared-exponential / Gibbs exponents): Cody-Waite reduction x = k ln2 + r,
@@ -192,6 +211,7 @@ GPT_HD void cov_params_init(CovParams& cp, int kid, int D, int nparams, const do
     cp.D = D;
     cp.nparams = nparams;
     for (int i = 0; i < GPT_MAX_PARAMS; i++) cp.p[i] = (i < nparams) ? params[i] : 0.0;
+    cp.comp = nullptr;
     cp.sig2 = cp.p[0] * cp.p[0];
     const int loff = (kid == GPT_KERNEL_MATERN) ? 2 : 1;
     for (int d = 0; d < GPT_MAX_DIM; d++) cp.inv_l[d] = 0.0;
@@ -648,8 +668,8 @@ GPT_HD double gibbs_cov(const CovParams& cp, const double* xi, const int32_t* ni
 // ------------------------------------------------------------------------------------------
 // dispatch
 // ------------------------------------------------------------------------------------------
-GPT_HD double cov_eval(const CovParams& cp, const double* xi, const int32_t* ni, const double* xj,
-                       const int32_t* nj, int hyper_deriv) {
+GPT_HD double cov_eval_leaf(const CovParams& cp, const double* xi, const int32_t* ni, const double* xj,
+                            const int32_t* nj, int hyper_deriv) {
     if (hyper_deriv >= 0 && cp.kid == GPT_KERNEL_GIBBS_AUX) {
         // only sigma_f is a device-side parameter: dk/dsigma_f = 2 k / sigma_f
         const double k = gibbs_cov_l(cp, xi[0], xi[1], xi[2], ni[0], xj[0], xj[1], xj[2], nj[0]);
@@ -663,4 +683,179 @@ GPT_HD double cov_eval(const CovParams& cp, const double* xi, const int32_t* ni,
         case GPT_KERNEL_GIBBS_AUX: return gibbs_cov_l(cp, xi[0], xi[1], xi[2], ni[0], xj[0], xj[1], xj[2], nj[0]);
         default: return gibbs_cov(cp, xi, ni, xj, nj);
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel algebra: sums and products of the kernels above, with derivative orders
+// ------------------------------------------------------------------------------------------
+// A product of L kernels under the derivative multi-index m = (ni, nj) (2 D slots) follows the general Leibniz rule:
+// the reference enumerates every subset of the multiset of unit derivatives (kernel/core.py:632-668); collecting
+// equal terms gives  sum_{a <= m} prod_s C(m_s, a_s) k1^(a) k2^(m - a),  applied recursively for three factors.
+// hyper_deriv (index into the concatenated parameter vector) differentiates the one leaf that owns the parameter:
+// terms without that leaf drop out (SumKernel: kernel/core.py:576-582; for products the reference raises
+// NotImplementedError, here the same Leibniz sum runs with the owning leaf's own hyper-derivative).
+GPT_HD double binom_small(int n, int k) {
+    double r = 1.0;
+    for (int i = 1; i <= k; i++) r = r * (double)(n - k + i) / (double)i;
+    return r;
+}
+
+// One out-of-line copy of the leaf closed forms serves every factor of every term (inlining them at each call site
+// multiplies the code of all kernels that evaluate covariances by the number of sites).
+#if defined(__CUDACC__)
+#define GPT_NOINLINE static __host__ __device__ __noinline__
+#else
+#define GPT_NOINLINE static inline
+#endif
+GPT_NOINLINE double cov_leaf_call(const CovParams& cp, const double* xi, const int32_t* ni, const double* xj,
+                                  const int32_t* nj, int hyper_deriv) {
+    return cov_eval_leaf(cp, xi, ni, xj, nj, hyper_deriv);
+}
+
+// sum over splits of (mi, mj) between leaf A and leaf B
+GPT_NOINLINE double comp_prod2(const CovParams& A, int hdA, const CovParams& B, int hdB, int D, const double* xi,
+                         const int32_t* mi, const double* xj, const int32_t* mj) {
+    int32_t ai[GPT_MAX_DIM], aj[GPT_MAX_DIM], bi[GPT_MAX_DIM], bj[GPT_MAX_DIM];
+    int total = 0;
+    for (int d = 0; d < D; d++) {
+        ai[d] = aj[d] = 0;
+        total += mi[d] + mj[d];
+    }
+    if (total == 0) return cov_leaf_call(A, xi, mi, xj, mj, hdA) * cov_leaf_call(B, xi, mi, xj, mj, hdB);
+    double sum = 0.0;
+    for (;;) {
+        double w = 1.0;
+        for (int d = 0; d < D; d++) {
+            bi[d] = mi[d] - ai[d];
+            bj[d] = mj[d] - aj[d];
+            w *= binom_small(mi[d], ai[d]) * binom_small(mj[d], aj[d]);
+        }
+        sum += w * cov_leaf_call(A, xi, ai, xj, aj, hdA) * cov_leaf_call(B, xi, bi, xj, bj, hdB);
+        // odometer over the 2 D slots
+        int s = 0;
+        for (; s < 2 * D; s++) {
+            int32_t* a = (s < D) ? &ai[s] : &aj[s - D];
+            const int lim = (s < D) ? mi[s] : mj[s - D];
+            if (*a < lim) {
+                (*a)++;
+                break;
+            }
+            *a = 0;
+        }
+        if (s == 2 * D) break;
+    }
+    return sum;
+}
+
+GPT_NOINLINE double comp_eval(const CovComposite& c, int D, const double* xi, const int32_t* ni, const double* xj, const int32_t* nj,
+                 int hyper_deriv) {
+    int owner = -1, hl = -1;
+    if (hyper_deriv >= 0) {
+        for (int q = 0; q < c.nleaf; q++)
+            if (hyper_deriv >= c.off[q] && hyper_deriv < c.off[q] + c.leaf[q].nparams) {
+                owner = q;
+                hl = hyper_deriv - c.off[q];
+            }
+        if (owner < 0) return NAN;
+    }
+    double total = 0.0;
+    for (int t = 0; t < c.nterms; t++) {
+        const int mask = c.mask[t];
+        if (owner >= 0 && !((mask >> owner) & 1)) continue;
+        int l[GPT_MAX_LEAVES], L = 0;
+        for (int q = 0; q < c.nleaf; q++)
+            if ((mask >> q) & 1) l[L++] = q;
+        if (L == 0) continue;
+        const int h0 = (l[0] == owner) ? hl : -1;
+        if (L == 1) {
+            total += cov_leaf_call(c.leaf[l[0]], xi, ni, xj, nj, h0);
+            continue;
+        }
+        const int h1 = (l[1] == owner) ? hl : -1;
+        if (L == 2) {
+            total += comp_prod2(c.leaf[l[0]], h0, c.leaf[l[1]], h1, D, xi, ni, xj, nj);
+            continue;
+        }
+        // three or four factors: split off the leading leaf (and the second for four), the last two go through comp_prod2
+        const int h2 = (l[2] == owner) ? hl : -1;
+        const int h3 = (L > 3 && l[3] == owner) ? hl : -1;
+        int32_t ai[GPT_MAX_DIM], aj[GPT_MAX_DIM], ri[GPT_MAX_DIM], rj[GPT_MAX_DIM];
+        for (int d = 0; d < D; d++) ai[d] = aj[d] = 0;
+        for (;;) {
+            double w = 1.0;
+            for (int d = 0; d < D; d++) {
+                ri[d] = ni[d] - ai[d];
+                rj[d] = nj[d] - aj[d];
+                w *= binom_small(ni[d], ai[d]) * binom_small(nj[d], aj[d]);
+            }
+            const double lead = w * cov_leaf_call(c.leaf[l[0]], xi, ai, xj, aj, h0);
+            if (L == 3) {
+                total += lead * comp_prod2(c.leaf[l[1]], h1, c.leaf[l[2]], h2, D, xi, ri, xj, rj);
+            } else {
+                int32_t bi[GPT_MAX_DIM], bj[GPT_MAX_DIM], si[GPT_MAX_DIM], sj[GPT_MAX_DIM];
+                for (int d = 0; d < D; d++) bi[d] = bj[d] = 0;
+                for (;;) {
+                    double w2 = 1.0;
+                    for (int d = 0; d < D; d++) {
+                        si[d] = ri[d] - bi[d];
+                        sj[d] = rj[d] - bj[d];
+                        w2 *= binom_small(ri[d], bi[d]) * binom_small(rj[d], bj[d]);
+                    }
+                    total += lead * w2 * cov_leaf_call(c.leaf[l[1]], xi, bi, xj, bj, h1) *
+                             comp_prod2(c.leaf[l[2]], h2, c.leaf[l[3]], h3, D, xi, si, xj, sj);
+                    int s = 0;
+                    for (; s < 2 * D; s++) {
+                        int32_t* b = (s < D) ? &bi[s] : &bj[s - D];
+                        const int lim = (s < D) ? ri[s] : rj[s - D];
+                        if (*b < lim) {
+                            (*b)++;
+                            break;
+                        }
+                        *b = 0;
+                    }
+                    if (s == 2 * D) break;
+                }
+            }
+            int s = 0;
+            for (; s < 2 * D; s++) {
+                int32_t* a = (s < D) ? &ai[s] : &aj[s - D];
+                const int lim = (s < D) ? ni[s] : nj[s - D];
+                if (*a < lim) {
+                    (*a)++;
+                    break;
+                }
+                *a = 0;
+            }
+            if (s == 2 * D) break;
+        }
+    }
+    return total;
+}
+
+GPT_HD double cov_eval(const CovParams& cp, const double* xi, const int32_t* ni, const double* xj,
+                       const int32_t* nj, int hyper_deriv) {
+    if (cp.kid == GPT_KERNEL_COMPOSITE) return comp_eval(*cp.comp, cp.D, xi, ni, xj, nj, hyper_deriv);
+    return cov_eval_leaf(cp, xi, ni, xj, nj, hyper_deriv);
+}
+
+// Host side of a composite: leaves initialised from the concatenated parameter vector.  `kids` / `nps` describe the
+// leaves, `masks` the product terms.  Returns the number of parameters, or -1 when the description is not valid.
+inline int comp_init(CovComposite& c, int D, int nleaf, const int32_t* kids, const int32_t* nps, int nterms,
+                     const int32_t* masks, const double* params) {
+    if (nleaf < 1 || nleaf > GPT_MAX_LEAVES || nterms < 1 || nterms > GPT_MAX_TERMS) return -1;
+    memset(&c, 0, sizeof(c));
+    c.nleaf = nleaf;
+    c.nterms = nterms;
+    int off = 0;
+    for (int q = 0; q < nleaf; q++) {
+        if (nps[q] < 1 || off + nps[q] > GPT_MAX_PARAMS) return -1;
+        c.off[q] = off;
+        cov_params_init(c.leaf[q], kids[q], D, nps[q], params + off);
+        off += nps[q];
+    }
+    for (int t = 0; t < nterms; t++) {
+        if (masks[t] <= 0 || masks[t] >= (1 << nleaf)) return -1;
+        c.mask[t] = masks[t];
+    }
+    return off;
 }

@@ -37,6 +37,22 @@ int gpt_hostcheck_cov_dual(int kid, int D, int nparams, const double* params, in
     return 0;
 }
 
+// kernel algebra: sum of products of leaves (the device's comp_eval, on the host)
+int gpt_hostcheck_composite_pairs(int D, int nleaf, const int32_t* kids, const int32_t* nps, int nterms,
+                                  const int32_t* masks, const double* params, int hyper_deriv, long npairs,
+                                  const double* Xi, const double* Xj, const int32_t* ni, const int32_t* nj, double* out) {
+    if (D > GPT_MAX_DIM) return -1;
+    CovComposite c;
+    const int total = comp_init(c, D, nleaf, kids, nps, nterms, masks, params);
+    if (total < 0) return -1;
+    CovParams cp;
+    cov_params_init(cp, GPT_KERNEL_COMPOSITE, D, total, params);
+    cp.comp = &c;
+    for (long p = 0; p < npairs; p++)
+        out[p] = cov_eval(cp, Xi + p * D, ni + p * D, Xj + p * D, nj + p * D, hyper_deriv);
+    return 0;
+}
+
 // out is (npairs, 2 + D): value, d/dsigma, d/dl_1..d/dl_D
 int gpt_hostcheck_se_all(int D, const double* params, long npairs, const double* Xi, const double* Xj,
                          const int32_t* ni, const int32_t* nj, double* out) {

@@ -18,7 +18,9 @@ import scipy.optimize
 import scipy.stats
 
 from .error_handling import GPArgumentError, GPImpossibleParamsError
+from ._lib import CompositeId
 from .kernel import DiagonalNoiseKernel, Kernel, ZeroKernel
+from .kernel.core import default_device
 from .utils import CombinedBounds
 
 __all__ = ["GaussianProcess", "Constraint"]
@@ -436,11 +438,14 @@ class GaussianProcess(object):
                 k.check_hyper_deriv([int(hyper_deriv)])
             k._check_orders(ni, ni if nj is None else np.atleast_2d(np.asarray(nj, dtype=int)))
             Xi_d, ni_d = k.device_points(Xi, ni)
+            # a kernel other than the GP's own is evaluated on the process-wide handle: defining another composite
+            # structure on the GP's handle would drop its resident factorisation
+            dev = default_device() if (k is not self.k and isinstance(desc[0], CompositeId)) else self._dev()
             if Xj is None:
-                return self._dev().compute_Kij(desc[0], desc[1], Xi_d, ni_d, hyper_deriv=hyper_deriv)
+                return dev.compute_Kij(desc[0], desc[1], Xi_d, ni_d, hyper_deriv=hyper_deriv)
             Xj_d, nj_d = k.device_points(np.atleast_2d(np.asarray(Xj, dtype=float)),
                                          np.atleast_2d(np.asarray(nj, dtype=int)))
-            return self._dev().compute_Kij(desc[0], desc[1], Xi_d, ni_d, Xj_d, nj_d, hyper_deriv=hyper_deriv)
+            return dev.compute_Kij(desc[0], desc[1], Xi_d, ni_d, Xj_d, nj_d, hyper_deriv=hyper_deriv)
         symmetric = Xj is None
         if symmetric:
             Xj, nj = Xi, ni

@@ -130,8 +130,101 @@ class DeviceKernel(Kernel):
 
 
 class BinaryKernel(Kernel):
-    """Two kernels combined, with concatenated hyperparameters (kernel/core.py:424-548).  Host-side composition:
-    each operand is evaluated through its own ``__call__`` (device kernels through ``gpt_cov_pairs``)."""
+    """Two kernels combined, with concatenated hyperparameters (kernel/core.py:424-548).
+
+    When every operand is a device kernel the whole tree is evaluated ON THE DEVICE: it is flattened into a sum of
+    products of its leaves (``_flatten``) and handed to the library as kernel id GPT_COMPOSITE
+    (``gpt_define_composite``), so assembly, factorisation, gradients, prediction and the batched call run exactly as
+    for a single kernel, with the general Leibniz rule over derivative orders applied per matrix entry.  Trees the
+    library does not take (more than 4 leaves / 8 terms / 10 parameters, user-defined operands, Gibbs kernels with a
+    host length-scale function) fall back to host-side composition of the operands' own calls, like the reference."""
+
+    supports_hyper_deriv = True
+    BATCHED_GRAD_SLOTS = 10
+
+    # ---- device composition ---------------------------------------------------------------------------------
+    def _flatten(self):
+        """(leaves, terms): the leaf kernels in parameter order and the product terms (tuples of leaf indices) whose
+        sum equals this kernel; None when an operand has no device closed form."""
+        def walk(k):
+            if isinstance(k, BinaryKernel):
+                a, b = walk(k.k1), walk(k.k2)
+                if a is None or b is None:
+                    return None
+                leaves = a[0] + b[0]
+                shift = len(a[0])
+                tb = [tuple(i + shift for i in t) for t in b[1]]
+                if isinstance(k, SumKernel):
+                    return leaves, a[1] + tb
+                if isinstance(k, ProductKernel):
+                    return leaves, [ta + t2 for ta in a[1] for t2 in tb]
+                return None
+            if isinstance(k, DeviceKernel) and k.kernel_id in (0, 1, 2, 3) and k.device_points_key() is None:
+                return [k], [(0,)]
+            return None
+        return walk(self)
+
+    def device_descriptor(self):
+        from .._lib import CompositeId, MAX_LEAVES, MAX_TERMS, MAX_PARAMS
+        flat = self._flatten()
+        if flat is None:
+            return None
+        leaves, terms = flat
+        if len(leaves) > MAX_LEAVES or len(terms) > MAX_TERMS or self.num_params > MAX_PARAMS:
+            return None
+        params = []
+        for k in leaves:
+            params.append(k.device_descriptor()[1])
+        masks = [sum(1 << i for i in t) for t in terms]
+        cid = CompositeId([k.kernel_id for k in leaves], [k.num_params for k in leaves], masks)
+        return (cid, np.concatenate(params))
+
+    def _leaf_offsets(self):
+        leaves = self._flatten()[0]
+        offs = np.cumsum([0] + [k.num_params for k in leaves])
+        return leaves, offs
+
+    def check_hyper_deriv(self, idxs):
+        """Per-leaf availability (d/dnu of a generic Matern operand is the one derivative the device lacks)."""
+        leaves, offs = self._leaf_offsets()
+        for i in idxs:
+            q = int(np.searchsorted(offs, int(i), side="right") - 1)
+            leaves[q].check_hyper_deriv([int(i) - int(offs[q])])
+
+    def _check_orders(self, ni, nj):
+        for k in self._flatten()[0]:
+            k._check_orders(ni, nj)
+
+    def device_points(self, X, n):
+        return X, n
+
+    def device_points_key(self):
+        return None
+
+    def batchable(self, with_deriv):
+        return True  # the library runs composite kernels theta after theta inside the batched call
+
+    def batch_rows_supported(self, param_rows):
+        param_rows = np.atleast_2d(param_rows)
+        leaves, offs = self._leaf_offsets()
+        ok = np.ones(param_rows.shape[0], dtype=bool)
+        for q, k in enumerate(leaves):
+            ok &= k.batch_rows_supported(param_rows[:, offs[q]:offs[q + 1]])
+        return ok
+
+    def _device_call(self, Xi, Xj, ni, nj, hyper_deriv):
+        """``__call__`` through ``gpt_cov_pairs`` when the tree is device-evaluable, else None."""
+        desc = self.device_descriptor()
+        if desc is None:
+            return None
+        Xi = np.atleast_2d(np.asarray(Xi, dtype=float))
+        Xj = np.atleast_2d(np.asarray(Xj, dtype=float))
+        ni = np.atleast_2d(np.asarray(ni, dtype=int))
+        nj = np.atleast_2d(np.asarray(nj, dtype=int))
+        if hyper_deriv is not None:
+            self.check_hyper_deriv([int(hyper_deriv)])
+        self._check_orders(ni, nj)
+        return default_device().cov_pairs(desc[0], desc[1], Xi, Xj, ni, nj, hyper_deriv=hyper_deriv)
 
     def __init__(self, k1, k2):
         if not isinstance(k1, Kernel) or not isinstance(k2, Kernel):
@@ -253,9 +346,13 @@ class BinaryKernel(Kernel):
 
 class SumKernel(BinaryKernel):
     """k1 + k2 (kernel/core.py:549-600).  Used by the GP when the noise kernel is neither ZeroKernel nor
-    DiagonalNoiseKernel (gaussian_process.py:1489-1490)."""
+    DiagonalNoiseKernel (gaussian_process.py:1489-1490).  Device operands: evaluated on the device (BinaryKernel);
+    otherwise the host composition below."""
 
     def __call__(self, Xi, Xj, ni, nj, hyper_deriv=None, symmetric=False):
+        out = self._device_call(Xi, Xj, ni, nj, hyper_deriv)
+        if out is not None:
+            return out
         if hyper_deriv is None:
             return (self.k1(Xi, Xj, ni, nj, symmetric=symmetric) + self.k2(Xi, Xj, ni, nj, symmetric=symmetric))
         if hyper_deriv < self.k1.num_params:
@@ -269,9 +366,14 @@ class ProductKernel(BinaryKernel):
     For a pair with combined orders m = (ni, nj) (2 D slots) the reference sums k1^(s) k2^(m - s) over every subset
     of the multiset of derivative slots; collecting equal terms gives
     sum_{a <= m} prod_i C(m_i, a_i) k1^(a) k2^(m - a), which is what is evaluated here (one call of each operand per
-    distinct split instead of one per subset).  Like the reference, ``hyper_deriv`` raises NotImplementedError."""
+    distinct split instead of one per subset).  Device operands: the same sum runs per entry on the device
+    (csrc/covfn.cuh: comp_eval), including ``hyper_deriv``; in the host composition ``hyper_deriv`` raises
+    NotImplementedError like the reference."""
 
     def __call__(self, Xi, Xj, ni, nj, hyper_deriv=None, symmetric=False):
+        out = self._device_call(Xi, Xj, ni, nj, hyper_deriv)
+        if out is not None:
+            return out
         if hyper_deriv is not None:
             raise NotImplementedError("hyper_deriv keyword not yet supported!")
         from itertools import product as cartesian

@@ -37,6 +37,10 @@ typedef struct gpt_handle gpt_handle;
                            * three columns (x, l(x), l'(x)) -- the length-scale profile is evaluated by the host l_func,
                            * derivative orders apply to column 0 only */
 
+#define GPT_COMPOSITE 5    /* SumKernel / ProductKernel trees over the kernels above  kernel/core.py:424-670
+                           * params: the operands' parameter vectors back to back (BinaryKernel, kernel/core.py:452-459);
+                           * structure from gpt_define_composite */
+
 #define GPT_ERR_USAGE (-1)
 #define GPT_ERR_CUDA (-2)
 #define GPT_ERR_UNSUPPORTED (-3)
@@ -62,6 +66,17 @@ int gpt_set_data(gpt_handle* h, int N, int M, int D, const double* X, const int3
 int gpt_set_y(gpt_handle* h, const double* y);
 /* Covariance kernel of the GP and the diag_factor jitter (gaussian_process.py:81-85, 1450). */
 int gpt_set_kernel(gpt_handle* h, int kernel_id, int nparams, double diag_factor);
+
+/* Kernel algebra on the device (SumKernel kernel/core.py:549-600, ProductKernel kernel/core.py:601-670).  The host flattens
+ * a tree of sums and products into  k = sum_t prod_{q in term t} leaf_q : `nleaf` operand kernels (SE, Matern-5/2, Matern,
+ * Gibbs-tanh; at most 4, at most 10 parameters in total) and `nterms` products (at most 8), term t multiplying the leaves
+ * whose bits are set in term_masks[t].  Products of kernels under derivative observations follow the general Leibniz
+ * rule over the derivative orders exactly like the reference's enumeration of derivative subsets (kernel/core.py:632-668).
+ * Afterwards kernel id GPT_COMPOSITE (nparams = sum of leaf_nparams) is accepted by gpt_set_kernel, gpt_cov_pairs and
+ * gpt_compute_Kij on this handle; hyper_deriv / grad_idx index the concatenated parameter vector (the reference has
+ * hyper-derivatives for sums only).  gpt_ll_batched runs composite kernels theta after theta on the device. */
+int gpt_define_composite(gpt_handle* h, int nleaf, const int32_t* leaf_kernel_ids, const int32_t* leaf_nparams,
+                         int nterms, const int32_t* term_masks);
 
 /* Kernel.__call__ on flattened pair lists (kernel/core.py:220-257): out[p] = k(Xi[p], Xj[p]; ni[p], nj[p]).
  * hyper_deriv = -1 for the value, else the index into params (every kernel; d/dnu of

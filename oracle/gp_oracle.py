@@ -378,7 +378,72 @@ _PAIRS = {
 }
 
 
+def _powerset(items):
+    """utils.py: powerset() as used by ProductKernel (kernel/core.py:645): every sub-multiset by position."""
+    from itertools import chain, combinations
+    return chain.from_iterable(combinations(items, r) for r in range(len(items) + 1))
+
+
+def _product_pairs(fa, fb, Xi, Xj, ni, nj):
+    """ProductKernel.__call__ (kernel/core.py:628-668): for every distinct row of [ni, nj] the multiset of unit
+    derivatives is split between the two factors in every possible way (the power set BY POSITION, so equal splits
+    are visited repeatedly -- that repetition is the binomial weight)."""
+    D = Xi.shape[1]
+    nij = np.hstack((ni, nj))
+    result = np.zeros(Xi.shape[0])
+    for row in np.unique(nij, axis=0):
+        pattern = []
+        for idx in range(len(row)):
+            pattern.extend(int(row[idx]) * [idx])
+        sel = (nij == row).all(axis=1)
+        cnt = int(sel.sum())
+        for sub in _powerset(list(range(len(pattern)))):
+            n1 = np.zeros((cnt, 2 * D), dtype=int)
+            n2 = np.zeros((cnt, 2 * D), dtype=int)
+            for pos in range(len(pattern)):
+                (n1 if pos in sub else n2)[:, pattern[pos]] += 1
+            result[sel] += fa(Xi[sel], Xj[sel], n1[:, :D], n1[:, D:]) * fb(Xi[sel], Xj[sel], n2[:, :D], n2[:, D:])
+    return result
+
+
+def composite_pairs(structure, params, Xi, Xj, ni, nj, hyper_deriv=None):
+    """Sum of products of leaf kernels: the flattened form of a SumKernel / ProductKernel tree
+    (kernel/core.py:549-670).  structure = (leaf_kids, leaf_nparams, term_masks); params is the reference's
+    concatenation of the operands' parameter vectors (kernel/core.py:452-459).  hyper_deriv follows SumKernel
+    (kernel/core.py:576-582: only the operand owning the parameter contributes); inside a product the owning factor is
+    replaced by its own hyper-derivative (the reference raises NotImplementedError there, kernel/core.py:626-627)."""
+    kids, nps, masks = structure
+    Xi = np.atleast_2d(np.asarray(Xi, dtype=float))
+    Xj = np.atleast_2d(np.asarray(Xj, dtype=float))
+    ni = np.atleast_2d(np.asarray(ni, dtype=int))
+    nj = np.atleast_2d(np.asarray(nj, dtype=int))
+    params = np.asarray(params, dtype=float)
+    offs = np.concatenate([[0], np.cumsum(nps)])
+    owner, hl = None, None
+    if hyper_deriv is not None:
+        owner = int(np.searchsorted(offs, hyper_deriv, side="right") - 1)
+        hl = int(hyper_deriv - offs[owner])
+
+    def leaf(q):
+        def f(xi, xj, mi, mj):
+            return _PAIRS[kids[q]](xi, xj, mi, mj, params[offs[q]:offs[q + 1]], hyper_deriv=hl if q == owner else None)
+        return f
+
+    total = np.zeros(Xi.shape[0])
+    for mask in masks:
+        members = [q for q in range(len(kids)) if (mask >> q) & 1]
+        if owner is not None and owner not in members:
+            continue
+        f = leaf(members[-1])
+        for q in reversed(members[:-1]):   # right-nested products: a * (b * (c ...))
+            f = (lambda fa, fb: (lambda xi, xj, mi, mj: _product_pairs(fa, fb, xi, xj, mi, mj)))(leaf(q), f)
+        total += f(Xi, Xj, ni, nj)
+    return total
+
+
 def kernel_pairs(kid, params, Xi, Xj, ni, nj, hyper_deriv=None):
+    if hasattr(kid, "structure"):  # composite descriptor (anything with .structure = (kids, nparams, masks))
+        return composite_pairs(kid.structure, params, Xi, Xj, ni, nj, hyper_deriv=hyper_deriv)
     return _PAIRS[kid](Xi, Xj, ni, nj, params, hyper_deriv=hyper_deriv)
 
 

@@ -562,6 +562,43 @@ def case_product():
          sum_hd1=ks(Xi, Xj, ni, nj, hyper_deriv=1), sum_hd4=ks(Xi, Xj, ni, nj, hyper_deriv=4))
 
 
+# ---------------------------------------------------------------- kernel algebra on the device: mixed trees, GP level
+def case_composite():
+    """(SE + Matern52) * SE in 2-D on pair lists with first-derivative orders, and a GaussianProcess whose kernel is
+    SE * Matern52 + SE in 1-D with value and derivative observations (ll, alpha, K, predictions) -- the reference's own
+    SumKernel / ProductKernel (kernel/core.py:549-670)."""
+    rs = RandomState(41)
+    ka = g.SquaredExponentialKernel(num_dim=2, initial_params=[1.3, 0.4, 0.9], param_bounds=[(0, 10)] * 3)
+    kb = g.Matern52Kernel(num_dim=2, initial_params=[0.7, 0.8, 0.6], param_bounds=[(0, 10)] * 3)
+    kc = g.SquaredExponentialKernel(num_dim=2, initial_params=[0.9, 1.5, 1.2], param_bounds=[(0, 10)] * 3)
+    k = (ka + kb) * kc
+    Mp = 80
+    Xi, Xj = rs.rand(Mp, 2), rs.rand(Mp, 2)
+    Xj[:6] = Xi[:6]
+    ni, nj = np.zeros((Mp, 2), dtype=int), np.zeros((Mp, 2), dtype=int)
+    ni[np.arange(Mp), rs.randint(0, 2, Mp)] = rs.randint(0, 2, Mp)   # at most one first derivative per side
+    nj[np.arange(Mp), rs.randint(0, 2, Mp)] = rs.randint(0, 2, Mp)
+    save("composite_pairs_2d", Xi=Xi, Xj=Xj, ni=ni, nj=nj, params=np.array([float(v) for v in k.params]),
+         K=k(Xi, Xj, ni, nj))
+    # GP level, 1-D
+    k1 = g.SquaredExponentialKernel(initial_params=[1.1, 0.9], param_bounds=[(0, 10)] * 2)
+    k2 = g.Matern52Kernel(initial_params=[0.8, 0.5], param_bounds=[(0, 10)] * 2)
+    k3 = g.SquaredExponentialKernel(initial_params=[0.4, 0.15], param_bounds=[(0, 10)] * 2)
+    kg = k1 * k2 + k3
+    X = np.sort(rs.rand(40)) * 3.0
+    y = np.sin(2 * X) + 0.3 * np.sin(15 * X) + 0.05 * rs.randn(40)
+    gp = g.GaussianProcess(kg)
+    gp.add_data(X, y, err_y=0.05)
+    gp.add_data(X[::5], 2 * np.cos(2 * X[::5]), err_y=0.3, n=1)
+    out = ll_and_grad(gp, False)
+    Xs = np.linspace(0.0, 3.0, 11)
+    res = gp.predict(Xs, full_output=True)
+    out.update(Xs=Xs, mean=res["mean"], std=res["std"], cov=res["cov"])
+    res1 = gp.predict(Xs, n=1, full_output=True)
+    out.update(mean_d1=res1["mean"], std_d1=res1["std"])
+    save("composite_gp_1d", params=np.array([float(v) for v in kg.params]), **gp_state(gp), **out)
+
+
 # ---------------------------------------------------------------- other Gibbs length-scale profiles (kernel/gibbs.py:508-902)
 def case_gibbs_profiles():
     rs = RandomState(21)
@@ -618,7 +655,7 @@ def case_warped():
 if __name__ == "__main__":
     cases = [case_se2d, case_se_pairs, case_matern52, case_matern_generic, case_gibbs, case_c5_full, case_demo,
              case_c3, case_c2, case_noise, case_hyperfd, case_product, case_gibbs_profiles, case_warped,
-             case_matern_real_nu, case_hyper_mp]
+             case_matern_real_nu, case_hyper_mp, case_composite]
     only = set(sys.argv[1:])          # e.g. `make_golden.py case_hyperfd` regenerates one family
     for c in cases:
         if not only or c.__name__ in only:

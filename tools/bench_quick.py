@@ -29,5 +29,7 @@ for mode, gi in (("ll+grad", [0, 1, 2]), ("ll only", None)):
         ts.append(time.perf_counter() - t0)
     t = min(ts)
     flop = B * 512.0 ** 3 * (1.0 if gi else 1 / 3.0)
+    if gi and len(sys.argv) > 2:
+        np.save(sys.argv[2], np.column_stack([ll, g]))
     print("%s: B=%d  %.2f ms  %.0f evals/s  %.2f TFLOP/s (M^3%s counted)  status ok=%s" % (
         mode, B, t * 1e3, B / t, flop / t * 1e-12, "" if gi else "/3", (st == 0).all()))
