@@ -107,7 +107,7 @@ __device__ __forceinline__ void issue_chunk(Smem& sm, int q) {
 }
 
 // acc += A[arow.., :] * B[brow.., :]^T over one chunk; LOWER: only the 8x8 products on and below the block diagonal
-template <bool LOWER>
+template <bool LOWER, int IMAX = 4>
 __device__ __forceinline__ void chunk_mma(const double* stage, int arow, int brow, const Lane& L, double (&acc)[4][4][2]) {
     const double* aS = stage + (arow + L.g) * BK;
     const double* bS = stage + CHUNK + (brow + L.g) * BK;
@@ -117,11 +117,11 @@ __device__ __forceinline__ void chunk_mma(const double* stage, int arow, int bro
         const int col = ((kk << 2) ^ sw) + L.t;
         double a[4], b[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) a[i] = aS[i * 8 * BK + col];
+        for (int i = 0; i < IMAX; i++) a[i] = aS[i * 8 * BK + col];
 #pragma unroll
         for (int j = 0; j < 4; j++) b[j] = bS[j * 8 * BK + col];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
+        for (int i = 0; i < IMAX; i++) {
 #pragma unroll
             for (int j = 0; j < 4; j++)
                 if (!LOWER || j <= i) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
@@ -156,6 +156,9 @@ __device__ __forceinline__ void run_job(Smem& sm, const Lane& L, int nsteps, con
         if (!zero && mine) {
             const double* stage = sm.R + slt * STAGE_D;
             if (DIAG && !offd) chunk_mma<true>(stage, arow, brow, L, acc);
+            // A upper triangular (A[r][k] = 0 for k < r): in the first chunk that reaches a warp's rows (chunk 0 for
+            // rows 0..31, chunk 2 for rows 32..63) only its first 16 rows meet non-zero columns
+            else if ((fl & 1) && (q % CPT) == (arow ? CPT / 2 : 0)) chunk_mma<false, 2>(stage, arow, brow, L, acc);
             else chunk_mma<false>(stage, arow, brow, L, acc);
         }
         __syncwarp();
@@ -210,8 +213,9 @@ __device__ __forceinline__ void mult_lower_global(const double* St, const double
     const double* aS = St + (L.wr * 32 + L.g) * LDT + L.t;
     const double* bG = Binv + (L.wc * 32 + L.g) * BK + L.t;
     const int sw = swz(L.g);
+    const int kfull = kmax - 16;  // the last 16 columns only meet rows 16..31 of the warp's B block (j >= 2), below
 #pragma unroll 1
-    for (int kb = 0; kb < kmax; kb += 16) {
+    for (int kb = 0; kb < kfull; kb += 16) {
         double b[4][4];
 #pragma unroll
         for (int kk = 0; kk < 4; kk++)
@@ -227,6 +231,26 @@ __device__ __forceinline__ void mult_lower_global(const double* St, const double
             for (int j = 0; j < 4; j++) {
 #pragma unroll
                 for (int i = 0; i < 4; i++) dmma884(out[i][j][0], out[i][j][1], a[i], b[kk][j]);
+            }
+        }
+    }
+    {
+        const int kb = kfull;
+        double b[4][2];
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++)
+#pragma unroll
+            for (int j = 2; j < 4; j++)
+                b[kk][j - 2] = bG[((kb + kk * 4) / BK) * CHUNK + j * 8 * BK + (((kb + kk * 4) % BK) ^ sw)];
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+            double a[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) a[i] = aS[i * 8 * LDT + kb + kk * 4];
+#pragma unroll
+            for (int j = 2; j < 4; j++) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) dmma884(out[i][j][0], out[i][j][1], a[i], b[kk][j - 2]);
             }
         }
     }
