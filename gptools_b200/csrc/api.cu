@@ -1481,7 +1481,11 @@ static int batched_serial(gpt_handle* h, int B, const double* d_thetas, const do
 
 static int batched_common(gpt_handle* h, int B, const double* d_thetas, const double* d_y, double* d_ll,
                           double* d_grad, const int32_t* grad_idx, int P, int* d_status, double* d_alpha) {
-    if (h->hasT || (h->M + 63) / 64 > 32 || h->kid == GPT_COMPOSITE) {
+    // composite kernels whose requested gradient entries fit the persistent kernel's slots run there as well
+    bool comp_serial = false;
+    if (h->kid == GPT_COMPOSITE && d_grad && P > 0 && grad_idx)
+        for (int q = 0; q < P; q++) comp_serial |= (grad_idx[q] < h->nparams && grad_idx[q] >= 1 + GPT_MAX_DIM);
+    if (h->hasT || (h->M + 63) / 64 > 32 || comp_serial) {
         if (h->kid == GPT_KERNEL_GIBBS_AUX)
             return fail(h, GPT_ERR_UNSUPPORTED, "gpt_ll_batched: the per-point length scales of GPT_GIBBS_AUX depend on theta; use gpt_ll");
         if (!supported_kernel_h(h, h->kid, h->D, h->nparams)) return fail(h, GPT_ERR_UNSUPPORTED, "gpt_ll_batched: kernel unsupported");
@@ -1489,7 +1493,7 @@ static int batched_common(gpt_handle* h, int B, const double* d_thetas, const do
     }
     if (h->kid == GPT_KERNEL_GIBBS_AUX)
         return fail(h, GPT_ERR_UNSUPPORTED, "gpt_ll_batched: the per-point length scales of GPT_GIBBS_AUX depend on theta; use gpt_ll");
-    if (!supported_kernel(h->kid, h->D, h->nparams)) return fail(h, GPT_ERR_UNSUPPORTED, "gpt_ll_batched: kernel unsupported");
+    if (!supported_kernel_h(h, h->kid, h->D, h->nparams)) return fail(h, GPT_ERR_UNSUPPORTED, "gpt_ll_batched: kernel unsupported");
     if (P < 0 || P > GPT_MAX_PARAMS) return fail(h, GPT_ERR_USAGE, "gpt_ll_batched: bad P");
     BatchedParams bp;
     bp.kid = h->kid; bp.D = h->D; bp.nparams = h->nparams;
@@ -1502,7 +1506,7 @@ static int batched_common(gpt_handle* h, int B, const double* d_thetas, const do
     bp.nidx = (d_grad && P > 0) ? P : 0;
     for (int q = 0; q < bp.nidx; q++) {
         if (grad_idx[q] < 0 || grad_idx[q] > h->nparams) return fail(h, GPT_ERR_USAGE, "gpt_ll_batched: bad grad_idx");
-        if (grad_idx[q] == 1 && h->kid == GPT_KERNEL_MATERN)
+        if (hyper_deriv_unavailable(h, h->kid, grad_idx[q]))
             return fail(h, GPT_ERR_UNSUPPORTED, "hyper-parameter derivatives: d/dnu of the Matern kernel is not available");
         if (h->kid != GPT_KERNEL_SE && grad_idx[q] < h->nparams && grad_idx[q] >= 1 + GPT_MAX_DIM)
             return fail(h, GPT_ERR_UNSUPPORTED, "gpt_ll_batched: hyper-parameter index beyond the batched gradient slots");
@@ -1523,6 +1527,14 @@ static int batched_common(gpt_handle* h, int B, const double* d_thetas, const do
             bp.eb_off = bp.ws_per_cta;
             bp.ws_per_cta += batched_lower_tiles(bp.nT) * 4096;
         }
+    }
+    if (h->kid == GPT_COMPOSITE) {
+        bp.comp_nleaf = h->comp_nleaf; bp.comp_nterms = h->comp_nterms;
+        for (int q = 0; q < GPT_MAX_LEAVES; q++) { bp.comp_kids[q] = h->comp_kids[q]; bp.comp_nps[q] = h->comp_nps[q]; }
+        for (int t = 0; t < GPT_MAX_TERMS; t++) bp.comp_masks[t] = h->comp_masks[t];
+        bp.comp_off = bp.ws_per_cta;
+        bp.ws_per_cta += (sizeof(CovComposite) + sizeof(double) - 1) / sizeof(double);
+        bp.ws_per_cta = (bp.ws_per_cta + 15) / 16 * 16;  // keep the next CTA's tiles 128-byte aligned
     }
     if ((rc = ensure(h, h->b_ws, sizeof(double) * bp.ws_per_cta * (size_t)ctas))) return rc;
     if ((rc = ensure(h, h->b_counter, sizeof(int)))) return rc;

@@ -731,8 +731,8 @@ __device__ __forceinline__ void grad_tile(const Smem& sm, const BatchedParams& p
 #pragma unroll
                 for (int q = 0; q < 1 + GPT_MAX_DIM; q++)
                     if ((want >> q) & 1u)
-                        gall[q] += w * cov_hyper_eval(sm.cp, p.X + (size_t)gi * p.D, p.n + (size_t)gi * p.D,
-                                                      p.X + (size_t)gj * p.D, p.n + (size_t)gj * p.D, q);
+                        gall[q] += w * cov_eval(sm.cp, p.X + (size_t)gi * p.D, p.n + (size_t)gi * p.D,
+                                                p.X + (size_t)gj * p.D, p.n + (size_t)gj * p.D, q);
             }
         }
     } else {
@@ -864,6 +864,11 @@ __global__ void __launch_bounds__(THREADS, GPT_B4_MINB) ll_batched4_kernel(Batch
         if (L.tid == 0) {
             const double* th = p.thetas + (size_t)b * np1;
             cov_params_init(sm.cp, p.kid, p.D, p.nparams, th);
+            if (p.kid == GPT_KERNEL_COMPOSITE) {  // the leaves of this theta live in the CTA's workspace
+                CovComposite* cc = reinterpret_cast<CovComposite*>(ws + p.comp_off);
+                comp_init(*cc, p.D, p.comp_nleaf, p.comp_kids, p.comp_nps, p.comp_nterms, p.comp_masks, th);
+                sm.cp.comp = cc;
+            }
             sm.noise2 = th[p.nparams] * th[p.nparams];
             int tab = (p.short_forms != 0) ? 1 : 0;
             for (int d = 0; d < p.D; d++)

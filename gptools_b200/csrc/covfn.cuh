@@ -840,10 +840,11 @@ GPT_HD double cov_eval(const CovParams& cp, const double* xi, const int32_t* ni,
 
 // Host side of a composite: leaves initialised from the concatenated parameter vector.  `kids` / `nps` describe the
 // leaves, `masks` the product terms.  Returns the number of parameters, or -1 when the description is not valid.
-inline int comp_init(CovComposite& c, int D, int nleaf, const int32_t* kids, const int32_t* nps, int nterms,
+GPT_HD int comp_init(CovComposite& c, int D, int nleaf, const int32_t* kids, const int32_t* nps, int nterms,
                      const int32_t* masks, const double* params) {
     if (nleaf < 1 || nleaf > GPT_MAX_LEAVES || nterms < 1 || nterms > GPT_MAX_TERMS) return -1;
-    memset(&c, 0, sizeof(c));
+    for (int q = 0; q < GPT_MAX_LEAVES; q++) c.off[q] = 0;
+    for (int t = 0; t < GPT_MAX_TERMS; t++) c.mask[t] = 0;
     c.nleaf = nleaf;
     c.nterms = nterms;
     int off = 0;

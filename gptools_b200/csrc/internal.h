@@ -138,6 +138,11 @@ struct BatchedParams {
     int short_forms = 0;     // SE, D <= 2, orders <= 1: short closed forms + cached exponentials (batched4.cu)
     size_t eb_off = 0;       // offset (doubles) inside the CTA workspace of the cached sigma^2 exp(-r^2/2) tiles
     long long* phase_cycles;  // optional (8): per-phase cycle sums, only with -DGPT_PHASE_TIMING
+    // kid == GPT_KERNEL_COMPOSITE: the structure (leaf kernels, parameter counts, product terms); every CTA keeps the
+    // leaves of its current theta in its workspace at comp_off (doubles)
+    int comp_nleaf = 0, comp_nterms = 0;
+    int32_t comp_kids[GPT_MAX_LEAVES] = {0}, comp_nps[GPT_MAX_LEAVES] = {0}, comp_masks[GPT_MAX_TERMS] = {0};
+    size_t comp_off = 0;
 };
 size_t batched_ws_doubles_per_cta(int nT);
 size_t batched_lower_tiles(int nT);

@@ -202,7 +202,7 @@ class BinaryKernel(Kernel):
         return None
 
     def batchable(self, with_deriv):
-        return True  # the library runs composite kernels theta after theta inside the batched call
+        return True  # the library decides: persistent many-theta kernel, or theta after theta beyond its gradient slots
 
     def batch_rows_supported(self, param_rows):
         param_rows = np.atleast_2d(param_rows)

@@ -74,7 +74,8 @@ int gpt_set_kernel(gpt_handle* h, int kernel_id, int nparams, double diag_factor
  * rule over the derivative orders exactly like the reference's enumeration of derivative subsets (kernel/core.py:632-668).
  * Afterwards kernel id GPT_COMPOSITE (nparams = sum of leaf_nparams) is accepted by gpt_set_kernel, gpt_cov_pairs and
  * gpt_compute_Kij on this handle; hyper_deriv / grad_idx index the concatenated parameter vector (the reference has
- * hyper-derivatives for sums only).  gpt_ll_batched runs composite kernels theta after theta on the device. */
+ * hyper-derivatives for sums only).  gpt_ll_batched runs composite kernels in its persistent many-theta kernel (the leaves
+ * of a theta live in the CTA's workspace); gradient requests beyond parameter index 6 run theta after theta instead. */
 int gpt_define_composite(gpt_handle* h, int nleaf, const int32_t* leaf_kernel_ids, const int32_t* leaf_nparams,
                          int nterms, const int32_t* term_masks);
 
