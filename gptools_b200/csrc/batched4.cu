@@ -64,7 +64,8 @@ struct Smem {
     unsigned int cnt[STAGES];         // warps done with the slot (mod 4); the last one refills it
     double piv[8];  // product of the 8 pivots of each 8x8 pivot block of the tile being factored
     double exptab[64];  // 2^(j/64), for exp_nonpos_tab
-    double rk[TB], zk[TB];
+    __align__(16) double rk[TB];
+    __align__(16) double zk[TB];  // read as double2 by acc_times_vec
     double red[4][GPT_MAX_PARAMS + 2];
     const double* a[MAXT];
     const double* b[MAXT];
@@ -204,6 +205,23 @@ __device__ __forceinline__ void acc_to_global(double* tile, const Lane& L, const
         }
 }
 
+// Row sums of (accumulator tile) x v over this warp's 32 columns -> part[wc * 64 + row]; v: 64 doubles in shared memory.
+// The two column halves are added by the caller after a CTA barrier (fixed order: deterministic).
+__device__ __forceinline__ void acc_times_vec(const double (&out)[4][4][2], const double* v, const Lane& L, double* part) {
+    double2 vv[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) vv[j] = *reinterpret_cast<const double2*>(v + L.wc * 32 + j * 8 + 2 * L.t);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) s = fma(out[i][j][1], vv[j].y, fma(out[i][j][0], vv[j].x, s));
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (L.t == 0) part[L.wc * 64 + L.wr * 32 + i * 8 + L.g] = s;
+    }
+}
+
 // out = St * Binv^T, St in shared (stride LDT), Binv a lower-triangular 64x64 tile in GLOBAL memory (tix layout):
 // the B fragments are fetched straight from L2, four k-steps per batch, so no shared buffer is needed for them.
 __device__ __forceinline__ void mult_lower_global(const double* St, const double* Binv, const Lane& L,
@@ -301,48 +319,46 @@ __device__ __forceinline__ void blk_mma(double* C, const double* A, const double
     *reinterpret_cast<double2*>(C + g * LDT + 2 * t) = c;
 }
 
-// Pivot block: P (8x8 SPD, lower valid) -> chol(P)^{-1} (lower, zeros above), every lane of ONE warp redundantly
-// (no shuffles, fully unrolled scalar Gauss-Jordan sweep in registers).  Returns prod of the pivots.
+// Pivot block: P (8x8 SPD, lower valid) -> chol(P)^{-1} (lower, zeros above) by ONE warp, in place: an LDL^T
+// Gauss-Jordan sweep with the block distributed over the lanes like a DMMA C fragment (lane = 4 row + q holds columns
+// 2q, 2q+1 of its row), pivot row / column broadcast by shuffles.  Every FP64 instruction of this serial chain waits
+// for a slot between the DMMAs of the co-resident CTAs, so what counts is their number: ~70 here, against ~290 when
+// every lane swept the whole block redundantly.  Returns the product of the pivots.
 __device__ __forceinline__ double diag8(Smem& sm, double* P, int lane, int row0) {
-    double p[8][8];
-#pragma unroll
-    for (int i = 0; i < 8; i++)
-#pragma unroll
-        for (int j = 0; j <= i; j++) p[i][j] = P[i * LDT + j];
-    __syncwarp();  // the result overwrites P: all lanes have read it
-    double dprod = 1.0;
-    double dsave[8];
+    const int r = lane >> 2, q = lane & 3;
+    const int c0 = 2 * q, c1 = c0 + 1;
+    const double2 pv = *reinterpret_cast<const double2*>(P + r * LDT + c0);
+    double p0 = pv.x, p1 = pv.y;  // entries above the diagonal (c > r) are never read by the sweep
+    double dprod = 1.0, myd = 1.0;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-        double d = p[j][j];
+        const double pub = (j & 1) ? p1 : p0;                               // this lane's entry of column pair j / 2
+        const double rj0 = __shfl_sync(0xffffffffu, p0, j * 4 + q);         // p[j][c0]
+        const double rj1 = __shfl_sync(0xffffffffu, p1, j * 4 + q);         // p[j][c1]
+        double d = __shfl_sync(0xffffffffu, pub, j * 4 + (j >> 1));         // p[j][j]
+        const double colr = __shfl_sync(0xffffffffu, pub, r * 4 + (j >> 1));   // p[r][j]
+        const double cc0 = __shfl_sync(0xffffffffu, pub, c0 * 4 + (j >> 1));   // p[c0][j]
+        const double cc1 = __shfl_sync(0xffffffffu, pub, c1 * 4 + (j >> 1));   // p[c1][j]
         if (!(d > 0.0)) {
             if (lane == 0 && sm.info == 0) sm.info = row0 + j + 1;
             d = 1.0;
         }
-        dsave[j] = d;
+        myd = (r == j) ? d : myd;
         dprod *= d;
         const double rinv = fast_rcp_pos(d);
-        double w[8];
-#pragma unroll
-        for (int c = 0; c < 8; c++) w[c] = (c > j) ? p[c][j] : ((c < j) ? p[j][c] : 0.0);
-#pragma unroll
-        for (int r = j + 1; r < 8; r++) {
-            const double mult = w[r] * rinv;
-#pragma unroll
-            for (int c = 0; c <= r; c++) {
-                if (c == j) p[r][c] = -mult;
-                else p[r][c] -= mult * w[c];
-            }
+        const double w0 = (c0 > j) ? cc0 : ((c0 < j) ? rj0 : 0.0);
+        const double w1 = (c1 > j) ? cc1 : ((c1 < j) ? rj1 : 0.0);
+        if (r > j) {
+            const double mult = colr * rinv;
+            p0 = (c0 == j) ? -mult : fma(-mult, w0, p0);
+            p1 = (c1 == j) ? -mult : fma(-mult, w1, p1);
         }
     }
-    // every lane holds every value: uniform (same address, same data) shared-memory stores; 64 lane-predicated
-    // branches here cost several times the elimination itself
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const double rs = fast_rsqrt_pos(dsave[i]);
-#pragma unroll
-        for (int j = 0; j < 8; j++) P[i * LDT + j] = (j < i) ? p[i][j] * rs : ((j == i) ? rs : 0.0);
-    }
+    const double rs = fast_rsqrt_pos(myd);
+    double2 o;
+    o.x = (c0 < r) ? p0 * rs : ((c0 == r) ? rs : 0.0);
+    o.y = (c1 < r) ? p1 * rs : ((c1 == r) ? rs : 0.0);
+    *reinterpret_cast<double2*>(P + r * LDT + c0) = o;
     __syncwarp();
     return dprod;
 }
@@ -877,6 +893,13 @@ __global__ void __launch_bounds__(THREADS, GPT_B4_MINB) ll_batched4_kernel(Batch
         }
         __syncthreads();
         const double* yb = p.y + (size_t)b * p.y_stride;
+        // running residual r = y - sum_j L(., j) z_j: every panel tile subtracts its share as it is produced (below), so
+        // the diagonal tile finds r_k complete instead of re-reading its block row from memory
+        if (L.tid < TB)
+            for (int k = 0; k < nT; k++) {
+                const int gi = k * TB + L.tid;
+                rvec[gi] = (gi < p.M) ? yb[gi] : 0.0;
+            }
         double logdet = 0.0, zz = 0.0;  // thread 0
         PT_DECL;
 
@@ -885,6 +908,8 @@ __global__ void __launch_bounds__(THREADS, GPT_B4_MINB) ll_batched4_kernel(Batch
         for (int q = 0; q < 1 + GPT_MAX_DIM; q++) gall[q] = 0.0;
         double tr_kinv = 0.0;
         const bool need_alpha = (p.nidx > 0) || (p.alpha_out != nullptr);
+        // with a gradient request sweep 2 produces L^{-T} tile by tile: alpha = L^{-T} z accumulates in its epilogues
+        const bool fused_alpha = (p.nidx > 0);
 
         // One job loop for the three tile sweeps, so that the operand ring, the panel product and the tile epilogues are
         // each instantiated ONCE: the four CTAs of an SM sit in different phases, and the instruction cache has to
@@ -896,7 +921,7 @@ __global__ void __launch_bounds__(THREADS, GPT_B4_MINB) ll_batched4_kernel(Batch
         for (int ph = 1; ph <= 3; ph++) {
             if (ph == 2) {
                 __threadfence_block();
-                if (need_alpha) {
+                if (need_alpha && !fused_alpha) {
                     PT_MARK(7);
                     // ======================= alpha = L^{-T} z (block back substitution) =======================
                     for (int i = L.tid; i < nT * TB; i += THREADS) rvec[i] = zvec[i];
@@ -929,7 +954,17 @@ __global__ void __launch_bounds__(THREADS, GPT_B4_MINB) ll_batched4_kernel(Batch
                 }
                 if (!(p.nidx > 0 && sm.info == 0)) break;
             }
-            if (ph == 3) __threadfence_block();
+            if (ph == 3) {
+                // alpha is complete; its sweep-2 updates were reductions performed at L2: read them back past L1 and
+                // store them again so that the plain loads of sweep 3 see them
+                __threadfence_block();
+                __syncthreads();
+                if (L.tid < TB)
+                    for (int k = 0; k < nT; k++) avec[k * TB + L.tid] = __ldcg(avec + k * TB + L.tid);
+                __syncthreads();
+                if (p.alpha_out != nullptr)
+                    for (int i = L.tid; i < p.M; i += THREADS) p.alpha_out[(size_t)b * p.M + i] = avec[i];
+            }
 #pragma unroll 1
             for (int o = (ph == 2) ? 1 : 0; o < nT; o++) {
                 const int i0 = (ph == 2) ? 0 : o, i1 = (ph == 2) ? o : nT;
@@ -945,6 +980,7 @@ __global__ void __launch_bounds__(THREADS, GPT_B4_MINB) ll_batched4_kernel(Batch
                         sm.b[L.tid] = bb;
                         sm.flag[L.tid] = (unsigned char)fl;
                     }
+                    if (ph == 2 && i == i0 && L.tid < TB) sm.zk[L.tid] = __ldcg(zvec + I * TB + L.tid);  // published by run_job's barrier
                     zero_acc(acc);
                     const double* ebt = ws + p.eb_off + (size_t)(I * (I + 1) / 2 + J) * TILE;
                     if (ph == 3 && sm.use_tab) {  // the cached exponentials of this tile: on their way to L2 while the products run
@@ -968,17 +1004,8 @@ __global__ void __launch_bounds__(THREADS, GPT_B4_MINB) ll_batched4_kernel(Batch
                         PT_MARK(1);
                         if (diag) {
                             const int k = J;
-                            // residual r_k = y_k - sum_j L(k,j) z_j : 2 threads per row, 32 columns each
-                            {
-                                const int r = L.tid >> 1, h2 = L.tid & 1;
-                                double s = 0.0;
-                                for (int j = 0; j < k; j++) s += row_dot32(slot(ws, k, j), r, h2 * 32, zvec + j * TB + h2 * 32);
-                                s += __shfl_xor_sync(0xffffffffu, s, 1);
-                                if (h2 == 0) {
-                                    const int gi = k * TB + r;
-                                    sm.rk[r] = ((gi < p.M) ? yb[gi] : 0.0) - s;
-                                }
-                            }
+                            // residual r_k = y_k - sum_j L(k,j) z_j: accumulated by the panel epilogues of the columns before
+                            if (L.tid < TB) sm.rk[L.tid] = __ldcg(rvec + k * TB + L.tid);
                             __syncthreads();
                             PT_MARK(4);
                             potrf_inv_tile(sm, L, St, k * TB);
@@ -1006,6 +1033,12 @@ __global__ void __launch_bounds__(THREADS, GPT_B4_MINB) ll_batched4_kernel(Batch
                                 for (int c = 0; c < TB; c++) s += sm.zk[c] * sm.zk[c];
                                 zz += s;
                             }
+                            if (fused_alpha && L.tid >= TB) {  // diagonal term of alpha_k = sum_I (L^{-1}(I,k))^T z_I
+                                const int a = L.tid - TB;
+                                double s = 0.0;
+                                for (int c = a; c < TB; c++) s = fma(St[c * LDT + a], sm.zk[c], s);
+                                avec[k * TB + a] = s;
+                            }
                         } else {
                             __syncthreads();
                         }
@@ -1014,10 +1047,17 @@ __global__ void __launch_bounds__(THREADS, GPT_B4_MINB) ll_batched4_kernel(Batch
                         // panel: L(I,k) = C(I,k) Inv_k^T   /   XT tile: -(sum) Inv_I^T
                         double out[4][4][2];
                         mult_lower_global(St, (ph == 1) ? slot(ws, J, J) : slot(ws, I, I), L, out);
+                        // sweep 1: r_I -= L(I,k) z_k;  sweep 2: alpha_J += (L^{-1}(I,J))^T z_I  (the stored tile is -out)
+                        acc_times_vec(out, sm.zk, L, sm.R + PTS_OFF);
                         acc_to_global(slot(ws, I, J), L, out, (ph == 1) ? 1.0 : -1.0);
                     }
                     if (ph != 3) {
                         __syncthreads();
+                        if (!diag && L.tid < TB) {
+                            const double* part = sm.R + PTS_OFF;
+                            double* target = (ph == 1) ? rvec + I * TB : avec + J * TB;
+                            atomicAdd(target + L.tid, -(part[L.tid] + part[64 + L.tid]));  // one update per address and job
+                        }
                         PT_MARK(3);
                     } else {
                         if constexpr (FD == 1 || FD == 2) {
