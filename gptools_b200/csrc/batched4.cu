@@ -222,56 +222,60 @@ __device__ __forceinline__ void acc_times_vec(const double (&out)[4][4][2], cons
     }
 }
 
-// out = St * Binv^T, St in shared (stride LDT), Binv a lower-triangular 64x64 tile in GLOBAL memory (tix layout):
-// the B fragments are fetched straight from L2, four k-steps per batch, so no shared buffer is needed for them.
+// out = St * Binv^T, St in shared (stride LDT), Binv a lower-triangular 64x64 tile in GLOBAL memory (tix layout).
+// The B fragments are fetched straight from L2 (no shared buffer), eight columns per group, ONE GROUP AHEAD of the
+// products that consume them (the loads of a group used to sit exposed in front of its DMMAs: the panel products ran
+// at a third of the efficiency of the ring-fed jobs).  Binv[n][c] = 0 for c > n: the four groups that cross the warp's
+// 32 rows of B use compile-time row ranges (8-row block j of B meets column group s only for j >= s).
+template <int JMIN>
+__device__ __forceinline__ void panel_load_b(double (&b)[2][4], const double* bG, int kcol, int sw) {
+#pragma unroll
+    for (int kk = 0; kk < 2; kk++)
+#pragma unroll
+        for (int j = JMIN; j < 4; j++)
+            b[kk][j] = bG[((kcol + kk * 4) / BK) * CHUNK + j * 8 * BK + (((kcol + kk * 4) % BK) ^ sw)];
+}
+template <int JMIN>
+__device__ __forceinline__ void panel_mma(double (&out)[4][4][2], const double* aS, int kcol, const double (&b)[2][4]) {
+#pragma unroll
+    for (int kk = 0; kk < 2; kk++) {
+        double a[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) a[i] = aS[i * 8 * LDT + kcol + kk * 4];
+#pragma unroll
+        for (int j = JMIN; j < 4; j++) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) dmma884(out[i][j][0], out[i][j][1], a[i], b[kk][j]);
+        }
+    }
+}
 __device__ __forceinline__ void mult_lower_global(const double* St, const double* Binv, const Lane& L,
                                                   double (&out)[4][4][2]) {
     zero_acc(out);
-    const int kmax = (L.wc + 1) * 32;  // Binv[n][c] = 0 for c > n
     const double* aS = St + (L.wr * 32 + L.g) * LDT + L.t;
     const double* bG = Binv + (L.wc * 32 + L.g) * BK + L.t;
     const int sw = swz(L.g);
-    const int kfull = kmax - 16;  // the last 16 columns only meet rows 16..31 of the warp's B block (j >= 2), below
+    const int base = L.wc * 32;  // first column of the triangular part of this warp's rows of B
+    double bc[2][4], bn[2][4];
+    panel_load_b<0>(bc, bG, 0, sw);
+    if (L.wc) {  // columns 0..31: dense for rows 32..63
 #pragma unroll 1
-    for (int kb = 0; kb < kfull; kb += 16) {
-        double b[4][4];
+        for (int kcol = 0; kcol < 32; kcol += 8) {
+            panel_load_b<0>(bn, bG, kcol + 8, sw);  // the last one is group 0 of the triangular part
+            panel_mma<0>(out, aS, kcol, bc);
 #pragma unroll
-        for (int kk = 0; kk < 4; kk++)
+            for (int kk = 0; kk < 2; kk++)
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-                b[kk][j] = bG[((kb + kk * 4) / BK) * CHUNK + j * 8 * BK + (((kb + kk * 4) % BK) ^ sw)];
-#pragma unroll
-        for (int kk = 0; kk < 4; kk++) {
-            double a[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) a[i] = aS[i * 8 * LDT + kb + kk * 4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-#pragma unroll
-                for (int i = 0; i < 4; i++) dmma884(out[i][j][0], out[i][j][1], a[i], b[kk][j]);
-            }
+                for (int j2 = 0; j2 < 4; j2++) bc[kk][j2] = bn[kk][j2];
         }
     }
-    {
-        const int kb = kfull;
-        double b[4][2];
-#pragma unroll
-        for (int kk = 0; kk < 4; kk++)
-#pragma unroll
-            for (int j = 2; j < 4; j++)
-                b[kk][j - 2] = bG[((kb + kk * 4) / BK) * CHUNK + j * 8 * BK + (((kb + kk * 4) % BK) ^ sw)];
-#pragma unroll
-        for (int kk = 0; kk < 4; kk++) {
-            double a[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) a[i] = aS[i * 8 * LDT + kb + kk * 4];
-#pragma unroll
-            for (int j = 2; j < 4; j++) {
-#pragma unroll
-                for (int i = 0; i < 4; i++) dmma884(out[i][j][0], out[i][j][1], a[i], b[kk][j - 2]);
-            }
-        }
-    }
+    panel_load_b<1>(bn, bG, base + 8, sw);
+    panel_mma<0>(out, aS, base, bc);
+    panel_load_b<2>(bc, bG, base + 16, sw);
+    panel_mma<1>(out, aS, base + 8, bn);
+    panel_load_b<3>(bn, bG, base + 24, sw);
+    panel_mma<2>(out, aS, base + 16, bc);
+    panel_mma<3>(out, aS, base + 24, bn);
 }
 
 // sum_{c < 32} tile(r, c0 + c) * v[c] for a workspace tile (tix layout), c0 a multiple of 32; 16-byte loads
