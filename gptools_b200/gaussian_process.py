@@ -655,7 +655,7 @@ class GaussianProcess(object):
             self.k.check_hyper_deriv(list(kfree))
             grad_idx = list(kfree) + ([nparams] if nn > 0 else [])
         need_alpha = bool(with_deriv and self.mu is not None and self.mu.num_free_params > 0)
-        full_eval = np.where(ok[:, None], full, np.tile(base_row, (B, 1)))
+        full_eval = full if ok.all() else np.where(ok[:, None], full, np.tile(base_row, (B, 1)))
         return dict(dev=dev, thetas=thetas, B=B, nk=nk, nn=nn, n_free=n_free, with_deriv=with_deriv, logp=logp, ok=ok,
                     y_batch=y_batch, grad_idx=grad_idx, need_alpha=need_alpha, full_eval=full_eval,
                     all_params=all_params, free_mask=free_mask)

@@ -229,13 +229,19 @@ class UniformJointPrior(JointPrior):
         nb = min(thetas.shape[1], len(self.bounds))
         if nb == 0:
             return np.zeros(thetas.shape[0])
-        lo = np.array([self.bounds[i][0] for i in range(nb)], dtype=float)
-        hi = np.array([self.bounds[i][1] for i in range(nb)], dtype=float)
-        inside = ((thetas[:, :nb] >= lo) & (thetas[:, :nb] <= hi)).all(axis=1)
+        lo = [float(self.bounds[i][0]) for i in range(nb)]
+        hi = [float(self.bounds[i][1]) for i in range(nb)]
+        # column by column: a broadcast over a last axis of length <= 10 costs several times as much in numpy
+        inside = None
         ll = 0.0
-        for width in (hi - lo):           # same accumulation order as the scalar call
-            ll += -np.log(width)
-        return np.where(inside, ll, -np.inf)
+        for i in range(nb):
+            col = thetas[:, i]
+            ok = (col >= lo[i]) & (col <= hi[i])
+            inside = ok if inside is None else (inside & ok)
+            ll += -np.log(hi[i] - lo[i])          # same accumulation order as the scalar call
+        out = np.full(thetas.shape[0], ll)
+        out[~inside] = -np.inf
+        return out
 
     def dlogpdf_batch(self, thetas, hyper_deriv):
         return np.zeros(np.atleast_2d(thetas).shape[0])

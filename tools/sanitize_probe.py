@@ -35,3 +35,16 @@ d.set_data(X, np.zeros((N, 1), int), rs.rand(Mo), np.full(Mo, 0.05), T)
 d.set_kernel(0, 2, 1e2)
 print(d.ll(np.array([1.0, 0.2]), 0.0, grad_idx=[0, 1]))
 print(d.predict(np.array([[0.5]]), np.zeros((1, 1), int), want_var=True))
+# kernel algebra on the device: (SE + Matern52) * SE through gpt_ll, the persistent batched kernel and predict
+import gptools_b200 as g
+se = lambda p: g.SquaredExponentialKernel(num_dim=2, initial_params=p, param_bounds=[(0, 10)] * 3)
+kc = (se([1.0, 0.4, 0.5]) + g.Matern52Kernel(num_dim=2, initial_params=[0.7, 0.8, 0.6], param_bounds=[(0, 10)] * 3)) * se([0.9, 1.5, 1.2])
+Xc = rs.rand(150, 2)
+gp = g.GaussianProcess(kc, use_hyper_deriv=True)
+gp.add_data(Xc, np.sin(3 * Xc[:, 0]) + 0.05 * rs.randn(150), err_y=0.05)
+gp.add_data(Xc[::10], 3 * np.cos(3 * Xc[::10, 0]), err_y=0.1, n=np.tile([1, 0], (15, 1)))
+th = np.array(gp.free_params[:], dtype=float)
+import warnings
+warnings.simplefilter("ignore")
+print(gp.update_hyperparameters(th)[0], gp.update_hyperparameters_batch(np.vstack([th, 1.02 * th]), with_deriv=True)[0])
+print(gp.predict(rs.rand(5, 2))[0])
