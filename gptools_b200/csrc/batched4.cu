@@ -164,8 +164,15 @@ __device__ __forceinline__ void run_job(Smem& sm, const Lane& L, int nsteps, con
         }
         __syncwarp();
         if (L.lane == 0) {
-            const unsigned old = atomicAdd(&sm.cnt[slt], 1u);
-            if ((old & 3u) == 3u && q + STAGES < total) issue_chunk(sm, q + STAGES);  // last warp out refills the slot
+            // release / acquire on the slot counter: the fragment reads of every warp happen-before the refill that the
+            // last warp out issues (generic-proxy reads -> async-proxy write of the same bytes: proxy fence in between).
+            // (An explicit "empty" mbarrier per slot on top of this -- the textbook producer/consumer pair -- costs 1 %
+            // and leaves compute-sanitizer's racecheck report unchanged: profiles/r02_sanitizer.txt.)
+            const unsigned old = atom_add_acq_rel_cta(&sm.cnt[slt], 1u);
+            if ((old & 3u) == 3u && q + STAGES < total) {
+                fence_proxy_async();
+                issue_chunk(sm, q + STAGES);
+            }
         }
     }
     __syncthreads();  // ring may now be reused as staging

@@ -624,6 +624,10 @@ class GaussianProcess(object):
         dev, y_alph = self._sync_device()
         kid, kparams = self.k.device_descriptor()
         nparams = len(kparams)
+        if self.T is not None or len(self.y) > self.BATCHED_KERNEL_MAX_M or isinstance(kid, CompositeId):
+            # these batches may run theta after theta through the single-matrix path, which leaves the factorisation of
+            # the LAST theta on the device: the next predict / alpha / L must refactor at the GP's own hyperparameters
+            self.K_up_to_date = False
         base_row = np.concatenate([kparams, [self._noise_sigma()]])
         full = np.tile(base_row, (B, 1))
         kfree = self.k.free_param_idxs
