@@ -81,6 +81,8 @@ SIGNATURES = {
     "gpt_ll_batched": (ctypes.c_int, [_vp, ctypes.c_int, _c_double_p, _c_double_p, _c_double_p, _c_double_p,
                                       _c_int32_p, ctypes.c_int, _c_int_p, _c_double_p]),
     "gpt_ll_batched_dev": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, _vp, _vp, _c_int32_p, ctypes.c_int, _vp, _vp]),
+    "gpt_predict_batched": (ctypes.c_int, [_vp, ctypes.c_int, _c_double_p, _c_double_p, ctypes.c_int, _c_double_p,
+                                           _c_int32_p, _c_double_p, _c_double_p, _c_double_p, _c_int_p]),
     "gpt_predict": (ctypes.c_int, [_vp, ctypes.c_int, _c_double_p, _c_int32_p, _c_double_p, _c_double_p,
                                    _c_double_p]),
     "gpt_predict_dev": (ctypes.c_int, [_vp, ctypes.c_int, _c_double_p, _c_int32_p, _vp, _vp]),
@@ -350,6 +352,30 @@ class Device(object):
         self._check(self._lib.gpt_ll_batched_dev(self._h, int(B), _vp(d_thetas), _vp(d_y_batch) if d_y_batch else None,
                                                  _vp(d_ll), _vp(d_grad) if d_grad else None, _ip(gi), P, _vp(d_status),
                                                  _vp(d_alpha) if d_alpha else None), "gpt_ll_batched_dev")
+
+    def predict_batched(self, thetas, Xs, ns, y_batch=None):
+        """Predictive mean and variance at every row of ``thetas`` (B, nparams + 1) in one launch.
+        Returns (mean (B, Ms), var (B, Ms), ll (B,), status (B,)); raises NotImplementedError when the library cannot
+        serve the batch with its persistent kernel (transformation matrix, more than 2048 observations)."""
+        self._own_structure()
+        thetas = _f64(np.atleast_2d(thetas))
+        B = thetas.shape[0]
+        if thetas.shape[1] != self.nparams + 1:
+            raise ValueError("thetas must be (B, nparams + 1)")
+        Xs = _f64(np.atleast_2d(Xs))
+        Ms = Xs.shape[0]
+        if Xs.shape[1] != self.D:
+            raise ValueError("Xs must be (Ms, %d)" % self.D)
+        ns = _i32(np.atleast_2d(ns), (Ms, self.D))
+        yb = _f64(y_batch, (B, self.M)) if y_batch is not None else None
+        mean = np.empty((B, Ms), dtype=np.float64)
+        var = np.empty((B, Ms), dtype=np.float64)
+        ll = np.empty(B, dtype=np.float64)
+        status = np.zeros(B, dtype=np.int32)
+        self._check(self._lib.gpt_predict_batched(self._h, B, _dp(thetas), _dp(yb), Ms, _dp(Xs), _ip(ns), _dp(mean),
+                                                  _dp(var), _dp(ll), status.ctypes.data_as(_c_int_p)),
+                    "gpt_predict_batched")
+        return mean, var, ll, status
 
     # -- prediction -------------------------------------------------------------------------------
     def predict(self, Xs, ns, want_var=True, want_cov=False):

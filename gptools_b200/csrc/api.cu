@@ -64,6 +64,7 @@ struct gpt_handle {
     DevBuf Xs, ns, Kst, Kso, kss, mean, var, cov, Rt, smp;
     // batched
     DevBuf b_thetas, b_y, b_ll, b_grad, b_status, b_alpha, b_ws, b_counter;
+    DevBuf b_Xext, b_next, b_pmean, b_pvar;  // batched prediction: extended point arrays, outputs
     DevBuf ds_C, ds_inv, ds_panel, ds_logdet, ds_info, ds_R, ds_Rt, ds_O, ds_mu, ds_jit;  // draw_sample scratch
     DevBuf flags;  // backsolve chain: one int per 128-row block
     DevBuf Vtmp;  // predict: one 128-column block of V^T (out-of-place multiply by the block inverse)
@@ -636,7 +637,8 @@ void gpt_destroy(gpt_handle* h) {
                      &h->gout, &h->u, &h->Sg, &h->Yt, &h->Xs, &h->ns, &h->Kst, &h->Kso, &h->kss, &h->mean, &h->var,
                      &h->cov, &h->Rt, &h->smp, &h->b_thetas, &h->b_y, &h->b_ll, &h->b_grad, &h->b_status,
                      &h->llred, &h->b_alpha, &h->b_ws, &h->b_counter, &h->Vtmp, &h->flags, &h->ds_C, &h->ds_inv, &h->ds_panel, &h->ds_logdet,
-                     &h->ds_info, &h->ds_R, &h->ds_Rt, &h->ds_O, &h->ds_mu, &h->ds_jit, &h->comp_dev};
+                     &h->ds_info, &h->ds_R, &h->ds_Rt, &h->ds_O, &h->ds_mu, &h->ds_jit, &h->comp_dev,
+                     &h->b_Xext, &h->b_next, &h->b_pmean, &h->b_pvar};
     for (DevBuf* b : all) release(*b);
     if (h->side_stream) {
         cudaStreamSynchronize(h->side_stream);
@@ -1479,8 +1481,19 @@ static int batched_serial(gpt_handle* h, int B, const double* d_thetas, const do
     return check_launch(h);
 }
 
+// Test points of a prediction batch (already appended to the extended point arrays h->b_Xext / h->b_next)
+struct PredictBatch {
+    int Ms = 0;
+    int max_order = 0;
+    double* d_mean = nullptr;
+    double* d_var = nullptr;
+};
+
 static int batched_common(gpt_handle* h, int B, const double* d_thetas, const double* d_y, double* d_ll,
-                          double* d_grad, const int32_t* grad_idx, int P, int* d_status, double* d_alpha) {
+                          double* d_grad, const int32_t* grad_idx, int P, int* d_status, double* d_alpha,
+                          const PredictBatch* pb = nullptr) {
+    if (pb && (h->hasT || (h->M + 63) / 64 > 32 || h->kid == GPT_KERNEL_GIBBS_AUX || (d_grad && P > 0)))
+        return fail(h, GPT_ERR_UNSUPPORTED, "gpt_predict_batched: needs the persistent many-theta kernel (no T, at most 2048 observations, no gradient request)");
     // composite kernels whose requested gradient entries fit the persistent kernel's slots run there as well
     bool comp_serial = false;
     if (h->kid == GPT_COMPOSITE && d_grad && P > 0 && grad_idx)
@@ -1499,7 +1512,12 @@ static int batched_common(gpt_handle* h, int B, const double* d_thetas, const do
     bp.kid = h->kid; bp.D = h->D; bp.nparams = h->nparams;
     bp.M = h->M; bp.nT = (h->M + 63) / 64;
     bp.X = ptr<double>(h->X); bp.n = ptr<int32_t>(h->n);
-    bp.low_order = (h->max_order <= 1) ? 1 : 0;
+    bp.low_order = (h->max_order <= 1 && (!pb || pb->max_order <= 1)) ? 1 : 0;
+    if (pb) {
+        bp.X = ptr<double>(h->b_Xext); bp.n = ptr<int32_t>(h->b_next);
+        bp.Ms = pb->Ms; bp.nTs = (pb->Ms + 63) / 64;
+        bp.pmean = pb->d_mean; bp.pvar = pb->d_var;
+    }
     bp.y = d_y ? d_y : ptr<double>(h->y); bp.y_stride = d_y ? h->M : 0;
     bp.diag = ptr<double>(h->diag);
     bp.B = B; bp.thetas = d_thetas;
@@ -1527,6 +1545,14 @@ static int batched_common(gpt_handle* h, int B, const double* d_thetas, const do
             bp.eb_off = bp.ws_per_cta;
             bp.ws_per_cta += batched_lower_tiles(bp.nT) * 4096;
         }
+    }
+    if (pb) {
+        bp.ts_off = bp.ws_per_cta;
+        bp.ws_per_cta += (size_t)bp.nTs * bp.nT * 4096;
+        bp.pv_off = bp.ws_per_cta;
+        bp.ws_per_cta += (size_t)2 * bp.nTs * 64;
+        if (sizeof(double) * bp.ws_per_cta * (size_t)ctas > ((size_t)24 << 30))
+            return fail(h, GPT_ERR_UNSUPPORTED, "gpt_predict_batched: too many test points for one call (workspace > 24 GB); split them");
     }
     if (h->kid == GPT_COMPOSITE) {
         bp.comp_nleaf = h->comp_nleaf; bp.comp_nterms = h->comp_nterms;
@@ -1572,6 +1598,54 @@ int gpt_ll_batched_dev(gpt_handle* h, int B, const double* d_thetas, const doubl
     if (h->M < 1 || h->kid < 0) return fail(h, GPT_ERR_USAGE, "gpt_ll_batched: set_data / set_kernel first");
     CUDA_OK(h, cudaSetDevice(h->device));
     return batched_common(h, B, d_thetas, d_y_batch, d_ll, d_grad, grad_idx, P, d_status, d_alpha_out);
+}
+
+int gpt_predict_batched(gpt_handle* h, int B, const double* thetas, const double* y_batch, int Ms, const double* Xs,
+                        const int32_t* ns, double* mean, double* var, double* ll, int* status) {
+    if (h && (B == 0 || Ms == 0)) return 0;  // empty batch / no test points
+    if (!h || B < 1 || Ms < 1 || !thetas || !Xs || !ns || !mean || !var || !status)
+        return fail(h, GPT_ERR_USAGE, "gpt_predict_batched: bad arguments");
+    if (h->M < 1 || h->kid < 0) return fail(h, GPT_ERR_USAGE, "gpt_predict_batched: set_data / set_kernel first");
+    CUDA_OK(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const int np1 = h->nparams + 1, M = h->M, D = h->D;
+    const int rows_train = (M + 63) / 64 * 64;
+    int rc;
+    // extended point arrays: the training rows padded to whole tiles, then the test points
+    const size_t next = (size_t)rows_train + Ms;
+    if ((rc = ensure(h, h->b_Xext, sizeof(double) * next * D))) return rc;
+    if ((rc = ensure(h, h->b_next, sizeof(int32_t) * next * D))) return rc;
+    CUDA_OK(h, cudaMemsetAsync(h->b_Xext.p, 0, sizeof(double) * next * D, s));
+    CUDA_OK(h, cudaMemsetAsync(h->b_next.p, 0, sizeof(int32_t) * next * D, s));
+    CUDA_OK(h, cudaMemcpyAsync(h->b_Xext.p, h->X.p, sizeof(double) * (size_t)M * D, cudaMemcpyDeviceToDevice, s));
+    CUDA_OK(h, cudaMemcpyAsync(h->b_next.p, h->n.p, sizeof(int32_t) * (size_t)M * D, cudaMemcpyDeviceToDevice, s));
+    CUDA_OK(h, cudaMemcpyAsync(ptr<double>(h->b_Xext) + (size_t)rows_train * D, Xs, sizeof(double) * (size_t)Ms * D,
+                               cudaMemcpyHostToDevice, s));
+    CUDA_OK(h, cudaMemcpyAsync(ptr<int32_t>(h->b_next) + (size_t)rows_train * D, ns, sizeof(int32_t) * (size_t)Ms * D,
+                               cudaMemcpyHostToDevice, s));
+    PredictBatch pb;
+    pb.Ms = Ms;
+    for (size_t i = 0; i < (size_t)Ms * D; i++) {
+        if (ns[i] < 0) return fail(h, GPT_ERR_USAGE, "gpt_predict_batched: negative derivative order");
+        if (ns[i] > pb.max_order) pb.max_order = ns[i];
+    }
+    if ((rc = upload(h, h->b_thetas, thetas, sizeof(double) * (size_t)B * np1))) return rc;
+    if (y_batch && (rc = upload(h, h->b_y, y_batch, sizeof(double) * (size_t)B * M))) return rc;
+    if ((rc = ensure(h, h->b_ll, sizeof(double) * B))) return rc;
+    if ((rc = ensure(h, h->b_status, sizeof(int) * B))) return rc;
+    if ((rc = ensure(h, h->b_pmean, sizeof(double) * (size_t)B * Ms))) return rc;
+    if ((rc = ensure(h, h->b_pvar, sizeof(double) * (size_t)B * Ms))) return rc;
+    pb.d_mean = ptr<double>(h->b_pmean);
+    pb.d_var = ptr<double>(h->b_pvar);
+    rc = batched_common(h, B, ptr<double>(h->b_thetas), y_batch ? ptr<double>(h->b_y) : nullptr, ptr<double>(h->b_ll),
+                        nullptr, nullptr, 0, ptr<int>(h->b_status), nullptr, &pb);
+    if (rc) return rc;
+    CUDA_OK(h, cudaMemcpyAsync(mean, h->b_pmean.p, sizeof(double) * (size_t)B * Ms, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(h, cudaMemcpyAsync(var, h->b_pvar.p, sizeof(double) * (size_t)B * Ms, cudaMemcpyDeviceToHost, s));
+    if (ll) CUDA_OK(h, cudaMemcpyAsync(ll, h->b_ll.p, sizeof(double) * B, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(h, cudaMemcpyAsync(status, h->b_status.p, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(h, cudaStreamSynchronize(s));
+    return 0;
 }
 
 int gpt_ll_batched(gpt_handle* h, int B, const double* thetas, const double* y_batch, double* ll, double* grad,

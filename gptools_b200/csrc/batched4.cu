@@ -86,6 +86,15 @@ struct Lane {
     int tid, warp, lane, g, t, wr, wc;
 };
 
+// Row gi of the (extended) point arrays carries a point: a training row, or a test row of a prediction batch.
+__device__ __forceinline__ bool row_ok(const BatchedParams& p, int gi) {
+    return gi < p.M || (gi >= p.nT * TB && gi < p.nT * TB + p.Ms);
+}
+// Tile (t, J) of the test rows of a prediction batch
+__device__ __forceinline__ double* tslot(double* ws, const BatchedParams& p, int t, int J) {
+    return ws + p.ts_off + ((size_t)t * p.nT + J) * TILE;
+}
+
 // ---- workspace tile layout: chunk-major, pre-swizzled -------------------------------------------------------------
 // A 64x64 tile is stored as CPT chunks of 64 rows x BK columns; inside a chunk row r holds its BK columns with the
 // XOR swizzle that makes the DMMA fragment reads conflict-free.  A chunk is therefore ONE contiguous block of
@@ -223,6 +232,19 @@ __device__ __forceinline__ void acc_times_vec(const double (&out)[4][4][2], cons
         double s = 0.0;
 #pragma unroll
         for (int j = 0; j < 4; j++) s = fma(out[i][j][1], vv[j].y, fma(out[i][j][0], vv[j].x, s));
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (L.t == 0) part[L.wc * 64 + L.wr * 32 + i * 8 + L.g] = s;
+    }
+}
+
+// Row sums of squares of the accumulator tile over this warp's 32 columns -> part[wc * 64 + row]
+__device__ __forceinline__ void acc_row_sumsq(const double (&out)[4][4][2], const Lane& L, double* part) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) s = fma(out[i][j][1], out[i][j][1], fma(out[i][j][0], out[i][j][0], s));
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
         if (L.t == 0) part[L.wc * 64 + L.wr * 32 + i * 8 + L.g] = s;
@@ -449,7 +471,7 @@ __device__ void potrf_inv_tile(Smem& sm, const Lane& L, double* V, int row0) {
 }
 
 __device__ __forceinline__ double ktot_entry(const Smem& sm, const BatchedParams& p, int gi, int gj) {
-    if (gi < p.M && gj < p.M) {
+    if (row_ok(p, gi) && gj < p.M) {
         double v = cov_eval(sm.cp, p.X + (size_t)gi * p.D, p.n + (size_t)gi * p.D, p.X + (size_t)gj * p.D,
                             p.n + (size_t)gj * p.D, -1);
         if (gi == gj) v += sm.noise2 + p.diag[gi];
@@ -464,7 +486,7 @@ __device__ __forceinline__ void stage_rows(Smem& sm, const BatchedParams& p, con
         if (L.tid < TB) {
             const int r = L.tid;
             const int gi = I * TB + r;
-            const bool ok = gi < p.M;
+            const bool ok = row_ok(p, gi);
             double* pts = sm.R + PTS_OFF;
             int pk = 0;
 #pragma unroll
@@ -559,7 +581,7 @@ __device__ __forceinline__ void gen_ktot_tab(const Smem& sm, const BatchedParams
         const double vd = v + dj;
         v = (gi == gj) ? vd : v;
         const double pad = (gi == gj) ? 1.0 : 0.0;
-        v = (col_ok && gi < p.M) ? v : pad;
+        v = (col_ok && row_ok(p, gi)) ? v : pad;
         const double out = v - st_get(St, r, c, DIAG);
         if (!DIAG || c <= r) St[r * LDT + c] = out;
     }
@@ -697,7 +719,7 @@ __device__ __forceinline__ void gen_ktot_tile(const Smem& sm, const BatchedParam
                 double v = se_value_low<FD, true>(h, pi, pj);
                 v = (gi == gj) ? v + dj : v;
                 const double pad = (gi == gj) ? 1.0 : 0.0;
-                v = (col_ok && gi < p.M) ? v : pad;
+                v = (col_ok && row_ok(p, gi)) ? v : pad;
                 if (!(diag_tile && c > r)) St[r * LDT + c] = v - (diag_tile ? st_lower(St, r, c) : St[r * LDT + c]);
             }
         } else {
@@ -707,7 +729,7 @@ __device__ __forceinline__ void gen_ktot_tile(const Smem& sm, const BatchedParam
                 if (diag_tile && c > r) continue;
                 const int gi = I * TB + r;
                 double v;
-                if (col_ok && gi < p.M) {
+                if (col_ok && row_ok(p, gi)) {
                     PointReg<FD> pi;
                     if constexpr (FD <= 2) pi = staged_point<FD>(pts, r);
                     else pi = load_point<FD>(p.X, p.n, gi);
@@ -824,11 +846,11 @@ __device__ __forceinline__ void grad_tile(const Smem& sm, const BatchedParams& p
 
 // Operands of contraction step `st` of the job that produces tile (I, J) in sweep ph; returns the structure flags
 // (bit0: A upper triangular, bit2: B upper triangular).
-__device__ __forceinline__ int job_step(double* ws, int nT, int ph, int I, int J, int st, const double*& aa,
-                                        const double*& bb) {
+__device__ __forceinline__ int job_step(double* ws, const BatchedParams& p, int nT, int ph, int I, int J, int st,
+                                        const double*& aa, const double*& bb) {
     int fl = 0;
-    if (ph == 1) {  // S(I,k) = sum_{j<k} L(I,j) L(k,j)^T
-        aa = slot(ws, I, st);
+    if (ph == 1) {  // S(I,k) = sum_{j<k} L(I,j) L(k,j)^T   (I >= nT: a test row block of a prediction batch)
+        aa = (I < nT) ? slot(ws, I, st) : tslot(ws, p, I - nT, st);
         bb = slot(ws, J, st);
     } else if (ph == 2) {  // sum_{m=J}^{I-1} XT(J,m)-as-stored * L(I,m)^T
         const int m = J + st;
@@ -906,11 +928,13 @@ __global__ void __launch_bounds__(THREADS, GPT_B4_MINB) ll_batched4_kernel(Batch
         const double* yb = p.y + (size_t)b * p.y_stride;
         // running residual r = y - sum_j L(., j) z_j: every panel tile subtracts its share as it is produced (below), so
         // the diagonal tile finds r_k complete instead of re-reading its block row from memory
-        if (L.tid < TB)
+        if (L.tid < TB) {
             for (int k = 0; k < nT; k++) {
                 const int gi = k * TB + L.tid;
                 rvec[gi] = (gi < p.M) ? yb[gi] : 0.0;
             }
+            for (int k = 0; k < 2 * p.nTs; k++) ws[p.pv_off + (size_t)k * TB + L.tid] = 0.0;  // running mean, sum of squares
+        }
         double logdet = 0.0, zz = 0.0;  // thread 0
         PT_DECL;
 
@@ -978,7 +1002,8 @@ __global__ void __launch_bounds__(THREADS, GPT_B4_MINB) ll_batched4_kernel(Batch
             }
 #pragma unroll 1
             for (int o = (ph == 2) ? 1 : 0; o < nT; o++) {
-                const int i0 = (ph == 2) ? 0 : o, i1 = (ph == 2) ? o : nT;
+                // sweep 1 of a prediction batch: the test row blocks follow the training rows of every column
+                const int i0 = (ph == 2) ? 0 : o, i1 = (ph == 2) ? o : ((ph == 1) ? nT + p.nTs : nT);
 #pragma unroll 1
                 for (int i = i0; i < i1; i++) {
                     const int I = (ph == 2) ? o : i, J = (ph == 2) ? i : o;
@@ -986,14 +1011,14 @@ __global__ void __launch_bounds__(THREADS, GPT_B4_MINB) ll_batched4_kernel(Batch
                     const int nsteps = (ph == 1) ? J : ((ph == 2) ? I - J : nT - I);
                     if (L.tid < nsteps) {
                         const double *aa, *bb;
-                        const int fl = job_step(ws, nT, ph, I, J, L.tid, aa, bb);
+                        const int fl = job_step(ws, p, nT, ph, I, J, L.tid, aa, bb);
                         sm.a[L.tid] = aa;
                         sm.b[L.tid] = bb;
                         sm.flag[L.tid] = (unsigned char)fl;
                     }
                     if (ph == 2 && i == i0 && L.tid < TB) sm.zk[L.tid] = __ldcg(zvec + I * TB + L.tid);  // published by run_job's barrier
                     zero_acc(acc);
-                    const double* ebt = ws + p.eb_off + (size_t)(I * (I + 1) / 2 + J) * TILE;
+                    const double* ebt = ws + p.eb_off + (size_t)((I < nT ? I * (I + 1) / 2 : 0) + J) * TILE;
                     if (ph == 3 && sm.use_tab) {  // the cached exponentials of this tile: on their way to L2 while the products run
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(ebt + L.tid * 16));
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(ebt + 2048 + L.tid * 16));
@@ -1007,7 +1032,7 @@ __global__ void __launch_bounds__(THREADS, GPT_B4_MINB) ll_batched4_kernel(Batch
                     if (ph == 1) {
                         // C = K_tot - S in place (K_tot generated from the closed forms, never stored)
                         if constexpr (FD == 1 || FD == 2) {
-                            if (sm.use_tab) gen_ktot_tab<FD>(sm, p, St, L.tid, I, J, p.eb_off ? const_cast<double*>(ebt) : nullptr);
+                            if (sm.use_tab) gen_ktot_tab<FD>(sm, p, St, L.tid, I, J, (p.eb_off && I < nT) ? const_cast<double*>(ebt) : nullptr);
                             else gen_ktot_tile<FD>(sm, p, St, L.tid, I, J);
                         } else {
                             gen_ktot_tile<FD>(sm, p, St, L.tid, I, J);
@@ -1059,15 +1084,23 @@ __global__ void __launch_bounds__(THREADS, GPT_B4_MINB) ll_batched4_kernel(Batch
                         double out[4][4][2];
                         mult_lower_global(St, (ph == 1) ? slot(ws, J, J) : slot(ws, I, I), L, out);
                         // sweep 1: r_I -= L(I,k) z_k;  sweep 2: alpha_J += (L^{-1}(I,J))^T z_I  (the stored tile is -out)
+                        // test row block: mean_t += L*(t,k) z_k,  sumsq_t += |L*(t,k)|^2 row by row
                         acc_times_vec(out, sm.zk, L, sm.R + PTS_OFF);
-                        acc_to_global(slot(ws, I, J), L, out, (ph == 1) ? 1.0 : -1.0);
+                        if (I >= nT) acc_row_sumsq(out, L, sm.R + PTS_OFF + 128);
+                        acc_to_global((I < nT) ? slot(ws, I, J) : tslot(ws, p, I - nT, J), L, out, (ph == 1) ? 1.0 : -1.0);
                     }
                     if (ph != 3) {
                         __syncthreads();
                         if (!diag && L.tid < TB) {
                             const double* part = sm.R + PTS_OFF;
-                            double* target = (ph == 1) ? rvec + I * TB : avec + J * TB;
-                            atomicAdd(target + L.tid, -(part[L.tid] + part[64 + L.tid]));  // one update per address and job
+                            if (I < nT) {
+                                double* target = (ph == 1) ? rvec + I * TB : avec + J * TB;
+                                atomicAdd(target + L.tid, -(part[L.tid] + part[64 + L.tid]));  // one update per address and job
+                            } else {
+                                double* pm = ws + p.pv_off + (size_t)(I - nT) * TB;
+                                atomicAdd(pm + L.tid, part[L.tid] + part[64 + L.tid]);
+                                atomicAdd(pm + (size_t)p.nTs * TB + L.tid, part[128 + L.tid] + part[192 + L.tid]);
+                            }
                         }
                         PT_MARK(3);
                     } else {
@@ -1085,6 +1118,13 @@ __global__ void __launch_bounds__(THREADS, GPT_B4_MINB) ll_batched4_kernel(Batch
 
         // =========================== outputs ===========================
         __syncthreads();
+        if (p.Ms > 0) {  // prediction batch: mean = L* z; |L*|^2 row by row (predict_var_finish_kernel adds the prior variance)
+            const double* pm = ws + p.pv_off;
+            for (int s2 = L.tid; s2 < p.Ms; s2 += THREADS) {
+                p.pmean[(size_t)b * p.Ms + s2] = __ldcg(pm + s2);
+                p.pvar[(size_t)b * p.Ms + s2] = __ldcg(pm + (size_t)p.nTs * TB + s2);
+            }
+        }
         if (p.nidx > 0) {
 #pragma unroll
             for (int q = 0; q < 1 + GPT_MAX_DIM; q++) {
@@ -1130,6 +1170,29 @@ __global__ void __launch_bounds__(THREADS, GPT_B4_MINB) ll_batched4_kernel(Batch
                     atomicAdd((unsigned long long*)p.phase_cycles + q, (unsigned long long)pt_acc[q]);
 #endif
         }
+    }
+}
+
+// var[b][s] = k_theta_b(x*_s, x*_s) - |L^-1 k*_s|^2: the prior variance of every test point from the closed forms (kept out of
+// the persistent kernel, whose SE instantiations would otherwise carry the generic closed forms and their stack frame).
+// One CTA per theta.
+__global__ void predict_var_finish_kernel(BatchedParams p) {
+    __shared__ CovParams cp;
+    __shared__ CovComposite comp;
+    const int b = blockIdx.x;
+    if (threadIdx.x == 0) {
+        const double* th = p.thetas + (size_t)b * (p.nparams + 1);
+        cov_params_init(cp, p.kid, p.D, p.nparams, th);
+        if (p.kid == GPT_KERNEL_COMPOSITE) {
+            comp_init(comp, p.D, p.comp_nleaf, p.comp_kids, p.comp_nps, p.comp_nterms, p.comp_masks, th);
+            cp.comp = &comp;
+        }
+    }
+    __syncthreads();
+    for (int s2 = threadIdx.x; s2 < p.Ms; s2 += blockDim.x) {
+        const size_t gi = (size_t)p.nT * TB + s2;
+        const double kss = cov_eval(cp, p.X + gi * p.D, p.n + gi * p.D, p.X + gi * p.D, p.n + gi * p.D, -1);
+        p.pvar[(size_t)b * p.Ms + s2] = kss - p.pvar[(size_t)b * p.Ms + s2];
     }
 }
 
@@ -1179,4 +1242,5 @@ void launch_ll_batched4(const BatchedParams& p, int num_ctas, cudaStream_t s) {
     else if (p.kid == GPT_KERNEL_SE && p.D == 2) launch_t<2>(p, num_ctas, s);
     else if (p.kid == GPT_KERNEL_SE && p.D == 3) launch_t<3>(p, num_ctas, s);
     else launch_t<0>(p, num_ctas, s);
+    if (p.Ms > 0) predict_var_finish_kernel<<<p.B, 128, 0, s>>>(p);
 }

@@ -138,6 +138,15 @@ struct BatchedParams {
     int short_forms = 0;     // SE, D <= 2, orders <= 1: short closed forms + cached exponentials (batched4.cu)
     size_t eb_off = 0;       // offset (doubles) inside the CTA workspace of the cached sigma^2 exp(-r^2/2) tiles
     long long* phase_cycles;  // optional (8): per-phase cycle sums, only with -DGPT_PHASE_TIMING
+    // batched prediction (gpt_predict_batched): Ms test points appended to the point arrays as extra tile rows.  X / n then
+    // hold nT * 64 rows for the training set (zero padded) followed by the Ms test points; the sweep-1 panel tiles of a
+    // test row block are the rows L*(t, k) = (L^{-1} K*)^T of the extended factor: mean = sum_k L*(t,k) z_k,
+    // var = k** - sum_k |L*(t,k)|^2 row by row.
+    int Ms = 0, nTs = 0;
+    size_t ts_off = 0;       // workspace offset (doubles) of the nTs x nT test-row tiles
+    size_t pv_off = 0;       // workspace offset of the running mean (nTs * 64) and sum of squares (nTs * 64)
+    double* pmean = nullptr; // B x Ms
+    double* pvar = nullptr;  // B x Ms
     // kid == GPT_KERNEL_COMPOSITE: the structure (leaf kernels, parameter counts, product terms); every CTA keeps the
     // leaves of its current theta in its workspace at comp_off (doubles)
     int comp_nleaf = 0, comp_nterms = 0;

@@ -1143,6 +1143,66 @@ class GaussianProcess(object):
         sampler.run_mcmc(theta0, nsamp)
         return sampler
 
+    def predict_batch(self, thetas, Xstar, n=0, noise=False):
+        """Predictive mean and standard deviation at ``Xstar`` for EVERY row of ``thetas`` (B, num_free_params) in one
+        device launch -- the per-sample unit of ``compute_from_MCMC`` (update_hyperparameters + predict,
+        gaussian_process.py:1944-1969), batched.  The test points ride along as extra tile rows of each theta's
+        factorisation (``gpt_predict_batched``).
+
+        Returns ``(mean (B, M*), std (B, M*), good (B,))``; rows with ``good == False`` (zero prior probability,
+        covariance not positive definite) are NaN, where the per-sample loop skips the sample.  Returns ``None`` when the
+        batch cannot run in the persistent kernel (transformation matrix, more than 2048 observations, host-evaluated
+        kernels, theta-dependent point columns): the caller then predicts sample by sample.  The GP's own
+        hyperparameters are left unchanged."""
+        thetas = np.atleast_2d(np.asarray(thetas, dtype=float))
+        if (not self._device_mode() or self.k.device_points_key() is not None or self.T is not None or
+                len(self.y) > self.BATCHED_KERNEL_MAX_M):
+            return None
+        Xstar = np.atleast_2d(np.asarray(Xstar, dtype=float))
+        if self.num_dim == 1 and Xstar.shape[0] == 1:
+            Xstar = Xstar.T
+        if Xstar.shape[1] != self.num_dim:
+            raise ValueError("Second dimension of Xstar must be equal to self.num_dim!")
+        if not _has_iter(n):
+            n = n * np.ones(Xstar.shape, dtype=int)
+        else:
+            n = np.atleast_2d(np.asarray(n, dtype=int))
+            if self.num_dim == 1 and n.shape[0] == 1:
+                n = n.T
+        if n.shape != Xstar.shape or (n < 0).any():
+            raise ValueError("n must be non-negative and match the shape of Xstar!")
+        self.k._check_orders(self.n, n)
+        plan = self._batch_prepare(thetas, False)
+        Xs_d, ns_d = self.k.device_points(Xstar, n)
+        try:
+            mean, var, ll, status = plan["dev"].predict_batched(plan["full_eval"], Xs_d, ns_d, y_batch=plan["y_batch"])
+        except NotImplementedError:
+            return None
+        good = plan["ok"] & (status == 0)
+        nk, nn = plan["nk"], plan["nn"]
+        if self.mu is not None:
+            saved = np.array(self.mu.params, dtype=float)
+            try:
+                if self.mu.num_free_params > 0:
+                    for b in np.nonzero(good)[0]:
+                        self.mu.set_hyperparams(thetas[b, nk + nn:])
+                        mean[b] += self.mu(Xstar, n)
+                else:
+                    mean += self.mu(Xstar, n)[None, :]
+            finally:
+                self.mu.params[:] = saved
+        if noise and not isinstance(self.noise_k, ZeroKernel):
+            if not (isinstance(self.noise_k, DiagonalNoiseKernel) and
+                    type(self.noise_k).__call__ is DiagonalNoiseKernel.__call__):
+                return None
+            sig = plan["full_eval"][:, -1]
+            var = var + (sig ** 2.0)[:, None] * np.all(n == np.asarray(self.noise_k.n), axis=1)[None, :]
+        with np.errstate(invalid="ignore"):
+            std = np.sqrt(var)
+        mean[~good] = np.nan
+        std[~good] = np.nan
+        return mean, std, good
+
     def compute_from_MCMC(self, X, n=0, return_mean=True, return_std=True, return_cov=False, return_samples=False,
                           return_mean_func=False, num_samples=1, noise=False, samp_kwargs={}, sampler=None,
                           flat_trace=None, burn=0, thin=1, **kwargs):
@@ -1167,6 +1227,30 @@ class GaussianProcess(object):
         if nranks > 1:
             lo, hi = parallel.shard_bounds(len(flat_trace), rank, nranks)
             flat_trace = flat_trace[lo:hi]
+        # mean / std requests: every sample of the slice in ONE launch (gpt_predict_batched); everything else (full
+        # covariances, samples, output transforms, kernels outside the persistent batched kernel) sample by sample
+        if (len(flat_trace) > 0 and not return_cov and not return_samples and output_transform is None and
+                not getattr(self, "_mcmc_predict_by_loop", False)):
+            res_b = self.predict_batch(flat_trace, X, n=n, noise=noise)
+            if res_b is not None:
+                mean_b, std_b, good = res_b
+                saved_mu = None if self.mu is None else np.array(self.mu.params, dtype=float)
+                nk_, nn_ = self.k.num_free_params, self.noise_k.num_free_params
+                try:
+                    for b_ in np.nonzero(good)[0]:
+                        out['mean'].append(mean_b[b_])
+                        out['std'].append(std_b[b_])
+                        if return_mean_func and self.mu is not None:
+                            self.mu.set_hyperparams(flat_trace[b_, nk_ + nn_:])
+                            Xm = np.atleast_2d(np.asarray(X, dtype=float))
+                            if self.num_dim == 1 and Xm.shape[0] == 1:
+                                Xm = Xm.T
+                            nm = n if _has_iter(n) else n * np.ones(Xm.shape, dtype=int)
+                            out['mean_func'].append(self.mu(Xm, np.atleast_2d(np.asarray(nm, dtype=int))))
+                finally:
+                    if saved_mu is not None:
+                        self.mu.params[:] = saved_mu
+                flat_trace = flat_trace[:0]
         try:
             for th in flat_trace:
                 val = self.update_hyperparameters(th)

@@ -134,6 +134,18 @@ int gpt_ll_batched(gpt_handle* h, int B, const double* thetas, const double* y_b
 int gpt_ll_batched_dev(gpt_handle* h, int B, const double* d_thetas, const double* d_y_batch, double* d_ll,
                        double* d_grad, const int32_t* grad_idx, int P, int* d_status, double* d_alpha_out);
 
+/* Predictions at MANY hyper-parameter vectors: the loop of compute_from_MCMC / predict_MCMC over the retained samples
+ * (gaussian_process.py:1944-1969: update_hyperparameters + predict per sample, farmed to a process pool) as ONE launch of
+ * the persistent many-theta kernel.  The Ms test points ride along as extra tile rows of the factorisation: the panel
+ * tiles of a test row block are the rows of (L^-1 K*)^T, so mean = (L^-1 K*)^T z and var = diag(K**) - |L^-1 K*|^2
+ * accumulate in the epilogues with no second pass (predict core, gaussian_process.py:965-1006).
+ *   thetas (B x (nparams + 1)), y_batch (B x M or NULL) as in gpt_ll_batched; Xs (Ms x D), ns (Ms x D)
+ *   mean, var (B x Ms); ll (B) or NULL; status (B): potrf info per theta (rows with status != 0 are undefined)
+ * Needs the persistent kernel: no transformation matrix, at most 2048 observations (else GPT_ERR_UNSUPPORTED and the
+ * caller predicts theta by theta). */
+int gpt_predict_batched(gpt_handle* h, int B, const double* thetas, const double* y_batch, int Ms, const double* Xs,
+                        const int32_t* ns, double* mean, double* var, double* ll, int* status);
+
 /* predict numeric core (gaussian_process.py:965-1006) with the state of the last gpt_ll:
  *   mean (Ms); var (Ms) or NULL: diag(K**) - |L^-1 K*|^2 ; cov (Ms x Ms) or NULL: K** - v'v */
 int gpt_predict(gpt_handle* h, int Ms, const double* Xs, const int32_t* ns, double* mean, double* var, double* cov);

@@ -100,6 +100,22 @@ class FakeDevice(object):
                 grad[b] = out[1]
         return (ll, grad, st, alpha) if return_alpha else (ll, grad, st)
 
+    def predict_batched(self, thetas, Xs, ns, y_batch=None):
+        self.calls.append("predict_batched")
+        thetas = np.atleast_2d(thetas)
+        B, Ms = len(thetas), len(Xs)
+        mean, var = np.zeros((B, Ms)), np.zeros((B, Ms))
+        ll, st = np.zeros(B), np.zeros(B, dtype=np.int32)
+        for b in range(B):
+            out = self._run(thetas[b, :-1], thetas[b, -1], None, y=None if y_batch is None else y_batch[b])
+            if out is None:
+                st[b] = 1
+                continue
+            r = out[0]
+            m, _, cov = orc.predict(self.kernel_id, thetas[b, :-1], self.X, self.n, r["L"], r["alpha"], Xs, ns, T=self.T)
+            mean[b], var[b], ll[b] = m, np.diag(cov), r["ll"]
+        return mean, var, ll, st
+
     def predict(self, Xs, ns, want_var=True, want_cov=False):
         self.calls.append("predict")
         mean, std, cov = orc.predict(self.kernel_id, self._params, self.X, self.n, self._state["L"],

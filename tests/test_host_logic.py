@@ -584,3 +584,41 @@ def test_lockstep_multistart_equals_sequential_starts():
     assert_close(pb, pq, rtol=1e-10)                        # the GP is left at the optimum in both modes
     assert calls_b.count("ll_batched") > 0 and calls_q.count("ll_batched") == 0
     assert calls_b.count("ll_batched") < calls_q.count("ll") / 2   # one launch serves all waiting starts
+
+
+def test_compute_from_MCMC_uses_one_batched_prediction_and_matches_the_per_sample_loop():
+    """gaussian_process.py:1944-1969: update_hyperparameters + predict per retained sample.  Mean / std requests go
+    through ONE batched device call (gpt_predict_batched); the per-sample loop (still used for covariances / samples)
+    gives the same lists, samples outside the prior support are dropped by both, predict_MCMC combines them by the law of
+    total variance."""
+    gp = with_fake(_kat1_gp())
+    rs = np.random.RandomState(5)
+    th0 = np.array(gp.free_params[:], dtype=float)
+    trace = th0 * np.exp(0.05 * rs.randn(6, len(th0)))
+    trace[2, 0] = -1.0                                     # zero prior probability: skipped
+    Xs = rs.rand(5, 2)
+    n_calls = len(gp._dev_obj.calls)
+    res_b = gp.compute_from_MCMC(Xs, flat_trace=trace)
+    calls = gp._dev_obj.calls[n_calls:]
+    assert calls.count("predict_batched") == 1 and calls.count("predict") == 0
+    gp._mcmc_predict_by_loop = True
+    res_l = gp.compute_from_MCMC(Xs, flat_trace=trace)
+    gp._mcmc_predict_by_loop = False
+    assert len(res_b['mean']) == len(res_l['mean']) == 5
+    for a, b in zip(res_b['mean'], res_l['mean']):
+        assert_close(a, b, rtol=1e-10, atol=1e-12)
+    for a, b in zip(res_b['std'], res_l['std']):
+        assert_close(a, b, rtol=1e-7, atol=1e-10)
+    assert_close(np.asarray(gp.free_params[:], float), th0, rtol=0, atol=0)   # the GP's own parameters are untouched
+    out = gp.predict_MCMC(Xs, flat_trace=trace)
+    means = np.array(res_l['mean'])
+    stds = np.array(res_l['std'])
+    assert_close(out['mean'], means.mean(axis=0), rtol=1e-10)
+    assert_close(out['std'], np.sqrt((stds ** 2).mean(axis=0) + np.var(means, axis=0, ddof=1)), rtol=1e-7)
+    # derivative predictions and per-theta mean-function parameters take the same route
+    res_d = gp.compute_from_MCMC(Xs, n=np.tile([1, 0], (5, 1)), flat_trace=trace[:2])
+    gp._mcmc_predict_by_loop = True
+    res_dl = gp.compute_from_MCMC(Xs, n=np.tile([1, 0], (5, 1)), flat_trace=trace[:2])
+    gp._mcmc_predict_by_loop = False
+    for a, b in zip(res_d['mean'], res_dl['mean']):
+        assert_close(a, b, rtol=1e-9, atol=1e-11)
