@@ -211,12 +211,18 @@ __device__ __forceinline__ void acc_to_tile(double* tile, const Lane& L, const d
         }
 }
 
-__device__ __forceinline__ void acc_to_global(double* tile, const Lane& L, const double (&acc)[4][4][2], double scale) {
+// tile = +-acc: the sign flip is an integer operation on the high word (a multiplication by -1 would be 32 more FP64
+// instructions per thread waiting for the shared FP64 pipe)
+__device__ __forceinline__ double flip_sign(double x, int flip) {
+    return __hiloint2double(__double2hiint(x) ^ flip, __double2loint(x));
+}
+__device__ __forceinline__ void acc_to_global(double* tile, const Lane& L, const double (&acc)[4][4][2], bool negate) {
+    const int flip = negate ? (int)0x80000000 : 0;
 #pragma unroll
     for (int i = 0; i < 4; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            double2 v = make_double2(scale * acc[i][j][0], scale * acc[i][j][1]);
+            double2 v = make_double2(flip_sign(acc[i][j][0], flip), flip_sign(acc[i][j][1], flip));
             *reinterpret_cast<double2*>(tile + tix(L.wr * 32 + i * 8 + L.g, L.wc * 32 + j * 8 + 2 * L.t)) = v;
         }
 }
@@ -1087,7 +1093,7 @@ __global__ void __launch_bounds__(THREADS, GPT_B4_MINB) ll_batched4_kernel(Batch
                         // test row block: mean_t += L*(t,k) z_k,  sumsq_t += |L*(t,k)|^2 row by row
                         acc_times_vec(out, sm.zk, L, sm.R + PTS_OFF);
                         if (I >= nT) acc_row_sumsq(out, L, sm.R + PTS_OFF + 128);
-                        acc_to_global((I < nT) ? slot(ws, I, J) : tslot(ws, p, I - nT, J), L, out, (ph == 1) ? 1.0 : -1.0);
+                        acc_to_global((I < nT) ? slot(ws, I, J) : tslot(ws, p, I - nT, J), L, out, ph != 1);
                     }
                     if (ph != 3) {
                         __syncthreads();

@@ -161,3 +161,20 @@ def test_compute_from_MCMC_and_predict_MCMC_batched_vs_loop():
     gp._mcmc_predict_by_loop = False
     assert_close(out_b["mean"], out_l["mean"], rtol=1e-9, atol=1e-10)
     assert_close(out_b["std"], out_l["std"], rtol=1e-7, atol=1e-10)
+
+
+def test_mean_function_with_free_parameters():
+    """Per-theta mean-function parameters: y - mu_theta(X) travels as the per-theta right-hand side, mu_theta(X*) is added
+    on the host -- same numbers as the per-sample path."""
+    rs = np.random.RandomState(8)
+    X = np.sort(rs.rand(100)) * 3
+    y = 2.0 + np.sin(2 * X) + 0.05 * rs.randn(100)
+    k = g.SquaredExponentialKernel(initial_params=[1.0, 0.7], param_bounds=[(0, 10)] * 2)
+    mu = g.ConstantMeanFunction(initial_params=[1.8], param_bounds=[(-5, 5)])
+    gp = g.GaussianProcess(k, X=X, y=y, err_y=0.05, mu=mu)
+    th0 = np.array(gp.free_params[:], dtype=float)
+    assert len(th0) == 3
+    thetas = th0 + 0.05 * rs.randn(6, 3)
+    Xs = np.linspace(0, 3, 50)
+    _check(gp, thetas, Xs, 0, prior_var=thetas[:, :1] ** 2)
+    _check(gp, thetas, Xs, 1, prior_var=(thetas[:, :1] / thetas[:, 1:2]) ** 2)
