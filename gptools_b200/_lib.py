@@ -31,6 +31,9 @@ class CompositeId(int):
     def structure(self):
         return (self.leaf_kids, self.leaf_nparams, self.term_masks)
 
+    def __reduce__(self):  # pickle / deepcopy: an int subclass would otherwise be rebuilt from its value alone
+        return (CompositeId, self.structure)
+
     def __eq__(self, other):
         if isinstance(other, CompositeId):
             return self.structure == other.structure

@@ -170,6 +170,8 @@ def test_kernel_trees_flatten_to_sum_of_products():
     kid2, _ = ((a + b) * c).device_descriptor()
     assert kid2.structure == ((SE, M52, SE), (2, 2, 2), (0b101, 0b110))
     assert kid != kid2 and kid == (a * b + c).device_descriptor()[0] and kid == 5
+    import copy, pickle
+    assert pickle.loads(pickle.dumps(kid)) == kid and copy.deepcopy(kid2).structure == kid2.structure
     d = _se([0.7, 0.9])
     kid3, _ = ((a + b) * (c + d)).device_descriptor()
     assert kid3.structure[2] == (0b0101, 0b1001, 0b0110, 0b1010)
