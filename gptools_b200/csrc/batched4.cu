@@ -66,7 +66,7 @@ struct Smem {
     double exptab[64];  // 2^(j/64), for exp_nonpos_tab
     __align__(16) double rk[TB];
     __align__(16) double zk[TB];  // read as double2 by acc_times_vec
-    double red[4][GPT_MAX_PARAMS + 2];
+    double red[4][GPT_MAX_PARAMS + 3];
     const double* a[MAXT];
     const double* b[MAXT];
     unsigned char flag[MAXT];  // bit0: A operand upper triangular, bit2: B operand upper triangular
@@ -763,6 +763,11 @@ __device__ __forceinline__ void grad_tile(const Smem& sm, const BatchedParams& p
         unsigned want = 0;  // requested kernel parameters (bit q), gall has 1 + GPT_MAX_DIM slots
         for (int q = 0; q < p.nidx; q++)
             if (p.idx[q] < p.nparams && p.idx[q] < 1 + GPT_MAX_DIM) want |= 1u << p.idx[q];
+        // k = sigma_f^2 g for every kernel: dk/dsigma_f = 2 k / sigma_f, and with K_tot = K + D (D = noise^2 + err^2 + jitter)
+        //   1/2 (a' dK a - tr(K_tot^-1 dK)) = (a'(y - D a) - M + sum_i K_tot^-1_ii D_i) / sigma_f
+        // -- no closed-form evaluation at all (the sums over i are taken at the outputs); a composite has no common factor
+        const bool sig_id = (sm.cp.kid != GPT_KERNEL_SE) && (sm.cp.kid != GPT_KERNEL_COMPOSITE) && (want & 1u);
+        if (sig_id) want &= ~1u;
 #pragma unroll 1
         for (int u = 0; u < 32; u++) {
             const int r = (tid >> 6) + 2 * u;
@@ -772,6 +777,7 @@ __device__ __forceinline__ void grad_tile(const Smem& sm, const BatchedParams& p
             double w = avec[gi] * aj - kinv;
             if (diag_tile && c == r) {
                 tr_kinv += kinv;
+                if (sig_id) gall[0] += kinv * (sm.noise2 + p.diag[gi]);  // sum_i K^-1_ii D_i for the sigma_f identity
                 w *= 0.5;
             }
             if (sm.cp.kid == GPT_KERNEL_SE) {
@@ -1140,16 +1146,32 @@ __global__ void __launch_bounds__(THREADS, GPT_B4_MINB) ll_batched4_kernel(Batch
             const double s = warp_sum(tr_kinv);
             if (L.lane == 0) sm.red[L.warp][GPT_MAX_PARAMS] = s;
             __syncthreads();
-            bool want_noise = false;
-            for (int q = 0; q < p.nidx; q++) want_noise |= (p.idx[q] == p.nparams);
-            double aa = 0.0;
-            if (want_noise) {
-                double part = 0.0;
-                for (int i = L.tid; i < p.M; i += THREADS) part += avec[i] * avec[i];
+            bool want_noise = false, want_sig = false;
+            for (int q = 0; q < p.nidx; q++) {
+                want_noise |= (p.idx[q] == p.nparams);
+                want_sig |= (p.idx[q] == 0);
+            }
+            // the sigma_f identity of grad_tile (generic closed forms, single kernels)
+            const bool sig_id = (FD == 0) && want_sig && sm.cp.kid != GPT_KERNEL_SE && sm.cp.kid != GPT_KERNEL_COMPOSITE;
+            double aa = 0.0, ay = 0.0;
+            if (want_noise || sig_id) {
+                double part = 0.0, part2 = 0.0;
+                for (int i = L.tid; i < p.M; i += THREADS) {
+                    const double a = avec[i];
+                    part += a * a;
+                    part2 += a * (yb[i] - a * (sm.noise2 + p.diag[i]));
+                }
                 part = warp_sum(part);
-                if (L.lane == 0) sm.red[L.warp][GPT_MAX_PARAMS + 1] = part;
+                part2 = warp_sum(part2);
+                if (L.lane == 0) {
+                    sm.red[L.warp][GPT_MAX_PARAMS + 1] = part;
+                    sm.red[L.warp][GPT_MAX_PARAMS + 2] = part2;
+                }
                 __syncthreads();
-                for (int w = 0; w < 4; w++) aa += sm.red[w][GPT_MAX_PARAMS + 1];
+                for (int w = 0; w < 4; w++) {
+                    aa += sm.red[w][GPT_MAX_PARAMS + 1];
+                    ay += sm.red[w][GPT_MAX_PARAMS + 2];
+                }
             }
             if (L.tid == 0) {
                 double tr = 0.0;
@@ -1159,6 +1181,10 @@ __global__ void __launch_bounds__(THREADS, GPT_B4_MINB) ll_batched4_kernel(Batch
                     double gsum = 0.0;
                     if (p.idx[q] == p.nparams) {
                         gsum = sn * (aa - tr);  // gaussian_process.py:1484-1488: noise kernel derivative 2 sigma_n I
+                    } else if (sig_id && p.idx[q] == 0) {
+                        double kd = 0.0;
+                        for (int w = 0; w < 4; w++) kd += sm.red[w][0];
+                        gsum = (sm.cp.p[0] != 0.0) ? (ay - (double)p.M + kd) / sm.cp.p[0] : 0.0;
                     } else {
                         for (int w = 0; w < 4; w++) gsum += sm.red[w][p.idx[q]];
                     }
