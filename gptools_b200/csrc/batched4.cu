@@ -1,23 +1,27 @@
-// Batched ll + gradient: FOUR independent theta streams per SM.
+// Batched ll + gradient (+ prediction): FOUR independent theta streams per SM.
 //
-// One persistent CTA per theta: phase 1 left-looking Cholesky with generated K tiles and inverted diagonal tiles,
-// back substitution, phase 2 XT = L^{-T} in place, phase 3 K^{-1} tiles contracted with regenerated dK tiles
-// (tools/tile_model.py is the numpy model of the tile recurrences).  Cut for latency tolerance: measurements on
-// the first-generation kernel (256 threads, 2 CTAs/SM; git history, profiles/r01a_*): the FP64 pipe -- which DMMA and scalar DFMA share on B200 (profiles/microbench/fp64_overlap.cu)
-// -- was only ~63% busy because each CTA spends half of its time in latency-bound non-GEMM phases and only two
-// CTAs (= two thetas) fit on an SM.  Here a CTA is 4 warps / 128 threads with a ~39 KB footprint, so four CTAs
-// (four thetas) share an SM and the chance that nobody feeds the tensor pipe drops from ~29% to ~8%:
+// One persistent CTA per theta, one job loop over three tile sweeps (tools/tile_model.py is the numpy model of the tile
+// recurrences): sweep 1 left-looking Cholesky with generated K tiles and inverted diagonal tiles, sweep 2 XT = L^{-T} in
+// place, sweep 3 K^{-1} tiles contracted with regenerated dK tiles.  Cut for latency tolerance: the FP64 pipe -- which DMMA
+// and scalar DFMA share on B200 (profiles/microbench/fp64_overlap.cu) -- was only ~63% busy in the first-generation kernel
+// (256 threads, 2 CTAs/SM; git history, profiles/r01a_*) because each CTA spends half of its time in latency-bound
+// non-GEMM phases.  Here a CTA is 4 warps / 128 threads with a ~39 KB footprint, so four CTAs (four thetas) share an SM:
 //   * one 64x64 output tile per job, 32x32 warp tiles (16 DMMA.8x8x4 per k-step, 64 accumulator registers);
 //   * operands stream through a ring of 64xBK chunks (A, B) filled by BULK ASYNC COPIES (cp.async.bulk, the TMA engine)
 //     that complete on mbarriers: the workspace tiles are stored chunk-major and pre-swizzled (tix()), so a chunk is
 //     one contiguous copy issued by a single lane; warps wait on the chunk's mbarrier, never on each other (the
 //     warp that releases a slot last refills it), so the four warps of a CTA -- which sit on four different SM
 //     sub-partitions -- drift by up to a ring's depth instead of meeting at a CTA barrier after every chunk;
-//   * diagonal output tiles: the two warps on the 32x32 diagonal blocks issue only the 10 lower 8x8 products of
-//     their 16, the other two warps split the contraction of the off-diagonal block between them;
-//   * no dedicated diagonal-tile buffer: the Gauss-Jordan sweep runs in registers (32 entries per thread) and
-//     its result goes straight to the workspace; panel products take their B fragments directly from L2.
-// Algorithmic work: M^3 flop per theta; roofline = FP64 tensor pipe.
+//   * structural zeros are removed at compile-time granularity, never by predication inside a DMMA stream: diagonal
+//     output tiles run a split job (two warps issue the 10 lower 8x8 products of their 16, the other two share the
+//     off-diagonal block), triangular operands skip whole chunks and use a half-height chunk_mma instance in the first
+//     chunk that reaches a warp's rows, the panel products follow the exact 8x8-block triangle of the inverse tile;
+//   * no dedicated diagonal-tile buffer: the Gauss-Jordan sweep works in the staging tile, its 8x8 pivot blocks
+//     distributed over the lanes of one warp; panel products take their B fragments from L2, one group ahead;
+//   * nothing is rebuilt from re-read tiles: the residual y - sum L z, alpha = L^{-T} z and (prediction batches) the
+//     predictive mean and |L^{-1} k*|^2 are accumulated from the panel tiles while they are still in registers;
+//   * prediction batches (gpt_predict_batched): the test points are extra tile rows of sweep 1.
+// Algorithmic work: M^3 flop per theta; roofline = FP64 tensor pipe (DESIGN.md sections 3, 4).
 #include <stdio.h>
 #include <stdlib.h>
 
