@@ -860,8 +860,13 @@ static int gradient_device(gpt_handle* h, const int32_t* grad_idx, int P, int* s
     gp.X = ptr<double>(h->X); gp.n = ptr<int32_t>(h->n); gp.N = h->N;
     gp.nidx = 0;
     int noise_slot = -1;
+    // sigma_f of a single non-SE kernel (k = sigma_f^2 g) without T: from the identity of launch_sigma_identity instead
+    // of a pass of dual-number closed forms over M^2 / 2 entries; its value goes behind the entries grad_reduce writes
+    const bool sig_id_ok = !h->hasT && (h->kid == GPT_KERNEL_MATERN52 || h->kid == GPT_KERNEL_MATERN || h->kid == GPT_KERNEL_GIBBS_TANH);
+    int sig_slot = -1;
     for (int q = 0; q < P; q++) {
         if (grad_idx[q] == h->nparams) noise_slot = q;
+        else if (sig_id_ok && grad_idx[q] == 0 && sig_slot < 0) sig_slot = q;
         else { slot[gp.nidx] = q; gp.idx[gp.nidx++] = grad_idx[q]; }
     }
     const int nt = (h->N + 63) / 64;
@@ -902,6 +907,12 @@ static int gradient_device(gpt_handle* h, const int32_t* grad_idx, int P, int* s
     }
     launch_trace_and_sumsq(ptr<double>(h->Kinv), h->Mp, ptr<double>(h->alpha), h->M, ptr<double>(h->gout) + GPT_MAX_PARAMS, s);
     h->launches++;
+    if (sig_slot >= 0) {
+        launch_sigma_identity(ptr<double>(h->Kinv), h->Mp, ptr<double>(h->alpha), ptr<double>(h->y), ptr<double>(h->diag),
+                              h->noise_sigma * h->noise_sigma, h->M, h->cp.p[0], ptr<double>(h->gout) + gp.nidx, s);
+        h->launches++;
+        slot[gp.nidx++] = sig_slot;
+    }
     *nkern = gp.nidx;
     *noise_slot_out = noise_slot;
     return check_launch(h);

@@ -773,6 +773,31 @@ void launch_grad_reduce(const GradReduceParams& p, cudaStream_t s) {
     grad_final_kernel<<<p.nidx, 256, 0, s>>>(p.partials, nt * nt, p.nidx, p.out);
 }
 
+// d ll / d sigma_f for a kernel k = sigma_f^2 g without a closed-form pass: with K_tot = K + D (D diagonal),
+//   1/2 (a' dK a - tr(K_tot^-1 dK)) = (sum_i [a_i (y_i - a_i D_i) + (K_tot^-1)_ii D_i] - n) / sigma_f,  D_i = d[i] + noise2
+__global__ void sigma_identity_kernel(const double* __restrict__ Kinv, long ld, const double* __restrict__ a,
+                                      const double* __restrict__ y, const double* __restrict__ d, double noise2, int n,
+                                      double sigma_f, double* __restrict__ out) {
+    __shared__ double sh[256];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const double Di = d[i] + noise2;
+        acc += a[i] * (y[i] - a[i] * Di) + Kinv[(long)i * ld + i] * Di;
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = (sigma_f != 0.0) ? (sh[0] - (double)n) / sigma_f : 0.0;
+}
+
+void launch_sigma_identity(const double* Kinv, long ld, const double* a, const double* y, const double* d, double noise2,
+                           int n, double sigma_f, double* out, cudaStream_t s) {
+    sigma_identity_kernel<<<1, 256, 0, s>>>(Kinv, ld, a, y, d, noise2, n, sigma_f, out);
+}
+
 void launch_trace_and_sumsq(const double* A, long lda, const double* v, int n, double* out, cudaStream_t s) {
     trace_sumsq_kernel<<<1, 256, 0, s>>>(A, lda, v, n, out);
 }

@@ -97,6 +97,10 @@ struct GradReduceParams {
 void launch_grad_reduce(const GradReduceParams& p, cudaStream_t s);
 // out[0] = -1/2 z^T z - sum_k logdet[k] - M/2 log(2 pi): the fused log-likelihood reduction (one CTA, fixed order)
 void launch_ll_reduce(const double* z, int M, const double* logdet, int nblk, double* out, cudaStream_t s);
+// out[0] = (sum_i [a_i (y_i - a_i D_i) + Kinv_ii D_i] - n) / sigma_f, D_i = d[i] + noise2: the sigma_f entry of the gradient
+// for kernels of the form sigma_f^2 g, no transformation matrix
+void launch_sigma_identity(const double* Kinv, long ld, const double* a, const double* y, const double* d, double noise2,
+                           int n, double sigma_f, double* out, cudaStream_t s);
 // out[0] = sum_{i<n} A[i][i], out[1] = sum_{i<n} v[i]^2
 void launch_trace_and_sumsq(const double* A, long lda, const double* v, int n, double* out, cudaStream_t s);
 
