@@ -38,7 +38,7 @@ def build(force=False, verbose=False):
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
     hdrs = [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS]
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
-    objs = []
+    objs, jobs = [], []
     for src in srcs:
         obj = src[:-3] + ".o"
         objs.append(obj)
@@ -46,7 +46,11 @@ def build(force=False, verbose=False):
             cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-I", INCLUDE, "-c", src, "-o", obj]
             if verbose:
                 print(" ".join(cmd))
-            subprocess.check_call(cmd)
+            jobs.append(cmd)
+    if jobs:  # the translation units are independent: compile them side by side
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as pool:
+            list(pool.map(subprocess.check_call, jobs))
     if force or _stale(LIB, objs):
         cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-cudart", "static"]
         if verbose:
