@@ -121,7 +121,9 @@ __device__ __forceinline__ void issue_chunk(Smem& sm, int q) {
 }
 
 // acc += A[arow.., :] * B[brow.., :]^T over one chunk; LOWER: only the 8x8 products on and below the block diagonal
-template <bool LOWER, int IMAX = 4>
+// TRI: the A operand is upper triangular and this chunk's 16 columns start at the first row of block IMAX - 2, so the
+// last block (IMAX - 1, eight rows further down) only meets the chunk's upper eight columns (kk >= 2).
+template <bool LOWER, int IMAX = 4, bool TRI = false>
 __device__ __forceinline__ void chunk_mma(const double* stage, int arow, int brow, const Lane& L, double (&acc)[4][4][2]) {
     const double* aS = stage + (arow + L.g) * BK;
     const double* bS = stage + CHUNK + (brow + L.g) * BK;
@@ -136,6 +138,7 @@ __device__ __forceinline__ void chunk_mma(const double* stage, int arow, int bro
         for (int j = 0; j < 4; j++) b[j] = bS[j * 8 * BK + col];
 #pragma unroll
         for (int i = 0; i < IMAX; i++) {
+            if (TRI && i == IMAX - 1 && kk < 2) continue;
 #pragma unroll
             for (int j = 0; j < 4; j++)
                 if (!LOWER || j <= i) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
@@ -171,8 +174,10 @@ __device__ __forceinline__ void run_job(Smem& sm, const Lane& L, int nsteps, con
             const double* stage = sm.R + slt * STAGE_D;
             if (DIAG && !offd) chunk_mma<true>(stage, arow, brow, L, acc);
             // A upper triangular (A[r][k] = 0 for k < r): in the first chunk that reaches a warp's rows (chunk 0 for
-            // rows 0..31, chunk 2 for rows 32..63) only its first 16 rows meet non-zero columns
-            else if ((fl & 1) && (q % CPT) == (arow ? CPT / 2 : 0)) chunk_mma<false, 2>(stage, arow, brow, L, acc);
+            // rows 0..31, chunk 2 for rows 32..63) only its first 16 rows meet non-zero columns, and in that chunk and
+            // the next the last 8-row block only the upper eight columns: the exact 8x8-block triangle, at compile time
+            else if ((fl & 1) && (q % CPT) == (arow ? CPT / 2 : 0)) chunk_mma<false, 2, true>(stage, arow, brow, L, acc);
+            else if ((fl & 1) && (q % CPT) == (arow ? CPT / 2 : 0) + 1) chunk_mma<false, 4, true>(stage, arow, brow, L, acc);
             else chunk_mma<false>(stage, arow, brow, L, acc);
         }
         __syncwarp();
