@@ -17,6 +17,9 @@ for name, kid, th0 in (("matern52", 1, [1.0, 0.8]), ("matern nu=2.5", 2, [1.0, 2
     d.set_kernel(kid, len(th0), 1e2)
     gi = [0, len(th0) - 1] if kid != 3 else [0, 1, 2]
     for mode, g in (("ll+grad", gi), ("ll", None)):
-        d.ll_batched(th[:8], grad_idx=g)
-        t0 = time.perf_counter(); ll, gr, st = d.ll_batched(th, grad_idx=g); t = time.perf_counter() - t0
+        d.ll_batched(th, grad_idx=g)        # full-size warm-up: workspace allocation stays out of the timing
+        ts = []
+        for _ in range(2):
+            t0 = time.perf_counter(); ll, gr, st = d.ll_batched(th, grad_idx=g); ts.append(time.perf_counter() - t0)
+        t = min(ts)
         print("%-14s %-8s B=%d %.1f ms  %.0f evals/s ok=%s" % (name, mode, B, t * 1e3, B / t, (st == 0).all()))
