@@ -480,17 +480,38 @@ class GaussianProcess(object):
         if self._device_mode():
             kid, kparams = self.k.device_descriptor()
             grad_idx = None
+            fd_cols = {}
             if want_grad:
                 self.k.check_hyper_deriv(list(self.k.free_param_idxs))
-                grad_idx = list(self.k.free_param_idxs)
+                free_idx = [int(i) for i in self.k.free_param_idxs]
+                fd_set = set(int(i) for i in getattr(self.k, "fd_hyper_idxs", ()))
+                grad_idx = [i for i in free_idx if i not in fd_set]
                 if nn_free > 0:
                     grad_idx.append(len(kparams))
+                # parameters without a closed-form hyper-derivative on the device (the Matern order nu): Richardson
+                # central differences of the device's ll, evaluated BEFORE the main call so that the factorisation
+                # left resident belongs to the GP's own parameters
+                from .kernel.core import richardson_difference
+
+                def ll_at(p_):
+                    val, _, st = dev.ll(p_, self._noise_sigma(), grad_idx=None)
+                    if st != 0:
+                        raise numpy.linalg.LinAlgError("%d-th leading minor of the array is not positive definite" % st)
+                    return val
+                for col, i in enumerate(free_idx):
+                    if i in fd_set:
+                        fd_cols[col] = float(richardson_difference(ll_at, kparams, i,
+                                                                   self.k.FD_HYPER_REL_STEP * abs(kparams[i])))
             ll, grad, status = dev.ll(kparams, self._noise_sigma(), grad_idx=grad_idx)
             if status != 0:
                 raise numpy.linalg.LinAlgError(
                     "%d-th leading minor of the array is not positive definite" % status)
             if want_grad and grad is not None:
-                ll_deriv[:len(grad)] = grad
+                an_cols = [c for c in range(nk_free) if c not in fd_cols] + list(range(nk_free, nk_free + nn_free))
+                for c, v in zip(an_cols, grad):
+                    ll_deriv[c] = v
+                for c, v in fd_cols.items():
+                    ll_deriv[c] = v
         else:
             K = self.compute_Kij(self.X, None, self.n, None, noise=False)
             if isinstance(self.noise_k, ZeroKernel):

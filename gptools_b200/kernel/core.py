@@ -70,10 +70,26 @@ class Kernel(ParamHolder):
         return (r2l2, l_mat) if return_l else r2l2
 
 
+def richardson_difference(f, params, i, h):
+    """(4 D(h/2) - D(h)) / 3 with D the central difference of ``f`` along ``params[i]``: error O(h^4)."""
+    def D(hh):
+        pp, pm = np.array(params, dtype=float), np.array(params, dtype=float)
+        pp[i] += hh
+        pm[i] -= hh
+        return (np.asarray(f(pp), dtype=float) - np.asarray(f(pm), dtype=float)) / (2.0 * hh)
+    return (4.0 * D(0.5 * h) - D(h)) / 3.0
+
+
 class DeviceKernel(Kernel):
     """A kernel evaluated by libgptb200 (``kernel_id`` names the device function in csrc/covfn.cuh)."""
 
     supports_hyper_deriv = False
+
+    #: parameter indices whose hyper-derivative has no closed form on the device and is taken by Richardson-extrapolated
+    #: central differences of the device's own evaluation instead (MaternKernel: the order nu)
+    fd_hyper_idxs = ()
+    #: relative step of those differences
+    FD_HYPER_REL_STEP = 2e-3
 
     def device_descriptor(self):
         self._check_params_for_device()
@@ -100,6 +116,8 @@ class DeviceKernel(Kernel):
     def batchable(self, with_deriv):
         """False when ``gpt_ll_batched`` cannot serve this kernel's free parameters (the caller then evaluates one
         theta at a time through ``gpt_ll``)."""
+        if with_deriv and set(self.fd_hyper_idxs) & set(int(i) for i in self.free_param_idxs):
+            return False
         if with_deriv and self.kernel_id != 0:
             return not np.any(np.asarray(self.free_param_idxs) >= self.BATCHED_GRAD_SLOTS)
         return True
@@ -126,6 +144,9 @@ class DeviceKernel(Kernel):
         kid, params = self.device_descriptor()
         Xi, ni = self.device_points(Xi, ni)
         Xj, nj = self.device_points(Xj, nj)
+        if hyper_deriv is not None and int(hyper_deriv) in self.fd_hyper_idxs:
+            return richardson_difference(lambda p_: default_device().cov_pairs(kid, p_, Xi, Xj, ni, nj), params,
+                                         int(hyper_deriv), self.FD_HYPER_REL_STEP * abs(params[int(hyper_deriv)]))
         return default_device().cov_pairs(kid, params, Xi, Xj, ni, nj, hyper_deriv=hyper_deriv)
 
 
@@ -184,8 +205,19 @@ class BinaryKernel(Kernel):
         offs = np.cumsum([0] + [k.num_params for k in leaves])
         return leaves, offs
 
+    @property
+    def fd_hyper_idxs(self):
+        """Parameter indices (into the concatenated vector) differentiated by finite differences: those of the leaves."""
+        flat = self._flatten()
+        if flat is None:
+            return ()
+        leaves, offs = self._leaf_offsets()
+        return tuple(int(offs[q]) + int(i) for q, k in enumerate(leaves) for i in k.fd_hyper_idxs)
+
+    FD_HYPER_REL_STEP = 2e-3
+
     def check_hyper_deriv(self, idxs):
-        """Per-leaf availability (d/dnu of a generic Matern operand is the one derivative the device lacks)."""
+        """Per-leaf availability."""
         leaves, offs = self._leaf_offsets()
         for i in idxs:
             q = int(np.searchsorted(offs, int(i), side="right") - 1)
@@ -202,7 +234,9 @@ class BinaryKernel(Kernel):
         return None
 
     def batchable(self, with_deriv):
-        return True  # the library decides: persistent many-theta kernel, or theta after theta beyond its gradient slots
+        # the library decides: persistent many-theta kernel, or theta after theta beyond its gradient slots; free
+        # parameters differentiated by finite differences take the per-theta path
+        return not (with_deriv and set(self.fd_hyper_idxs) & set(int(i) for i in self.free_param_idxs))
 
     def batch_rows_supported(self, param_rows):
         param_rows = np.atleast_2d(param_rows)
@@ -224,6 +258,9 @@ class BinaryKernel(Kernel):
         if hyper_deriv is not None:
             self.check_hyper_deriv([int(hyper_deriv)])
         self._check_orders(ni, nj)
+        if hyper_deriv is not None and int(hyper_deriv) in self.fd_hyper_idxs:
+            return richardson_difference(lambda p_: default_device().cov_pairs(desc[0], p_, Xi, Xj, ni, nj), desc[1],
+                                         int(hyper_deriv), self.FD_HYPER_REL_STEP * abs(desc[1][int(hyper_deriv)]))
         return default_device().cov_pairs(desc[0], desc[1], Xi, Xj, ni, nj, hyper_deriv=hyper_deriv)
 
     def __init__(self, k1, k2):

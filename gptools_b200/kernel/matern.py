@@ -35,15 +35,15 @@ class MaternKernel(DeviceKernel):
     (kernel/matern.py:444-457) -- for any nu > 0 (K_nu of real order by Temme's method; the closed form for
     half-integer nu) and total derivative order <= 2 per pair, which covers value + first-derivative observations
     and predictions.  ``hyper_deriv`` is supported for sigma_f and the length scales (dual numbers,
-    csrc/covfn_hyper.cuh); nu must be a fixed parameter then (the reference has no hyper-derivatives at all here)."""
+    csrc/covfn_hyper.cuh) and -- by Richardson-extrapolated central differences of the device evaluation -- for nu (the
+    reference has no hyper-derivatives at all here)."""
 
     kernel_id = 2
     supports_hyper_deriv = True
 
-    def check_hyper_deriv(self, idxs):
-        if 1 in [int(i) for i in idxs]:
-            raise NotImplementedError("The derivative with respect to nu is not available: fix nu "
-                                      "(fixed_params=[False, True, ...]) to use hyperparameter derivatives")
+    #: d/dnu has no closed form (it needs dK_nu/dnu): Richardson-extrapolated central differences of the device's own
+    #: evaluation (of K in ``__call__``, of ll in ``GaussianProcess.compute_K_L_alpha_ll``), relative error ~1e-8
+    fd_hyper_idxs = (1,)
 
     def __init__(self, num_dim=1, **kwargs):
         names = [r'\sigma_f', r'\nu'] + ['l_{:d}'.format(i + 1) for i in range(num_dim)]

@@ -207,9 +207,9 @@ def test_composite_hyper_deriv_checks_follow_the_leaves():
     a = _se([1.0, 0.5])
     m = g.MaternKernel(initial_params=[1.0, 2.5, 0.7], param_bounds=[(0, 10)] * 3)
     k = a * m
-    k.check_hyper_deriv([0, 1, 2, 4])
-    with pytest.raises(NotImplementedError):
-        k.check_hyper_deriv([3])                                 # nu of the Matern operand
+    k.check_hyper_deriv([0, 1, 2, 3, 4])
+    assert k.fd_hyper_idxs == (3,)                               # nu of the Matern operand: finite differences
+    assert not k.batchable(True) and k.batchable(False)
     rows = np.array([[1.0, 0.5, 1.0, 2.5, 0.7], [1.0, 0.5, 1.0, -1.0, 0.7]])
     assert list(k.batch_rows_supported(rows)) == [True, False]
 

@@ -322,9 +322,23 @@ def test_matern_and_gibbs_optimise_with_device_gradient():
     f, df = gpm.update_hyperparameters(gm["params"][[0, 2]])
     assert_close(-df, gm["ll_grad_fd"], rtol=0.0, atol=1e-5 * np.abs(gm["ll_grad_fd"]).max())
     km_free = g.MaternKernel(num_dim=1, initial_params=gm["params"], param_bounds=[(0, 10)] * 3)
-    gpf = g.GaussianProcess(km_free, use_hyper_deriv=True, X=gm["X"][:nv, 0], y=gm["y"][:nv], err_y=gm["err_y"][:nv])
-    with pytest.raises(NotImplementedError):
-        gpf.compute_K_L_alpha_ll()
+    # nu free: its ll derivative comes from Richardson central differences of the device's own ll (no closed form
+    # for dK_nu/dnu); checked against an independent Richardson difference of the ORACLE's ll
+    gpf = g.GaussianProcess(km_free, use_hyper_deriv=True)
+    gpf.add_data(gm["X"][:nv, 0], gm["y"][:nv], err_y=gm["err_y"][:nv])
+    gpf.add_data(gm["X"][nv:, 0], gm["y"][nv:], err_y=gm["err_y"][nv:], n=1)
+    ff, dff = gpf.update_hyperparameters(gm["params"])
+    assert_close(-ff, gm["ll"], rtol=1e-9)
+    assert_close(-dff[[0, 2]], gm["ll_grad_fd"], rtol=0.0, atol=1e-5 * np.abs(gm["ll_grad_fd"]).max())
+    from oracle import gp_oracle as orc
+    from helpers import richardson_fd
+    ll_o = lambda p_: orc.compute_K_L_alpha_ll(2, p_, gpf.X, gpf.n, gpf.y, gpf.err_y)["ll"]
+    dnu = richardson_fd(ll_o, np.array(gm["params"], dtype=float), 1, 1e-3 * gm["params"][1])
+    assert abs(-dff[1] - dnu) <= 1e-5 * max(1.0, np.abs(dff).max()), (-dff[1], dnu)
+    # the batched entry with nu free and gradients: per-theta path, same numbers
+    fB, dfB = gpf.update_hyperparameters_batch(np.vstack([gm["params"], gm["params"]]), with_deriv=True)
+    assert_close(fB[1], ff, rtol=1e-12)
+    assert_close(dfB[1], dff, rtol=1e-9, atol=1e-12)
     # Gibbs-tanh with transformed observations
     gg = load_golden("hyperfd_gibbs_T")
     kg = g.GibbsKernel1dTanh(initial_params=gg["params"], param_bounds=[(0, 10), (0, 5), (0, 5), (0, 1), (0, 2)])
@@ -548,3 +562,24 @@ def test_batched_entry_with_T_and_beyond_2048_observations():
     bad = np.array([[1.0, 0.7], [1.0, 1e3], [1.1, 0.6]])
     fb = gp2.update_hyperparameters_batch(bad, with_deriv=False)
     assert np.isfinite(fb[0]) and np.isfinite(fb[2])
+
+
+def test_matern_order_derivative_against_mpmath():
+    """dk/dnu of the generic Matern kernel (Kernel.__call__ with hyper_deriv=1): Richardson central differences of the
+    device evaluation against 30-digit mpmath derivatives of the reference's covariance function
+    k = sigma^2 2^(1-nu)/Gamma(nu) (sqrt(2 nu) r/l)^nu K_nu(sqrt(2 nu) r/l) (kernel/matern.py:296-312), value entries."""
+    import mpmath as mp
+    mp.mp.dps = 30
+    rs = np.random.RandomState(12)
+    for nu in (1.5, 2.2, 3.0):
+        k = g.MaternKernel(num_dim=1, initial_params=[1.3, nu, 0.7], param_bounds=[(0, 10)] * 3)
+        Xi, Xj = rs.rand(12, 1) * 2, rs.rand(12, 1) * 2
+        z = np.zeros((12, 1), dtype=int)
+        got = k(Xi, Xj, z, z, hyper_deriv=1)
+
+        def kfun(v, r):
+            x = mp.sqrt(2 * v) * r / mp.mpf("0.7")
+            return mp.mpf("1.3") ** 2 * 2 ** (1 - v) / mp.gamma(v) * x ** v * mp.besselk(v, x)
+        want = np.array([float(mp.diff(lambda v: kfun(v, mp.mpf(float(abs(a - b)))), mp.mpf(nu)))
+                         for a, b in zip(Xi[:, 0], Xj[:, 0])])
+        assert_close(got, want, rtol=1e-6, atol=1e-8 * np.abs(want).max(), what="dk/dnu at nu = %g" % nu)

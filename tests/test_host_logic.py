@@ -299,8 +299,13 @@ def test_unsupported_orders_raise_before_any_device_call():
     with pytest.raises(ValueError):
         mk.device_descriptor()
     mk = g.MaternKernel(num_dim=1, initial_params=[1.0, 2.5, 0.5], param_bounds=[(0, 10)] * 3)
-    with pytest.raises(NotImplementedError):          # d/dnu is the one derivative the device does not have
-        mk(np.zeros((1, 1)), np.zeros((1, 1)), np.zeros((1, 1), int), np.zeros((1, 1), int), hyper_deriv=1)
+    # d/dnu has no closed form on the device: finite differences of the device evaluation (GPU suite); with nu free and
+    # gradients requested the batched entry is not used
+    assert mk.fd_hyper_idxs == (1,) and not mk.batchable(True) and mk.batchable(False)
+    mk.check_hyper_deriv([0, 1, 2])
+    mkf = g.MaternKernel(num_dim=1, initial_params=[1.0, 2.5, 0.5], fixed_params=[False, True, False],
+                         param_bounds=[(0, 10)] * 3)
+    assert mkf.batchable(True)
 
 
 def test_pickle_drops_the_device_handle():
