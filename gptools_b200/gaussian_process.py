@@ -629,6 +629,8 @@ class GaussianProcess(object):
         Everything else (host kernels, GibbsKernel1d with a user length-scale function) takes the per-theta loop."""
         if not self._device_mode() or self.k.device_points_key() is not None:
             return False
+        if with_deriv and set(getattr(self.k, "fd_hyper_idxs", ())) & set(int(i) for i in self.k.free_param_idxs):
+            return False  # a free parameter whose gradient entry is a finite difference of ll: per-theta path
         persistent = self.T is None and len(self.y) <= self.BATCHED_KERNEL_MAX_M
         if persistent and not self.k.batchable(with_deriv):
             return False
