@@ -178,3 +178,16 @@ def test_mean_function_with_free_parameters():
     Xs = np.linspace(0, 3, 50)
     _check(gp, thetas, Xs, 0, prior_var=thetas[:, :1] ** 2)
     _check(gp, thetas, Xs, 1, prior_var=(thetas[:, :1] / thetas[:, 1:2]) ** 2)
+
+
+def test_randomised_batched_vs_single_theta_paths():
+    """tools/fuzz_batched.py: random sizes (1 ... 700, tile edges), dimensions, derivative orders, kernels (SE, Matern-5/2,
+    generic Matern, sums), noise: ll, gradient and batched prediction of the persistent kernel against the single-theta
+    path."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_batched.py"), "30", "7"], cwd=root,
+                         capture_output=True, text=True)
+    assert out.returncode == 0 and "fuzz OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
