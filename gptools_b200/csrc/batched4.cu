@@ -702,6 +702,156 @@ __device__ __forceinline__ void grad_tab(const Smem& sm, const BatchedParams& p,
     gall[0] += (sm.cp.p[0] != 0.0) ? 2.0 * wk / sm.cp.p[0] : 0.0;
 }
 
+// ---- Matern 5/2 short forms (KIND == 1: D <= 2, at most one first derivative per point) ---------------------------------
+// With il2_d = 1 / l_d^2, tau = x_i - x_j, r2 = sum tau_d^2 il2_d, s = sqrt(5 r2), e = exp(-s), Bf = (1 + s) e
+// (reference kernel/src/matern.c:61-186; the same closed forms as matern52_cov / matern52_cov_dual in covfn.cuh):
+//   value            k00 = sig2 (1 + s + 5/3 r2) e
+//   row deriv a      k10 = -5/3 sig2 Bf tau_a il2_a              col deriv b   k01 = +5/3 sig2 Bf tau_b il2_b
+//   both             k11 = 5/3 sig2 (Bf [a == b] il2_a - 5 e tau_a tau_b il2_a il2_b)
+// and their derivatives with respect to l_d through dr2/dl_d = -2 tau_d^2 il2_d / l_d, d il2_d / dl_d = -2 il2_d / l_d,
+// d(1 + s + 5/3 r2)e / dr2 = -5/6 Bf, dBf/dr2 = -5/2 e, de/dr2 = -5 e / (2 s).  sigma_f: trace identity at the outputs.
+template <int FD>
+struct M52Entry {
+    double e, Bf, s, r2, tau[FD];
+};
+template <int FD>
+__device__ __forceinline__ M52Entry<FD> m52_entry(const double* pts, int r, const double (&xj)[FD], const double (&il2)[FD],
+                                                   const double* etab) {
+    M52Entry<FD> t;
+    t.r2 = 0.0;
+#pragma unroll
+    for (int d = 0; d < FD; d++) {
+        t.tau[d] = pts[r * FD + d] - xj[d];
+        t.r2 = fma(t.tau[d] * t.tau[d], il2[d], t.r2);
+    }
+    const double q = 5.0 * t.r2;
+    t.s = (q > 0.0) ? q * fast_rsqrt_pos(q) : 0.0;
+    t.e = exp_nonpos_tab(-t.s, etab);
+    t.Bf = (1.0 + t.s) * t.e;
+    return t;
+}
+
+template <int FD>
+__device__ __forceinline__ void m52_gen(const Smem& sm, const BatchedParams& p, double* St, int tid, int I, int Jc) {
+    const bool DIAG = (I == Jc);
+    const int c = tid & (TB - 1);
+    const int gj = Jc * TB + c;
+    const bool col_ok = gj < p.M;
+    double il2[FD], xj[FD];
+    int bcol = -1;  // dimension of the column point's derivative
+#pragma unroll
+    for (int d = 0; d < FD; d++) {
+        il2[d] = sm.cp.inv_l[d] * sm.cp.inv_l[d];
+        xj[d] = col_ok ? __ldg(p.X + (size_t)gj * FD + d) : 0.0;
+        if (col_ok && __ldg(p.n + (size_t)gj * FD + d) != 0) bcol = d;
+    }
+    const double dj = col_ok ? sm.noise2 + __ldg(p.diag + gj) : 0.0;
+    const double c53 = 1.6666666666666667 * sm.cp.sig2;
+    const double* pts = sm.R + PTS_OFF;
+    const int* ord = reinterpret_cast<const int*>(pts + PTS_ORD);
+#pragma unroll UNROLL
+    for (int u = 0; u < 32; u++) {
+        const int r = (tid >> 6) + 2 * u;
+        const int gi = I * TB + r;
+        const M52Entry<FD> t = m52_entry<FD>(pts, r, xj, il2, sm.exptab);
+        const int pk = ord[r];
+        int arow = -1;
+#pragma unroll
+        for (int d = 0; d < FD; d++)
+            if ((pk >> (8 * d)) & 255) arow = d;
+        double ta = 0.0, ia = 0.0, tb = 0.0, ib = 0.0;
+#pragma unroll
+        for (int d = 0; d < FD; d++) {
+            ta = (d == arow) ? t.tau[d] : ta;
+            ia = (d == arow) ? il2[d] : ia;
+            tb = (d == bcol) ? t.tau[d] : tb;
+            ib = (d == bcol) ? il2[d] : ib;
+        }
+        const double v00 = sm.cp.sig2 * fma(1.6666666666666667, t.r2, 1.0 + t.s) * t.e;
+        const double v10 = -c53 * t.Bf * ta * ia;
+        const double v01 = c53 * t.Bf * tb * ib;
+        const double v11 = c53 * (((arow == bcol) ? t.Bf * ia : 0.0) - 5.0 * t.e * (ta * ia) * (tb * ib));
+        double v = (arow < 0) ? ((bcol < 0) ? v00 : v01) : ((bcol < 0) ? v10 : v11);
+        const double vd = v + dj;
+        v = (gi == gj) ? vd : v;
+        const double pad = (gi == gj) ? 1.0 : 0.0;
+        v = (col_ok && row_ok(p, gi)) ? v : pad;
+        const double out = v - st_get(St, r, c, DIAG);
+        if (!DIAG || c <= r) St[r * LDT + c] = out;
+    }
+}
+
+template <int FD>
+__device__ __forceinline__ void m52_grad(const Smem& sm, const BatchedParams& p, const double* St, int tid, int I, int J,
+                                         const double* __restrict__ avec, double (&gall)[1 + GPT_MAX_DIM], double& tr_kinv) {
+    const bool DIAG = (I == J);
+    const int c = tid & (TB - 1);
+    const int gj = J * TB + c;
+    if (gj >= p.M) return;
+    const double aj = avec[gj];
+    double il2[FD], xj[FD];
+    int bcol = -1;
+#pragma unroll
+    for (int d = 0; d < FD; d++) {
+        il2[d] = sm.cp.inv_l[d] * sm.cp.inv_l[d];
+        xj[d] = __ldg(p.X + (size_t)gj * FD + d);
+        if (__ldg(p.n + (size_t)gj * FD + d) != 0) bcol = d;
+    }
+    const double c53 = 1.6666666666666667 * sm.cp.sig2;
+    const double* pts = sm.R + PTS_OFF;
+    const int* ord = reinterpret_cast<const int*>(pts + PTS_ORD);
+    double gl[FD];
+#pragma unroll
+    for (int d = 0; d < FD; d++) gl[d] = 0.0;
+    const int u0 = (DIAG && c >= 32) ? 16 : 0;
+#pragma unroll 2
+    for (int u = u0; u < 32; u++) {
+        const int r = (tid >> 6) + 2 * u;
+        const int gi = I * TB + r;
+        const bool use = (gi < p.M) && (!DIAG || c <= r);
+        const bool on_diag = DIAG && (c == r);
+        const double kinv = st_get(St, r, (DIAG && c > r) ? r : c, DIAG);
+        double w = fma(pts[PTS_ALPHA + r], aj, -kinv);
+        w = on_diag ? 0.5 * w : w;
+        w = use ? w : 0.0;
+        if (use && on_diag) {
+            tr_kinv += kinv;
+            gall[0] += kinv * (sm.noise2 + p.diag[gi]);  // sum_i K^-1_ii D_i for the sigma_f identity
+        }
+        const M52Entry<FD> t = m52_entry<FD>(pts, r, xj, il2, sm.exptab);
+        const int pk = ord[r];
+        int arow = -1;
+#pragma unroll
+        for (int d = 0; d < FD; d++)
+            if ((pk >> (8 * d)) & 255) arow = d;
+        double ta = 0.0, ia = 0.0, tb = 0.0, ib = 0.0;
+#pragma unroll
+        for (int d = 0; d < FD; d++) {
+            ta = (d == arow) ? t.tau[d] : ta;
+            ia = (d == arow) ? il2[d] : ia;
+            tb = (d == bcol) ? t.tau[d] : tb;
+            ib = (d == bcol) ? il2[d] : ib;
+        }
+        const double es = (t.s > 0.0) ? t.e / t.s : 0.0;   // e / s: multiplies tau_a tau_b tau_d^2 (-> 0 with s)
+        const double wc = w * c53;
+#pragma unroll
+        for (int d = 0; d < FD; d++) {
+            // g = dk/dl_d * l_d / (5/3 sig2)   (the common 1 / l_d is applied once at the end)
+            const double q = t.tau[d] * t.tau[d] * il2[d];         // tau_d^2 / l_d^2 = -l_d/2 dr2/dl_d
+            const double g00 = t.Bf * q;
+            const double g10 = -(ta * ia) * fma(5.0 * t.e, q, (d == arow) ? -2.0 * t.Bf : 0.0);
+            const double g01 = (tb * ib) * fma(5.0 * t.e, q, (d == bcol) ? -2.0 * t.Bf : 0.0);
+            const double dab = (arow == bcol) ? ia * fma(5.0 * t.e, q, (d == arow) ? -2.0 * t.Bf : 0.0) : 0.0;
+            const double cnt = ((d == arow) ? 1.0 : 0.0) + ((d == bcol) ? 1.0 : 0.0);
+            const double g11 = dab - 5.0 * (ta * ia) * (tb * ib) * fma(5.0 * es, q, -2.0 * t.e * cnt);
+            const double g = (arow < 0) ? ((bcol < 0) ? g00 : g01) : ((bcol < 0) ? g10 : g11);
+            gl[d] = fma(wc, g, gl[d]);
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < FD; d++) gall[1 + d] += gl[d] * sm.cp.inv_l[d];
+}
+
 // C = K_tot - S in place on the staging tile.  Thread tid owns column c = tid & 63 and rows (tid >> 6) + 2u.
 template <int FD>
 __device__ __forceinline__ void gen_ktot_tile(const Smem& sm, const BatchedParams& p, double* St, int tid, int I, int Jc) {
@@ -892,7 +1042,7 @@ __device__ __forceinline__ int job_step(double* ws, const BatchedParams& p, int 
     return fl;
 }
 
-template <int FD>
+template <int FD, int KIND = 0>
 __global__ void __launch_bounds__(THREADS, GPT_B4_MINB) ll_batched4_kernel(BatchedParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
@@ -1052,7 +1202,9 @@ __global__ void __launch_bounds__(THREADS, GPT_B4_MINB) ll_batched4_kernel(Batch
                     __syncthreads();
                     if (ph == 1) {
                         // C = K_tot - S in place (K_tot generated from the closed forms, never stored)
-                        if constexpr (FD == 1 || FD == 2) {
+                        if constexpr (KIND == 1) {
+                            m52_gen<FD>(sm, p, St, L.tid, I, J);
+                        } else if constexpr (FD == 1 || FD == 2) {
                             if (sm.use_tab) gen_ktot_tab<FD>(sm, p, St, L.tid, I, J, (p.eb_off && I < nT) ? const_cast<double*>(ebt) : nullptr);
                             else gen_ktot_tile<FD>(sm, p, St, L.tid, I, J);
                         } else {
@@ -1125,7 +1277,9 @@ __global__ void __launch_bounds__(THREADS, GPT_B4_MINB) ll_batched4_kernel(Batch
                         }
                         PT_MARK(3);
                     } else {
-                        if constexpr (FD == 1 || FD == 2) {
+                        if constexpr (KIND == 1) {
+                            m52_grad<FD>(sm, p, St, L.tid, I, J, avec, gall, tr_kinv);
+                        } else if constexpr (FD == 1 || FD == 2) {
                             if (sm.use_tab) grad_tab<FD>(sm, p, St, L.tid, I, J, avec, ebt, gall, tr_kinv);
                             else grad_tile<FD>(sm, p, St, L.tid, I, J, avec, gall, tr_kinv);
                         } else {
@@ -1161,7 +1315,7 @@ __global__ void __launch_bounds__(THREADS, GPT_B4_MINB) ll_batched4_kernel(Batch
                 want_sig |= (p.idx[q] == 0);
             }
             // the sigma_f identity of grad_tile (generic closed forms, single kernels)
-            const bool sig_id = (FD == 0) && want_sig && sm.cp.kid != GPT_KERNEL_SE && sm.cp.kid != GPT_KERNEL_COMPOSITE;
+            const bool sig_id = (FD == 0 || KIND == 1) && want_sig && sm.cp.kid != GPT_KERNEL_SE && sm.cp.kid != GPT_KERNEL_COMPOSITE;
             double aa = 0.0, ay = 0.0;
             if (want_noise || sig_id) {
                 double part = 0.0, part2 = 0.0;
@@ -1248,18 +1402,18 @@ static size_t smem_request() {
     return bytes;
 }
 
-template <int FD>
+template <int FD, int KIND = 0>
 void launch_t(const BatchedParams& p, int num_ctas, cudaStream_t s) {
     const size_t smem_bytes = smem_request();
-    cudaFuncSetAttribute(ll_batched4_kernel<FD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    cudaFuncSetAttribute(ll_batched4_kernel<FD, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
 #ifdef GPT_PHASE_TIMING
     {
         int nb = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ll_batched4_kernel<FD>, THREADS, sizeof(Smem));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ll_batched4_kernel<FD, KIND>, THREADS, sizeof(Smem));
         fprintf(stderr, "[batched4] smem %zu B per CTA, occupancy %d CTAs/SM, grid %d\n", sizeof(Smem), nb, num_ctas);
     }
 #endif
-    ll_batched4_kernel<FD><<<num_ctas, THREADS, smem_bytes, s>>>(p);
+    ll_batched4_kernel<FD, KIND><<<num_ctas, THREADS, smem_bytes, s>>>(p);
 }
 
 }  // namespace
@@ -1282,6 +1436,9 @@ void launch_ll_batched4(const BatchedParams& p, int num_ctas, cudaStream_t s) {
     if (p.kid == GPT_KERNEL_SE && p.D == 1) launch_t<1>(p, num_ctas, s);
     else if (p.kid == GPT_KERNEL_SE && p.D == 2) launch_t<2>(p, num_ctas, s);
     else if (p.kid == GPT_KERNEL_SE && p.D == 3) launch_t<3>(p, num_ctas, s);
+    // Matern 5/2 in one or two dimensions with at most first derivatives: its own short closed forms
+    else if (p.kid == GPT_KERNEL_MATERN52 && p.D == 1 && p.low_order && !getenv("GPT_B4_LONG_FORMS")) launch_t<1, 1>(p, num_ctas, s);
+    else if (p.kid == GPT_KERNEL_MATERN52 && p.D == 2 && p.low_order && !getenv("GPT_B4_LONG_FORMS")) launch_t<2, 1>(p, num_ctas, s);
     else launch_t<0>(p, num_ctas, s);
     if (p.Ms > 0) predict_var_finish_kernel<<<p.B, 128, 0, s>>>(p);
 }
