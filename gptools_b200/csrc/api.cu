@@ -840,6 +840,12 @@ int gpt_compute_Kij(gpt_handle* h, int kernel_id, int D, int nparams, const doub
     a.out = ptr<double>(dout); a.ldo = Mj; a.rows_pad = Mi; a.cols_pad = Mj;
     a.hyper_deriv = hyper_deriv; a.swap_roles = 0; a.symmetric = 0;
     a.diag_add = nullptr; a.diag_const = 0.0; a.pad_identity = 0;
+    {
+        int mo = 0;  // every derivative order <= 1: the short SE / Matern-5/2 tile generators apply
+        for (size_t i = 0; i < (size_t)Mi * D; i++) mo = ni[i] > mo ? ni[i] : mo;
+        if (!sym) for (size_t i = 0; i < (size_t)Mj * D; i++) mo = nj[i] > mo ? nj[i] : mo;
+        a.low_order = (mo <= 1) ? 1 : 0;
+    }
     launch_assemble(a, h->stream);
     h->launches++;
     cudaError_t e = cudaMemcpyAsync(K_out, dout.p, sizeof(double) * (size_t)Mi * Mj, cudaMemcpyDeviceToHost, h->stream);
@@ -1179,10 +1185,11 @@ static int predict_core(gpt_handle* h, int Ms, const double* Xs, const int32_t* 
     const int CH = predict_chunk_rows(h, Ms, cov);
     if ((rc = upload(h, h->Xs, Xs, sizeof(double) * (size_t)Ms * D))) return rc;
     if ((rc = upload(h, h->ns, ns, sizeof(int32_t) * (size_t)Ms * D))) return rc;
+    int max_ns = 0;
+    for (size_t i = 0; i < (size_t)Ms * D; i++) max_ns = ns[i] > max_ns ? ns[i] : max_ns;
+    const int low_order = (h->max_order <= 1 && max_ns <= 1) ? 1 : 0;  // the short SE / Matern-5/2 tile generators apply
     if (!var && !cov) {
         // mean only: K(X*, X) alpha fused with tile generation, nothing materialised (u = alpha, or T^T alpha)
-        int max_ns = 0;
-        for (size_t i = 0; i < (size_t)Ms * D; i++) max_ns = ns[i] > max_ns ? ns[i] : max_ns;
         const double* u = ptr<double>(h->alpha);
         if (h->hasT) {
             if ((rc = ensure(h, h->u, sizeof(double) * Np))) return rc;
@@ -1194,7 +1201,7 @@ static int predict_core(gpt_handle* h, int Ms, const double* Xs, const int32_t* 
         if ((rc = ensure(h, h->Kst, sizeof(double) * (size_t)nsplit * Ms))) return rc;
         if ((rc = ensure(h, h->mean, sizeof(double) * (size_t)round_up(Ms, NB)))) return rc;
         launch_predict_mean_fused(h->cp, ptr<double>(h->X), ptr<int32_t>(h->n), u, N, ptr<double>(h->Xs),
-                                  ptr<int32_t>(h->ns), Ms, (h->max_order <= 1 && max_ns <= 1) ? 1 : 0,
+                                  ptr<int32_t>(h->ns), Ms, low_order,
                                   ptr<double>(h->Kst), ptr<double>(h->mean), s);
         h->launches += 2;
         return check_launch(h);
@@ -1218,6 +1225,7 @@ static int predict_core(gpt_handle* h, int Ms, const double* Xs, const int32_t* 
         a.out = ptr<double>(h->Kst); a.ldo = Np; a.rows_pad = rows_pad; a.cols_pad = Np;
         a.hyper_deriv = -1; a.swap_roles = 1; a.symmetric = 0;
         a.diag_add = nullptr; a.diag_const = 0.0; a.pad_identity = 0;
+        a.low_order = low_order;
         launch_assemble(a, s);
         h->launches++;
         double* Ko = nullptr;
@@ -1238,6 +1246,7 @@ static int predict_core(gpt_handle* h, int Ms, const double* Xs, const int32_t* 
                 c.out = ptr<double>(h->cov); c.ldo = Sp; c.rows_pad = Sp; c.cols_pad = Sp;
                 c.hyper_deriv = -1; c.swap_roles = 0; c.symmetric = 0;
                 c.diag_add = nullptr; c.diag_const = 0.0; c.pad_identity = 0;
+                c.low_order = (max_ns <= 1) ? 1 : 0;
                 launch_assemble(c, s);
                 // padding columns (>= M) of V are zero rows of the identity-padded system: K* is zero there
                 GemmParams g;

@@ -18,13 +18,15 @@ constexpr int TS = 64;
 // Squared-exponential value tiles, input dimension FD <= 3, derivative orders <= 1 on both sides: register-resident
 // branch-free closed forms with the table-based exp (se_fast.cuh) instead of the generic cov_eval -- the generic
 // path keeps per-dimension arrays in local memory and branches per entry.
-template <int FD>
+// KIND 0: squared exponential; KIND 1: Matern 5/2 (m52_value_low)
+template <int FD, int KIND>
 __device__ __forceinline__ void assemble_tile_se_low(const AssembleParams& p, const double* sxr, const int32_t* snr,
                                                      const double* sxc, const int32_t* snc, const double* etab,
                                                      int r0, int c0, int tid) {
     using namespace sefast;
     SEHoist<FD> h = se_hoist<FD>(p.cp);
     h.etab = etab;
+    const M52Hoist<FD> hm = m52_hoist<FD>(p.cp, etab);
     const int ty = tid >> 4, tx = tid & 15;
     PointReg<FD> pc[4];
 #pragma unroll
@@ -49,7 +51,9 @@ __device__ __forceinline__ void assemble_tile_se_low(const AssembleParams& p, co
             const int c = c0 + tx + 16 * b;
             // out[r][c] = k(row_r, col_c), or k(col_c, row_r) with swapped roles (the sign depends on which side
             // carries the odd derivative order)
-            double v = p.swap_roles ? se_value_low<FD, true>(h, pc[b], pr) : se_value_low<FD, true>(h, pr, pc[b]);
+            double v;
+            if constexpr (KIND == 1) v = p.swap_roles ? m52_value_low<FD>(hm, pc[b], pr) : m52_value_low<FD>(hm, pr, pc[b]);
+            else v = p.swap_roles ? se_value_low<FD, true>(h, pc[b], pr) : se_value_low<FD, true>(h, pr, pc[b]);
             const bool inside = r < p.Mr && c < p.Mc;
             v = inside ? v : 0.0;
             if (p.symmetric && r == c) {
@@ -79,7 +83,7 @@ __device__ __forceinline__ void stage_tile_points(const AssembleParams& p, doubl
 // The SE / orders <= 1 value tiles have their OWN kernel: inside the generic kernel they inherited its 255 registers
 // (cov_eval covers Matern with K_nu of real order, Gibbs, Hermite recurrences ...) and ran at one CTA per SM --
 // 12% occupancy, 14% of the FP64 pipe, 250 GB/s of output (profiles/r02j_*).  Three CTAs per SM here.
-template <int FD>
+template <int FD, int KIND>
 __global__ void __launch_bounds__(256, 3) assemble_se_low_kernel(AssembleParams p) {
     if (p.lower_tiles_only && blockIdx.x > blockIdx.y) return;  // the Cholesky never reads tiles above the diagonal
     __shared__ double sxr[TS * GPT_MAX_DIM];
@@ -90,7 +94,7 @@ __global__ void __launch_bounds__(256, 3) assemble_se_low_kernel(AssembleParams 
     const int r0 = blockIdx.y * TS, c0 = blockIdx.x * TS;
     stage_tile_points(p, sxr, sxc, snr, snc, etab, r0, c0, threadIdx.x);
     __syncthreads();
-    assemble_tile_se_low<FD>(p, sxr, snr, sxc, snc, etab, r0, c0, threadIdx.x);
+    assemble_tile_se_low<FD, KIND>(p, sxr, snr, sxc, snc, etab, r0, c0, threadIdx.x);
 }
 
 __global__ void __launch_bounds__(256) assemble_kernel(AssembleParams p) {
@@ -157,9 +161,16 @@ __global__ void cov_pairs_kernel(CovParams cp, int hyper_deriv, long npairs, con
 void launch_assemble(const AssembleParams& p, cudaStream_t s) {
     dim3 grid((p.cols_pad + TS - 1) / TS, (p.rows_pad + TS - 1) / TS);
     if (p.cp.kid == GPT_KERNEL_SE && p.hyper_deriv < 0 && p.low_order && p.cp.D <= 3) {
-        if (p.cp.D == 1) assemble_se_low_kernel<1><<<grid, 256, 0, s>>>(p);
-        else if (p.cp.D == 2) assemble_se_low_kernel<2><<<grid, 256, 0, s>>>(p);
-        else assemble_se_low_kernel<3><<<grid, 256, 0, s>>>(p);
+        if (p.cp.D == 1) assemble_se_low_kernel<1, 0><<<grid, 256, 0, s>>>(p);
+        else if (p.cp.D == 2) assemble_se_low_kernel<2, 0><<<grid, 256, 0, s>>>(p);
+        else assemble_se_low_kernel<3, 0><<<grid, 256, 0, s>>>(p);
+        return;
+    }
+    // Matern 5/2 value tiles (its points carry at most one first derivative: kernel/matern.py:545-546)
+    if (p.cp.kid == GPT_KERNEL_MATERN52 && p.hyper_deriv < 0 && p.low_order && p.cp.D <= 3) {
+        if (p.cp.D == 1) assemble_se_low_kernel<1, 1><<<grid, 256, 0, s>>>(p);
+        else if (p.cp.D == 2) assemble_se_low_kernel<2, 1><<<grid, 256, 0, s>>>(p);
+        else assemble_se_low_kernel<3, 1><<<grid, 256, 0, s>>>(p);
         return;
     }
     assemble_kernel<<<grid, 256, 0, s>>>(p);

@@ -53,7 +53,7 @@ __global__ void prior_diag_kernel(CovParams cp, const double* __restrict__ Xs, c
 constexpr int PM_THREADS = 128;
 constexpr int PM_STAGE = 128;
 
-template <int FD>
+template <int FD, int KIND = 0>
 __global__ void __launch_bounds__(PM_THREADS) predict_mean_kernel(CovParams cp, const double* __restrict__ X,
                                                                   const int32_t* __restrict__ n,
                                                                   const double* __restrict__ u, int N,
@@ -93,6 +93,25 @@ __global__ void __launch_bounds__(PM_THREADS) predict_mean_kernel(CovParams cp, 
 #pragma unroll 1
             for (int r = 0; r < cnt; r++)
                 acc += cov_eval(cp, sx + r * GPT_MAX_DIM, sn + r * GPT_MAX_DIM, xs, ms, -1) * su[r];
+        } else if constexpr (KIND == 1) {
+            // Matern 5/2 (points with at most one first derivative): branch-free, all 128 staged rows (u = 0 beyond cnt)
+            const M52Hoist<FD> hm = m52_hoist<FD>(cp, etab);
+            PointReg<FD> pj;
+#pragma unroll
+            for (int d = 0; d < FD; d++) {
+                pj.x[d] = xs[d];
+                pj.n[d] = ms[d];
+            }
+#pragma unroll 8
+            for (int r = 0; r < PM_STAGE; r++) {
+                PointReg<FD> pi;
+#pragma unroll
+                for (int d = 0; d < FD; d++) {
+                    pi.x[d] = sx[r * GPT_MAX_DIM + d];
+                    pi.n[d] = sn[r * GPT_MAX_DIM + d];
+                }
+                acc = fma(m52_value_low<FD>(hm, pi, pj), su[r], acc);
+            }
         } else {
             SEHoist<FD> h = se_hoist<FD>(cp);
             h.etab = etab;
@@ -164,6 +183,10 @@ void launch_predict_mean_fused(const CovParams& cp, const double* X, const int32
         predict_mean_kernel<2><<<grid, PM_THREADS, 0, s>>>(cp, X, n, u, N, Xs, ns, Ms, per_split, low_order, partial);
     else if (cp.kid == GPT_KERNEL_SE && cp.D == 3)
         predict_mean_kernel<3><<<grid, PM_THREADS, 0, s>>>(cp, X, n, u, N, Xs, ns, Ms, per_split, low_order, partial);
+    else if (cp.kid == GPT_KERNEL_MATERN52 && cp.D == 1 && low_order)
+        predict_mean_kernel<1, 1><<<grid, PM_THREADS, 0, s>>>(cp, X, n, u, N, Xs, ns, Ms, per_split, low_order, partial);
+    else if (cp.kid == GPT_KERNEL_MATERN52 && cp.D == 2 && low_order)
+        predict_mean_kernel<2, 1><<<grid, PM_THREADS, 0, s>>>(cp, X, n, u, N, Xs, ns, Ms, per_split, low_order, partial);
     else
         predict_mean_kernel<0><<<grid, PM_THREADS, 0, s>>>(cp, X, n, u, N, Xs, ns, Ms, per_split, low_order, partial);
     sum_partials_kernel<<<(Ms + 255) / 256, 256, 0, s>>>(partial, nsplit, Ms, mean);

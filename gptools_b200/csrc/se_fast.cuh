@@ -165,4 +165,53 @@ __device__ __forceinline__ void se_value_grad_low(const SEHoist<D>& h, const Poi
     }
 }
 
+// ---- Matern 5/2, at most one first derivative per point (the Matern52Kernel contract, kernel/matern.py:545-546) -----
+// k(a, b) with r2 = sum tau_d^2 / l_d^2, s = sqrt(5 r2), tau = x_a - x_b (reference kernel/src/matern.c:61-186):
+//   value  sig2 (1 + s + 5/3 r2) e^-s;   d/dx_a,i: -5/3 sig2 (1 + s) e^-s tau_i / l_i^2;   d/dx_b,j: the same with +;
+//   both:  5/3 sig2 e^-s ((1 + s) [i == j] / l_i^2 - 5 tau_i tau_j / (l_i^2 l_j^2)).   Branch-free (selects), table exp.
+template <int D>
+struct M52Hoist {
+    double sig2, c53;
+    double il2[D];
+    const double* etab;
+};
+
+template <int D>
+__device__ __forceinline__ M52Hoist<D> m52_hoist(const CovParams& cp, const double* etab) {
+    M52Hoist<D> h;
+    h.sig2 = cp.sig2;
+    h.c53 = 1.6666666666666667 * cp.sig2;
+#pragma unroll
+    for (int d = 0; d < D; d++) h.il2[d] = cp.inv_l[d] * cp.inv_l[d];
+    h.etab = etab;
+    return h;
+}
+
+template <int D>
+__device__ __forceinline__ double m52_value_low(const M52Hoist<D>& h, const PointReg<D>& a, const PointReg<D>& b) {
+    double r2 = 0.0, ta = 0.0, ia = 0.0, tb = 0.0, ib = 0.0;
+    int da = -1, db = -1;
+#pragma unroll
+    for (int d = 0; d < D; d++) {
+        const double tau = a.x[d] - b.x[d];
+        r2 = fma(tau * tau, h.il2[d], r2);
+        const bool oa = a.n[d] != 0, ob = b.n[d] != 0;
+        da = oa ? d : da;
+        db = ob ? d : db;
+        ta = oa ? tau : ta;
+        ia = oa ? h.il2[d] : ia;
+        tb = ob ? tau : tb;
+        ib = ob ? h.il2[d] : ib;
+    }
+    const double q = 5.0 * r2;
+    const double s = (q > 0.0) ? q * fast_rsqrt_pos(q) : 0.0;
+    const double e = exp_nonpos_tab(-s, h.etab);
+    const double Bf = (1.0 + s) * e;
+    const double v00 = h.sig2 * fma(1.6666666666666667, r2, 1.0 + s) * e;
+    const double v10 = -h.c53 * Bf * ta * ia;
+    const double v01 = h.c53 * Bf * tb * ib;
+    const double v11 = h.c53 * (((da == db) ? Bf * ia : 0.0) - 5.0 * e * (ta * ia) * (tb * ib));
+    return (da < 0) ? ((db < 0) ? v00 : v01) : ((db < 0) ? v10 : v11);
+}
+
 }  // namespace sefast
