@@ -97,6 +97,84 @@ __global__ void __launch_bounds__(256, 3) assemble_se_low_kernel(AssembleParams 
     assemble_tile_se_low<FD, KIND>(p, sxr, snr, sxc, snc, etab, r0, c0, threadIdx.x);
 }
 
+// Gibbs kernel in one dimension (kernel/gibbs.py:324-423; gibbs_cov_l in covfn.cuh), derivative orders <= 1: the length
+// scale l(x) and l'(x) of the 64 row and 64 column points are evaluated ONCE per tile (tanh profile: kernel/gibbs.py:458-461;
+// AUX: they arrive as point columns 1 and 2), the entries then cost one reciprocal, one square root and one table exp each.
+// Inside the generic kernel every entry paid two tanh, a division, sqrt and the library exp at one CTA per SM: the
+// latent covariance of config 5 (4001^2 entries) was most of its 1.7 ms log-likelihood.
+template <bool AUX>
+__global__ void __launch_bounds__(256, 3) assemble_gibbs_low_kernel(AssembleParams p) {
+    if (p.lower_tiles_only && blockIdx.x > blockIdx.y) return;
+    __shared__ double sr[TS][3], sc[TS][3];  // x, l(x), l'(x)
+    __shared__ int32_t nr[TS], nc[TS];
+    __shared__ double etab[64];
+    const int r0 = blockIdx.y * TS, c0 = blockIdx.x * TS;
+    const int tid = threadIdx.x;
+    const int D = p.cp.D;  // 1, or 3 with the auxiliary columns
+    if (tid < 2 * TS) {
+        const bool row = tid < TS;
+        const int l = row ? tid : tid - TS;
+        const int gi = (row ? r0 : c0) + l;
+        const bool ok = gi < (row ? p.Mr : p.Mc);
+        const double* X = row ? p.Xr : p.Xc;
+        const int32_t* n = row ? p.nr : p.nc;
+        double x = 0.0, lx = 1.0, lx1 = 0.0;
+        if (ok) {
+            x = X[(long)gi * D];
+            if (AUX) {
+                lx = X[(long)gi * D + 1];
+                lx1 = X[(long)gi * D + 2];
+            } else {
+                gibbs_tanh_l(p.cp, x, lx, lx1);
+            }
+        }
+        double* dst = row ? sr[l] : sc[l];
+        dst[0] = x;
+        dst[1] = lx;
+        dst[2] = lx1;
+        (row ? nr : nc)[l] = ok ? n[(long)gi * D] : 0;
+    }
+    if (tid < 64) etab[tid] = GPT_EXP2_64[tid];
+    __syncthreads();
+    const int ty = tid >> 4, tx = tid & 15;
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        const int lr = ty + 16 * a;
+        const int r = r0 + lr;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int lc = tx + 16 * b;
+            const int c = c0 + lc;
+            // out[r][c] = k(row_r, col_c), or k(col_c, row_r) with swapped roles
+            const double* pa = p.swap_roles ? sc[lc] : sr[lr];
+            const double* pb = p.swap_roles ? sr[lr] : sc[lc];
+            const int na = p.swap_roles ? nc[lc] : nr[lr], nb = p.swap_roles ? nr[lr] : nc[lc];
+            const double lx = pa[1], lx1 = pa[2], ly = pb[1], ly1 = pb[2];
+            const double d = pa[0] - pb[0];
+            const double S = lx * lx + ly * ly;
+            const double iS = (S > 0.0) ? fast_rcp_pos(S) : 1.0 / S;
+            const double z = 2.0 * lx * ly * iS;
+            const double k00 = ((z > 0.0) ? z * fast_rsqrt_pos(z) : sqrt(z)) * exp_nonpos_tab(-d * d * iS, etab);
+            const double Ax = lx1 / (2.0 * lx) - lx * lx1 * iS - 2.0 * d * iS + 2.0 * d * d * lx * lx1 * iS * iS;
+            const double Ay = ly1 / (2.0 * ly) - ly * ly1 * iS + 2.0 * d * iS + 2.0 * d * d * ly * ly1 * iS * iS;
+            const double dAx = 2.0 * lx * lx1 * ly * ly1 * iS * iS + 2.0 * iS + 4.0 * d * ly * ly1 * iS * iS -
+                               4.0 * d * lx * lx1 * iS * iS - 8.0 * d * d * lx * lx1 * ly * ly1 * iS * iS * iS;
+            double f = 1.0;
+            f = (na && !nb) ? Ax : f;
+            f = (!na && nb) ? Ay : f;
+            f = (na && nb) ? fma(Ax, Ay, dAx) : f;
+            double v = p.cp.sig2 * k00 * f;
+            const bool inside = r < p.Mr && c < p.Mc;
+            v = inside ? v : 0.0;
+            if (p.symmetric && r == c) {
+                if (inside) v += p.diag_const + (p.diag_add ? p.diag_add[r] : 0.0);
+                else if (p.pad_identity) v = 1.0;
+            }
+            if (r < p.rows_pad && c < p.cols_pad) p.out[(long)r * p.ldo + c] = v;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) assemble_kernel(AssembleParams p) {
     if (p.lower_tiles_only && blockIdx.x > blockIdx.y) return;  // the Cholesky never reads tiles above the diagonal
     __shared__ double sxr[TS * GPT_MAX_DIM];
@@ -171,6 +249,14 @@ void launch_assemble(const AssembleParams& p, cudaStream_t s) {
         if (p.cp.D == 1) assemble_se_low_kernel<1, 1><<<grid, 256, 0, s>>>(p);
         else if (p.cp.D == 2) assemble_se_low_kernel<2, 1><<<grid, 256, 0, s>>>(p);
         else assemble_se_low_kernel<3, 1><<<grid, 256, 0, s>>>(p);
+        return;
+    }
+    if (p.hyper_deriv < 0 && p.low_order && p.cp.kid == GPT_KERNEL_GIBBS_TANH && p.cp.D == 1) {
+        assemble_gibbs_low_kernel<false><<<grid, 256, 0, s>>>(p);
+        return;
+    }
+    if (p.hyper_deriv < 0 && p.low_order && p.cp.kid == GPT_KERNEL_GIBBS_AUX && p.cp.D == 3) {
+        assemble_gibbs_low_kernel<true><<<grid, 256, 0, s>>>(p);
         return;
     }
     assemble_kernel<<<grid, 256, 0, s>>>(p);
