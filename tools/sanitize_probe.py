@@ -48,3 +48,15 @@ import warnings
 warnings.simplefilter("ignore")
 print(gp.update_hyperparameters(th)[0], gp.update_hyperparameters_batch(np.vstack([th, 1.02 * th]), with_deriv=True)[0])
 print(gp.predict(rs.rand(5, 2))[0])
+# batched prediction (test points as extra tile rows) for SE and Matern-5/2 (their own short-form instantiations) and
+# the Matern-5/2 batched gradient
+for kk in (g.SquaredExponentialKernel(num_dim=2, initial_params=[1.0, 0.4, 0.5], param_bounds=[(0, 10)] * 3),
+           g.Matern52Kernel(num_dim=2, initial_params=[1.0, 0.6, 0.7], param_bounds=[(0, 10)] * 3)):
+    gq = g.GaussianProcess(kk, use_hyper_deriv=True)
+    gq.add_data(Xc, np.sin(3 * Xc[:, 0]) + 0.05 * rs.randn(150), err_y=0.05)
+    gq.add_data(Xc[::10], 3 * np.cos(3 * Xc[::10, 0]), err_y=0.1, n=np.tile([1, 0], (15, 1)))
+    tq = np.array(gq.free_params[:], dtype=float)
+    tb = np.vstack([tq, 1.03 * tq, 0.97 * tq])
+    fq, dq = gq.update_hyperparameters_batch(tb, with_deriv=True)
+    mq, sq, okq = gq.predict_batch(tb, rs.rand(70, 2), n=np.tile([0, 1], (70, 1)))
+    print(type(kk).__name__, fq[0], dq[0], float(mq[0, 0]), float(sq[0, 0]), okq.all())
