@@ -687,6 +687,20 @@ class GaussianProcess(object):
                     y_batch=y_batch, grad_idx=grad_idx, need_alpha=need_alpha, full_eval=full_eval,
                     all_params=all_params, free_mask=free_mask)
 
+    def _batch_plan_from_gathered(self, thetas, with_deriv, logp):
+        """The part of a ``_batch_prepare`` plan that ``_batch_finish`` reads, for a batch whose per-row log-prior was
+        computed elsewhere (-inf marks rows outside the prior support or not evaluable): the sharded entry prepares
+        every row on one rank only and gathers the log-prior with the device results."""
+        B = thetas.shape[0]
+        nk, nn = self.k.num_free_params, self.noise_k.num_free_params
+        all_params = np.empty((B, len(self.params)))
+        all_params[:] = np.asarray(self.params[:], dtype=float)
+        free_mask = ~np.asarray(self.fixed_params[:], dtype=bool)
+        all_params[:, free_mask] = thetas
+        logp = np.asarray(logp, dtype=float)
+        return dict(thetas=thetas, B=B, nk=nk, nn=nn, n_free=len(self.free_params), with_deriv=with_deriv, logp=logp,
+                    ok=np.isfinite(logp), need_alpha=False, all_params=all_params, free_mask=free_mask)
+
     def _batch_finish(self, plan, ll, grad, status, alpha=None):
         """-ll / -grad from the device results of ``_batch_prepare``'s rows (prior terms, inf / zero masks)."""
         B, nk, nn, n_free = plan["B"], plan["nk"], plan["nn"], plan["n_free"]

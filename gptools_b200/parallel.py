@@ -127,11 +127,14 @@ def _device_handles(gp):
     return dev, tdev, stream
 
 
-def _theta_batch_device(gp, plan, lo, hi, counts):
-    """Local slice [lo, hi) of a prepared theta batch on this rank's GPU, results gathered device to device.
+def _theta_batch_device(gp, plan, counts):
+    """The rows of ``plan`` (this rank's slice of a theta batch, prepared by ``gp._batch_prepare``) on this rank's GPU,
+    results gathered device to device.  Returns (ll, grad, status, logp) for the WHOLE batch.
 
-    Send-buffer layout per rank (bytes): ll  nmax x f64 | grad  nmax x P x f64 | status  nmax x i32 (padded to 8):
-    the kernel's output pointers are views of it."""
+    Send-buffer layout per rank (bytes): ll  nmax x f64 | grad  nmax x P x f64 | log-prior  nmax x f64 | status
+    nmax x i32 (padded to 8): the kernel's output pointers are views of it; the log-prior of the local rows (-inf where
+    the row is outside the prior support or not evaluable) is copied in next to them, so that the host-side prior
+    arithmetic is done once per row across the job instead of once per row on every rank."""
     import torch
     dist = _dist()
     world_size = dist.get_world_size()
@@ -140,25 +143,29 @@ def _theta_batch_device(gp, plan, lo, hi, counts):
     P = len(grad_idx) if grad_idx else 0
     nmax = max(counts)
     off_grad = 8 * nmax
-    off_status = off_grad + 8 * nmax * P
+    off_logp = off_grad + 8 * nmax * P
+    off_status = off_logp + 8 * nmax
     nbytes = off_status + 8 * ((4 * nmax + 7) // 8)
     send = torch.zeros(nbytes, dtype=torch.uint8, device=tdev)
-    nloc = hi - lo
+    nloc = plan["B"]
     if nloc > 0:
-        th = torch.from_numpy(np.ascontiguousarray(plan["full_eval"][lo:hi])).to(tdev, non_blocking=True)
+        th = torch.from_numpy(np.ascontiguousarray(plan["full_eval"])).to(tdev, non_blocking=True)
         base = send.data_ptr()
         dev.ll_batched_dev(nloc, th.data_ptr(), base, base + off_status, d_grad=(base + off_grad) if P else 0,
                            grad_idx=grad_idx)
+        logp = np.where(plan["ok"], plan["logp"], -np.inf)
+        send[off_logp:off_logp + 8 * nloc].copy_(torch.from_numpy(logp.view(np.uint8)), non_blocking=True)
     recv = torch.empty(world_size * nbytes, dtype=torch.uint8, device=tdev)
     dist.all_gather_into_tensor(recv, send)
     host = recv.cpu().numpy().reshape(world_size, nbytes)
     ll = np.concatenate([host[r, :8 * counts[r]].view(np.float64) for r in range(world_size)])
     status = np.concatenate([host[r, off_status:off_status + 4 * counts[r]].view(np.int32) for r in range(world_size)])
+    logp_all = np.concatenate([host[r, off_logp:off_logp + 8 * counts[r]].view(np.float64) for r in range(world_size)])
     grad = None
     if P:
         grad = np.concatenate([host[r, off_grad:off_grad + 8 * counts[r] * P].view(np.float64).reshape(counts[r], P)
                                for r in range(world_size)], axis=0)
-    return ll, grad, status
+    return ll, grad, status, logp_all
 
 
 def update_hyperparameters_batch_sharded(gp, thetas, with_deriv=None):
@@ -176,10 +183,14 @@ def update_hyperparameters_batch_sharded(gp, thetas, with_deriv=None):
     counts = shard_counts(B, world_size)
     lo, hi = shard_bounds(B, rank, world_size)
     if gp._batchable(with_deriv):
+        if _on_nccl(dist) and (gp.mu is None or gp.mu.num_free_params == 0):
+            # every rank prepares (parameter rows, prior, validity) ITS slice only; the log-prior travels with the results
+            plan = gp._batch_prepare(thetas[lo:hi] if hi > lo else thetas[:1], with_deriv)
+            if hi == lo:
+                plan["B"] = 0  # more ranks than rows: this rank only takes part in the gather
+            ll, grad, status, logp = _theta_batch_device(gp, plan, counts)
+            return gp._batch_finish(gp._batch_plan_from_gathered(thetas, with_deriv, logp), ll, grad, status)
         plan = gp._batch_prepare(thetas, with_deriv)  # host arithmetic over the whole batch, identical on all ranks
-        if _on_nccl(dist) and plan["y_batch"] is None and not plan["need_alpha"]:
-            ll, grad, status = _theta_batch_device(gp, plan, lo, hi, counts)
-            return gp._batch_finish(plan, ll, grad, status)
         # per-theta mean-function residuals / alpha (host arrays in the C-ABI), or the gloo backend
         P = len(plan["grad_idx"]) if plan["grad_idx"] else 0
         M = len(gp.y)

@@ -23,6 +23,13 @@ th = np.array([1.0, 0.3, 0.4]) * np.exp(0.1 * rs.randn(37, 3))       # ragged sp
 f_s, df_s = parallel.update_hyperparameters_batch_sharded(gp, th, with_deriv=True)
 f_l, df_l = gp.update_hyperparameters_batch(th, with_deriv=True)
 assert np.array_equal(f_s, f_l) and np.array_equal(df_s, df_l), "theta sharding differs from the local batch"
+f1 = parallel.update_hyperparameters_batch_sharded(gp, th[:1], with_deriv=False)      # fewer rows than ranks
+assert np.array_equal(f1, gp.update_hyperparameters_batch(th[:1], with_deriv=False))
+thb = th.copy()
+thb[5, 1] = -1.0                                                                     # outside the prior support
+fb, dfb = parallel.update_hyperparameters_batch_sharded(gp, thb, with_deriv=True)
+fl, dfl = gp.update_hyperparameters_batch(thb, with_deriv=True)
+assert np.isinf(fb[5]) and np.array_equal(fb, fl) and np.array_equal(dfb, dfl), "prior masking through the gather"
 Xs = rs.rand(1001, 2)
 m_s, s_s = parallel.predict_sharded(gp, Xs)
 m_l, s_l = gp.predict(Xs)
