@@ -697,9 +697,10 @@ class GaussianProcess(object):
         all_params[:] = np.asarray(self.params[:], dtype=float)
         free_mask = ~np.asarray(self.fixed_params[:], dtype=bool)
         all_params[:, free_mask] = thetas
-        logp = np.asarray(logp, dtype=float)
+        logp = None if logp is None else np.asarray(logp, dtype=float)   # None: filled in by the caller after the gather
         return dict(thetas=thetas, B=B, nk=nk, nn=nn, n_free=len(self.free_params), with_deriv=with_deriv, logp=logp,
-                    ok=np.isfinite(logp), need_alpha=False, all_params=all_params, free_mask=free_mask)
+                    ok=None if logp is None else np.isfinite(logp), need_alpha=False, all_params=all_params,
+                    free_mask=free_mask)
 
     def _batch_finish(self, plan, ll, grad, status, alpha=None):
         """-ll / -grad from the device results of ``_batch_prepare``'s rows (prior terms, inf / zero masks)."""

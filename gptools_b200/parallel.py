@@ -127,7 +127,7 @@ def _device_handles(gp):
     return dev, tdev, stream
 
 
-def _theta_batch_device(gp, plan, counts):
+def _theta_batch_device(gp, plan, counts, while_running=None):
     """The rows of ``plan`` (this rank's slice of a theta batch, prepared by ``gp._batch_prepare``) on this rank's GPU,
     results gathered device to device.  Returns (ll, grad, status, logp) for the WHOLE batch.
 
@@ -157,7 +157,14 @@ def _theta_batch_device(gp, plan, counts):
         send[off_logp:off_logp + 8 * nloc].copy_(torch.from_numpy(logp.view(np.uint8)), non_blocking=True)
     recv = torch.empty(world_size * nbytes, dtype=torch.uint8, device=tdev)
     dist.all_gather_into_tensor(recv, send)
+    extra = while_running() if while_running is not None else None  # host work hidden behind the kernel and the gather
     host = recv.cpu().numpy().reshape(world_size, nbytes)
+    if min(counts) == nmax:  # equal slices: the gathered blocks are contiguous per field
+        ll = host[:, :8 * nmax].copy().view(np.float64).reshape(-1)
+        status = host[:, off_status:off_status + 4 * nmax].copy().view(np.int32).reshape(-1)
+        logp_all = host[:, off_logp:off_logp + 8 * nmax].copy().view(np.float64).reshape(-1)
+        grad = host[:, off_grad:off_grad + 8 * nmax * P].copy().view(np.float64).reshape(-1, P) if P else None
+        return ll, grad, status, logp_all, extra
     ll = np.concatenate([host[r, :8 * counts[r]].view(np.float64) for r in range(world_size)])
     status = np.concatenate([host[r, off_status:off_status + 4 * counts[r]].view(np.int32) for r in range(world_size)])
     logp_all = np.concatenate([host[r, off_logp:off_logp + 8 * counts[r]].view(np.float64) for r in range(world_size)])
@@ -165,7 +172,7 @@ def _theta_batch_device(gp, plan, counts):
     if P:
         grad = np.concatenate([host[r, off_grad:off_grad + 8 * counts[r] * P].view(np.float64).reshape(counts[r], P)
                                for r in range(world_size)], axis=0)
-    return ll, grad, status, logp_all
+    return ll, grad, status, logp_all, extra
 
 
 def update_hyperparameters_batch_sharded(gp, thetas, with_deriv=None):
@@ -188,8 +195,12 @@ def update_hyperparameters_batch_sharded(gp, thetas, with_deriv=None):
             plan = gp._batch_prepare(thetas[lo:hi] if hi > lo else thetas[:1], with_deriv)
             if hi == lo:
                 plan["B"] = 0  # more ranks than rows: this rank only takes part in the gather
-            ll, grad, status, logp = _theta_batch_device(gp, plan, counts)
-            return gp._batch_finish(gp._batch_plan_from_gathered(thetas, with_deriv, logp), ll, grad, status)
+            # the frame of the whole-batch plan (parameter rows of every theta) is built while the GPUs work
+            ll, grad, status, logp, full = _theta_batch_device(
+                gp, plan, counts, while_running=lambda: gp._batch_plan_from_gathered(thetas, with_deriv, None))
+            full["logp"] = logp
+            full["ok"] = np.isfinite(logp)
+            return gp._batch_finish(full, ll, grad, status)
         plan = gp._batch_prepare(thetas, with_deriv)  # host arithmetic over the whole batch, identical on all ranks
         # per-theta mean-function residuals / alpha (host arrays in the C-ABI), or the gloo backend
         P = len(plan["grad_idx"]) if plan["grad_idx"] else 0
