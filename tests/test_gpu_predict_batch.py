@@ -191,3 +191,32 @@ def test_randomised_batched_vs_single_theta_paths():
     out = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_batched.py"), "30", "7"], cwd=root,
                          capture_output=True, text=True)
     assert out.returncode == 0 and "fuzz OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_c3_full_size_batch_prediction():
+    """Config-3 size (4096 thetas, M = 512, 2-D SE with derivative observations): one launch predicts at 128 points for
+    every theta; rows drawn at random agree with the single-theta path, every row is finite, and the batch entry
+    reproduces the reference's KAT-5 values (ll of eight thetas of the batch, predictive mean / std at theta 0)."""
+    import bench
+    X, n, y, err = bench.c3_problem()
+    k = g.SquaredExponentialKernel(num_dim=2, initial_params=[1.0, 0.3, 0.4], param_bounds=[(0, 10)] * 3)
+    gp = g.GaussianProcess(k, X=X, y=y, err_y=err, n=n)
+    th = bench.theta_batch(4096)
+    Xs = np.random.RandomState(2).rand(128, 2)
+    mean, std, good = gp.predict_batch(th, Xs)
+    assert good.all() and np.isfinite(mean).all() and np.isfinite(std).all() and (std > 0).all()
+    for b in (0, 1234, 4095):
+        gp.update_hyperparameters(th[b])
+        m, s = gp.predict(Xs)
+        assert_close(mean[b], m, rtol=1e-9, atol=1e-10, what="mean of theta %d" % b)
+        assert np.all(np.abs(std[b] ** 2 - s ** 2) <= 1e-9 * th[b, 0] ** 2)
+    # the reference's own numbers (KAT-5, SURVEY 8d): ll of eight thetas of the batch, predictions at theta 0
+    gd = load_golden("c3_kat5")
+    assert_close(th[gd["theta_idx"]], gd["theta"], rtol=1e-8)
+    dev, _ = gp._sync_device()
+    full = np.hstack([th[gd["theta_idx"]], np.zeros((8, 1))])
+    m8, v8, ll, st = dev.predict_batched(full, gd["Xs"], np.zeros(gd["Xs"].shape, dtype=int))
+    assert (st == 0).all()
+    assert_close(ll + float(gd["log_prior"]), gd["ll"], rtol=1e-9, what="ll next to the predictions")
+    assert_close(m8[0], gd["mean"], rtol=1e-8, what="mean at theta 0 vs the reference")
+    assert_close(np.sqrt(v8[0]), gd["std"], rtol=1e-5, what="std at theta 0 vs the reference")
