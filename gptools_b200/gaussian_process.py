@@ -666,7 +666,8 @@ class GaussianProcess(object):
         ok = np.isfinite(logp)
         # rows the device closed forms do not cover (e.g. a Matern nu that is not a half-integer): same result as the
         # per-theta path, which raises before the device call and returns inf
-        ok &= self.k.batch_rows_supported(full[:, :nparams])
+        rows_ok = self.k.batch_rows_supported(full[:, :nparams])
+        ok &= rows_ok
         y_batch = None
         if self.mu is not None and self.mu.num_free_params > 0:
             y_batch = np.empty((B, len(self.y)))
@@ -685,7 +686,7 @@ class GaussianProcess(object):
         full_eval = full if ok.all() else np.where(ok[:, None], full, np.tile(base_row, (B, 1)))
         return dict(dev=dev, thetas=thetas, B=B, nk=nk, nn=nn, n_free=n_free, with_deriv=with_deriv, logp=logp, ok=ok,
                     y_batch=y_batch, grad_idx=grad_idx, need_alpha=need_alpha, full_eval=full_eval,
-                    all_params=all_params, free_mask=free_mask)
+                    all_params=all_params, free_mask=free_mask, full=full, rows_ok=rows_ok, base_row=base_row)
 
     def _batch_plan_from_gathered(self, thetas, with_deriv, logp):
         """The part of a ``_batch_prepare`` plan that ``_batch_finish`` reads, for a batch whose per-row log-prior was
@@ -1187,8 +1188,10 @@ class GaussianProcess(object):
         gaussian_process.py:1944-1969), batched.  The test points ride along as extra tile rows of each theta's
         factorisation (``gpt_predict_batched``).
 
-        Returns ``(mean (B, M*), std (B, M*), good (B,))``; rows with ``good == False`` (zero prior probability,
-        covariance not positive definite) are NaN, where the per-sample loop skips the sample.  Returns ``None`` when the
+        Returns ``(mean (B, M*), std (B, M*), good (B,))``; rows with ``good == False`` (covariance not positive
+        definite, parameters the closed forms do not take) are NaN, where the per-sample loop skips the sample.  Like the
+        reference's per-sample wrapper (gaussian_process.py:2301-2330), a sample outside the prior support is still
+        predicted: only a failing prediction drops it.  Returns ``None`` when the
         batch cannot run in the persistent kernel (transformation matrix, more than 2048 observations, host-evaluated
         kernels, theta-dependent point columns): the caller then predicts sample by sample.  The GP's own
         hyperparameters are left unchanged."""
@@ -1213,10 +1216,11 @@ class GaussianProcess(object):
         plan = self._batch_prepare(thetas, False)
         Xs_d, ns_d = self.k.device_points(Xstar, n)
         try:
-            mean, var, ll, status = plan["dev"].predict_batched(plan["full_eval"], Xs_d, ns_d, y_batch=plan["y_batch"])
+            rows = np.where(plan["rows_ok"][:, None], plan["full"], plan["base_row"][None, :])
+            mean, var, ll, status = plan["dev"].predict_batched(rows, Xs_d, ns_d, y_batch=plan["y_batch"])
         except NotImplementedError:
             return None
-        good = plan["ok"] & (status == 0)
+        good = plan["rows_ok"] & (status == 0)
         nk, nn = plan["nk"], plan["nn"]
         if self.mu is not None:
             saved = np.array(self.mu.params, dtype=float)
@@ -1233,7 +1237,7 @@ class GaussianProcess(object):
             if not (isinstance(self.noise_k, DiagonalNoiseKernel) and
                     type(self.noise_k).__call__ is DiagonalNoiseKernel.__call__):
                 return None
-            sig = plan["full_eval"][:, -1]
+            sig = rows[:, -1]
             var = var + (sig ** 2.0)[:, None] * np.all(n == np.asarray(self.noise_k.n), axis=1)[None, :]
         with np.errstate(invalid="ignore"):
             std = np.sqrt(var)
@@ -1252,7 +1256,7 @@ class GaussianProcess(object):
             flat_trace = sampler.chain[:, burn::thin, :]
             flat_trace = flat_trace.reshape((-1, flat_trace.shape[2]))
         else:
-            flat_trace = np.asarray(flat_trace, dtype=float)
+            flat_trace = np.asarray(flat_trace, dtype=float)[burn::thin, :]   # gaussian_process.py:1938
         saved = np.array(self.free_params[:], dtype=float)
         out = {k_: [] for k_ in ('mean', 'std', 'cov', 'samp', 'mean_func')}
         # the hyperparameter samples are independent units (the reference maps them over a process pool,
@@ -1291,12 +1295,15 @@ class GaussianProcess(object):
                 flat_trace = flat_trace[:0]
         try:
             for th in flat_trace:
-                val = self.update_hyperparameters(th)
-                if np.isinf(val if np.isscalar(val) else val[0]):
+                # the reference's wrapper (gaussian_process.py:2301-2330) ignores the value update_hyperparameters
+                # returns (inf for zero prior probability) and drops a sample only when the prediction itself fails
+                try:
+                    self.update_hyperparameters(th)
+                    res = self.predict(X, n=n, noise=noise, full_output=True, return_samples=return_samples,
+                                       num_samples=num_samples, samp_kwargs=samp_kwargs,
+                                       return_mean_func=return_mean_func, output_transform=output_transform)
+                except Exception:
                     continue
-                res = self.predict(X, n=n, noise=noise, full_output=True, return_samples=return_samples,
-                                   num_samples=num_samples, samp_kwargs=samp_kwargs,
-                                   return_mean_func=return_mean_func, output_transform=output_transform)
                 out['mean'].append(res['mean'])
                 out['std'].append(res['std'])
                 if return_cov:

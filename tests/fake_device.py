@@ -46,7 +46,7 @@ class FakeDevice(object):
             r = orc.compute_K_L_alpha_ll(self.kernel_id, params, self.X, self.n, self.y if y is None else y,
                                          self.err_y, T=self.T, noise_sigma=noise_sigma, diag_factor=self.diag_factor,
                                          grad_idx=gi if gi else None)
-        except np.linalg.LinAlgError:
+        except (np.linalg.LinAlgError, ValueError):   # not positive definite / non-finite entries: a potrf status on the device
             return None
         grad = None
         if grad_idx is not None:

@@ -599,6 +599,29 @@ def case_composite():
     save("composite_gp_1d", params=np.array([float(v) for v in kg.params]), **gp_state(gp), **out)
 
 
+# ---------------------------------------------------------------- compute_from_MCMC / predict_MCMC (gaussian_process.py:1840-2254)
+def case_mcmc_predict():
+    """predict_MCMC over a given trace of hyperparameter samples: the law of total variance over the per-sample
+    predictions (one sample lies outside the prior support: the reference's per-sample wrapper predicts it all the same,
+    gaussian_process.py:2301-2330).  num_proc = 2: with one process the reference iterates a Python-3 map object twice."""
+    rs = RandomState(3)
+    X = np.sort(rs.rand(40)) * 4
+    y = np.sin(2 * X) + 0.1 * rs.randn(40)
+    k = g.SquaredExponentialKernel(initial_params=[1.0, 0.7], param_bounds=[(0.05, 5), (0.1, 3)])
+    gp = g.GaussianProcess(k, X=X, y=y, err_y=0.1)
+    gp.add_data(X[::8], 2 * np.cos(2 * X[::8]), err_y=0.3, n=1)
+    trace = np.array([1.0, 0.7]) * np.exp(0.1 * rs.randn(12, 2))
+    trace[3, 1] = 9.0
+    Xs = np.linspace(0, 4, 9)
+    out = gp.predict_MCMC(Xs, flat_trace=trace, num_proc=2, return_samples=False)
+    out1 = gp.predict_MCMC(Xs, n=1, flat_trace=trace, num_proc=2, return_samples=False)
+    res = gp.compute_from_MCMC(Xs, flat_trace=trace, num_proc=2)
+    thin = gp.predict_MCMC(Xs, flat_trace=trace, burn=2, thin=3, num_proc=2, return_samples=False)
+    save("mcmc_predict_se1d", trace=trace, Xs=Xs, mean=out['mean'], std=out['std'], mean_d1=out1['mean'],
+         std_d1=out1['std'], means=np.array(res['mean']), stds=np.array(res['std']), mean_thin=thin['mean'],
+         std_thin=thin['std'], **gp_state(gp))
+
+
 # ---------------------------------------------------------------- other Gibbs length-scale profiles (kernel/gibbs.py:508-902)
 def case_gibbs_profiles():
     rs = RandomState(21)
@@ -655,7 +678,7 @@ def case_warped():
 if __name__ == "__main__":
     cases = [case_se2d, case_se_pairs, case_matern52, case_matern_generic, case_gibbs, case_c5_full, case_demo,
              case_c3, case_c2, case_noise, case_hyperfd, case_product, case_gibbs_profiles, case_warped,
-             case_matern_real_nu, case_hyper_mp, case_composite]
+             case_matern_real_nu, case_hyper_mp, case_composite, case_mcmc_predict]
     only = set(sys.argv[1:])          # e.g. `make_golden.py case_hyperfd` regenerates one family
     for c in cases:
         if not only or c.__name__ in only:

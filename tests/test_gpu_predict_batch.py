@@ -128,11 +128,16 @@ def test_against_the_oracle_and_bad_rows():
     k = g.SquaredExponentialKernel(num_dim=2, initial_params=[1.0, 0.3, 0.4], param_bounds=[(0, 10)] * 3)
     gp = g.GaussianProcess(k, X=X, y=y, err_y=err, n=n)
     th = bench.theta_batch(6)
-    th[1, 1] = -0.5                                      # outside the uniform prior
-    Xs = np.random.RandomState(2).rand(100, 2)
+    th[1, 0] = 1e170                                     # sigma_f^2 overflows: covariance not positive definite
+    th[2, 1] = -th[2, 1]                                 # outside the uniform prior, yet a valid covariance: the reference's
+    Xs = np.random.RandomState(2).rand(100, 2)           # per-sample wrapper predicts it (gaussian_process.py:2301-2330)
     mean, std, good = gp.predict_batch(th, Xs)
     assert list(good) == [True, False, True, True, True, True]
     assert np.isnan(mean[1]).all() and np.isnan(std[1]).all()
+    t2 = th[2].copy()
+    t2[1] = -t2[1]
+    m2, s2, _ = gp.predict_batch(t2[None, :], Xs)
+    assert_close(mean[2], m2[0], rtol=1e-12, atol=1e-13)  # k depends on l^2 only
     for b in (0, 5):
         r = orc.compute_K_L_alpha_ll(0, th[b], gp.X, gp.n, gp.y, gp.err_y)
         m, s, _ = orc.predict(0, th[b], gp.X, gp.n, r["L"], r["alpha"], Xs, np.zeros((100, 2), int))
@@ -220,3 +225,25 @@ def test_c3_full_size_batch_prediction():
     assert_close(ll + float(gd["log_prior"]), gd["ll"], rtol=1e-9, what="ll next to the predictions")
     assert_close(m8[0], gd["mean"], rtol=1e-8, what="mean at theta 0 vs the reference")
     assert_close(np.sqrt(v8[0]), gd["std"], rtol=1e-5, what="std at theta 0 vs the reference")
+
+
+def test_predict_MCMC_matches_the_reference_on_the_device():
+    """Golden mcmc_predict_se1d from the reference's predict_MCMC / compute_from_MCMC, through gpt_predict_batched."""
+    gd = load_golden("mcmc_predict_se1d")
+    k = g.SquaredExponentialKernel(initial_params=[1.0, 0.7], param_bounds=[(0.05, 5), (0.1, 3)])
+    gp = g.GaussianProcess(k)
+    nv = int((gd["n"][:, 0] == 0).sum())
+    gp.add_data(gd["X"][:nv, 0], gd["y"][:nv], err_y=gd["err_y"][:nv])
+    gp.add_data(gd["X"][nv:, 0], gd["y"][nv:], err_y=gd["err_y"][nv:], n=1)
+    res = gp.compute_from_MCMC(gd["Xs"], flat_trace=gd["trace"])
+    assert_close(np.array(res["mean"]), gd["means"], rtol=1e-8, atol=1e-10, what="per-sample means")
+    assert_close(np.array(res["std"]), gd["stds"], rtol=1e-6, atol=1e-9, what="per-sample stds")
+    out = gp.predict_MCMC(gd["Xs"], flat_trace=gd["trace"])
+    assert_close(out["mean"], gd["mean"], rtol=1e-8, atol=1e-10)
+    assert_close(out["std"], gd["std"], rtol=1e-6, atol=1e-9)
+    out1 = gp.predict_MCMC(gd["Xs"], n=1, flat_trace=gd["trace"])
+    assert_close(out1["mean"], gd["mean_d1"], rtol=1e-8, atol=1e-9)
+    assert_close(out1["std"], gd["std_d1"], rtol=1e-6, atol=1e-9)
+    thin = gp.predict_MCMC(gd["Xs"], flat_trace=gd["trace"], burn=2, thin=3)
+    assert_close(thin["mean"], gd["mean_thin"], rtol=1e-8, atol=1e-10)
+    assert_close(thin["std"], gd["std_thin"], rtol=1e-6, atol=1e-9)

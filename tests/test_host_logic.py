@@ -600,7 +600,8 @@ def test_compute_from_MCMC_uses_one_batched_prediction_and_matches_the_per_sampl
     rs = np.random.RandomState(5)
     th0 = np.array(gp.free_params[:], dtype=float)
     trace = th0 * np.exp(0.05 * rs.randn(6, len(th0)))
-    trace[2, 0] = -1.0                                     # zero prior probability: skipped
+    trace[2, 0] = -1.0                                     # zero prior probability: predicted all the same (reference)
+    trace[4, 0] = 1e170                                    # sigma_f^2 overflows: not positive definite, dropped
     Xs = rs.rand(5, 2)
     n_calls = len(gp._dev_obj.calls)
     res_b = gp.compute_from_MCMC(Xs, flat_trace=trace)
@@ -609,7 +610,7 @@ def test_compute_from_MCMC_uses_one_batched_prediction_and_matches_the_per_sampl
     gp._mcmc_predict_by_loop = True
     res_l = gp.compute_from_MCMC(Xs, flat_trace=trace)
     gp._mcmc_predict_by_loop = False
-    assert len(res_b['mean']) == len(res_l['mean']) == 5
+    assert len(res_b['mean']) == len(res_l['mean']) == 5   # six samples, one dropped
     for a, b in zip(res_b['mean'], res_l['mean']):
         assert_close(a, b, rtol=1e-10, atol=1e-12)
     for a, b in zip(res_b['std'], res_l['std']):
@@ -627,3 +628,29 @@ def test_compute_from_MCMC_uses_one_batched_prediction_and_matches_the_per_sampl
     gp._mcmc_predict_by_loop = False
     for a, b in zip(res_d['mean'], res_dl['mean']):
         assert_close(a, b, rtol=1e-9, atol=1e-11)
+
+
+def test_predict_MCMC_matches_the_reference():
+    """The reference's own predict_MCMC / compute_from_MCMC on a 12-sample trace (golden mcmc_predict_se1d; one sample outside
+    the prior support, which its per-sample wrapper predicts all the same; burn / thin applied to a given trace): per-sample
+    means and standard deviations, the marginalised mean / std (law of total variance), derivative predictions."""
+    gd = load_golden("mcmc_predict_se1d")
+    k = g.SquaredExponentialKernel(initial_params=[1.0, 0.7], param_bounds=[(0.05, 5), (0.1, 3)])
+    gp = with_fake(g.GaussianProcess(k))
+    nv = int((gd["n"][:, 0] == 0).sum())
+    gp.add_data(gd["X"][:nv, 0], gd["y"][:nv], err_y=gd["err_y"][:nv])
+    gp.add_data(gd["X"][nv:, 0], gd["y"][nv:], err_y=gd["err_y"][nv:], n=1)
+    for by_loop in (False, True):
+        gp._mcmc_predict_by_loop = by_loop
+        res = gp.compute_from_MCMC(gd["Xs"], flat_trace=gd["trace"])
+        assert_close(np.array(res["mean"]), gd["means"], rtol=1e-8, atol=1e-10, what="per-sample means")
+        assert_close(np.array(res["std"]), gd["stds"], rtol=1e-6, atol=1e-9, what="per-sample stds")
+        out = gp.predict_MCMC(gd["Xs"], flat_trace=gd["trace"])
+        assert_close(out["mean"], gd["mean"], rtol=1e-8, atol=1e-10)
+        assert_close(out["std"], gd["std"], rtol=1e-6, atol=1e-9)
+        out1 = gp.predict_MCMC(gd["Xs"], n=1, flat_trace=gd["trace"])
+        assert_close(out1["mean"], gd["mean_d1"], rtol=1e-8, atol=1e-9)
+        assert_close(out1["std"], gd["std_d1"], rtol=1e-6, atol=1e-9)
+        thin = gp.predict_MCMC(gd["Xs"], flat_trace=gd["trace"], burn=2, thin=3)
+        assert_close(thin["mean"], gd["mean_thin"], rtol=1e-8, atol=1e-10)
+        assert_close(thin["std"], gd["std_thin"], rtol=1e-6, atol=1e-9)
