@@ -597,6 +597,16 @@ def case_composite():
     res1 = gp.predict(Xs, n=1, full_output=True)
     out.update(mean_d1=res1["mean"], std_d1=res1["std"])
     save("composite_gp_1d", params=np.array([float(v) for v in kg.params]), **gp_state(gp), **out)
+    # SE + SE in 2-D with value and derivative observations and the reference's OWN ll gradient (SumKernel forwards
+    # hyper_deriv to the operand that owns the parameter, kernel/core.py:576-582; both operands are SE kernels)
+    ks = (g.SquaredExponentialKernel(num_dim=2, initial_params=[1.2, 0.5, 0.7], param_bounds=[(0, 10)] * 3) +
+          g.SquaredExponentialKernel(num_dim=2, initial_params=[0.4, 0.15, 0.2], param_bounds=[(0, 10)] * 3))
+    Xg = rs.rand(30, 2)
+    gps = g.GaussianProcess(ks)
+    gps.add_data(Xg, np.sin(3 * Xg[:, 0]) * np.cos(2 * Xg[:, 1]) + 0.05 * rs.randn(30), err_y=0.05)
+    gps.add_data(Xg[::5], 3 * np.cos(3 * Xg[::5, 0]) * np.cos(2 * Xg[::5, 1]), err_y=0.2, n=np.tile([1, 0], (6, 1)))
+    outs = ll_and_grad(gps, True)
+    save("composite_sum_grad_2d", params=np.array([float(v) for v in ks.params]), **gp_state(gps), **outs)
 
 
 # ---------------------------------------------------------------- compute_from_MCMC / predict_MCMC (gaussian_process.py:1840-2254)

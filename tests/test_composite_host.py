@@ -75,6 +75,16 @@ def test_oracle_composite_gp_matches_reference():
     assert_close(np.ravel(r["alpha"]), gd["alpha"], rtol=1e-7, atol=1e-9 * np.abs(gd["alpha"]).max(), what="alpha")
 
 
+def test_oracle_composite_gradient_matches_reference():
+    """SE + SE in 2-D with derivative observations: ll and the reference's own ll gradient (SumKernel hyper_deriv,
+    kernel/core.py:576-582) -- pins the oracle's composite hyper-derivative path that the GPU tests compare against."""
+    gd = load_golden("composite_sum_grad_2d")
+    st = _Struct(((SE, SE), (3, 3), (0b01, 0b10)))
+    r = orc.compute_K_L_alpha_ll(st, gd["params"], gd["X"], gd["n"], gd["y"], gd["err_y"], grad_idx=list(range(6)))
+    assert_close(r["ll"], float(gd["ll"]) - float(gd["log_prior"]), rtol=1e-10, what="ll")
+    assert_close(r["ll_deriv"], gd["ll_deriv"], rtol=1e-8, atol=1e-10 * np.abs(gd["ll_deriv"]).max(), what="ll gradient")
+
+
 # ------------------------------------------------------------------ the device source, compiled for the host
 def test_device_composite_source_matches_reference_goldens(lib):
     gd = load_golden("kernel_algebra_se2d")
