@@ -632,6 +632,22 @@ def case_mcmc_predict():
          std_thin=thin['std'], **gp_state(gp))
 
 
+# ---------------------------------------------------------------- compute_ll_matrix (gaussian_process.py:1607-1692)
+def case_ll_matrix():
+    """The log-posterior over a regular grid of the free hyperparameters (KAT-1 problem: SE 2-D, value + both gradient
+    observations), as the reference's own nested loop computes it."""
+    rs = RandomState(0)
+    X = rs.rand(6, 2)
+    k = g.SquaredExponentialKernel(num_dim=2, initial_params=[1.3, 0.7, 1.1], param_bounds=[(0, 10)] * 3)
+    gp = g.GaussianProcess(k)
+    gp.add_data(X, np.sin(X).sum(1), err_y=0.01)
+    gp.add_data(X, np.cos(X[:, 0]), n=np.tile([1, 0], (6, 1)), err_y=0.01)
+    gp.add_data(X, np.cos(X[:, 1]), n=np.tile([0, 1], (6, 1)), err_y=0.01)
+    bounds, num_pts = [(1.0, 1.5), (0.5, 0.9), (0.9, 1.3)], [2, 3, 2]
+    ll_vals, pv = gp.compute_ll_matrix(bounds, num_pts)
+    save("ll_matrix_kat1", bounds=np.array(bounds), num_pts=np.array(num_pts), ll_vals=ll_vals, p0=pv[0], p1=pv[1], p2=pv[2])
+
+
 # ---------------------------------------------------------------- other Gibbs length-scale profiles (kernel/gibbs.py:508-902)
 def case_gibbs_profiles():
     rs = RandomState(21)
@@ -688,7 +704,7 @@ def case_warped():
 if __name__ == "__main__":
     cases = [case_se2d, case_se_pairs, case_matern52, case_matern_generic, case_gibbs, case_c5_full, case_demo,
              case_c3, case_c2, case_noise, case_hyperfd, case_product, case_gibbs_profiles, case_warped,
-             case_matern_real_nu, case_hyper_mp, case_composite, case_mcmc_predict]
+             case_matern_real_nu, case_hyper_mp, case_composite, case_mcmc_predict, case_ll_matrix]
     only = set(sys.argv[1:])          # e.g. `make_golden.py case_hyperfd` regenerates one family
     for c in cases:
         if not only or c.__name__ in only:

@@ -56,6 +56,11 @@ def test_kat1_se2d_end_to_end():
     nj = np.tile(gp.n, (18, 1))
     assert_close(k(Xi, Xj, ni, nj).reshape(18, 18), gd["K"], rtol=1e-12, atol=1e-14)
     assert_close(k(Xi, Xj, ni, nj, hyper_deriv=2).reshape(18, 18), gd["dK2"], rtol=1e-10, atol=1e-13)
+    # compute_ll_matrix (gaussian_process.py:1607-1692): the reference's grid, here one batched launch
+    gl = load_golden("ll_matrix_kat1")
+    ll_vals, pv = gp.compute_ll_matrix([tuple(b) for b in gl["bounds"]], [int(v) for v in gl["num_pts"]])
+    assert_close(ll_vals, gl["ll_vals"], rtol=1e-9, what="ll grid")
+    assert_close(pv[1], gl["p1"], rtol=0, atol=0)
 
 
 def test_kat2_matern52_and_kat3_gibbs_T_draw():

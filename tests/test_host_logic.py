@@ -239,6 +239,11 @@ def test_compute_ll_matrix_shape_and_values():
     assert ll_vals.shape == (2, 3, 2)
     v = gp.update_hyperparameters(np.array([pv[0][1], pv[1][2], pv[2][0]]))
     assert_close(ll_vals[1, 2, 0], -v, rtol=1e-12)
+    # the reference's own grid (gaussian_process.py:1607-1692): same values, same parameter axes
+    gd = load_golden("ll_matrix_kat1")
+    assert_close(ll_vals, gd["ll_vals"], rtol=1e-9, what="ll grid")
+    for a, b in zip(pv, (gd["p0"], gd["p1"], gd["p2"])):
+        assert_close(a, b, rtol=0, atol=0)
 
 
 # ------------------------------------------------------------------ predict / draw_sample host logic
